@@ -379,6 +379,47 @@ def residual_rows_from_streams(mesh: MeshArrays, st: StreamsPy) -> list:
     return out
 
 
+def residual_rows_encoder_side(mesh: MeshArrays, st: StreamsPy) -> list:
+    """Like residual_rows_from_streams, but for a mesh in ENCODER numbering: the k-th DATA residual
+    of a list goes to the attribute row its emitting element is bound to (vertex and face lists;
+    used by smoke() and tests to decode on the mesh that was just encoded)."""
+    face_of = np.repeat(np.arange(mesh.nf, dtype=np.int64), np.diff(mesh.face_off.astype(np.int64)))
+    out = []
+    for l, la in enumerate(mesh.lists):
+        lb = la.copy()
+        lb.rows[:] = 0
+        if la.target == T_VTX:
+            h = mesh.face_off[mesh.order[:, 0]].astype(np.int64) + mesh.order[:, 1]
+            ent = mesh.edges[h, 0].astype(np.int64)
+            regs, off, lists, bind, nb = mesh.vtx_regs, mesh.off_reg_vtx, mesh.reg_vtxlist, mesh.bind_vtx, mesh.nb_vtx
+        elif la.target == T_FACE:
+            of = mesh.order_f if mesh.order_f is not None else np.stack([np.arange(mesh.nf), np.zeros(mesh.nf)], 1)
+            ent = of[:, 0].astype(np.int64)
+            regs, off, lists, bind, nb = mesh.face_regs, mesh.off_reg_face, mesh.reg_facelist, mesh.bind_face, mesh.nb_face
+        else:
+            raise NotImplementedError("corner lists: use the decoder-side mesh")
+        slot = np.full(len(off) - 1, -1, dtype=np.int64)
+        for r in range(len(off) - 1):
+            for a in range(off[r + 1] - off[r]):
+                if lists[off[r] + a] == l:
+                    slot[r] = a
+        a_of = slot[regs[ent]]
+        ent = ent[a_of >= 0]
+        rows_idx = bind[ent * nb + a_of[a_of >= 0]].astype(np.int64)
+        _, first = np.unique(rows_idx, return_index=True)
+        data_rows = rows_idx[np.sort(first)]          # row of the k-th DATA emission
+        sym = st.lists[l].symbols
+        assert sym.shape[0] == data_rows.shape[0]
+        pos = 0
+        for j in range(la.ncomp):
+            sz = TYPE_SIZE[la.stype(j)]
+            o = la.offsets[j]
+            lb.rows[data_rows, o:o + sz] = sym[:, pos:pos + sz]
+            pos += sz
+        out.append(lb)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # library loading
 # ----------------------------------------------------------------------------------------------
@@ -433,8 +474,12 @@ def load_library():
     lib.hb_dmesh_encode.restype = C.c_int
     lib.hb_dmesh_fetch_streams.argtypes = [vp, C.POINTER(C.POINTER(Streams))]
     lib.hb_dmesh_fetch_streams.restype = C.c_int
-    lib.hb_dmesh_load_residuals.argtypes = [vp]
-    lib.hb_dmesh_load_residuals.restype = C.c_int
+    lib.hb_dmesh_set_bounds.argtypes = [vp, u32, vp, vp, vp]
+    lib.hb_dmesh_set_bounds.restype = C.c_int
+    lib.hb_dmesh_snapshot.argtypes = [vp]
+    lib.hb_dmesh_snapshot.restype = C.c_int
+    lib.hb_dmesh_restore.argtypes = [vp]
+    lib.hb_dmesh_restore.restype = C.c_int
     lib.hb_dmesh_decode.argtypes = [vp]
     lib.hb_dmesh_decode.restype = C.c_int
     lib.hb_dmesh_fetch_rows.argtypes = [vp, u32, vp]
@@ -451,7 +496,7 @@ EXPORTED_SYMBOLS = [
     "hb_ctx_create", "hb_ctx_destroy", "hb_last_error", "hb_last_timing", "hb_kernel_launches",
     "hb_bounds", "hb_requant", "hb_attr_encode", "hb_streams_free", "hb_attr_decode",
     "hb_dmesh_upload", "hb_dmesh_free", "hb_dmesh_quantize", "hb_dmesh_dequantize", "hb_dmesh_encode",
-    "hb_dmesh_fetch_streams", "hb_dmesh_load_residuals", "hb_dmesh_decode", "hb_dmesh_fetch_rows",
+    "hb_dmesh_fetch_streams", "hb_dmesh_set_bounds", "hb_dmesh_snapshot", "hb_dmesh_restore", "hb_dmesh_decode", "hb_dmesh_fetch_rows",
     "hb_dmesh_fetch_bounds", "hb_ctx_sync",
 ]
 
@@ -567,8 +612,17 @@ class DeviceMesh:
         finally:
             self.ctx.lib.hb_streams_free(sp)
 
-    def load_residuals(self):
-        self.ctx._check(self.ctx.lib.hb_dmesh_load_residuals(self.h), "hb_dmesh_load_residuals")
+    def set_bounds(self, l: int, mn=None, mx=None, sc=None):
+        ptr = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.uint8).ctypes.data
+        keep = [np.ascontiguousarray(a, dtype=np.uint8) for a in (mn, mx, sc) if a is not None]
+        self.ctx._check(self.ctx.lib.hb_dmesh_set_bounds(self.h, l, ptr(mn), ptr(mx), ptr(sc)), "hb_dmesh_set_bounds")
+        del keep
+
+    def snapshot(self):
+        self.ctx._check(self.ctx.lib.hb_dmesh_snapshot(self.h), "hb_dmesh_snapshot")
+
+    def restore(self):
+        self.ctx._check(self.ctx.lib.hb_dmesh_restore(self.h), "hb_dmesh_restore")
 
     def decode(self):
         self.ctx._check(self.ctx.lib.hb_dmesh_decode(self.h), "hb_dmesh_decode")

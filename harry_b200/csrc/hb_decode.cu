@@ -1,0 +1,189 @@
+// hb_decode.cu -- decode side: reconstruction of attribute values from residual rows
+// (AttrDecoder<RD>::decode, formats/hry/attrcode.h:443-550, after the host drained the symbol
+// stream -- SURVEY.md 3.2).
+//
+// Scheduling (DESIGN.md "Decode"): a row can be reconstructed once every candidate row of its
+// prediction is reconstructed.
+//   * FACE lists: prediction is always 0 -> embarrassingly parallel map.
+//   * CORNER lists: shallow DAG (depth <= fan size).  Level-synchronous wavefronts: each sweep
+//     reconstructs every element whose candidates are all done; levels are discovered on the fly.
+//   * VTX lists: the DAG over the traversal order is a CHAIN (every new vertex is predicted across
+//     a gate that ends in the vertex decoded just before it; depth ~ N).  One thread per
+//     (list, component) walks the chain in traversal order over rank-space records; parallelism
+//     comes from components, lists and -- for batches -- meshes.
+#include "hb_lists.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// VTX: chain walker
+// ------------------------------------------------------------------------------------------------
+struct WalkArgs {
+	int ncomp;
+	uint8_t stype[HB_MAX_COMP], quant[HB_MAX_COMP];
+	const uint32_t *erow, *first, *cand_off, *cand;
+	unsigned long long *rp;
+	uint32_t n;
+};
+
+__global__ void __launch_bounds__(32) k_decode_vertex_chain(const WalkArgs *__restrict__ args)
+{
+	const WalkArgs &a = args[blockIdx.x];
+	const int j = threadIdx.x;
+	if (j >= a.ncomp) return;
+	const int st = a.stype[j], q = a.quant[j], nc = a.ncomp;
+	const uint32_t n = a.n;
+	const uint32_t *__restrict__ erow = a.erow, *__restrict__ first = a.first, *__restrict__ coff = a.cand_off, *__restrict__ cand = a.cand;
+	unsigned long long *rp = a.rp;
+	uint32_t c0 = n ? coff[0] : 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		const uint32_t c1 = coff[i + 1];
+		const uint32_t row = erow[i];
+		if (row != HB_NONE) {
+			const uint32_t fi = first[row];
+			if (fi != i) {
+				rp[(size_t)i * nc + j] = rp[(size_t)fi * nc + j]; // HIST reference: value already decoded
+			} else {
+				const uint32_t K = c1 - c0;
+				const unsigned long long pred = combine_candidates(st, K, [&](uint32_t kk) {
+					const uint32_t *tr = cand + 3 * (size_t)(c0 + kk);
+					return hb_predict(st, rp[(size_t)tr[0] * nc + j], rp[(size_t)tr[1] * nc + j], rp[(size_t)tr[2] * nc + j], q);
+				});
+				rp[(size_t)i * nc + j] = hb_dec(st, rp[(size_t)i * nc + j], pred, q);
+			}
+		}
+		c0 = c1;
+	}
+}
+
+// rank-space records -> AoS rows (DATA elements own their row)
+__global__ void __launch_bounds__(256) k_scatter_rp(ListParams p, const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, const unsigned long long *__restrict__ rp)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	if (row == HB_NONE || first[row] != i) return;
+	uint8_t *dst = p.rows + (size_t)row * p.stride;
+	for (int j = 0; j < p.ncomp; ++j) hb_st_bits(dst + p.offset[j], p.size[j], rp[(size_t)i * p.ncomp + j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FACE: prediction 0 (Appendix C.2) -> decodeDelta(delta, 0): identity for integer storage types,
+// un-flip for floats (prediction.h:64-72)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_decode_face(ListParams p, const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	if (row == HB_NONE || first[row] != i) return;
+	uint8_t *dst = p.rows + (size_t)row * p.stride;
+	for (int j = 0; j < p.ncomp; ++j) {
+		const unsigned long long d = hb_ld_bits(dst + p.offset[j], p.size[j]);
+		hb_st_bits(dst + p.offset[j], p.size[j], hb_dec(p.stype[j], d, 0, p.quant[j]));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// CORNER: level-synchronous wavefront sweeps
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(256) k_decode_corner_sweep(ListParams p, const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first,
+                                                              const uint32_t *__restrict__ cand_off, const uint32_t *__restrict__ cand, uint32_t n,
+                                                              unsigned long long *rp, volatile uint8_t *done, uint32_t *__restrict__ remaining)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	if (row == HB_NONE || done[i]) return;
+	const uint32_t fi = first[row];
+	bool ready = true;
+	if (fi != i) {
+		ready = done[fi] != 0; // HIST / LHIST reference: copy once the owning element is decoded
+	} else {
+		const uint32_t c0 = cand_off[i], c1 = cand_off[i + 1];
+		for (uint32_t k = c0; k < c1 && ready; ++k) ready = done[cand[k]] != 0;
+	}
+	if (!ready) { atomicAdd(remaining, 1u); return; }
+	__threadfence();
+	if (fi != i) {
+		for (int j = 0; j < p.ncomp; ++j) rp[(size_t)i * p.ncomp + j] = ld_cg_u64(rp + (size_t)fi * p.ncomp + j);
+	} else {
+		const uint32_t c0 = cand_off[i], K = cand_off[i + 1] - c0;
+		for (int j = 0; j < p.ncomp; ++j) {
+			const int st = p.stype[j];
+			const unsigned long long pred = combine_candidates(st, K, [&](uint32_t kk) { return ld_cg_u64(rp + (size_t)cand[c0 + kk] * p.ncomp + j); });
+			rp[(size_t)i * p.ncomp + j] = hb_dec(st, ld_cg_u64(rp + (size_t)i * p.ncomp + j), pred, p.quant[j]);
+		}
+	}
+	__threadfence();
+	done[i] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+int hb_decode_lists(hb_dmesh *m)
+{
+	hb_ctx *ctx = m->ctx;
+	HB_TRY(hb_build_conn(m));
+	bool need_v = false, need_c = false;
+	for (int l = 0; l < m->nlists; ++l) {
+		const int cls = m->lists[l].p.target;
+		if (cls == CLS_VTX && m->lists[l].p.ncomp) need_v = true;
+		if (cls == CLS_CORNER && m->lists[l].p.ncomp) need_c = true;
+	}
+	if (need_v) HB_TRY(hb_build_vertex_candidates(m));
+	if (need_c && m->any_corner) HB_TRY(hb_build_corner_candidates(m));
+
+	std::vector<WalkArgs> walks;
+	std::vector<int> walk_lists;
+	for (int l = 0; l < m->nlists; ++l) {
+		DevList &dl = m->lists[l];
+		const ListParams &p = dl.p;
+		const int cls = p.target;
+		if (p.ncomp == 0 || (cls != CLS_VTX && cls != CLS_FACE && cls != CLS_CORNER)) continue;
+		if (cls == CLS_CORNER && !m->any_corner) continue;
+		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE));
+		const uint32_t n = dl.n_elems;
+		if (!n) continue;
+		if (cls == CLS_FACE) {
+			HB_LAUNCH(ctx, k_decode_face, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, n);
+		} else if (cls == CLS_VTX) {
+			WalkArgs w;
+			w.ncomp = p.ncomp;
+			for (int j = 0; j < p.ncomp; ++j) { w.stype[j] = p.stype[j]; w.quant[j] = p.quant[j]; }
+			w.erow = dl.d_erow; w.first = dl.d_first; w.cand_off = m->d_vc_off; w.cand = m->d_vc_tri; w.rp = dl.d_rp; w.n = n;
+			walks.push_back(w);
+			walk_lists.push_back(l);
+		} else {
+			uint8_t *done = nullptr;
+			uint32_t *remaining = nullptr;
+			HB_TRY(hb_dalloc_t(m, &done, (size_t)n + 1));
+			HB_TRY(hb_dalloc_t(m, &remaining, 1));
+			HB_CUDA(ctx, cudaMemsetAsync(done, 0, (size_t)n + 1, ctx->stream));
+			uint32_t prev = 0xffffffffu;
+			for (uint32_t sweep = 0;; ++sweep) {
+				HB_CUDA(ctx, cudaMemsetAsync(remaining, 0, sizeof(uint32_t), ctx->stream));
+				HB_LAUNCH(ctx, k_decode_corner_sweep, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, m->d_cc_off, m->d_cc_idx, n, dl.d_rp, done, remaining);
+				uint32_t rem = 0;
+				HB_CUDA(ctx, cudaMemcpyAsync(&rem, remaining, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+				HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				if (rem == 0) break;
+				if (rem >= prev && sweep > 0) return hb_fail(ctx, HB_ERR_INVALID, "corner decode: dependency cycle (%u elements stuck)", rem);
+				prev = rem;
+			}
+			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, n, dl.d_rp);
+		}
+	}
+	if (!walks.empty()) {
+		WalkArgs *d_walks = nullptr;
+		HB_TRY(hb_dalloc_t(m, &d_walks, walks.size()));
+		HB_CUDA(ctx, cudaMemcpyAsync(d_walks, walks.data(), sizeof(WalkArgs) * walks.size(), cudaMemcpyHostToDevice, ctx->stream));
+		HB_LAUNCH(ctx, k_decode_vertex_chain, (uint32_t)walks.size(), 32, 0, d_walks);
+		// the pageable source buffer must outlive the async copy
+		HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		for (size_t k = 0; k < walks.size(); ++k) {
+			DevList &dl = m->lists[walk_lists[k]];
+			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(dl.n_elems, 256), 256, 0, dl.p, dl.d_erow, dl.d_first, dl.n_elems, dl.d_rp);
+		}
+	}
+	return 0;
+}

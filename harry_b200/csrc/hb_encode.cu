@@ -1,0 +1,365 @@
+// hb_encode.cu -- encode side of the attribute coder (AttrCoder<WR>::encode,
+// formats/hry/attrcode.h:321-416) as data-parallel kernels:
+//   elem_rows      element -> bound attribute row (or none), per list
+//   first_ref      first reference of every attribute row (atomicMin) = its DATA emission
+//                  (GlobalHistory, attrcode.h:23-53)
+//   lhist          per-(corner slot, vertex) local history (LocalHistory, attrcode.h:54-80)
+//   gather_rp      rows -> rank-space value records (SoA-by-traversal-order transposition)
+//   K5 encode_main prediction from the fan candidates, residual (pred::encodeDelta), byte-plane
+//                  symbol rows, per-context 256-bin histograms, type / history-offset streams
+#include "hb_lists.cuh"
+
+// ------------------------------------------------------------------------------------------------
+template <int CLS>
+__global__ void __launch_bounds__(256) k_elem_rows(ElemCtx c, int l, uint32_t nrows, uint32_t *__restrict__ erow, uint32_t *__restrict__ bound_flag, int *err)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= c.n) return;
+	uint32_t row, entity;
+	int a;
+	bool ok = elem_lookup<CLS>(c, i, l, row, a, entity);
+	if (ok && row >= nrows) { atomicExch(err, 7); ok = false; }
+	erow[i] = ok ? row : HB_NONE;
+	if (bound_flag) bound_flag[i] = ok ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_first_ref(const uint32_t *__restrict__ erow, uint32_t n, uint32_t *__restrict__ first)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	if (row != HB_NONE) atomicMin(&first[row], i);
+}
+
+__global__ void __launch_bounds__(256) k_data_flags(const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, uint32_t *__restrict__ dflag)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	dflag[i] = (row != HB_NONE && first[row] == i) ? 1u : 0u;
+}
+
+// rows (AoS, by attribute index) -> rank-space records: u64 container per component, element-major
+__global__ void __launch_bounds__(256) k_gather_rp(ListParams p, const uint32_t *__restrict__ erow, uint32_t n, unsigned long long *__restrict__ rp)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	if (row == HB_NONE) return;
+	const uint8_t *src = p.rows + (size_t)row * p.stride;
+	for (int j = 0; j < p.ncomp; ++j) rp[(size_t)i * p.ncomp + j] = hb_ld_bits(src + p.offset[j], p.size[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// local history of corner bindings
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vinc_count(const uint4 *__restrict__ he, const uint32_t *__restrict__ celem_h, const uint16_t *__restrict__ face_regs,
+                                                     const int *__restrict__ reg_ncorner, uint32_t n, uint32_t *__restrict__ cnt)
+{
+	const uint32_t ce = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ce >= n) return;
+	const uint4 r = he[celem_h[ce]];
+	if (reg_ncorner[face_regs[r.w]] > 0) atomicAdd(&cnt[r.x], 1u);
+}
+__global__ void __launch_bounds__(256) k_vinc_fill(const uint4 *__restrict__ he, const uint32_t *__restrict__ celem_h, const uint16_t *__restrict__ face_regs,
+                                                    const int *__restrict__ reg_ncorner, uint32_t n, const uint32_t *__restrict__ off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ vinc)
+{
+	const uint32_t ce = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ce >= n) return;
+	const uint4 r = he[celem_h[ce]];
+	if (reg_ncorner[face_regs[r.w]] > 0) vinc[off[r.x] + atomicAdd(&cursor[r.x], 1u)] = ce;
+}
+
+__device__ void sort_u32(uint32_t *a, uint32_t n)
+{
+	if (n < 32) { // insertion sort
+		for (uint32_t i = 1; i < n; ++i) {
+			const uint32_t x = a[i];
+			uint32_t j = i;
+			while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; --j; }
+			a[j] = x;
+		}
+		return;
+	}
+	// heap sort for the rare huge fan (sphere poles)
+	for (uint32_t start = n / 2; start-- > 0;) {
+		uint32_t root = start;
+		for (;;) {
+			uint32_t child = 2 * root + 1;
+			if (child >= n) break;
+			if (child + 1 < n && a[child] < a[child + 1]) ++child;
+			if (a[root] >= a[child]) break;
+			const uint32_t t = a[root]; a[root] = a[child]; a[child] = t;
+			root = child;
+		}
+	}
+	for (uint32_t end = n; end-- > 1;) {
+		const uint32_t t = a[0]; a[0] = a[end]; a[end] = t;
+		uint32_t root = 0;
+		for (;;) {
+			uint32_t child = 2 * root + 1;
+			if (child >= end) break;
+			if (child + 1 < end && a[child] < a[child + 1]) ++child;
+			if (a[root] >= a[child]) break;
+			const uint32_t u = a[root]; a[root] = a[child]; a[child] = u;
+			root = child;
+		}
+	}
+}
+
+// One thread per vertex: its corner elements in emission order, and per binding slot the list of
+// distinct attribute indices seen so far.  A hit yields the offset size-1-pos (attrcode.h:67-74).
+__global__ void __launch_bounds__(128) k_lhist(const uint4 *__restrict__ he, const uint32_t *__restrict__ celem_h, const uint16_t *__restrict__ face_regs,
+                                                const int *__restrict__ reg_ncorner, const uint32_t *__restrict__ bind_corner, uint32_t nb_corner, uint32_t nv,
+                                                const uint32_t *__restrict__ off, uint32_t *__restrict__ vinc, uint32_t *__restrict__ dist, uint32_t ncel, uint32_t *__restrict__ lh)
+{
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= nv) return;
+	const uint32_t b = off[v], cnt = off[v + 1] - b;
+	if (cnt == 0) return;
+	sort_u32(vinc + b, cnt);
+	for (uint32_t a = 0; a < nb_corner; ++a) {
+		uint32_t nd = 0;
+		for (uint32_t k = 0; k < cnt; ++k) {
+			const uint32_t ce = vinc[b + k];
+			const uint32_t h = celem_h[ce];
+			if ((uint32_t)reg_ncorner[face_regs[he[h].w]] <= a) continue;
+			const uint32_t idx = bind_corner[(size_t)h * nb_corner + a];
+			uint32_t hit = HB_NONE;
+			for (uint32_t q = 0; q < nd; ++q)
+				if (dist[b + q] == idx) { hit = nd - 1 - q; break; }
+			lh[(size_t)a * ncel + ce] = hit;
+			if (hit == HB_NONE) dist[b + nd++] = idx;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: prediction + residual + byte-plane symbols + histograms
+// ------------------------------------------------------------------------------------------------
+#define ENC_THREADS 256
+#define HIST_SMEM_CTX 24 // contexts histogrammed in shared memory; the rest goes to global atomics
+
+struct EncodeArgs {
+	const uint32_t *erow, *ek, *first, *dord; // ek == nullptr: emission index == element index
+	const unsigned long long *rp;             // rank-space values (VTX / CORNER)
+	const uint32_t *cand_off, *cand;          // VTX: rank triples, CORNER: corner elements
+	const uint32_t *lh;                       // CORNER: local-history offsets of this list's slot table base
+	uint32_t ncel;
+	const uint16_t *face_regs;
+	const int16_t *slot_corner;
+	uint32_t nlists;
+	const uint32_t *celem_h;
+	const uint4 *he;
+	uint8_t *type;
+	uint32_t *aux;
+	uint8_t *sym;
+	unsigned long long *hist, *type_hist;
+	uint32_t n;
+	int l;
+};
+
+template <int CLS>
+__global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, EncodeArgs a)
+{
+	extern __shared__ uint32_t s_hist[]; // [min(sym_stride, HIST_SMEM_CTX)][256] + 4 type counters
+	const int nctx_s = (int)(p.sym_stride < HIST_SMEM_CTX ? p.sym_stride : HIST_SMEM_CTX);
+	for (int k = threadIdx.x; k < nctx_s * 256 + 4; k += ENC_THREADS) s_hist[k] = 0;
+	__syncthreads();
+	uint32_t *s_type = s_hist + nctx_s * 256;
+
+	const uint32_t i = blockIdx.x * ENC_THREADS + threadIdx.x;
+	const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
+	if (row != HB_NONE) {
+		const uint32_t k = a.ek ? a.ek[i] : i;
+		const uint32_t fi = a.first[row];
+		int t = HB_DATA;
+		uint32_t aux = 0;
+		if (fi != i) {
+			t = HB_HIST;
+			aux = a.dord[i] - 1u - a.dord[fi]; // tidx - 1 - g, attrcode.h:43-52
+			if (CLS == CLS_CORNER) {
+				// the local history is consulted first (attrcode.h:377-381)
+				const uint32_t h = a.celem_h[i];
+				const int slot = a.slot_corner[(uint32_t)a.face_regs[a.he[h].w] * a.nlists + (uint32_t)a.l];
+				const uint32_t lo = a.lh[(size_t)slot * a.ncel + i];
+				if (lo != HB_NONE) { t = HB_LHIST; aux = lo; }
+			}
+		}
+		a.type[k] = (uint8_t)t;
+		a.aux[k] = aux;
+		atomicAdd(&s_type[t], 1u);
+		if (t == HB_DATA) {
+			const uint32_t d = a.dord[i];
+			uint8_t *out = a.sym + (size_t)d * p.sym_stride;
+			uint32_t c0 = 0, K = 0;
+			if (CLS != CLS_FACE) { c0 = a.cand_off[i]; K = a.cand_off[i + 1] - c0; }
+			for (int j = 0; j < p.ncomp; ++j) {
+				const int st = p.stype[j], q = p.quant[j];
+				unsigned long long raw, pred = 0;
+				if (CLS == CLS_FACE) {
+					// face prediction is always 0 (Appendix C.2): no rank-space copy needed
+					raw = hb_ld_bits(p.rows + (size_t)row * p.stride + p.offset[j], p.size[j]);
+				} else {
+					raw = a.rp[(size_t)i * p.ncomp + j];
+					if (CLS == CLS_VTX) {
+						pred = combine_candidates(st, K, [&](uint32_t kk) {
+							const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
+							return hb_predict(st, a.rp[(size_t)tr[0] * p.ncomp + j], a.rp[(size_t)tr[1] * p.ncomp + j], a.rp[(size_t)tr[2] * p.ncomp + j], q);
+						});
+					} else {
+						pred = combine_candidates(st, K, [&](uint32_t kk) { return a.rp[(size_t)a.cand[c0 + kk] * p.ncomp + j]; });
+					}
+				}
+				const unsigned long long res = hb_enc(st, raw, pred, q);
+				hb_st_bits(out + p.sym_off[j], p.size[j], res);
+				for (int b = 0; b < p.size[j]; ++b) {
+					const uint32_t ctx = p.sym_off[j] + b, s = (uint32_t)(res >> (8 * b)) & 0xffu;
+					if ((int)ctx < nctx_s) atomicAdd(&s_hist[ctx * 256 + s], 1u);
+					else atomicAdd(&a.hist[(size_t)ctx * 256 + s], 1ull);
+				}
+			}
+		}
+	}
+	__syncthreads();
+	for (int k = threadIdx.x; k < nctx_s * 256; k += ENC_THREADS)
+		if (s_hist[k]) atomicAdd(&a.hist[k], (unsigned long long)s_hist[k]);
+	if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&a.type_hist[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+static ElemCtx make_elem_ctx(hb_dmesh *m, int cls)
+{
+	ElemCtx c;
+	c.he = m->d_he;
+	c.ord_v = m->d_ord_v;
+	c.ford_h = m->d_ford_h;
+	c.celem_h = m->d_celem_h;
+	c.vtx_regs = m->d_vtx_regs;
+	c.face_regs = m->d_face_regs;
+	c.nlists = m->nlists;
+	if (cls == CLS_VTX) { c.bind = m->d_bind_vtx; c.slot = m->d_slot_vtx; c.nb = m->nb_vtx; c.n = m->norder; }
+	else if (cls == CLS_FACE) { c.bind = m->d_bind_face; c.slot = m->d_slot_face; c.nb = m->nb_face; c.n = m->norder_f; }
+	else { c.bind = m->d_bind_corner; c.slot = m->d_slot_corner; c.nb = m->nb_corner; c.n = m->n_corner_elems; }
+	return c;
+}
+
+// true when every region of the class binds list l (then emission index == element index)
+static bool bound_everywhere(hb_dmesh *m, int cls, int l)
+{
+	const std::vector<int16_t> &slot = cls == CLS_VTX ? m->h_slot_vtx : cls == CLS_FACE ? m->h_slot_face : m->h_slot_corner;
+	const int nregs = cls == CLS_VTX ? m->nregs_vtx : m->nregs_face;
+	for (int r = 0; r < nregs; ++r)
+		if (slot[(size_t)r * m->nlists + l] < 0) return false;
+	return true;
+}
+
+int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp)
+{
+	hb_ctx *ctx = m->ctx;
+	DevList &dl = m->lists[l];
+	const int cls = dl.p.target;
+	ElemCtx c = make_elem_ctx(m, cls);
+	const uint32_t n = c.n;
+	dl.n_elems = n;
+	HB_TRY(hb_dalloc_t(m, &dl.d_erow, (size_t)n + 1));
+	HB_TRY(hb_dalloc_t(m, &dl.d_first, (size_t)dl.p.nrows + 1));
+	HB_TRY(hb_dalloc_t(m, &dl.d_dord, (size_t)n + 2));
+	dl.d_ek = nullptr;
+	const bool everywhere = bound_everywhere(m, cls, l);
+	if (!everywhere) HB_TRY(hb_dalloc_t(m, &dl.d_ek, (size_t)n + 2));
+	HB_CUDA(ctx, cudaMemsetAsync(dl.d_first, 0xff, sizeof(uint32_t) * ((size_t)dl.p.nrows + 1), ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(dl.d_dord, 0, sizeof(uint32_t) * ((size_t)n + 2), ctx->stream));
+	if (n) {
+		const uint32_t g = hb_div_up(n, 256);
+		if (cls == CLS_VTX) HB_LAUNCH(ctx, k_elem_rows<CLS_VTX>, g, 256, 0, c, l, dl.p.nrows, dl.d_erow, dl.d_ek, ctx->d_err);
+		else if (cls == CLS_FACE) HB_LAUNCH(ctx, k_elem_rows<CLS_FACE>, g, 256, 0, c, l, dl.p.nrows, dl.d_erow, dl.d_ek, ctx->d_err);
+		else HB_LAUNCH(ctx, k_elem_rows<CLS_CORNER>, g, 256, 0, c, l, dl.p.nrows, dl.d_erow, dl.d_ek, ctx->d_err);
+		if (dl.d_ek) HB_TRY(hb_scan_exclusive_u32(ctx, dl.d_ek, dl.d_ek, n, nullptr));
+		HB_LAUNCH(ctx, k_first_ref, g, 256, 0, dl.d_erow, n, dl.d_first);
+		HB_LAUNCH(ctx, k_data_flags, g, 256, 0, dl.d_erow, dl.d_first, n, dl.d_dord);
+		HB_TRY(hb_scan_exclusive_u32(ctx, dl.d_dord, dl.d_dord, n, nullptr));
+		if (need_rp && dl.p.ncomp) {
+			HB_TRY(hb_dalloc_t(m, &dl.d_rp, (size_t)n * dl.p.ncomp + 1));
+			HB_LAUNCH(ctx, k_gather_rp, g, 256, 0, dl.p, dl.d_erow, n, dl.d_rp);
+		}
+	} else if (dl.d_ek) {
+		HB_CUDA(ctx, cudaMemsetAsync(dl.d_ek, 0, sizeof(uint32_t) * 2, ctx->stream));
+	}
+	return 0;
+}
+
+static int build_lhist(hb_dmesh *m)
+{
+	hb_ctx *ctx = m->ctx;
+	if (m->d_lh || !m->n_corner_elems || !m->nb_corner) return 0;
+	const uint32_t ncel = m->n_corner_elems;
+	uint32_t *off = nullptr, *cursor = nullptr, *vinc = nullptr, *dist = nullptr;
+	HB_TRY(hb_dalloc_t(m, &off, (size_t)m->nv + 2));
+	HB_TRY(hb_dalloc_t(m, &cursor, (size_t)m->nv + 1));
+	HB_TRY(hb_dalloc_t(m, &vinc, (size_t)ncel + 1));
+	HB_TRY(hb_dalloc_t(m, &dist, (size_t)ncel + 1));
+	HB_TRY(hb_dalloc_t(m, &m->d_lh, (size_t)m->nb_corner * ncel + 1));
+	HB_CUDA(ctx, cudaMemsetAsync(off, 0, sizeof(uint32_t) * ((size_t)m->nv + 2), ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * ((size_t)m->nv + 1), ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(m->d_lh, 0xff, sizeof(uint32_t) * ((size_t)m->nb_corner * ncel + 1), ctx->stream));
+	const uint32_t g = hb_div_up(ncel, 256);
+	HB_LAUNCH(ctx, k_vinc_count, g, 256, 0, m->d_he, m->d_celem_h, m->d_face_regs, m->d_reg_ncorner, ncel, off);
+	HB_TRY(hb_scan_exclusive_u32(ctx, off, off, m->nv, nullptr));
+	HB_LAUNCH(ctx, k_vinc_fill, g, 256, 0, m->d_he, m->d_celem_h, m->d_face_regs, m->d_reg_ncorner, ncel, off, cursor, vinc);
+	HB_LAUNCH(ctx, k_lhist, hb_div_up(m->nv, 128), 128, 0, m->d_he, m->d_celem_h, m->d_face_regs, m->d_reg_ncorner, m->d_bind_corner, (uint32_t)m->nb_corner, m->nv, off, vinc, dist, ncel, m->d_lh);
+	return 0;
+}
+
+int hb_encode_lists(hb_dmesh *m)
+{
+	hb_ctx *ctx = m->ctx;
+	HB_TRY(hb_build_conn(m));
+	bool need_v = false, need_c = false;
+	for (int l = 0; l < m->nlists; ++l) {
+		const int cls = m->lists[l].p.target;
+		if (cls == CLS_VTX && m->lists[l].p.ncomp) need_v = true;
+		if (cls == CLS_CORNER) need_c = true;
+	}
+	if (need_v) HB_TRY(hb_build_vertex_candidates(m));
+	if (need_c && m->any_corner) {
+		HB_TRY(hb_build_corner_candidates(m));
+		HB_TRY(build_lhist(m));
+	}
+	for (int l = 0; l < m->nlists; ++l) {
+		DevList &dl = m->lists[l];
+		const ListParams &p = dl.p;
+		const int cls = p.target;
+		if (cls != CLS_VTX && cls != CLS_FACE && cls != CLS_CORNER) { dl.n_elems = 0; continue; }
+		if (cls == CLS_CORNER && !m->any_corner) { dl.n_elems = 0; continue; }
+		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE));
+		const uint32_t n = dl.n_elems;
+		HB_TRY(hb_dalloc_t(m, &dl.d_type, (size_t)n + 1));
+		HB_TRY(hb_dalloc_t(m, &dl.d_aux, (size_t)n + 1));
+		HB_TRY(hb_dalloc_t(m, &dl.d_sym, (size_t)n * p.sym_stride + 8));
+		HB_TRY(hb_dalloc_t(m, &dl.d_hist, (size_t)p.sym_stride * 256 + 4));
+		dl.d_type_hist = dl.d_hist + (size_t)p.sym_stride * 256;
+		HB_CUDA(ctx, cudaMemsetAsync(dl.d_hist, 0, sizeof(unsigned long long) * ((size_t)p.sym_stride * 256 + 4), ctx->stream));
+		if (!n) continue;
+		EncodeArgs a;
+		a.erow = dl.d_erow; a.ek = dl.d_ek; a.first = dl.d_first; a.dord = dl.d_dord;
+		a.rp = dl.d_rp;
+		a.cand_off = cls == CLS_VTX ? m->d_vc_off : m->d_cc_off;
+		a.cand = cls == CLS_VTX ? m->d_vc_tri : m->d_cc_idx;
+		a.lh = m->d_lh; a.ncel = m->n_corner_elems;
+		a.face_regs = m->d_face_regs; a.slot_corner = m->d_slot_corner; a.nlists = m->nlists;
+		a.celem_h = m->d_celem_h; a.he = m->d_he;
+		a.type = dl.d_type; a.aux = dl.d_aux; a.sym = dl.d_sym; a.hist = dl.d_hist; a.type_hist = dl.d_type_hist;
+		a.n = n; a.l = l;
+		const int nctx_s = (int)(p.sym_stride < HIST_SMEM_CTX ? p.sym_stride : HIST_SMEM_CTX);
+		const size_t smem = sizeof(uint32_t) * ((size_t)nctx_s * 256 + 4);
+		const uint32_t g = hb_div_up(n, ENC_THREADS);
+		if (cls == CLS_VTX) HB_LAUNCH(ctx, k_encode_main<CLS_VTX>, g, ENC_THREADS, smem, p, a);
+		else if (cls == CLS_FACE) HB_LAUNCH(ctx, k_encode_main<CLS_FACE>, g, ENC_THREADS, smem, p, a);
+		else HB_LAUNCH(ctx, k_encode_main<CLS_CORNER>, g, ENC_THREADS, smem, p, a);
+	}
+	m->encoded = true;
+	return 0;
+}

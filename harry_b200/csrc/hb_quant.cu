@@ -1,0 +1,314 @@
+// hb_quant.cu -- quantization kernels:
+//   K1 bounds_reduce   per-component min / max over all rows       (structs/quant.h:30-38)
+//      scale           per interpretation-group scale (tiny)       (structs/quant.h:46-96)
+//   K2/K8 requant      float/int <-> fixed point, in place, AoS    (structs/quant.h:98-221)
+//
+// Mapping: one thread per (row, component) scalar, flattened as e = row * ncomp + comp, so that
+// for the usual all-float rows consecutive lanes touch consecutive 4-byte words (fully coalesced
+// 128-byte requests) even though the layout is AoS.  The thread count is a multiple of ncomp, so
+// each thread keeps one component for the whole grid-stride loop.
+#include "hb_internal.cuh"
+
+#include <float.h>
+
+// monotone u64 sort keys: unsigned order of the key == numeric order of the value
+__device__ __forceinline__ unsigned long long key_of(unsigned long long bits, int type)
+{
+	switch (type) {
+	case HB_FLOAT: { const uint32_t b = (uint32_t)bits; return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
+	case HB_DOUBLE: return bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
+	case HB_LONG: return bits ^ 0x8000000000000000ull;
+	case HB_INT: return (unsigned long long)((long long)(int32_t)bits) ^ 0x8000000000000000ull;
+	case HB_SHORT: return (unsigned long long)((long long)(int16_t)bits) ^ 0x8000000000000000ull;
+	case HB_CHAR: return (unsigned long long)((long long)(int8_t)bits) ^ 0x8000000000000000ull;
+	default: return bits; // unsigned types
+	}
+}
+__device__ __forceinline__ unsigned long long value_of(unsigned long long key, int type)
+{
+	switch (type) {
+	case HB_FLOAT: { const uint32_t k = (uint32_t)key; return k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu); }
+	case HB_DOUBLE: return key ^ ((key >> 63) ? 0x8000000000000000ull : ~0ull);
+	case HB_LONG: case HB_INT: case HB_SHORT: case HB_CHAR: return key ^ 0x8000000000000000ull;
+	default: return key;
+	}
+}
+// numeric_limits<T>::max() / ::min() as bit patterns (quant.h:32-33; min() of a floating type is
+// the smallest positive normal -- Appendix C.1)
+__device__ __forceinline__ unsigned long long seed_bits(int type, bool for_min)
+{
+	switch (type) {
+	case HB_FLOAT: return for_min ? 0x7f7fffffu : 0x00800000u;
+	case HB_DOUBLE: return for_min ? 0x7fefffffffffffffull : 0x0010000000000000ull;
+	case HB_ULONG: return for_min ? ~0ull : 0ull;
+	case HB_LONG: return for_min ? 0x7fffffffffffffffull : 0x8000000000000000ull;
+	case HB_UINT: return for_min ? 0xffffffffull : 0ull;
+	case HB_INT: return for_min ? 0x7fffffffull : 0x80000000ull;
+	case HB_USHORT: return for_min ? 0xffffull : 0ull;
+	case HB_SHORT: return for_min ? 0x7fffull : 0x8000ull;
+	case HB_UCHAR: return for_min ? 0xffull : 0ull;
+	default: return for_min ? 0x7full : 0x80ull;
+	}
+}
+
+// scratch per component: [0] min key, [1] max key, [2] first row holding -0.0, [3] first row holding +0.0
+__global__ void k_bounds_init(ListParams p, unsigned long long *__restrict__ scratch)
+{
+	const int j = threadIdx.x;
+	if (j >= p.ncomp) return;
+	scratch[4 * j + 0] = key_of(seed_bits(p.type[j], true), p.type[j]);
+	scratch[4 * j + 1] = key_of(seed_bits(p.type[j], false), p.type[j]);
+	scratch[4 * j + 2] = ~0ull;
+	scratch[4 * j + 3] = ~0ull;
+}
+
+__global__ void __launch_bounds__(256) k_bounds_reduce(ListParams p, unsigned long long *__restrict__ scratch, uint32_t rows_per_step)
+{
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t total_threads = rows_per_step * (uint32_t)p.ncomp;
+	if (tid >= total_threads) return;
+	const int j = (int)(tid % (uint32_t)p.ncomp);
+	const int type = p.type[j];
+	const int size = hb_type_size(type);
+	const bool is_fp = type == HB_FLOAT || type == HB_DOUBLE;
+	unsigned long long kmin = key_of(seed_bits(type, true), type), kmax = key_of(seed_bits(type, false), type);
+	unsigned long long zneg = ~0ull, zpos = ~0ull;
+	const uint8_t *base = p.rows + p.offset[j];
+	for (uint32_t row = tid / (uint32_t)p.ncomp; row < p.nrows; row += rows_per_step) {
+		const unsigned long long bits = hb_ld_bits(base + (size_t)row * p.stride, size);
+		if (is_fp) {
+			// NaN never replaces a bound (both comparisons are false)
+			const bool nan = type == HB_FLOAT ? ((bits & 0x7fffffffu) > 0x7f800000u) : ((bits & 0x7fffffffffffffffull) > 0x7ff0000000000000ull);
+			if (nan) continue;
+			// -0.0 == +0.0 for the reference's `<`: remember which zero came first in row order
+			const unsigned long long mag = type == HB_FLOAT ? (bits & 0x7fffffffu) : (bits & 0x7fffffffffffffffull);
+			if (mag == 0) {
+				const bool neg = type == HB_FLOAT ? (bits >> 31) != 0 : (bits >> 63) != 0;
+				if (neg) zneg = zneg < row ? zneg : row;
+				else zpos = zpos < row ? zpos : row;
+			}
+		}
+		const unsigned long long k = key_of(bits, type);
+		kmin = k < kmin ? k : kmin;
+		kmax = k > kmax ? k : kmax;
+	}
+	atomicMin(&scratch[4 * j + 0], kmin);
+	atomicMax(&scratch[4 * j + 1], kmax);
+	if (zneg != ~0ull) atomicMin(&scratch[4 * j + 2], zneg);
+	if (zpos != ~0ull) atomicMin(&scratch[4 * j + 3], zpos);
+}
+
+// bounds rows: [0] min, [1] max, [2] scale -- `stride` bytes each, components at their row offsets
+__global__ void k_bounds_finish(ListParams p, const unsigned long long *__restrict__ scratch, uint8_t *__restrict__ bounds)
+{
+	const int j = threadIdx.x;
+	if (j >= p.ncomp) return;
+	const int type = p.type[j];
+	const int size = hb_type_size(type);
+	unsigned long long mn = value_of(scratch[4 * j + 0], type);
+	const unsigned long long mx = value_of(scratch[4 * j + 1], type);
+	if (type == HB_FLOAT || type == HB_DOUBLE) {
+		// minimum is a zero: its sign is that of the first zero in row order (`e < cur` is false
+		// between -0.0 and +0.0, so a later zero never replaces an earlier one)
+		const unsigned long long mag = type == HB_FLOAT ? (mn & 0x7fffffffu) : (mn & 0x7fffffffffffffffull);
+		if (mag == 0) {
+			const bool neg_first = scratch[4 * j + 2] < scratch[4 * j + 3];
+			mn = neg_first ? (type == HB_FLOAT ? 0x80000000ull : 0x8000000000000000ull) : 0ull;
+		}
+	}
+	hb_st_bits(bounds + p.offset[j], size, mn);
+	hb_st_bits(bounds + p.stride + p.offset[j], size, mx);
+}
+
+// quant.h:46-96 for groups whose members share one type
+__global__ void k_scale(ListParams p, uint8_t *__restrict__ bounds, const uint8_t *__restrict__ groups, int *err)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const uint8_t *mnr = bounds, *mxr = bounds + p.stride;
+	uint8_t *scr = bounds + 2 * (size_t)p.stride;
+	for (int k = 0; k < p.ncomp; ++k) {
+		if (groups[k] != k) continue;
+		const int t = p.type[k];
+		const int size = hb_type_size(t);
+		unsigned long long s_bits;
+		if (t == HB_FLOAT) {
+			float s = FLT_MIN;
+			for (int j = 0; j < p.ncomp; ++j) {
+				if (groups[j] != k) continue;
+				if (p.type[j] != t) { atomicExch(err, 6); continue; }
+				const float r = __fsub_rn(__uint_as_float((uint32_t)hb_ld_bits(mxr + p.offset[j], 4)), __uint_as_float((uint32_t)hb_ld_bits(mnr + p.offset[j], 4)));
+				s = s < r ? r : s;
+			}
+			s_bits = __float_as_uint(s);
+		} else if (t == HB_DOUBLE) {
+			double s = DBL_MIN;
+			for (int j = 0; j < p.ncomp; ++j) {
+				if (groups[j] != k) continue;
+				if (p.type[j] != t) { atomicExch(err, 6); continue; }
+				const double r = __dsub_rn(__longlong_as_double((long long)hb_ld_bits(mxr + p.offset[j], 8)), __longlong_as_double((long long)hb_ld_bits(mnr + p.offset[j], 8)));
+				s = s < r ? r : s;
+			}
+			s_bits = (unsigned long long)__double_as_longlong(s);
+		} else {
+			const bool sg = t == HB_LONG || t == HB_INT || t == HB_SHORT || t == HB_CHAR;
+			long long s_i = 0;
+			unsigned long long s_u = 0;
+			if (sg) s_i = hb_bits_to_i64(seed_bits(t, false), t);
+			for (int j = 0; j < p.ncomp; ++j) {
+				if (groups[j] != k) continue;
+				if (p.type[j] != t) { atomicExch(err, 6); continue; }
+				unsigned long long r = hb_ld_bits(mxr + p.offset[j], size) - hb_ld_bits(mnr + p.offset[j], size);
+				if (size < 8) r &= (1ull << (8 * size)) - 1ull;
+				if (sg) {
+					const long long ri = hb_bits_to_i64(r, t);
+					s_i = s_i < ri ? ri : s_i;
+				} else {
+					s_u = s_u < r ? r : s_u;
+				}
+			}
+			s_bits = sg ? (unsigned long long)s_i : s_u;
+		}
+		for (int j = 0; j < p.ncomp; ++j)
+			if (groups[j] == k) hb_st_bits(scr + p.offset[j], size, s_bits);
+	}
+}
+
+// quant.h:98-112, integer flavour, evaluated in T (narrow types compute in int and truncate)
+__device__ __forceinline__ unsigned long long rescale_int(int t, unsigned long long val, unsigned long long from, unsigned long long to)
+{
+	switch (t) {
+	case HB_ULONG: return from ? val / from * to + val % from * to / from : 0;
+	case HB_LONG: { const long long v = (long long)val, f = (long long)from, o = (long long)to; return f ? (unsigned long long)(v / f * o + v % f * o / f) : 0; }
+	case HB_UINT: { const uint32_t v = (uint32_t)val, f = (uint32_t)from, o = (uint32_t)to; return f ? (uint32_t)(v / f * o + v % f * o / f) : 0; }
+	case HB_INT: { const int32_t v = (int32_t)val, f = (int32_t)from, o = (int32_t)to; return f ? (uint32_t)((uint32_t)(v / f) * (uint32_t)o + (uint32_t)((int32_t)((uint32_t)(v % f) * (uint32_t)o) / f)) : 0; }
+	case HB_USHORT: { const int v = (uint16_t)val, f = (uint16_t)from, o = (uint16_t)to; return f ? (uint16_t)(v / f * o + v % f * o / f) : 0; }
+	case HB_SHORT: { const int v = (int16_t)val, f = (int16_t)from, o = (int16_t)to; return f ? (uint16_t)(int16_t)(v / f * o + v % f * o / f) : 0; }
+	case HB_UCHAR: { const int v = (uint8_t)val, f = (uint8_t)from, o = (uint8_t)to; return f ? (uint8_t)(v / f * o + v % f * o / f) : 0; }
+	default: { const int v = (int8_t)val, f = (int8_t)from, o = (int8_t)to; return f ? (uint8_t)(int8_t)(v / f * o + v % f * o / f) : 0; }
+	}
+}
+
+struct RequantParams {
+	uint8_t dq[HB_MAX_COMP]; // destination quantization bits per component
+};
+
+// quant.h:114-214 for every (row, component); four separately rounded float operations
+// (no FMA contraction), truncating float -> integer conversion.
+__global__ void __launch_bounds__(256) k_requant(ListParams p, RequantParams rq, const uint8_t *__restrict__ bounds, uint32_t rows_per_step)
+{
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t total_threads = rows_per_step * (uint32_t)p.ncomp;
+	if (tid >= total_threads) return;
+	const int j = (int)(tid % (uint32_t)p.ncomp);
+	const int t = p.type[j];
+	const int sq = p.quant[j], dq = rq.dq[j];
+	if (sq == 0 && dq == 0) return; // quant.h:118-121
+	const int tsize = hb_type_size(t);
+	const int st_src = sq ? (sq <= 8 ? HB_UCHAR : sq <= 16 ? HB_USHORT : sq <= 32 ? HB_UINT : HB_ULONG) : t;
+	const int st_dst = dq ? (dq <= 8 ? HB_UCHAR : dq <= 16 ? HB_USHORT : dq <= 32 ? HB_UINT : HB_ULONG) : t;
+	const int ssize = hb_type_size(st_src), dsize = hb_type_size(st_dst);
+	const unsigned long long m_src = sq ? (unsigned long long)(long long)(int32_t)((1u << sq) - 1u) : 0;
+	const unsigned long long m_dst = dq ? (unsigned long long)(long long)(int32_t)((1u << dq) - 1u) : 0;
+	const unsigned long long mn_b = hb_ld_bits(bounds + p.offset[j], tsize);
+	const unsigned long long sc_b = hb_ld_bits(bounds + 2 * (size_t)p.stride + p.offset[j], tsize);
+	const float mn_f = __uint_as_float((uint32_t)mn_b), sc_f = __uint_as_float((uint32_t)sc_b);
+	const float m_dst_f = (float)(int32_t)m_dst, m_src_f = (float)(int32_t)m_src;
+	const bool sg = t == HB_LONG || t == HB_INT || t == HB_SHORT || t == HB_CHAR;
+	uint8_t *base = p.rows + p.offset[j];
+	for (uint32_t row = tid / (uint32_t)p.ncomp; row < p.nrows; row += rows_per_step) {
+		uint8_t *ptr = base + (size_t)row * p.stride;
+		unsigned long long q;
+		if (sq) {
+			q = hb_ld_bits(ptr, ssize);
+		} else if (t == HB_FLOAT) {
+			const float x = __uint_as_float((uint32_t)hb_ld_bits(ptr, 4));
+			const float d = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, mn_f), sc_f), m_dst_f), 0.5f);
+			q = (unsigned long long)d; // quant.h:135
+		} else {
+			const unsigned long long v = hb_ld_bits(ptr, tsize) - mn_b;
+			q = rescale_int(t, v, sc_b, m_dst);
+			if (sg) q = (unsigned long long)hb_bits_to_i64(q, t);
+		}
+		if (sq && dq) q = q / m_src * m_dst + q % m_src * m_dst / m_src; // quant.h:167-169
+		if (dq) {
+			hb_st_bits(ptr, dsize, q); // the other bytes of the slot keep their old contents
+		} else if (t == HB_FLOAT) {
+			const float x = __fadd_rn(__fmul_rn(__fdiv_rn((float)q, m_src_f), sc_f), mn_f); // quant.h:182
+			hb_st_bits(ptr, 4, __float_as_uint(x));
+		} else {
+			hb_st_bits(ptr, tsize, rescale_int(t, q, m_src, sc_b) + mn_b);
+		}
+	}
+}
+
+static uint32_t pick_rows_per_step(hb_ctx *ctx, const ListParams &p)
+{
+	// ~8 resident blocks of 256 threads per SM, rounded so that threads = rows_per_step * ncomp
+	const uint64_t want_threads = (uint64_t)ctx->sm_count * 8 * 256;
+	uint64_t rps = want_threads / (uint64_t)p.ncomp;
+	if (rps > p.nrows) rps = p.nrows;
+	if (rps == 0) rps = 1;
+	return (uint32_t)rps;
+}
+
+int hb_list_bounds(hb_dmesh *m, uint32_t l)
+{
+	hb_ctx *ctx = m->ctx;
+	DevList &dl = m->lists[l];
+	const ListParams &p = dl.p;
+	if (p.ncomp == 0) return 0;
+	for (int j = 0; j < p.ncomp; ++j)
+		if (p.quant[j]) return hb_fail(ctx, HB_ERR_INVALID, "set_bounds on a quantized list (the reference only calls it on unquantized data)");
+	unsigned long long *scratch = nullptr;
+	HB_CUDA(ctx, cudaMallocAsync((void **)&scratch, sizeof(unsigned long long) * 4 * HB_MAX_COMP, ctx->stream));
+	HB_LAUNCH(ctx, k_bounds_init, 1, HB_MAX_COMP, 0, p, scratch);
+	if (p.nrows) {
+		const uint32_t rps = pick_rows_per_step(ctx, p);
+		HB_LAUNCH(ctx, k_bounds_reduce, hb_div_up((uint64_t)rps * p.ncomp, 256), 256, 0, p, scratch, rps);
+	}
+	HB_LAUNCH(ctx, k_bounds_finish, 1, HB_MAX_COMP, 0, p, scratch, dl.d_bounds);
+	HB_CUDA(ctx, cudaFreeAsync(scratch, ctx->stream));
+	return 0;
+}
+
+int hb_list_scale(hb_dmesh *m, uint32_t l, const uint8_t *groups)
+{
+	hb_ctx *ctx = m->ctx;
+	DevList &dl = m->lists[l];
+	if (dl.p.ncomp == 0) return 0;
+	uint8_t *d_groups = nullptr;
+	HB_CUDA(ctx, cudaMallocAsync((void **)&d_groups, HB_MAX_COMP, ctx->stream));
+	HB_CUDA(ctx, cudaMemcpyAsync(d_groups, groups, dl.p.ncomp, cudaMemcpyHostToDevice, ctx->stream));
+	HB_LAUNCH(ctx, k_scale, 1, 32, 0, dl.p, dl.d_bounds, d_groups, ctx->d_err);
+	HB_CUDA(ctx, cudaFreeAsync(d_groups, ctx->stream));
+	return 0;
+}
+
+int hb_list_requant(hb_dmesh *m, uint32_t l, const uint8_t *new_quant)
+{
+	hb_ctx *ctx = m->ctx;
+	DevList &dl = m->lists[l];
+	ListParams &p = dl.p;
+	if (p.ncomp == 0) return 0;
+	RequantParams rq;
+	bool any = false;
+	for (int j = 0; j < p.ncomp; ++j) {
+		rq.dq[j] = new_quant[j];
+		if (new_quant[j] > 8 * hb_type_size(p.type[j])) return hb_fail(ctx, HB_ERR_INVALID, "requant: %d bits do not fit component %d", new_quant[j], j);
+		if (p.quant[j] == 0 && new_quant[j] == 0) continue;
+		any = true;
+		if (p.type[j] == HB_DOUBLE) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "requant: double lists (the reference shifts an int by >= 32 bits, undefined)");
+		if (p.quant[j] > 31 || new_quant[j] > 31) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "requant: more than 31 bits (the reference computes 1 << q in int, undefined)");
+	}
+	if (any && p.nrows) {
+		const uint32_t rps = pick_rows_per_step(ctx, p);
+		HB_LAUNCH(ctx, k_requant, hb_div_up((uint64_t)rps * p.ncomp, 256), 256, 0, p, rq, dl.d_bounds, rps);
+	}
+	for (int j = 0; j < p.ncomp; ++j) p.quant[j] = new_quant[j];
+	hb_list_desc tmp;
+	tmp.ncomp = (uint16_t)p.ncomp;
+	for (int j = 0; j < p.ncomp; ++j) { tmp.type[j] = p.type[j]; tmp.quant[j] = p.quant[j]; tmp.offset[j] = p.offset[j]; }
+	tmp.rows = p.rows; tmp.nrows = p.nrows; tmp.stride = p.stride; tmp.target = (uint8_t)p.target;
+	hb_fill_list_params(p, tmp);
+	return 0;
+}

@@ -179,13 +179,18 @@ void hb_dmesh_free(hb_dmesh *m);
 /* bounds + scale (per `groups`: component j shares the scale of component groups[j], the
  * interpretation-group leader, quant.h:54-91) + requant of list `l`, all on the device. */
 int hb_dmesh_quantize(hb_dmesh *m, uint32_t l, const uint8_t *new_quant, const uint8_t *groups);
+/* requant(clear): back to the unquantized types using the bounds rows held on the device */
 int hb_dmesh_dequantize(hb_dmesh *m, uint32_t l);
-int hb_dmesh_encode(hb_dmesh *m);                    /* kernels only, streams stay on device */
-int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out);
-int hb_dmesh_load_residuals(hb_dmesh *m);            /* device: streams -> residual rows (decode input) */
-int hb_dmesh_decode(hb_dmesh *m);                    /* kernels only */
-int hb_dmesh_fetch_rows(hb_dmesh *m, uint32_t l, void *rows_out); /* nrows * stride bytes */
+/* decode side: min / max rows come from the .hry header, the scale row from set_scale */
+int hb_dmesh_set_bounds(hb_dmesh *m, uint32_t l, const void *min_row, const void *max_row, const void *scale_row);
 int hb_dmesh_fetch_bounds(hb_dmesh *m, uint32_t l, void *min_row, void *max_row, void *scale_row);
+int hb_dmesh_encode(hb_dmesh *m);                    /* kernels only, streams stay on the device */
+int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out);
+int hb_dmesh_decode(hb_dmesh *m);                    /* kernels only, rows reconstructed in place */
+int hb_dmesh_fetch_rows(hb_dmesh *m, uint32_t l, void *rows_out); /* nrows * stride bytes */
+/* keep / restore a device copy of all rows + quantization state (stages work in place) */
+int hb_dmesh_snapshot(hb_dmesh *m);
+int hb_dmesh_restore(hb_dmesh *m);
 int hb_ctx_sync(hb_ctx *ctx);
 
 #ifdef __cplusplus

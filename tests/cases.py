@@ -1,0 +1,96 @@
+"""Shared test cases: the small BASELINE configs as flattened meshes (numpy), built through the
+reference harness (oracle/_ref/libharry_ref.so: the unmodified reference's readers, quantizer and
+Cut-Border-Machine traversal).  Test infrastructure only."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+import oracle_lib as ol
+from harry_b200 import capi, meshgen
+
+# name -> (generator, quantization triples (list, component or -1, bits))
+CASES = {
+    "sphere_lossless": (lambda d: _ply(d, "s.ply", meshgen.uv_sphere(40, 80)), []),
+    "sphere_q14": (lambda d: _ply(d, "s.ply", meshgen.uv_sphere(40, 80)), [(1, -1, 14)]),
+    "sphere_noise_q12": (lambda d: _ply(d, "sn.ply", meshgen.uv_sphere(33, 51, noise_seed=3)), [(1, -1, 12)]),
+    "sphere_q8_mixed": (lambda d: _ply(d, "s2.ply", meshgen.uv_sphere(20, 31, noise_seed=5)), [(1, 0, 8), (1, 2, 20)]),
+    "poly_lossless": (lambda d: _ply(d, "p.ply", meshgen.poly_grid(24)), []),
+    "poly_q10": (lambda d: _ply(d, "p.ply", meshgen.poly_grid(24)), [(1, -1, 10), (0, -1, 9)]),
+    "obj_q14_q10": (lambda d: _obj(d, "o.obj", False), [(0, -1, 14), (2, -1, 10)]),
+    "obj_lossless": (lambda d: _obj(d, "o.obj", False), []),
+    "obj_multi_q14": (lambda d: _obj(d, "om.obj", True), [(0, -1, 14)]),
+    "obj_multi_all": (lambda d: _obj(d, "om.obj", True), [(0, -1, 12), (1, -1, 9), (2, -1, 10), (3, -1, 11)]),
+}
+CONFIG1 = ("sphere35k_lossless", lambda d: _ply(d, "s35k.ply", meshgen.uv_sphere(133, 264)), [])
+
+
+def _ply(d, name, mesh):
+    p = os.path.join(d, name)
+    if not os.path.exists(p):
+        meshgen.write_ply(p, mesh)
+    return p
+
+
+def _obj(d, name, multi):
+    p = os.path.join(d, name)
+    if not os.path.exists(p):
+        meshgen.write_obj_latlong(p, 14, 20, multi_region=multi)
+    return p
+
+
+class Case:
+    """Everything the parity tests need for one config, all produced by the real reference."""
+
+    def __init__(self, workdir: str, name: str, gen, loq):
+        self.name = name
+        self.loq = loq
+        path = gen(workdir)
+        rm = ol.RefMesh(path)
+        self.raw = rm.arrays()                       # as read (unquantized), bounds set by the reader
+        self.raw_bounds = [(rm.bounds_row(l, 0, la.stride), rm.bounds_row(l, 1, la.stride))
+                           for l, la in enumerate(self.raw.lists)]
+        for l in range(len(self.raw.lists)):
+            rm.set_scale(l)
+        self.raw_scale = [rm.bounds_row(l, 2, la.stride) for l, la in enumerate(self.raw.lists)]
+        if loq:
+            rm.requant(loq)
+        rm.traverse()
+        self.enc = rm.arrays()                       # quantized + traversal order + final twin table
+        self.enc_streams = rm.attr_encode()          # real AttrCoder<Capture> + real model histograms
+        hry = os.path.join(workdir, name + ".hry")
+        rm.write(hry)
+        self.hry_path = hry
+        self.src_path = path
+        rd = ol.RefMesh(hry)
+        self.dec = rd.arrays()                       # decoder-side mesh with the decoded values
+        self.dec_streams = rd.logged_streams()       # what the real decoder read from the file
+        self.dec_bounds = [(rd.bounds_row(l, 0, la.stride), rd.bounds_row(l, 1, la.stride))
+                           for l, la in enumerate(self.dec.lists)]
+        if loq:
+            rd.requant([], clear=True)
+            self.deq = rd.arrays()                   # after requant(clear)
+            self.deq_scale = [rd.bounds_row(l, 2, la.stride) for l, la in enumerate(self.dec.lists)]
+        else:
+            self.deq = None
+        rm.close()
+        rd.close()
+
+    def decode_input(self) -> capi.MeshArrays:
+        m = self.dec.copy()
+        m.lists = capi.residual_rows_from_streams(self.dec, self.dec_streams)
+        return m
+
+
+_cache = {}
+
+
+def get_case(workdir: str, name: str) -> Case:
+    if name not in _cache:
+        if name == CONFIG1[0]:
+            _cache[name] = Case(workdir, name, CONFIG1[1], CONFIG1[2])
+        else:
+            gen, loq = CASES[name]
+            _cache[name] = Case(workdir, name, gen, loq)
+    return _cache[name]
