@@ -73,6 +73,8 @@ class MeshDesc(C.Structure):
         ("reg_cornerlist", C.c_void_p),
         ("reg_vtxlist", C.c_void_p),
         ("lists", C.POINTER(ListDesc)),
+        ("emit_type", C.POINTER(C.c_void_p)),
+        ("emit_count", C.POINTER(C.c_uint32)),
     ]
 
 
@@ -208,6 +210,7 @@ class MeshArrays:
     reg_cornerlist: np.ndarray
     reg_vtxlist: np.ndarray
     lists: list                  # [ListArrays]
+    emit_types: list | None = None   # decode only: per list uint8 type stream (or None)
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -262,6 +265,22 @@ class MeshArrays:
             arr[i] = l.to_desc()
         d.lists = arr
         self._keep = [arr]
+        if self.emit_types is not None:
+            tarr = (C.c_void_p * max(1, len(self.lists)))()
+            carr = (C.c_uint32 * max(1, len(self.lists)))()
+            held = []
+            for i in range(len(self.lists)):
+                t = self.emit_types[i] if i < len(self.emit_types) else None
+                if t is None or len(t) == 0:
+                    tarr[i] = None
+                else:
+                    t = np.ascontiguousarray(t, dtype=np.uint8)
+                    held.append(t)
+                    tarr[i] = t.ctypes.data
+                    carr[i] = len(t)
+            d.emit_type = tarr
+            d.emit_count = carr
+            self._keep += [tarr, carr, held]
         return d
 
 

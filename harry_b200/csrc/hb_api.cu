@@ -31,6 +31,7 @@ static const char *device_error_text(int code)
 	case 5: return "fan walk does not terminate (inconsistent twin table)";
 	case 6: return "mixed-type interpretation group";
 	case 7: return "attribute binding out of range";
+	case 8: return "emit_type stream shorter than the number of emissions";
 	default: return "unknown device error";
 	}
 }
@@ -276,7 +277,15 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh *m)
 	HB_TRY(upload(m, (void **)&m->d_slot_vtx, m->h_slot_vtx.data(), sizeof(int16_t) * m->h_slot_vtx.size()));
 	HB_TRY(upload(m, (void **)&m->d_slot_face, m->h_slot_face.data(), sizeof(int16_t) * m->h_slot_face.size()));
 	HB_TRY(upload(m, (void **)&m->d_slot_corner, m->h_slot_corner.data(), sizeof(int16_t) * m->h_slot_corner.size()));
-	for (int l = 0; l < d->nlists; ++l) HB_TRY(add_list(m, d->lists[l], true));
+	for (int l = 0; l < d->nlists; ++l) {
+		HB_TRY(add_list(m, d->lists[l], true));
+		if (d->emit_type && d->emit_type[l]) {
+			if (!d->emit_count) return hb_fail(ctx, HB_ERR_INVALID, "mesh: emit_type without emit_count");
+			DevList &dl = m->lists.back();
+			dl.emit_count = d->emit_count[l];
+			HB_TRY(upload(m, (void **)&dl.d_emit_type, d->emit_type[l], dl.emit_count));
+		}
+	}
 	return 0;
 }
 

@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(256) k_decode_face(ListParams p, const uint32_
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) { return __ldcg(p); }
 
+// One sweep: every not-yet-done DATA element whose candidate rows are all available is
+// reconstructed.  A candidate row that is emitted LATER than this element (or never) reads as
+// zero, exactly like the reference's zero-initialised rows (see harry_b200.h, emit_type).
 __global__ void __launch_bounds__(256) k_decode_corner_sweep(ListParams p, const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first,
                                                               const uint32_t *__restrict__ cand_off, const uint32_t *__restrict__ cand, uint32_t n,
                                                               unsigned long long *rp, volatile uint8_t *done, uint32_t *__restrict__ remaining)
@@ -94,26 +97,22 @@ __global__ void __launch_bounds__(256) k_decode_corner_sweep(ListParams p, const
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint32_t row = erow[i];
-	if (row == HB_NONE || done[i]) return;
-	const uint32_t fi = first[row];
+	if (row == HB_NONE || first[row] != i || done[i]) return;
+	const uint32_t c0 = cand_off[i], K = cand_off[i + 1] - c0;
 	bool ready = true;
-	if (fi != i) {
-		ready = done[fi] != 0; // HIST / LHIST reference: copy once the owning element is decoded
-	} else {
-		const uint32_t c0 = cand_off[i], c1 = cand_off[i + 1];
-		for (uint32_t k = c0; k < c1 && ready; ++k) ready = done[cand[k]] != 0;
+	for (uint32_t k = 0; k < K && ready; ++k) {
+		const uint32_t o = first[erow[cand[c0 + k]]];
+		if (o < i) ready = done[o] != 0; // o == HB_NONE or o > i: not emitted yet -> zeros
 	}
 	if (!ready) { atomicAdd(remaining, 1u); return; }
 	__threadfence();
-	if (fi != i) {
-		for (int j = 0; j < p.ncomp; ++j) rp[(size_t)i * p.ncomp + j] = ld_cg_u64(rp + (size_t)fi * p.ncomp + j);
-	} else {
-		const uint32_t c0 = cand_off[i], K = cand_off[i + 1] - c0;
-		for (int j = 0; j < p.ncomp; ++j) {
-			const int st = p.stype[j];
-			const unsigned long long pred = combine_candidates(st, K, [&](uint32_t kk) { return ld_cg_u64(rp + (size_t)cand[c0 + kk] * p.ncomp + j); });
-			rp[(size_t)i * p.ncomp + j] = hb_dec(st, ld_cg_u64(rp + (size_t)i * p.ncomp + j), pred, p.quant[j]);
-		}
+	for (int j = 0; j < p.ncomp; ++j) {
+		const int st = p.stype[j];
+		const unsigned long long pred = combine_candidates(st, K, [&](uint32_t kk) -> unsigned long long {
+			const uint32_t o = first[erow[cand[c0 + kk]]];
+			return o < i ? ld_cg_u64(rp + (size_t)o * p.ncomp + j) : 0ull;
+		});
+		rp[(size_t)i * p.ncomp + j] = hb_dec(st, ld_cg_u64(rp + (size_t)i * p.ncomp + j), pred, p.quant[j]);
 	}
 	__threadfence();
 	done[i] = 1;
@@ -141,7 +140,7 @@ int hb_decode_lists(hb_dmesh *m)
 		const int cls = p.target;
 		if (p.ncomp == 0 || (cls != CLS_VTX && cls != CLS_FACE && cls != CLS_CORNER)) continue;
 		if (cls == CLS_CORNER && !m->any_corner) continue;
-		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE));
+		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE, true));
 		const uint32_t n = dl.n_elems;
 		if (!n) continue;
 		if (cls == CLS_FACE) {

@@ -31,6 +31,34 @@ __global__ void __launch_bounds__(256) k_first_ref(const uint32_t *__restrict__ 
 	if (row != HB_NONE) atomicMin(&first[row], i);
 }
 
+// corner lists: an element answered by the local history never reaches the global history
+// (attrcode.h:377-381), so it must not count as a reference
+__global__ void __launch_bounds__(256) k_first_ref_corner(const uint32_t *__restrict__ erow, uint32_t n, const uint4 *__restrict__ he, const uint32_t *__restrict__ celem_h,
+                                                          const uint16_t *__restrict__ face_regs, const int16_t *__restrict__ slot_corner, uint32_t nlists, int l,
+                                                          const uint32_t *__restrict__ lh, uint32_t ncel, uint32_t *__restrict__ first)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	if (row == HB_NONE) return;
+	const int slot = slot_corner[(uint32_t)face_regs[he[celem_h[i]].w] * nlists + (uint32_t)l];
+	if (lh[(size_t)slot * ncel + i] != HB_NONE) return;
+	atomicMin(&first[row], i);
+}
+
+// decode with drained type symbols: the DATA emission owns its row
+__global__ void __launch_bounds__(256) k_owner_from_types(const uint32_t *__restrict__ erow, const uint32_t *__restrict__ ek, const uint8_t *__restrict__ types, uint32_t ntypes,
+                                                          uint32_t n, uint32_t *__restrict__ first, int *err)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	if (row == HB_NONE) return;
+	const uint32_t k = ek ? ek[i] : i;
+	if (k >= ntypes) { atomicExch(err, 8); return; }
+	if (types[k] == HB_DATA) first[row] = i;
+}
+
 __global__ void __launch_bounds__(256) k_data_flags(const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, uint32_t *__restrict__ dflag)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,16 +203,18 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 		const uint32_t fi = a.first[row];
 		int t = HB_DATA;
 		uint32_t aux = 0;
-		if (fi != i) {
+		bool lhit = false;
+		if (CLS == CLS_CORNER) {
+			// the local history is consulted first (attrcode.h:377-381); it is keyed by binding
+			// slot, so a hit may even name a row this list has not emitted (first[row] unset)
+			const uint32_t h = a.celem_h[i];
+			const int slot = a.slot_corner[(uint32_t)a.face_regs[a.he[h].w] * a.nlists + (uint32_t)a.l];
+			const uint32_t lo = a.lh[(size_t)slot * a.ncel + i];
+			if (lo != HB_NONE) { t = HB_LHIST; aux = lo; lhit = true; }
+		}
+		if (!lhit && fi != i) {
 			t = HB_HIST;
 			aux = a.dord[i] - 1u - a.dord[fi]; // tidx - 1 - g, attrcode.h:43-52
-			if (CLS == CLS_CORNER) {
-				// the local history is consulted first (attrcode.h:377-381)
-				const uint32_t h = a.celem_h[i];
-				const int slot = a.slot_corner[(uint32_t)a.face_regs[a.he[h].w] * a.nlists + (uint32_t)a.l];
-				const uint32_t lo = a.lh[(size_t)slot * a.ncel + i];
-				if (lo != HB_NONE) { t = HB_LHIST; aux = lo; }
-			}
 		}
 		a.type[k] = (uint8_t)t;
 		a.aux[k] = aux;
@@ -256,7 +286,7 @@ static bool bound_everywhere(hb_dmesh *m, int cls, int l)
 	return true;
 }
 
-int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp)
+int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp, bool decode)
 {
 	hb_ctx *ctx = m->ctx;
 	DevList &dl = m->lists[l];
@@ -278,7 +308,12 @@ int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp)
 		else if (cls == CLS_FACE) HB_LAUNCH(ctx, k_elem_rows<CLS_FACE>, g, 256, 0, c, l, dl.p.nrows, dl.d_erow, dl.d_ek, ctx->d_err);
 		else HB_LAUNCH(ctx, k_elem_rows<CLS_CORNER>, g, 256, 0, c, l, dl.p.nrows, dl.d_erow, dl.d_ek, ctx->d_err);
 		if (dl.d_ek) HB_TRY(hb_scan_exclusive_u32(ctx, dl.d_ek, dl.d_ek, n, nullptr));
-		HB_LAUNCH(ctx, k_first_ref, g, 256, 0, dl.d_erow, n, dl.d_first);
+		if (decode && dl.d_emit_type)
+			HB_LAUNCH(ctx, k_owner_from_types, g, 256, 0, dl.d_erow, dl.d_ek, dl.d_emit_type, dl.emit_count, n, dl.d_first, ctx->d_err);
+		else if (!decode && cls == CLS_CORNER && m->d_lh)
+			HB_LAUNCH(ctx, k_first_ref_corner, g, 256, 0, dl.d_erow, n, m->d_he, m->d_celem_h, m->d_face_regs, m->d_slot_corner, (uint32_t)m->nlists, l, m->d_lh, m->n_corner_elems, dl.d_first);
+		else
+			HB_LAUNCH(ctx, k_first_ref, g, 256, 0, dl.d_erow, n, dl.d_first);
 		HB_LAUNCH(ctx, k_data_flags, g, 256, 0, dl.d_erow, dl.d_first, n, dl.d_dord);
 		HB_TRY(hb_scan_exclusive_u32(ctx, dl.d_dord, dl.d_dord, n, nullptr));
 		if (need_rp && dl.p.ncomp) {
@@ -334,7 +369,7 @@ int hb_encode_lists(hb_dmesh *m)
 		const int cls = p.target;
 		if (cls != CLS_VTX && cls != CLS_FACE && cls != CLS_CORNER) { dl.n_elems = 0; continue; }
 		if (cls == CLS_CORNER && !m->any_corner) { dl.n_elems = 0; continue; }
-		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE));
+		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE, false));
 		const uint32_t n = dl.n_elems;
 		HB_TRY(hb_dalloc_t(m, &dl.d_type, (size_t)n + 1));
 		HB_TRY(hb_dalloc_t(m, &dl.d_aux, (size_t)n + 1));

@@ -62,6 +62,8 @@ struct DevList {
 	uint32_t *d_first = nullptr;  // per attribute row: first referencing element (its DATA emission)
 	uint32_t *d_dord = nullptr;   // exclusive scan of DATA flags (n_elems + 1)
 	unsigned long long *d_rp = nullptr; // rank-space value records, ncomp u64 containers per element
+	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
+	uint32_t emit_count = 0;
 	uint8_t *d_rows_backup = nullptr;   // hb_dmesh_snapshot
 	uint8_t backup_quant[HB_MAX_COMP];
 };
@@ -133,7 +135,7 @@ int hb_scan_exclusive_u32(hb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, ui
 int hb_build_conn(hb_dmesh *m);             // he[], ranks, orders
 int hb_build_vertex_candidates(hb_dmesh *m); // vc_off / vc_tri
 int hb_build_corner_candidates(hb_dmesh *m); // cc_off / cc_idx
-int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp);
+int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp, bool decode);
 int hb_encode_lists(hb_dmesh *m);
 int hb_decode_lists(hb_dmesh *m);
 int hb_list_bounds(hb_dmesh *m, uint32_t l);

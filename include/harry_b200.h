@@ -87,6 +87,9 @@ typedef struct hb_list_desc {
  * order_f   traversal order of the faces with their gate corner (attrcode.h:298,315-319).
  *           NULL means faces in index order with gate corner 0 (the decoder's order, :543-548).
  * *_regs, bind_*, off_reg_*, reg_*list: mesh::attr::Bindings (structs/attr.h:101-189).
+ *
+ * Decode-side value semantics (attrcode.h:443-531): attribute rows start zeroed and are filled in
+ * DATA-emission order, so a prediction candidate whose row has not been emitted yet reads as 0.
  */
 typedef struct hb_mesh_desc {
 	uint32_t nv, nf, ne;
@@ -109,6 +112,14 @@ typedef struct hb_mesh_desc {
 	const int32_t *off_reg_vtx;    /* nregs_vtx + 1 */
 	const uint16_t *reg_facelist, *reg_cornerlist, *reg_vtxlist;
 	hb_list_desc *lists; /* nlists */
+	/* Decode only, optional: emit_type[l] = the type symbols (hb_attr_type) of list l in emission
+	 * order, as drained from the stream.  They identify which element carried each DATA row.
+	 * NULL (or a NULL entry) = "the first element referencing a row carried it", which holds
+	 * whenever no corner binding slot is shared by different lists across face regions (the
+	 * reference's LocalHistory is keyed by slot, attrcode.h:296,377: there an LHIST hit can
+	 * precede the DATA emission of the row it names). */
+	const uint8_t *const *emit_type;
+	const uint32_t *emit_count; /* nlists: length of emit_type[l] (required with emit_type) */
 } hb_mesh_desc;
 
 /*

@@ -919,22 +919,87 @@ static void reconstruct_row(coder *c, int l, uint32_t idx, const uint64_t *pred)
 	}
 }
 
+/* Decode-side candidate gathering differs from the encoder in one point: the reference decoder's
+ * rows start zeroed and are filled at their DATA emission (attrcode.h:458-461), so a candidate
+ * row that has not been emitted yet contributes zeros.  `done[l][row]` tracks emission. */
+static int predict_vertex_row_dec(coder *c, int l, int slot, uint8_t *const *done, uint64_t *pred)
+{
+	const hb_mesh_desc *m = c->m;
+	const hb_list_desc *L = &m->lists[l];
+	const list_info *li = &c->li[l];
+	const size_t k = c->cand.n / 3;
+	uint64_t stackbuf[64], *tmp = stackbuf;
+	if (k > 64) {
+		tmp = (uint64_t *)malloc(k * sizeof(uint64_t));
+		if (!tmp) FAIL(HB_ERR_NOMEM, "out of memory");
+	}
+	const uint8_t *rows = (const uint8_t *)L->rows;
+	for (int j = 0; j < L->ncomp; ++j) {
+		for (size_t i = 0; i < k; ++i) {
+			uint64_t v[3];
+			for (int t = 0; t < 3; ++t) {
+				const uint32_t r = m->bind_vtx_attr[(size_t)c->cand.v[3 * i + t] * m->nb_vtx + slot];
+				if (r >= L->nrows) { if (tmp != stackbuf) free(tmp); FAIL(HB_ERR_INVALID, "vertex binding out of range"); }
+				v[t] = done[l][r] ? ld_bits(rows + (size_t)r * L->stride + L->offset[j], li->stype[j]) : 0;
+			}
+			tmp[i] = ho_predict(li->stype[j], v[0], v[1], v[2], li->q[j]);
+		}
+		pred[j] = combine_candidates(li->stype[j], tmp, k);
+	}
+	if (tmp != stackbuf) free(tmp);
+	return 0;
+}
+
+static int predict_corner_row_dec(coder *c, int l, int slot, uint8_t *const *done, uint64_t *pred)
+{
+	const hb_mesh_desc *m = c->m;
+	const hb_list_desc *L = &m->lists[l];
+	const list_info *li = &c->li[l];
+	const size_t k = c->cand.n;
+	uint64_t stackbuf[64], *tmp = stackbuf;
+	if (k > 64) {
+		tmp = (uint64_t *)malloc(k * sizeof(uint64_t));
+		if (!tmp) FAIL(HB_ERR_NOMEM, "out of memory");
+	}
+	const uint8_t *rows = (const uint8_t *)L->rows;
+	for (int j = 0; j < L->ncomp; ++j) {
+		for (size_t i = 0; i < k; ++i) {
+			const uint32_t r = m->bind_corner_attr[(size_t)c->cand.v[i] * m->nb_corner + slot];
+			if (r >= L->nrows) { if (tmp != stackbuf) free(tmp); FAIL(HB_ERR_INVALID, "corner binding out of range"); }
+			tmp[i] = done[l][r] ? ld_bits(rows + (size_t)r * L->stride + L->offset[j], li->stype[j]) : 0;
+		}
+		pred[j] = combine_candidates(li->stype[j], tmp, k);
+	}
+	if (tmp != stackbuf) free(tmp);
+	return 0;
+}
+
+/* Is this emission of list l the one that carried the row?  With the drained type stream: the
+ * emission's type symbol is DATA.  Without: the first reference of the row (see harry_b200.h). */
+static int is_data_emission(const hb_mesh_desc *m, int l, uint32_t *cursor, uint8_t *const *done, uint32_t idx)
+{
+	const uint32_t k = cursor[l]++;
+	if (m->emit_type && m->emit_type[l]) return m->emit_type[l][k] == HB_DATA;
+	return !done[l][idx];
+}
+
 /* attrcode.h:534-550 with the symbol drain factored out: the rows hold residuals,
- * the binding tables are complete; a row is reconstructed at its first reference in emission
- * order (that reference was the DATA emission, every later one a HIST / LHIST). */
+ * the binding tables are complete. */
 int ho_attr_decode(const hb_mesh_desc *m)
 {
 	coder c;
 	int rc = coder_init(&c, m);
-	uint8_t **seen = NULL;
+	uint8_t **done = NULL;
+	uint32_t *cursor = NULL;
 	uint64_t pred[HB_MAX_COMP];
 	const uint32_t nface_order = m->order_f ? m->norder_f : m->nf;
-	if (rc) goto done;
-	seen = (uint8_t **)calloc(m->nlists + 1, sizeof(uint8_t *));
-	if (!seen) { rc = HB_ERR_NOMEM; goto done; }
+	if (rc) goto done_;
+	done = (uint8_t **)calloc(m->nlists + 1, sizeof(uint8_t *));
+	cursor = (uint32_t *)calloc(m->nlists + 1, sizeof(uint32_t));
+	if (!done || !cursor) { rc = HB_ERR_NOMEM; goto done_; }
 	for (int l = 0; l < m->nlists; ++l) {
-		seen[l] = (uint8_t *)calloc(m->lists[l].nrows + 1, 1);
-		if (!seen[l]) { rc = HB_ERR_NOMEM; goto done; }
+		done[l] = (uint8_t *)calloc(m->lists[l].nrows + 1, 1);
+		if (!done[l]) { rc = HB_ERR_NOMEM; goto done_; }
 	}
 	for (uint32_t i = 0; i < m->norder && rc == 0; ++i) { /* vtx_post :443-470 */
 		int ok;
@@ -949,10 +1014,10 @@ int ho_attr_decode(const hb_mesh_desc *m)
 			const int l = m->reg_vtxlist[m->off_reg_vtx[r] + a];
 			const uint32_t idx = m->bind_vtx_attr[(size_t)v * m->nb_vtx + a];
 			if (idx >= m->lists[l].nrows) { rc = HB_ERR_INVALID; snprintf(g_err, sizeof g_err, "binding out of range"); break; }
-			if (seen[l][idx]) continue;
-			seen[l][idx] = 1;
-			rc = predict_vertex_row(&c, l, a, pred);
+			if (!is_data_emission(m, l, cursor, done, idx)) continue;
+			rc = predict_vertex_row_dec(&c, l, a, done, pred);
 			if (rc == 0) reconstruct_row(&c, l, idx, pred);
+			done[l][idx] = 1;
 		}
 	}
 	for (uint32_t i = 0; i < nface_order && rc == 0; ++i) { /* face_post :476-501, corner_post :502-531 */
@@ -968,9 +1033,9 @@ int ho_attr_decode(const hb_mesh_desc *m)
 			const int l = m->reg_facelist[m->off_reg_face[r] + a];
 			const uint32_t idx = m->bind_face_attr[(size_t)f * m->nb_face + a];
 			if (idx >= m->lists[l].nrows) { rc = HB_ERR_INVALID; snprintf(g_err, sizeof g_err, "binding out of range"); break; }
-			if (seen[l][idx]) continue;
-			seen[l][idx] = 1;
+			if (!is_data_emission(m, l, cursor, done, idx)) continue;
 			reconstruct_row(&c, l, idx, pred);
+			done[l][idx] = 1;
 		}
 		const uint32_t f0 = m->face_off[f], deg = m->face_off[f + 1] - f0;
 		const int ncs = m->off_reg_corner[r + 1] - m->off_reg_corner[r];
@@ -984,18 +1049,19 @@ int ho_attr_decode(const hb_mesh_desc *m)
 				const int l = m->reg_cornerlist[m->off_reg_corner[r] + a];
 				const uint32_t idx = m->bind_corner_attr[(size_t)h * m->nb_corner + a];
 				if (idx >= m->lists[l].nrows) { rc = HB_ERR_INVALID; snprintf(g_err, sizeof g_err, "binding out of range"); break; }
-				if (seen[l][idx]) continue;
-				seen[l][idx] = 1;
-				rc = predict_corner_row(&c, l, a, pred);
+				if (!is_data_emission(m, l, cursor, done, idx)) continue;
+				rc = predict_corner_row_dec(&c, l, a, done, pred);
 				if (rc == 0) reconstruct_row(&c, l, idx, pred);
+				done[l][idx] = 1;
 			}
 		}
 	}
-done:
-	if (seen) {
-		for (int l = 0; l < m->nlists; ++l) free(seen[l]);
-		free(seen);
+done_:
+	if (done) {
+		for (int l = 0; l < m->nlists; ++l) free(done[l]);
+		free(done);
 	}
+	free(cursor);
 	coder_free(&c);
 	return rc;
 }

@@ -80,6 +80,7 @@ class Case:
     def decode_input(self) -> capi.MeshArrays:
         m = self.dec.copy()
         m.lists = capi.residual_rows_from_streams(self.dec, self.dec_streams)
+        m.emit_types = [ls.type for ls in self.dec_streams.lists]
         return m
 
 
