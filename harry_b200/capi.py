@@ -471,6 +471,14 @@ def load_library():
     lib.hb_last_timing.restype = None
     lib.hb_kernel_launches.argtypes = [vp]
     lib.hb_kernel_launches.restype = C.c_uint64
+    lib.hb_ctx_profile.argtypes = [vp, C.c_int]
+    lib.hb_ctx_profile.restype = C.c_int
+    lib.hb_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.hb_ctx_profile_report.restype = C.c_int
+    lib.hb_ctx_mark.argtypes = [vp, C.c_int]
+    lib.hb_ctx_mark.restype = C.c_int
+    lib.hb_ctx_elapsed.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    lib.hb_ctx_elapsed.restype = C.c_int
     lib.hb_bounds.argtypes = [vp, C.POINTER(ListDesc), vp, vp]
     lib.hb_bounds.restype = C.c_int
     lib.hb_requant.argtypes = [vp, C.POINTER(ListDesc), C.POINTER(C.c_uint8), vp, vp]
@@ -513,6 +521,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "hb_ctx_create", "hb_ctx_destroy", "hb_last_error", "hb_last_timing", "hb_kernel_launches",
+    "hb_ctx_profile", "hb_ctx_profile_report", "hb_ctx_mark", "hb_ctx_elapsed",
     "hb_bounds", "hb_requant", "hb_attr_encode", "hb_streams_free", "hb_attr_decode",
     "hb_dmesh_upload", "hb_dmesh_free", "hb_dmesh_quantize", "hb_dmesh_dequantize", "hb_dmesh_encode",
     "hb_dmesh_fetch_streams", "hb_dmesh_set_bounds", "hb_dmesh_snapshot", "hb_dmesh_restore", "hb_dmesh_decode", "hb_dmesh_fetch_rows",
@@ -556,6 +565,27 @@ class Context:
 
     def sync(self):
         self._check(self.lib.hb_ctx_sync(self.h), "hb_ctx_sync")
+
+    def profile(self, enable: bool):
+        self._check(self.lib.hb_ctx_profile(self.h, 1 if enable else 0), "hb_ctx_profile")
+
+    def profile_report(self) -> dict:
+        """{kernel name: (launches, total ms)} since profiling was enabled / last report."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.hb_ctx_profile_report(self.h, buf, len(buf)), "hb_ctx_profile_report")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out
+
+    def mark(self, idx: int):
+        self._check(self.lib.hb_ctx_mark(self.h, idx), "hb_ctx_mark")
+
+    def elapsed(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.hb_ctx_elapsed(self.h, a, b, C.byref(ms)), "hb_ctx_elapsed")
+        return ms.value
 
     # quant::set_bounds
     def bounds(self, la: ListArrays):

@@ -96,6 +96,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx)
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	for (int i = 0; i < 6; ++i)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
 	if (ctx->d_err) cudaFree(ctx->d_err);
 	if (ctx->h_err) cudaFreeHost(ctx->h_err);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -111,6 +112,64 @@ extern "C" void hb_last_timing(hb_ctx *ctx, float *kernel_ms, float *copy_ms)
 }
 
 extern "C" uint64_t hb_kernel_launches(hb_ctx *ctx) { return ctx->launches; }
+
+cudaEvent_t hb_prof_event(hb_ctx *ctx)
+{
+	cudaEvent_t e = nullptr;
+	cudaEventCreate(&e);
+	ctx->ev_pool.push_back(e);
+	return e;
+}
+
+// Per-kernel timing: while enabled, every launch is bracketed by CUDA events on the context
+// stream.  hb_ctx_profile_report() synchronizes, writes one line per kernel name
+// ("name launches total_ms\n") into buf and clears the records.
+extern "C" int hb_ctx_profile(hb_ctx *ctx, int enable)
+{
+	ctx->profiling = enable != 0;
+	return 0;
+}
+extern "C" int hb_ctx_profile_report(hb_ctx *ctx, char *buf, size_t len)
+{
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	struct Acc { const char *name; int n; double ms; };
+	std::vector<Acc> acc;
+	for (auto &r : ctx->prof) {
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, r.a, r.b);
+		bool found = false;
+		for (auto &a : acc)
+			if (strcmp(a.name, r.name) == 0) { a.n++; a.ms += ms; found = true; break; }
+		if (!found) acc.push_back(Acc{ r.name, 1, ms });
+	}
+	size_t pos = 0;
+	if (len) buf[0] = 0;
+	for (auto &a : acc) {
+		int w = snprintf(buf + pos, pos < len ? len - pos : 0, "%s %d %.6f\n", a.name, a.n, a.ms);
+		if (w < 0 || pos + (size_t)w >= len) break;
+		pos += (size_t)w;
+	}
+	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+	ctx->ev_pool.clear();
+	ctx->prof.clear();
+	return 0;
+}
+// events on the context stream for timing a region of device-resident stages
+extern "C" int hb_ctx_mark(hb_ctx *ctx, int idx)
+{
+	if (idx < 0 || idx >= 6) return hb_fail(ctx, HB_ERR_INVALID, "mark index out of range");
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	HB_CUDA(ctx, cudaEventRecord(ctx->ev[idx], ctx->stream));
+	return 0;
+}
+extern "C" int hb_ctx_elapsed(hb_ctx *ctx, int a, int b, float *ms)
+{
+	if (a < 0 || a >= 6 || b < 0 || b >= 6) return hb_fail(ctx, HB_ERR_INVALID, "mark index out of range");
+	HB_CUDA(ctx, cudaEventSynchronize(ctx->ev[b]));
+	HB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev[a], ctx->ev[b]));
+	return 0;
+}
 
 extern "C" int hb_ctx_sync(hb_ctx *ctx)
 {

@@ -12,6 +12,7 @@
 //     (list, component) walks the chain in traversal order over rank-space records; parallelism
 //     comes from components, lists and -- for batches -- meshes.
 #include "hb_lists.cuh"
+#include "hb_decode_spec.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // VTX: chain walker
@@ -52,6 +53,100 @@ __global__ void __launch_bounds__(32) k_decode_vertex_chain(const WalkArgs *__re
 		}
 		c0 = c1;
 	}
+}
+
+// ---- speculative path helpers ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_spec_prep(const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, uint8_t *__restrict__ kind, uint32_t *__restrict__ src)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	uint8_t k = 0;
+	uint32_t s = 0;
+	if (row != HB_NONE) {
+		const uint32_t fi = first[row];
+		if (fi == i) k = 1;
+		else if (fi < i) { k = 2; s = fi; }
+	}
+	kind[i] = k;
+	src[i] = s;
+}
+
+// AoS rows -> compact rank-space records (ncp elements of esize bytes per element)
+__global__ void __launch_bounds__(256) k_gather_compact(ListParams p, const uint32_t *__restrict__ erow, uint32_t n, uint8_t *__restrict__ out, int esize, int ncp)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	uint8_t *dst = out + (size_t)i * ncp * esize;
+	if (row == HB_NONE) {
+		for (int j = 0; j < ncp; ++j) hb_st_bits(dst + j * esize, esize, 0);
+		return;
+	}
+	const uint8_t *srcp = p.rows + (size_t)row * p.stride;
+	for (int j = 0; j < ncp; ++j) hb_st_bits(dst + j * esize, esize, j < p.ncomp ? hb_ld_bits(srcp + p.offset[j], esize) : 0);
+}
+
+__global__ void __launch_bounds__(256) k_scatter_compact(ListParams p, const uint32_t *__restrict__ erow, const uint8_t *__restrict__ kind, uint32_t n, const uint8_t *__restrict__ x, int esize, int ncp)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || kind[i] != 1) return;
+	uint8_t *dst = p.rows + (size_t)erow[i] * p.stride;
+	const uint8_t *srcp = x + (size_t)i * ncp * esize;
+	for (int j = 0; j < p.ncomp; ++j) hb_st_bits(dst + p.offset[j], esize, hb_ld_bits(srcp + j * esize, esize));
+}
+
+template <typename T, bool FP>
+static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args)
+{
+	switch (ncomp) {
+	case 1: HB_LAUNCH(ctx, (k_decode_vertex_spec<T, 1, FP>), 1, SPEC_THREADS, 0, d_args); break;
+	case 2: HB_LAUNCH(ctx, (k_decode_vertex_spec<T, 2, FP>), 1, SPEC_THREADS, 0, d_args); break;
+	case 3: HB_LAUNCH(ctx, (k_decode_vertex_spec<T, 3, FP>), 1, SPEC_THREADS, 0, d_args); break;
+	default: HB_LAUNCH(ctx, (k_decode_vertex_spec<T, 4, FP>), 1, SPEC_THREADS, 0, d_args); break;
+	}
+	return 0;
+}
+
+static bool spec_eligible(const ListParams &p)
+{
+	if (p.ncomp < 1 || p.ncomp > 4) return false;
+	const int st = p.uniform_stype;
+	return st == HB_UCHAR || st == HB_USHORT || st == HB_UINT || st == HB_FLOAT;
+}
+
+// reconstruct one vertex list with the speculative chunk-parallel kernel
+static int decode_vertex_spec(hb_dmesh *m, int l)
+{
+	hb_ctx *ctx = m->ctx;
+	DevList &dl = m->lists[l];
+	const ListParams &p = dl.p;
+	const uint32_t n = dl.n_elems;
+	const int st = p.uniform_stype;
+	const int esize = hb_type_size(st);
+	const int ncp = p.ncomp == 3 ? 4 : p.ncomp;
+	HB_TRY(hb_dalloc_t(m, &dl.d_kind, (size_t)n + 1));
+	HB_TRY(hb_dalloc_t(m, &dl.d_src, (size_t)n + 1));
+	HB_TRY(hb_dalloc_t(m, &dl.d_cres, (size_t)(n + 1) * ncp * esize));
+	HB_TRY(hb_dalloc_t(m, &dl.d_cx, (size_t)(n + 1) * ncp * esize));
+	HB_TRY(hb_dalloc_t(m, &dl.d_spec_args, 1));
+	HB_TRY(hb_dalloc_t(m, &dl.d_spec_stats, 4));
+	const uint32_t g = hb_div_up(n, 256);
+	HB_LAUNCH(ctx, k_spec_prep, g, 256, 0, dl.d_erow, dl.d_first, n, dl.d_kind, dl.d_src);
+	HB_LAUNCH(ctx, k_gather_compact, g, 256, 0, p, dl.d_erow, n, dl.d_cres, esize, ncp);
+	HB_CUDA(ctx, cudaMemsetAsync(dl.d_cx, 0, (size_t)(n + 1) * ncp * esize, ctx->stream));
+	SpecArgs a;
+	a.kind = dl.d_kind; a.src = dl.d_src; a.cand_off = m->d_vc_off; a.cand = m->d_vc_tri;
+	a.resid = dl.d_cres; a.x = dl.d_cx; a.n = n; a.stats = dl.d_spec_stats;
+	for (int j = 0; j < 4; ++j) a.bits[j] = j < p.ncomp ? (p.quant[j] ? p.quant[j] : 8 * esize) : 8 * esize;
+	HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_args, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `a` is a stack object
+	if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args)));
+	else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, p.ncomp, dl.d_spec_args)));
+	else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, p.ncomp, dl.d_spec_args)));
+	else HB_TRY((launch_spec<uint32_t, true>(ctx, p.ncomp, dl.d_spec_args)));
+	HB_LAUNCH(ctx, k_scatter_compact, g, 256, 0, p, dl.d_erow, dl.d_kind, n, dl.d_cx, esize, ncp);
+	return 0;
 }
 
 // rank-space records -> AoS rows (DATA elements own their row)
@@ -140,10 +235,13 @@ int hb_decode_lists(hb_dmesh *m)
 		const int cls = p.target;
 		if (p.ncomp == 0 || (cls != CLS_VTX && cls != CLS_FACE && cls != CLS_CORNER)) continue;
 		if (cls == CLS_CORNER && !m->any_corner) continue;
-		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE, true));
+		const bool spec = cls == CLS_VTX && spec_eligible(p);
+		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE && !spec, true));
 		const uint32_t n = dl.n_elems;
 		if (!n) continue;
-		if (cls == CLS_FACE) {
+		if (spec) {
+			HB_TRY(decode_vertex_spec(m, l));
+		} else if (cls == CLS_FACE) {
 			HB_LAUNCH(ctx, k_decode_face, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, n);
 		} else if (cls == CLS_VTX) {
 			WalkArgs w;

@@ -198,10 +198,12 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 
 	const uint32_t i = blockIdx.x * ENC_THREADS + threadIdx.x;
 	const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
+	int t = -1;                 // emission type of this element, -1 = no emission
+	unsigned long long res[HB_MAX_COMP > 8 ? 8 : HB_MAX_COMP]; // residuals of the first 8 components (register resident)
 	if (row != HB_NONE) {
 		const uint32_t k = a.ek ? a.ek[i] : i;
 		const uint32_t fi = a.first[row];
-		int t = HB_DATA;
+		t = HB_DATA;
 		uint32_t aux = 0;
 		bool lhit = false;
 		if (CLS == CLS_CORNER) {
@@ -218,7 +220,6 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 		}
 		a.type[k] = (uint8_t)t;
 		a.aux[k] = aux;
-		atomicAdd(&s_type[t], 1u);
 		if (t == HB_DATA) {
 			const uint32_t d = a.dord[i];
 			uint8_t *out = a.sym + (size_t)d * p.sym_stride;
@@ -241,14 +242,42 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 						pred = combine_candidates(st, K, [&](uint32_t kk) { return a.rp[(size_t)a.cand[c0 + kk] * p.ncomp + j]; });
 					}
 				}
-				const unsigned long long res = hb_enc(st, raw, pred, q);
-				hb_st_bits(out + p.sym_off[j], p.size[j], res);
-				for (int b = 0; b < p.size[j]; ++b) {
-					const uint32_t ctx = p.sym_off[j] + b, s = (uint32_t)(res >> (8 * b)) & 0xffu;
-					if ((int)ctx < nctx_s) atomicAdd(&s_hist[ctx * 256 + s], 1u);
-					else atomicAdd(&a.hist[(size_t)ctx * 256 + s], 1ull);
+				const unsigned long long r = hb_enc(st, raw, pred, q);
+				hb_st_bits(out + p.sym_off[j], p.size[j], r);
+				if (j < 8) {
+					res[j] = r;
+				} else { // rare wide rows: no aggregation
+					for (int b = 0; b < p.size[j]; ++b) {
+						const uint32_t ctx = p.sym_off[j] + b, s = (uint32_t)(r >> (8 * b)) & 0xffu;
+						if ((int)ctx < nctx_s) atomicAdd(&s_hist[ctx * 256 + s], 1u);
+						else atomicAdd(&a.hist[(size_t)ctx * 256 + s], 1ull);
+					}
 				}
 			}
+		}
+	}
+	// Histogram update, warp-aggregated: residuals of a smooth mesh are tiny, so most lanes hit
+	// the same bin (the high bytes are almost always 0).  Lanes with equal symbols are grouped with
+	// __match_any_sync and one lane adds the group size.
+	{
+		const bool is_data = t == HB_DATA;
+		const int ncj = p.ncomp < 8 ? p.ncomp : 8;
+		for (int j = 0; j < ncj; ++j) {
+			for (int b = 0; b < p.size[j]; ++b) {
+				const uint32_t ctx = p.sym_off[j] + b;
+				const uint32_t s = is_data ? (uint32_t)(res[j] >> (8 * b)) & 0xffu : 0x100u + (threadIdx.x & 31u);
+				const unsigned grp = __match_any_sync(0xffffffffu, s);
+				if (is_data && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31u)) {
+					const uint32_t cnt = __popc(grp);
+					if ((int)ctx < nctx_s) atomicAdd(&s_hist[ctx * 256 + s], cnt);
+					else atomicAdd(&a.hist[(size_t)ctx * 256 + s], (unsigned long long)cnt);
+				}
+			}
+		}
+		// emission-type counts: one shared-memory atomic per warp and type
+		for (int ty = 0; ty < 3; ++ty) {
+			const unsigned m = __ballot_sync(0xffffffffu, t == ty);
+			if (m && (threadIdx.x & 31u) == 0) atomicAdd(&s_type[ty], (uint32_t)__popc(m));
 		}
 	}
 	__syncthreads();

@@ -31,8 +31,15 @@ struct hb_ctx {
 	int *d_err = nullptr;   // device error flag (fan walk overflow, binding out of range)
 	int *h_err = nullptr;   // pinned mirror
 	int sm_count = 148;
+	// optional per-kernel timing (CUDA events around every launch on the context stream)
+	bool profiling = false;
+	struct ProfRec { const char *name; cudaEvent_t a, b; };
+	std::vector<ProfRec> prof;
+	std::vector<cudaEvent_t> ev_pool;
 };
+cudaEvent_t hb_prof_event(hb_ctx *ctx);
 
+struct SpecArgs;
 struct ListParams {
 	uint8_t *rows;          // AoS rows in HBM (nrows * stride)
 	uint32_t nrows, stride;
@@ -62,6 +69,12 @@ struct DevList {
 	uint32_t *d_first = nullptr;  // per attribute row: first referencing element (its DATA emission)
 	uint32_t *d_dord = nullptr;   // exclusive scan of DATA flags (n_elems + 1)
 	unsigned long long *d_rp = nullptr; // rank-space value records, ncomp u64 containers per element
+	// speculative vertex decode (hb_decode_spec.cuh)
+	uint8_t *d_kind = nullptr;
+	uint32_t *d_src = nullptr;
+	uint8_t *d_cres = nullptr, *d_cx = nullptr; // compact residual / value records
+	struct SpecArgs *d_spec_args = nullptr;
+	unsigned long long *d_spec_stats = nullptr;
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
 	uint8_t *d_rows_backup = nullptr;   // hb_dmesh_snapshot
@@ -118,8 +131,18 @@ int hb_fail(hb_ctx *ctx, int code, const char *fmt, ...);
 // every kernel launch goes through this (counts launches, checks the launch)
 #define HB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                              \
 	do {                                                                                            \
+		cudaEvent_t pa__ = nullptr, pb__ = nullptr;                                                 \
+		if ((ctx)->profiling) {                                                                     \
+			pa__ = hb_prof_event(ctx);                                                              \
+			pb__ = hb_prof_event(ctx);                                                              \
+			cudaEventRecord(pa__, (ctx)->stream);                                                   \
+		}                                                                                           \
 		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                            \
 		(ctx)->launches++;                                                                          \
+		if (pa__) {                                                                                 \
+			cudaEventRecord(pb__, (ctx)->stream);                                                   \
+			(ctx)->prof.push_back(hb_ctx::ProfRec{ #kernel, pa__, pb__ });                          \
+		}                                                                                           \
 		HB_CUDA((ctx), cudaGetLastError());                                                         \
 	} while (0)
 

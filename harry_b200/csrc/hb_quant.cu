@@ -66,7 +66,6 @@ __global__ void __launch_bounds__(256) k_bounds_reduce(ListParams p, unsigned lo
 {
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t total_threads = rows_per_step * (uint32_t)p.ncomp;
-	if (tid >= total_threads) return;
 	const int j = (int)(tid % (uint32_t)p.ncomp);
 	const int type = p.type[j];
 	const int size = hb_type_size(type);
@@ -74,7 +73,7 @@ __global__ void __launch_bounds__(256) k_bounds_reduce(ListParams p, unsigned lo
 	unsigned long long kmin = key_of(seed_bits(type, true), type), kmax = key_of(seed_bits(type, false), type);
 	unsigned long long zneg = ~0ull, zpos = ~0ull;
 	const uint8_t *base = p.rows + p.offset[j];
-	for (uint32_t row = tid / (uint32_t)p.ncomp; row < p.nrows; row += rows_per_step) {
+	for (uint32_t row = tid < total_threads ? tid / (uint32_t)p.ncomp : p.nrows; row < p.nrows; row += rows_per_step) {
 		const unsigned long long bits = hb_ld_bits(base + (size_t)row * p.stride, size);
 		if (is_fp) {
 			// NaN never replaces a bound (both comparisons are false)
@@ -92,10 +91,20 @@ __global__ void __launch_bounds__(256) k_bounds_reduce(ListParams p, unsigned lo
 		kmin = k < kmin ? k : kmin;
 		kmax = k > kmax ? k : kmax;
 	}
-	atomicMin(&scratch[4 * j + 0], kmin);
-	atomicMax(&scratch[4 * j + 1], kmax);
-	if (zneg != ~0ull) atomicMin(&scratch[4 * j + 2], zneg);
-	if (zpos != ~0ull) atomicMin(&scratch[4 * j + 3], zpos);
+	// block-level combine in shared memory (one slot per component), then one global atomic per
+	// block and component instead of one per thread
+	__shared__ unsigned long long s_red[4 * HB_MAX_COMP];
+	for (int k = threadIdx.x; k < 4 * p.ncomp; k += blockDim.x) s_red[k] = (k & 3) == 1 ? 0ull : ~0ull;
+	__syncthreads();
+	atomicMin(&s_red[4 * j + 0], kmin);
+	atomicMax(&s_red[4 * j + 1], kmax);
+	if (zneg != ~0ull) atomicMin(&s_red[4 * j + 2], zneg);
+	if (zpos != ~0ull) atomicMin(&s_red[4 * j + 3], zpos);
+	__syncthreads();
+	for (int k = threadIdx.x; k < 4 * p.ncomp; k += blockDim.x) {
+		if ((k & 3) == 1) atomicMax(&scratch[k], s_red[k]);
+		else if (s_red[k] != ~0ull) atomicMin(&scratch[k], s_red[k]);
+	}
 }
 
 // bounds rows: [0] min, [1] max, [2] scale -- `stride` bytes each, components at their row offsets

@@ -165,6 +165,14 @@ void hb_last_timing(hb_ctx *ctx, float *kernel_ms, float *copy_ms);
 /* Number of kernels this library launched on the context since creation. */
 uint64_t hb_kernel_launches(hb_ctx *ctx);
 
+/* Per-kernel timing: while enabled every kernel launch is bracketed by CUDA events on the
+ * context stream; the report synchronizes, writes "name launches total_ms\n" lines and resets. */
+int hb_ctx_profile(hb_ctx *ctx, int enable);
+int hb_ctx_profile_report(hb_ctx *ctx, char *buf, size_t len);
+/* Six user events on the context stream to time a region of device-resident stages. */
+int hb_ctx_mark(hb_ctx *ctx, int idx);
+int hb_ctx_elapsed(hb_ctx *ctx, int from_idx, int to_idx, float *ms);
+
 /* ---- quantization path (host buffers) --------------------------------------------------- */
 /* min_row / max_row: `stride` bytes each, laid out like a row of the list with every component
  * in its UNQUANTIZED type (Attr::bounds(), structs/attr.h:33,78-85).  Reproduces the

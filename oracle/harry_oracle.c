@@ -1065,3 +1065,111 @@ done_:
 	coder_free(&c);
 	return rc;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Debug / design aid (not part of the parity surface): CPU simulation of the speculative        */
+/* chunk-parallel reconstruction used by harry_b200/csrc/hb_decode_spec.cuh, for one quantized   */
+/* vertex list with identity bindings.  Prints the advance of the exact prefix per sweep.        */
+/* ------------------------------------------------------------------------------------------ */
+int ho_debug_spec_sim(const hb_mesh_desc *m, int l, uint32_t B, uint32_t T, uint32_t max_print)
+{
+	coder c;
+	int rc = coder_init(&c, m);
+	if (rc) return rc;
+	const hb_list_desc *L = &m->lists[l];
+	const list_info *li = &c.li[l];
+	const uint32_t n = m->norder;
+	uint32_t *off = (uint32_t *)calloc(n + 1, 4);
+	u32vec tri = { 0, 0, 0 };
+	uint32_t *rank = (uint32_t *)malloc(4 * (m->nv + 1));
+	memset(rank, 0xff, 4 * (m->nv + 1));
+	uint32_t *ordv = (uint32_t *)malloc(4 * (n + 1));
+	for (uint32_t i = 0; i < n; ++i) {
+		int ok;
+		const uint32_t h = order_halfedge(m, m->order, i, &ok);
+		const uint32_t v = c.org[h];
+		ordv[i] = v;
+		gather_vertex_candidates(&c, h, m->vtx_regs[v]);
+		c.vtx_done[v] = 1;
+		rank[v] = i;
+		off[i] = (uint32_t)(tri.n / 3);
+		for (size_t k = 0; k < c.cand.n; ++k) u32vec_push(&tri, rank[c.cand.v[k]]);
+	}
+	off[n] = (uint32_t)(tri.n / 3);
+	const int nc = L->ncomp;
+	/* residuals = rows (decode input); x = working values */
+	uint64_t *res = (uint64_t *)calloc((size_t)n * nc + 1, 8), *x = (uint64_t *)calloc((size_t)n * nc + 1, 8);
+	for (uint32_t i = 0; i < n; ++i)
+		for (int j = 0; j < nc; ++j) res[(size_t)i * nc + j] = ld_bits((const uint8_t *)L->rows + (size_t)m->bind_vtx_attr[(size_t)ordv[i] * m->nb_vtx] * L->stride + L->offset[j], li->stype[j]);
+	uint32_t done = 0, sweeps = 0;
+	uint64_t steps = 0;
+	uint64_t tmp[4096];
+	while (done < n) {
+		uint32_t p = 0xffffffffu;
+		/* emulate concurrent chunks: Jacobi semantics (all chunks read the previous sweep's values
+		 * of other chunks) via a snapshot would be expensive; run chunks in DESCENDING order so a
+		 * chunk never sees this sweep's results of an earlier chunk. */
+		uint32_t nchunks = T;
+		for (int64_t t = (int64_t)nchunks - 1; t >= 0; --t) {
+			const uint64_t start = (uint64_t)done + (uint64_t)t * B;
+			if (start >= n) continue;
+			const uint32_t end = (uint32_t)((start + B < n) ? start + B : n);
+			uint32_t fc = 0xffffffffu;
+			for (uint32_t i = (uint32_t)start; i < end; ++i) {
+				const uint32_t K = off[i + 1] - off[i];
+				int changed = 0;
+				for (int j = 0; j < nc; ++j) {
+					for (uint32_t k = 0; k < K && k < 4096; ++k) {
+						const uint32_t *tr = tri.v + 3 * (size_t)(off[i] + k);
+						tmp[k] = ho_predict(li->stype[j], x[(size_t)tr[0] * nc + j], x[(size_t)tr[1] * nc + j], x[(size_t)tr[2] * nc + j], li->q[j]);
+					}
+					const uint64_t pred = combine_candidates(li->stype[j], tmp, K);
+					const uint64_t nv = ho_decode_delta(li->stype[j], res[(size_t)i * nc + j], pred, li->q[j]);
+					if (nv != x[(size_t)i * nc + j]) { x[(size_t)i * nc + j] = nv; changed = 1; }
+				}
+				if (changed && fc == 0xffffffffu) fc = i;
+				++steps;
+			}
+			if (t == 0 && fc != 0xffffffffu) fc = end;
+			if (fc < p) p = fc;
+		}
+		const uint64_t wend = (uint64_t)done + (uint64_t)T * B;
+		const uint32_t nd = p != 0xffffffffu ? p : (uint32_t)(wend < n ? wend : n);
+		if (sweeps < max_print) printf("sweep %u: done %u -> %u (+%u)\n", sweeps, done, nd, nd - done);
+		done = nd;
+		++sweeps;
+	}
+	printf("n=%u B=%u T=%u sweeps=%u steps=%llu (%.2f per rank), sequential-equivalent depth %llu\n", n, B, T, sweeps, (unsigned long long)steps, (double)steps / n, (unsigned long long)sweeps * B);
+	free(off); free(tri.v); free(rank); free(ordv); free(res); free(x);
+	coder_free(&c);
+	return 0;
+}
+
+/* Debug: traversal-order candidate triples (ranks) of the vertices, CSR.  Caller frees with free(). */
+int ho_debug_vertex_candidates(const hb_mesh_desc *m, uint32_t **off_out, uint32_t **tri_out)
+{
+	coder c;
+	int rc = coder_init(&c, m);
+	if (rc) return rc;
+	const uint32_t n = m->norder;
+	uint32_t *off = (uint32_t *)calloc(n + 1, 4);
+	u32vec tri = { 0, 0, 0 };
+	uint32_t *rank = (uint32_t *)malloc(4 * (m->nv + 1));
+	memset(rank, 0xff, 4 * (m->nv + 1));
+	for (uint32_t i = 0; i < n && rc == 0; ++i) {
+		int ok;
+		const uint32_t h = order_halfedge(m, m->order, i, &ok);
+		const uint32_t v = c.org[h];
+		rc = gather_vertex_candidates(&c, h, m->vtx_regs[v]);
+		c.vtx_done[v] = 1;
+		if (rank[v] == 0xffffffffu) rank[v] = i;
+		off[i] = (uint32_t)(tri.n / 3);
+		for (size_t k = 0; k < c.cand.n; ++k) u32vec_push(&tri, rank[c.cand.v[k]]);
+	}
+	off[n] = (uint32_t)(tri.n / 3);
+	free(rank);
+	coder_free(&c);
+	*off_out = off;
+	*tri_out = tri.v;
+	return rc;
+}

@@ -6,6 +6,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -19,6 +20,24 @@ REF_CLI = os.path.join(ORACLE_DIR, "_ref", "harry")
 
 _oracle = None
 _ref = None
+
+
+class quiet_stdout:
+    """The reference prints progress bars and statistics on stdout (utils/progress.h:102-136,
+    formats/obj/reader.cc); keep them away from our stdout (bench.py prints one JSON line there)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+        return self
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+        return False
 
 
 def build_oracle():
@@ -142,7 +161,8 @@ class RefMesh:
 
     def __init__(self, path: str):
         self.lib = ref()
-        self.h = self.lib.ref_read(path.encode())
+        with quiet_stdout():
+            self.h = self.lib.ref_read(path.encode())
         if not self.h:
             raise RuntimeError(f"ref_read({path}): {self.lib.ref_last_error().decode()}")
 
@@ -170,10 +190,14 @@ class RefMesh:
         self._check(self.lib.ref_set_bounds(self.h), "set_bounds")
 
     def traverse(self):
-        self._check(self.lib.ref_traverse(self.h), "traverse")
+        with quiet_stdout():
+            rc = self.lib.ref_traverse(self.h)
+        self._check(rc, "traverse")
 
     def write(self, path: str):
-        self._check(self.lib.ref_write(self.h, path.encode()), "write")
+        with quiet_stdout():
+            rc = self.lib.ref_write(self.h, path.encode())
+        self._check(rc, "write")
 
     def arrays(self) -> capi.MeshArrays:
         """Deep numpy copy of the flattened mesh (current state)."""
@@ -216,12 +240,16 @@ class RefMesh:
         flat = [int(x) for t in loq for x in t]
         arr = (C.c_int * max(1, len(flat)))(*flat)
         t = (C.c_double * 6)()
-        self._check(self.lib.ref_time_path(self.h, len(loq), arr, t), "time_path")
+        with quiet_stdout():
+            rc = self.lib.ref_time_path(self.h, len(loq), arr, t)
+        self._check(rc, "time_path")
         return list(t)
 
 
 def ref_time_decode(hry_path: str):
     t = (C.c_double * 6)()
-    if ref().ref_time_decode(hry_path.encode(), t) != 0:
+    with quiet_stdout():
+        rc = ref().ref_time_decode(hry_path.encode(), t)
+    if rc != 0:
         raise RuntimeError(f"reference time_decode: {ref().ref_last_error().decode()}")
     return list(t)

@@ -1,8 +1,14 @@
-"""GPU parity: the CUDA path (through the C ABI) against the real reference's captured outputs and
-the CPU oracle, bit for bit.  Run on the B200 box: pytest -m gpu."""
+"""GPU parity: the CUDA path, called through the C ABI, against (a) the committed golden vectors,
+(b) the unmodified reference run live through oracle/_ref, and (c) the CPU oracle -- bit for bit.
+Run on the B200 box: pytest -m gpu."""
+import glob
+import os
+
 import numpy as np
 import pytest
 
+import checks
+import golden_io
 import oracle_lib as ol
 from cases import CASES, CONFIG1, get_case
 from harry_b200 import capi
@@ -10,6 +16,9 @@ from harry_b200 import capi
 pytestmark = pytest.mark.gpu
 
 needs_ref = pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref/libharry_ref.so not built")
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GIDS = [os.path.basename(p)[:-4] for p in GOLDEN]
+ALL = list(CASES.keys()) + [CONFIG1[0]]
 
 
 @pytest.fixture(scope="module")
@@ -19,55 +28,48 @@ def ctx():
     c.close()
 
 
-ALL = list(CASES.keys()) + [CONFIG1[0]]
+@pytest.fixture(scope="module")
+def impl(ctx):
+    return checks.CudaImpl(ctx)
 
 
-@needs_ref
-@pytest.mark.parametrize("name", ALL)
-def test_bounds_and_requant(ctx, workdir, name):
-    case = get_case(workdir, name)
-    for l, la in enumerate(case.raw.lists):
-        if la.ncomp == 0:
-            continue
-        mn, mx = ctx.bounds(la)
-        assert np.array_equal(mn, case.raw_bounds[l][0]), f"min row list {l}"
-        assert np.array_equal(mx, case.raw_bounds[l][1]), f"max row list {l}"
-        nq = case.enc.lists[l].quants
-        if nq != la.quants:
-            lb = la.copy()
-            ctx.requant(lb, nq, mn, case.raw_scale[l])
-            assert lb.quants == nq
-            assert np.array_equal(lb.rows, case.enc.lists[l].rows), f"quantized rows list {l}"
+# ---- committed golden vectors -----------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=GIDS)
+def test_golden_quant(impl, path):
+    checks.check_quant(impl, golden_io.GoldenCase(path))
 
 
-@needs_ref
-@pytest.mark.parametrize("name", ALL)
-def test_encode_streams(ctx, workdir, name):
-    case = get_case(workdir, name)
-    got = ctx.attr_encode(case.enc)
-    ok, why = got.equal(case.enc_streams)
-    assert ok, why
-    # and the CPU restatement agrees as well
+@pytest.mark.parametrize("path", GOLDEN, ids=GIDS)
+def test_golden_encode(impl, path):
+    case = golden_io.GoldenCase(path)
+    got = checks.check_encode(impl, case)
     ok, why = got.equal(ol.o_attr_encode(case.enc))
     assert ok, why
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=GIDS)
+def test_golden_decode(impl, path):
+    checks.check_decode(impl, golden_io.GoldenCase(path))
+
+
+# ---- live reference -----------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("name", ALL)
+def test_bounds_and_requant(impl, workdir, name):
+    checks.check_quant(impl, get_case(workdir, name))
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ALL)
+def test_encode_streams(impl, ctx, workdir, name):
+    checks.check_encode(impl, get_case(workdir, name))
     assert ctx.launches() > 0
 
 
 @needs_ref
 @pytest.mark.parametrize("name", ALL)
-def test_decode_rows(ctx, workdir, name):
-    case = get_case(workdir, name)
-    m = case.decode_input()
-    ctx.attr_decode(m)
-    for l, la in enumerate(case.dec.lists):
-        assert np.array_equal(m.lists[l].rows, la.rows), f"decoded rows list {l}"
-    if case.deq is not None:
-        for l, la in enumerate(case.dec.lists):
-            if not any(la.quants):
-                continue
-            lb = m.lists[l].copy()
-            ctx.requant(lb, [0] * la.ncomp, case.dec_bounds[l][0], case.deq_scale[l])
-            assert np.array_equal(lb.rows, case.deq.lists[l].rows), f"dequantized rows list {l}"
+def test_decode_rows(impl, workdir, name):
+    checks.check_decode(impl, get_case(workdir, name))
 
 
 @needs_ref
@@ -93,3 +95,50 @@ def test_device_resident_pipeline(ctx, workdir, name):
                 assert np.array_equal(dm.fetch_rows(l), case.enc.lists[l].rows)
         dm.restore()
     dm.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["sphere_q14", "sphere_lossless", "obj_q14_q10"])
+def test_device_resident_decode(ctx, workdir, name):
+    """decode twice from a device snapshot (the path bench.py times)"""
+    case = get_case(workdir, name)
+    m = case.decode_input()
+    dm = capi.DeviceMesh(ctx, m)
+    for l, (mn, mx) in enumerate(case.dec_bounds):
+        if m.lists[l].ncomp:
+            dm.set_bounds(l, mn, mx, case.deq_scale[l] if case.deq is not None else None)
+    dm.snapshot()
+    for rep in range(2):
+        dm.decode()
+        for l, la in enumerate(case.dec.lists):
+            if la.ncomp:
+                assert np.array_equal(dm.fetch_rows(l), la.rows), f"rep {rep} list {l}"
+        if case.deq is not None:
+            for l, la in enumerate(case.dec.lists):
+                if any(la.quants):
+                    dm.dequantize(l)
+                    assert np.array_equal(dm.fetch_rows(l), case.deq.lists[l].rows)
+        dm.restore()
+    dm.close()
+
+
+# ---- size-independent properties at larger sizes ------------------------------------------------
+def test_roundtrip_property_large(ctx):
+    """encode -> decode on the same (encoder-numbered) mesh is the identity for the quantized values,
+    at a size where the oracle still finishes in seconds; the oracle streams agree too."""
+    from harry_b200 import flatten, meshgen
+    pm = meshgen.uv_sphere(300, 601, noise_seed=9)           # 179 501 vertices
+    mesh = flatten.mesh_arrays(pm)
+    vl = mesh.lists[1]
+    mn, mx = ctx.bounds(vl)
+    sc = ol.o_scale(vl, mn, mx)
+    ctx.requant(vl, [14, 14, 14], mn, sc)
+    got = ctx.attr_encode(mesh)
+    ok, why = got.equal(ol.o_attr_encode(mesh))
+    assert ok, why
+    assert int(got.lists[1].hist.sum()) == 6 * mesh.nv        # checksum of checksums: one count per symbol
+    dec = mesh.copy()
+    dec.lists = capi.residual_rows_encoder_side(mesh, got)
+    ctx.attr_decode(dec)
+    cols = [0, 1, 4, 5, 8, 9]
+    assert np.array_equal(dec.lists[1].rows[:, cols], mesh.lists[1].rows[:, cols])
