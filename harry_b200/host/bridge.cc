@@ -1,0 +1,125 @@
+// bridge.cc -- see bridge.h
+#include "bridge.h"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace b200 {
+
+static hb_ctx *g_ctx = nullptr;
+
+hb_ctx *context()
+{
+	if (!g_ctx) {
+		const char *dev = std::getenv("HARRY_B200_DEVICE");
+		if (hb_ctx_create(dev ? std::atoi(dev) : 0, &g_ctx) != 0)
+			throw std::runtime_error(std::string("harry_b200: ") + hb_last_error(nullptr));
+	}
+	return g_ctx;
+}
+
+void fail(const char *what)
+{
+	throw std::runtime_error(std::string("harry_b200 ") + what + ": " + hb_last_error(g_ctx));
+}
+
+hb_list_desc describe_list(mesh::attr::Attr &attr)
+{
+	hb_list_desc L;
+	std::memset(&L, 0, sizeof L);
+	const mixing::Fmt &fmt = attr.fmt();
+	if (fmt.size() > HB_MAX_COMP) throw std::runtime_error("harry_b200: attribute list with more than 32 components");
+	L.rows = attr.data();
+	L.nrows = (uint32_t)attr.size();
+	L.stride = (uint32_t)fmt.bytes();
+	L.ncomp = (uint16_t)fmt.size();
+	L.target = (uint8_t)attr.target;
+	for (int j = 0; j < fmt.size(); ++j) {
+		L.type[j] = (uint8_t)fmt.type(j);
+		L.quant[j] = (uint8_t)fmt.quant(j);
+		L.offset[j] = (uint16_t)fmt.offset(j);
+	}
+	return L;
+}
+
+void flatten(mesh::Mesh &m, const std::vector<mesh::conn::fepair> &order, const std::vector<mesh::conn::fepair> *order_f, FlatMesh &out)
+{
+	static_assert(sizeof(mesh::conn::Conn::edgeorg) == 12, "Conn::edgeorg layout (structs/conn.h:73-76)");
+	static_assert(sizeof(mesh::conn::fepair) == 8, "fepair layout (structs/conn.h:22-31)");
+	hb_mesh_desc &d = out.desc;
+	std::memset(&d, 0, sizeof d);
+	d.nv = m.num_vtx();
+	d.nf = m.num_face();
+	d.ne = m.num_edge();
+	d.edges = m.conn.edges.data();
+	d.face_off = m.faces.offsets.data();
+	d.order = order.data();
+	d.norder = (uint32_t)order.size();
+	d.order_f = order_f ? order_f->data() : nullptr;
+	d.norder_f = order_f ? (uint32_t)order_f->size() : 0;
+	d.vtx_regs = m.attrs.vtx_regs.data();
+	d.face_regs = m.attrs.face_regs.data();
+	d.nb_face = m.attrs.num_bindings_face;
+	d.nb_vtx = m.attrs.num_bindings_vtx;
+	d.nb_corner = m.attrs.num_bindings_corner;
+	d.nregs_face = m.attrs.num_regs_face();
+	d.nregs_vtx = m.attrs.num_regs_vtx();
+	d.nlists = (uint16_t)m.attrs.size();
+	d.bind_face_attr = m.attrs.bindings_face_attr.data();
+	d.bind_vtx_attr = m.attrs.bindings_vtx_attr.data();
+	d.bind_corner_attr = m.attrs.bindings_corner_attr.data();
+	out.off_face.assign(m.attrs.off_reg_facelist.begin(), m.attrs.off_reg_facelist.end());
+	out.off_corner.assign(m.attrs.off_reg_cornerlist.begin(), m.attrs.off_reg_cornerlist.end());
+	out.off_vtx.assign(m.attrs.off_reg_vtxlist.begin(), m.attrs.off_reg_vtxlist.end());
+	d.off_reg_face = out.off_face.data();
+	d.off_reg_corner = out.off_corner.data();
+	d.off_reg_vtx = out.off_vtx.data();
+	d.reg_facelist = m.attrs.bindings_reg_facelist.data();
+	d.reg_cornerlist = m.attrs.bindings_reg_cornerlist.data();
+	d.reg_vtxlist = m.attrs.bindings_reg_vtxlist.data();
+	out.lists.clear();
+	for (size_t l = 0; l < m.attrs.size(); ++l) out.lists.push_back(describe_list(m.attrs[l]));
+	d.lists = out.lists.data();
+}
+
+}
+
+namespace quant {
+
+// quant::set_bounds (structs/quant.h:39-44): min / max rows of every list, on the GPU
+void set_bounds_b200(mesh::attr::Attrs &attrs)
+{
+	hb_ctx *ctx = b200::context();
+	for (mesh::listidx_t i = 0; i < attrs.size(); ++i) {
+		mesh::attr::Attr &attr = attrs[i];
+		if (attr.fmt().size() == 0) continue;
+		hb_list_desc L = b200::describe_list(attr);
+		if (hb_bounds(ctx, &L, attr.min().data(), attr.max().data()) != 0) b200::fail("set_bounds");
+	}
+}
+
+// quant::requant(Attrs&, vector<Quant>, clear) (structs/quant.h:222-242): the format bookkeeping
+// (backup_fmt / tmp / restore_fmt) and set_scale stay the reference's; the row conversion
+// requant(Attr&, Fmt) (:215-221) runs on the GPU
+void requant_b200(mesh::attr::Attrs &attrs, const std::vector<Quant> &quant, bool clear)
+{
+	hb_ctx *ctx = b200::context();
+	for (mesh::listidx_t l = 0; l < attrs.size(); ++l) attrs[l].backup_fmt();
+	if (clear)
+		for (mesh::listidx_t l = 0; l < attrs.size(); ++l)
+			for (int i = 0; i < attrs[l].fmt().size(); ++i) attrs[l].tmp().setquant(i, 0);
+	for (size_t i = 0; i < quant.size(); ++i) attrs[quant[i].l].tmp().setquant(quant[i].o, quant[i].q);
+	for (mesh::listidx_t l = 0; l < attrs.size(); ++l) {
+		mesh::attr::Attr &attr = attrs[l];
+		set_scale(attr);
+		if (attr.fmt().size()) {
+			hb_list_desc L = b200::describe_list(attr);
+			uint8_t nq[HB_MAX_COMP] = { 0 };
+			for (int j = 0; j < attr.tmp().size(); ++j) nq[j] = (uint8_t)attr.tmp().quant(j);
+			if (hb_requant(ctx, &L, nq, attr.min().data(), attr.scale().data()) != 0) b200::fail("requant");
+		}
+		attr.restore_fmt();
+	}
+}
+
+}
