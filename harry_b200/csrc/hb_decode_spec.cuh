@@ -1,29 +1,39 @@
 // hb_decode_spec.cuh -- speculative chunk-parallel reconstruction of vertex lists.
 //
 // Problem: x[i] = decodeDelta(residual[i], prediction(x[deps(i)])), deps(i) < i, and in a CBM
-// traversal one dependency is (almost) always rank i-1, so the DAG is a chain of depth ~N.
+// traversal one dependency is (almost) always rank i-1, so the level DAG is a chain of depth ~N.
 //
-// Scheme (exact for any input, see DESIGN.md "Speculative wavefront"):
-//   * ranks [0, done) are final.  The window [done, done + T*B) is cut into T chunks of B
-//     consecutive ranks; thread t recomputes chunk t SEQUENTIALLY, reading whatever values the
-//     other chunks currently hold (possibly stale) and writing its results in place.
-//   * each thread records the first rank of its chunk whose value CHANGED in this sweep; p = the
-//     minimum over all chunks.  Every rank in [done, p) was recomputed from dependencies of lower
-//     rank that did not change during the sweep, so by induction on the rank all of [done, p) equal
-//     the sequential solution: done = p.
-//   * chunk 0 starts at `done` and only reads final values, so it is exact after the sweep whether
-//     or not it changed (if it changed, p = its end): progress >= B ranks per sweep, i.e. never
-//     slower than a sequential walk, even if nothing else converges.
-//   * why it is fast: with averaged parallelogram prediction x[i] ~ (x[i-1] + known terms) / 2 + delta,
-//     an error in x[i-1] is halved at every step, so a chunk started from a wrong value is right
-//     after ~log2(range) steps; whole rings of the traversal converge in 2-3 sweeps.
-//   * B adapts: if a sweep advances by no more than one chunk (no contraction, e.g. lossless float
-//     lists pick ONE candidate), B grows so that the exact chunk 0 carries the progress.
+// Scheme (exact for ANY input; the speculation only decides how fast `done` advances):
+//   ranks [0, done) are final.  The window [done, done + T*B) is cut into T chunks of B consecutive
+//   ranks, one thread each.
+//
+//   HYPOTHESIS MODE (B = 8, integer lists).  Every sweep is a Jacobi step in three phases:
+//     1. compute: thread t recomputes its chunk sequentially from the STORED state of the window,
+//        three times: assuming the value of its predecessor rank (start - 1) is the stored value
+//        + e, e in {-1, 0, +1}, independently per component.  Why: averaged parallelogram prediction
+//        halves an upstream error per step, so after a few sweeps every stored value is within +-1
+//        of the truth, but a +-1 offset can persist indefinitely through the rounding (e.g. a
+//        coordinate that is constant along a ring has two adjacent fixed points).
+//        The three runs give, per component, a map  offset-in -> offset-out  (end value relative to
+//        the stored end value), or "unknown" if outside +-1.
+//     2. resolve: an inclusive prefix composition (block scan) of these maps, starting from offset 0
+//        for chunk 0 (its predecessor is final), yields the TRUE offset-in of every chunk, as long as
+//        every map along the way is defined.  A chunk is valid iff all chunks before it are valid,
+//        its offset-in is known, and every other window value it read is unchanged by the
+//        resolution (range query on prefix sums of per-chunk "changed" flags).
+//     3. write: valid chunks store the selected trajectories -- exact by induction: each was
+//        computed sequentially from final values, from the exact value of its predecessor rank and
+//        from window values equal to their final ones; done = start of the first invalid chunk.
+//        Invalid chunks store their offset-0 trajectory (plain Jacobi refresh).
+//     Chunk 0 is always valid, so progress >= B ranks per sweep.
+//   PLAIN MODE (adaptive B, used for lossless float lists -- they pick ONE candidate, no averaging,
+//   no contraction -- and whenever hypothesis sweeps stop paying): in-place recomputation; the
+//   first rank whose value changed bounds the exact prefix; chunk 0 is exact after the sweep.
 #pragma once
 #include "hb_lists.cuh"
 
 #define SPEC_THREADS 1024
-#define SPEC_B_MIN 8
+#define SPEC_HB 8            // chunk length in hypothesis mode
 #define SPEC_B_MAX 1024
 
 template <typename T, int NC> struct SpecRec;
@@ -41,12 +51,13 @@ struct SpecArgs {
 	void *x;                  // compact records: values (in/out)
 	uint32_t n;
 	int bits[4];              // quantization bits per component (prediction.h:22-25)
-	unsigned long long *stats; // [0] sweeps, [1] sequential steps (diagnostics)
+	unsigned long long *stats; // [0] sweeps, [1] hypothesis sweeps, [2] plain sweeps
 };
 
-// one reconstruction step for all components of a rank; FP = lossless float list (T == uint32_t bits)
-template <typename T, int NC, bool FP>
-__device__ __forceinline__ SpecRec<T, NC> spec_step(const SpecArgs &a, const SpecRec<T, NC> *x, uint32_t i, uint32_t c0, uint32_t K, const SpecRec<T, NC> &res)
+// one reconstruction step for all components of a rank.  `get(r)` returns the record of rank r.
+// FP = lossless float list (T == uint32_t holding the IEEE bits).
+template <typename T, int NC, bool FP, typename Get>
+__device__ __forceinline__ SpecRec<T, NC> spec_step(const SpecArgs &a, Get &&get, uint32_t c0, uint32_t K, const SpecRec<T, NC> &res)
 {
 	SpecRec<T, NC> out = res;
 	const uint32_t *__restrict__ tri = a.cand + 3 * (size_t)c0;
@@ -55,7 +66,7 @@ __device__ __forceinline__ SpecRec<T, NC> spec_step(const SpecArgs &a, const Spe
 #pragma unroll
 		for (int j = 0; j < NC; ++j) sum[j] = 0;
 		for (uint32_t k = 0; k < K; ++k) {
-			const SpecRec<T, NC> v0 = x[tri[3 * k]], v1 = x[tri[3 * k + 1]], v2 = x[tri[3 * k + 2]];
+			const SpecRec<T, NC> v0 = get(tri[3 * k]), v1 = get(tri[3 * k + 1]), v2 = get(tri[3 * k + 2]);
 #pragma unroll
 			for (int j = 0; j < NC; ++j) sum[j] += (long long)IntOps<T>::predict(v0.c[j], v1.c[j], v2.c[j], a.bits[j]);
 		}
@@ -69,7 +80,7 @@ __device__ __forceinline__ SpecRec<T, NC> spec_step(const SpecArgs &a, const Spe
 #pragma unroll
 		for (int j = 0; j < NC; ++j) sum[j] = 0.0;
 		for (uint32_t k = 0; k < K; ++k) {
-			const SpecRec<T, NC> v0 = x[tri[3 * k]], v1 = x[tri[3 * k + 1]], v2 = x[tri[3 * k + 2]];
+			const SpecRec<T, NC> v0 = get(tri[3 * k]), v1 = get(tri[3 * k + 1]), v2 = get(tri[3 * k + 2]);
 #pragma unroll
 			for (int j = 0; j < NC; ++j)
 				sum[j] = __dadd_rn(sum[j], (double)__fadd_rn(__uint_as_float(v0.c[j]), __fsub_rn(__uint_as_float(v1.c[j]), __uint_as_float(v2.c[j]))));
@@ -78,7 +89,7 @@ __device__ __forceinline__ SpecRec<T, NC> spec_step(const SpecArgs &a, const Spe
 #pragma unroll
 		for (int j = 0; j < NC; ++j) { avg[j] = K ? __double2float_rn(__ddiv_rn(sum[j], (double)(int)K)) : 0.f; best[j] = FLT_MAX; }
 		for (uint32_t k = 0; k < K; ++k) {
-			const SpecRec<T, NC> v0 = x[tri[3 * k]], v1 = x[tri[3 * k + 1]], v2 = x[tri[3 * k + 2]];
+			const SpecRec<T, NC> v0 = get(tri[3 * k]), v1 = get(tri[3 * k + 1]), v2 = get(tri[3 * k + 2]);
 #pragma unroll
 			for (int j = 0; j < NC; ++j)
 				best[j] = hb_closest_step(best[j], __fadd_rn(__uint_as_float(v0.c[j]), __fsub_rn(__uint_as_float(v1.c[j]), __uint_as_float(v2.c[j]))), avg[j]);
@@ -101,6 +112,72 @@ __device__ __forceinline__ bool spec_equal(const SpecRec<T, NC> &a, const SpecRe
 	return eq;
 }
 
+// ---- offset maps ----------------------------------------------------------------------------------
+// per component 3 entries (offset-in -1, 0, +1 -> index 0, 1, 2) of 2 bits: offset-out index, 3 = unknown.
+// component j occupies bits [6j, 6j + 6).
+__device__ __forceinline__ uint32_t map_get(uint32_t m, int j, uint32_t e) { return e == 3 ? 3u : (m >> (6 * j + 2 * e)) & 3u; }
+// apply a first, then b
+__device__ __forceinline__ uint32_t map_compose(uint32_t a, uint32_t b, int nc)
+{
+	uint32_t c = 0;
+	for (int j = 0; j < nc; ++j)
+		for (uint32_t e = 0; e < 3; ++e) c |= map_get(b, j, map_get(a, j, e)) << (6 * j + 2 * e);
+	return c;
+}
+#define SPEC_MAP_IDENTITY 0x00924924u // every component: 0 -> 0, 1 -> 1, 2 -> 2  (binary 100100 repeated)
+
+// inclusive block scan of maps (composition in thread order)
+__device__ __forceinline__ uint32_t block_scan_maps(uint32_t m, int nc, uint32_t *s_warp /* 32 */)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t up = __shfl_up_sync(0xffffffffu, m, d);
+		if (lane >= d) m = map_compose(up, m, nc);
+	}
+	if (lane == 31) s_warp[warp] = m;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = s_warp[lane];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, w, d);
+			if (lane >= d) w = map_compose(up, w, nc);
+		}
+		s_warp[lane] = w;
+	}
+	__syncthreads();
+	if (warp > 0) m = map_compose(s_warp[warp - 1], m, nc);
+	__syncthreads();
+	return m;
+}
+
+__device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *s_warp /* 32 */)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t x = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t up = __shfl_up_sync(0xffffffffu, x, d);
+		if (lane >= d) x += up;
+	}
+	if (lane == 31) s_warp[warp] = x;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = s_warp[lane];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, w, d);
+			if (lane >= d) w += up;
+		}
+		s_warp[lane] = w;
+	}
+	__syncthreads();
+	const uint32_t incl = x + (warp ? s_warp[warp - 1] : 0);
+	__syncthreads();
+	return incl - v; // exclusive
+}
+
 // one CTA per vertex list
 template <typename T, int NC, bool FP>
 __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const SpecArgs *__restrict__ args)
@@ -110,47 +187,158 @@ __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const Sp
 	const Rec *__restrict__ resid = (const Rec *)a.resid;
 	Rec *x = (Rec *)a.x;
 	const uint32_t n = a.n;
-	__shared__ uint32_t s_first_changed;
-	uint32_t done = 0, B = SPEC_B_MIN;
-	unsigned long long sweeps = 0;
+	const uint32_t t = threadIdx.x;
+	__shared__ uint32_t s_min, s_warp[32], s_excl[SPEC_THREADS], s_incl[SPEC_THREADS];
+	__shared__ uint8_t s_inner[SPEC_THREADS];
+	uint32_t done = 0, B = SPEC_HB;
+	bool hyp = !FP;            // hypothesis mode
+	int poor = 0;              // consecutive hypothesis sweeps that advanced by <= 2 chunks
+	unsigned long long sweeps = 0, hsweeps = 0;
 	while (done < n) {
-		if (threadIdx.x == 0) s_first_changed = 0xffffffffu;
-		__syncthreads();
-		const unsigned long long start64 = (unsigned long long)done + (unsigned long long)threadIdx.x * B;
-		uint32_t fc = 0xffffffffu;
-		if (start64 < n) {
-			const uint32_t start = (uint32_t)start64;
-			const uint32_t end = (n - start < B) ? n : start + B;
-			uint32_t c0 = a.cand_off[start];
-			for (uint32_t i = start; i < end; ++i) {
-				const uint32_t c1 = a.cand_off[i + 1];
-				const int kind = a.kind[i];
-				if (kind) {
-					const Rec old = x[i];
-					const Rec nw = kind == 2 ? x[a.src[i]] : spec_step<T, NC, FP>(a, (const Rec *)x, i, c0, c1 - c0, resid[i]);
-					if (!spec_equal<T, NC>(old, nw)) {
-						x[i] = nw;
-						if (fc == 0xffffffffu) fc = i;
+		uint32_t newdone;
+		if (hyp) {
+			// ---------------- phase 1: three trajectories from the stored state --------------------
+			const unsigned long long start64 = (unsigned long long)done + (unsigned long long)t * SPEC_HB;
+			const bool active = start64 < n;
+			const uint32_t start = active ? (uint32_t)start64 : n;
+			const uint32_t len = active ? ((n - start < SPEC_HB) ? n - start : SPEC_HB) : 0;
+			Rec traj[3][SPEC_HB], old[SPEC_HB];
+			uint32_t minread = 0xffffffffu; // lowest window rank read besides the predecessor rank
+			uint32_t map = SPEC_MAP_IDENTITY;
+			if (active) {
+				Rec pst = resid[0];
+				const bool pred_in_window = start > done; // chunk 0: the predecessor is final
+				if (pred_in_window) pst = x[start - 1];
+				for (uint32_t k = 0; k < len; ++k) old[k] = x[start + k];
+				uint32_t c0 = a.cand_off[start];
+				for (uint32_t k = 0; k < len; ++k) {
+					const uint32_t i = start + k;
+					const uint32_t c1 = a.cand_off[i + 1];
+					const int kind = a.kind[i];
+#pragma unroll
+					for (int e = 0; e < 3; ++e) {
+						auto get = [&](uint32_t r) -> Rec {
+							if (r >= start) return traj[e][r - start];
+							if (pred_in_window && r == start - 1) {
+								Rec v = pst;
+#pragma unroll
+								for (int j = 0; j < NC; ++j) v.c[j] = (T)(v.c[j] + (T)(e - 1));
+								return v;
+							}
+							if (r >= done && r < minread) minread = r;
+							return x[r];
+						};
+						if (kind == 1) traj[e][k] = spec_step<T, NC, FP>(a, get, c0, c1 - c0, resid[i]);
+						else if (kind == 2) traj[e][k] = get(a.src[i]);
+						else traj[e][k] = old[k];
 					}
+					c0 = c1;
 				}
-				c0 = c1;
+				// offset map: end value under offset-in e, relative to the stored end value
+				map = 0;
+#pragma unroll
+				for (int j = 0; j < NC; ++j)
+#pragma unroll
+					for (int e = 0; e < 3; ++e) {
+						const long long d = (long long)traj[e][len - 1].c[j] - (long long)old[len - 1].c[j] + 1;
+						map |= (uint32_t)((d >= 0 && d <= 2) ? d : 3) << (6 * j + 2 * e);
+					}
 			}
-			// chunk 0 starts at `done` and reads only final values: it is exact after this sweep
-			// whether or not it changed; if it changed, nothing behind it is validated
-			if (threadIdx.x == 0 && fc != 0xffffffffu) fc = end;
+			__syncthreads(); // every read of the stored state is done
+			// ---------------- phase 2: resolve the offsets across chunks ---------------------------
+			s_incl[t] = block_scan_maps(map, NC, s_warp);
+			__syncthreads();
+			const uint32_t before = t == 0 ? SPEC_MAP_IDENTITY : s_incl[t - 1];
+			uint32_t ein[NC]; // true offset-in index per component (3 = unknown)
+			bool known = true;
+#pragma unroll
+			for (int j = 0; j < NC; ++j) { ein[j] = map_get(before, j, 1u); known = known && ein[j] != 3u; }
+			// which of my ranks change under the selected trajectory?
+			bool chg_inner = false, chg_last = false;
+			if (active && known) {
+				for (uint32_t k = 0; k < len; ++k) {
+					bool ch = false;
+#pragma unroll
+					for (int j = 0; j < NC; ++j) ch = ch || traj[ein[j]][k].c[j] != old[k].c[j];
+					if (k + 1 == len) chg_last = ch;
+					else chg_inner = chg_inner || ch;
+				}
+			}
+			s_inner[t] = chg_inner ? 1 : 0;
+			s_excl[t] = block_scan_u32((chg_inner ? 1u : 0u) + (chg_last ? 1u : 0u), s_warp);
+			if (t == 0) s_min = 0xffffffffu;
+			__syncthreads();
+			bool valid = !active || known;
+			if (active && known && minread != 0xffffffffu && t > 0) {
+				// other window reads: chunks [dep, t-2] must be entirely unchanged, chunk t-1 unchanged
+				// except (possibly) its last rank, which the offset hypothesis accounts for
+				const uint32_t dep = (minread - done) / SPEC_HB;
+				const uint32_t changed_before = s_excl[t - 1] - s_excl[dep]; // chunks [dep, t-2]
+				if (changed_before != 0 || s_inner[t - 1]) valid = false;
+			}
+			if (!valid) atomicMin(&s_min, t);
+			__syncthreads();
+			const uint32_t first_bad = s_min; // first invalid chunk (chunk 0 is always valid)
+			// ---------------- phase 3: write ----------------------------------------------------------
+			if (active) {
+				const bool sel = t < first_bad;
+				for (uint32_t k = 0; k < len; ++k) {
+					Rec v = old[k];
+#pragma unroll
+					for (int j = 0; j < NC; ++j) v.c[j] = traj[sel ? ein[j] : 1][k].c[j];
+					if (!spec_equal<T, NC>(v, old[k])) x[start + k] = v;
+				}
+			}
+			const unsigned long long wend = (unsigned long long)done + (unsigned long long)(first_bad == 0xffffffffu ? SPEC_THREADS : first_bad) * SPEC_HB;
+			newdone = wend < n ? (uint32_t)wend : n;
+			const uint32_t adv = newdone - done;
+			poor = adv <= 2 * SPEC_HB ? poor + 1 : 0;
+			if (poor >= 3) { hyp = false; B = 2 * SPEC_HB; poor = 0; }
+			++hsweeps;
+			__syncthreads();
+		} else {
+			// ---------------- plain mode: in-place recomputation ---------------------------------------
+			if (t == 0) s_min = 0xffffffffu;
+			__syncthreads();
+			const unsigned long long start64 = (unsigned long long)done + (unsigned long long)t * B;
+			uint32_t fc = 0xffffffffu;
+			if (start64 < n) {
+				const uint32_t start = (uint32_t)start64;
+				const uint32_t end = (n - start < B) ? n : start + B;
+				uint32_t c0 = a.cand_off[start];
+				auto get = [&](uint32_t r) -> Rec { return x[r]; };
+				for (uint32_t i = start; i < end; ++i) {
+					const uint32_t c1 = a.cand_off[i + 1];
+					const int kind = a.kind[i];
+					if (kind) {
+						const Rec old = x[i];
+						const Rec nw = kind == 2 ? x[a.src[i]] : spec_step<T, NC, FP>(a, get, c0, c1 - c0, resid[i]);
+						if (!spec_equal<T, NC>(old, nw)) {
+							x[i] = nw;
+							if (fc == 0xffffffffu) fc = i;
+						}
+					}
+					c0 = c1;
+				}
+				// chunk 0 starts at `done` and reads only final values: it is exact after this sweep
+				// whether or not it changed; if it changed, nothing behind it is validated
+				if (t == 0 && fc != 0xffffffffu) fc = end;
+			}
+			if (fc != 0xffffffffu) atomicMin(&s_min, fc);
+			__syncthreads();
+			const uint32_t p = s_min;
+			const unsigned long long wend = (unsigned long long)done + (unsigned long long)SPEC_THREADS * B;
+			newdone = p != 0xffffffffu ? p : (wend < n ? (uint32_t)wend : n);
+			const uint32_t adv = newdone - done;
+			if (adv <= 2 * B && B < SPEC_B_MAX) B <<= 1;
+			else if (adv >= 16 * B) {
+				if (B > 2 * SPEC_HB) B >>= 1;
+				else if (!FP) { hyp = true; poor = 0; } // the window converges again: back to hypotheses
+			}
+			__syncthreads();
 		}
-		if (fc != 0xffffffffu) atomicMin(&s_first_changed, fc);
-		__syncthreads();
-		const uint32_t p = s_first_changed;
-		const unsigned long long wend = (unsigned long long)done + (unsigned long long)SPEC_THREADS * B;
-		const uint32_t newdone = p != 0xffffffffu ? p : (wend < n ? (uint32_t)wend : n);
-		const uint32_t adv = newdone - done;
-		// adapt the chunk length: no speculation benefit -> longer exact chunk 0; plenty -> shorter
-		if (adv <= 2 * B && B < SPEC_B_MAX) B <<= 1;
-		else if (adv >= 64 * B && B > SPEC_B_MIN) B >>= 1;
 		done = newdone;
 		++sweeps;
-		__syncthreads();
 	}
-	if (threadIdx.x == 0 && a.stats) { a.stats[0] = sweeps; }
+	if (t == 0 && a.stats) { a.stats[0] = sweeps; a.stats[1] = hsweeps; a.stats[2] = sweeps - hsweeps; }
 }

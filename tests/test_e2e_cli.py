@@ -80,3 +80,19 @@ def test_cli_error_behaviour(workdir):
     src = gen(workdir, "sphere_noise")
     r = subprocess.run([CLI, src, os.path.join(workdir, "x.hry"), "-l1", "-q40"], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="drop-in CLI not built")
+def test_cli_really_runs_the_gpu_path(workdir):
+    """no CPU fallback: with an unusable device the drop-in fails in each swapped call instead of
+    silently running the reference's CPU code"""
+    src = gen(workdir, "sphere_noise")
+    env = dict(os.environ, HARRY_B200_DEVICE="99")
+    r = subprocess.run([CLI, src, os.path.join(workdir, "y.hry")], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "harry_b200" in (r.stderr + r.stdout)      # set_bounds in the PLY reader
+    # a .hry written by the reference: reading it must hit hb_attr_decode
+    if os.path.exists(ol.REF_CLI):
+        hry = os.path.join(workdir, "z.hry")
+        run(ol.REF_CLI, src, hry)
+        r = subprocess.run([CLI, hry, os.path.join(workdir, "z.ply")], capture_output=True, text=True, env=env)
+        assert r.returncode != 0 and "harry_b200" in (r.stderr + r.stdout)
