@@ -511,6 +511,8 @@ def load_library():
     lib.hb_dmesh_decode.restype = C.c_int
     lib.hb_dmesh_fetch_rows.argtypes = [vp, u32, vp]
     lib.hb_dmesh_fetch_rows.restype = C.c_int
+    lib.hb_dmesh_decode_stats.argtypes = [vp, u32, C.POINTER(C.c_uint64)]
+    lib.hb_dmesh_decode_stats.restype = C.c_int
     lib.hb_dmesh_fetch_bounds.argtypes = [vp, u32, vp, vp, vp]
     lib.hb_dmesh_fetch_bounds.restype = C.c_int
     lib.hb_ctx_sync.argtypes = [vp]
@@ -525,7 +527,7 @@ EXPORTED_SYMBOLS = [
     "hb_bounds", "hb_requant", "hb_attr_encode", "hb_streams_free", "hb_attr_decode",
     "hb_dmesh_upload", "hb_dmesh_free", "hb_dmesh_quantize", "hb_dmesh_dequantize", "hb_dmesh_encode",
     "hb_dmesh_fetch_streams", "hb_dmesh_set_bounds", "hb_dmesh_snapshot", "hb_dmesh_restore", "hb_dmesh_decode", "hb_dmesh_fetch_rows",
-    "hb_dmesh_fetch_bounds", "hb_ctx_sync",
+    "hb_dmesh_fetch_bounds", "hb_dmesh_decode_stats", "hb_ctx_sync",
 ]
 
 
@@ -681,6 +683,11 @@ class DeviceMesh:
         out = np.zeros((la.nrows, la.stride), dtype=np.uint8)
         self.ctx._check(self.ctx.lib.hb_dmesh_fetch_rows(self.h, l, out.ctypes.data), "hb_dmesh_fetch_rows")
         return out
+
+    def decode_stats(self, l: int) -> list:
+        out = (C.c_uint64 * 8)()
+        self.ctx._check(self.ctx.lib.hb_dmesh_decode_stats(self.h, l, out), "hb_dmesh_decode_stats")
+        return [int(v) for v in out]
 
     def fetch_bounds(self, l: int):
         la = self.mesh.lists[l]

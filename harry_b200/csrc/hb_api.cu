@@ -450,6 +450,19 @@ extern "C" int hb_dmesh_restore(hb_dmesh *m)
 	return 0;
 }
 
+// diagnostics of the speculative vertex decoder for list l: sweeps, hypothesis sweeps, plain sweeps,
+// ranks finalized by hypothesis sweeps, sweeps stopped by an unknown offset
+extern "C" int hb_dmesh_decode_stats(hb_dmesh *m, uint32_t l, uint64_t *out8)
+{
+	if (l >= m->lists.size()) return hb_fail(m->ctx, HB_ERR_INVALID, "list %u out of range", l);
+	for (int k = 0; k < 8; ++k) out8[k] = 0;
+	if (!m->lists[l].d_spec_stats) return 0;
+	HB_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
+	HB_CUDA(m->ctx, cudaMemcpyAsync(out8, m->lists[l].d_spec_stats, 64, cudaMemcpyDeviceToHost, m->ctx->stream));
+	HB_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
+	return 0;
+}
+
 extern "C" int hb_dmesh_encode(hb_dmesh *m)
 {
 	HB_CUDA(m->ctx, cudaSetDevice(m->ctx->device));

@@ -96,16 +96,24 @@ __global__ void __launch_bounds__(256) k_scatter_compact(ListParams p, const uin
 	for (int j = 0; j < p.ncomp; ++j) hb_st_bits(dst + p.offset[j], esize, hb_ld_bits(srcp + j * esize, esize));
 }
 
+template <typename T, int NC, bool FP>
+static int launch_spec_nc(hb_ctx *ctx, const SpecArgs *d_args)
+{
+	const int threads = spec_threads<T, NC>();
+	const size_t smem = (size_t)threads * 4 * SPEC_HB * sizeof(SpecRec<T, NC>);
+	HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_spec<T, NC, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	HB_LAUNCH(ctx, (k_decode_vertex_spec<T, NC, FP>), 1, threads, smem, d_args);
+	return 0;
+}
 template <typename T, bool FP>
 static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args)
 {
 	switch (ncomp) {
-	case 1: HB_LAUNCH(ctx, (k_decode_vertex_spec<T, 1, FP>), 1, SPEC_THREADS, 0, d_args); break;
-	case 2: HB_LAUNCH(ctx, (k_decode_vertex_spec<T, 2, FP>), 1, SPEC_THREADS, 0, d_args); break;
-	case 3: HB_LAUNCH(ctx, (k_decode_vertex_spec<T, 3, FP>), 1, SPEC_THREADS, 0, d_args); break;
-	default: HB_LAUNCH(ctx, (k_decode_vertex_spec<T, 4, FP>), 1, SPEC_THREADS, 0, d_args); break;
+	case 1: return launch_spec_nc<T, 1, FP>(ctx, d_args);
+	case 2: return launch_spec_nc<T, 2, FP>(ctx, d_args);
+	case 3: return launch_spec_nc<T, 3, FP>(ctx, d_args);
+	default: return launch_spec_nc<T, 4, FP>(ctx, d_args);
 	}
-	return 0;
 }
 
 static bool spec_eligible(const ListParams &p)
@@ -130,7 +138,8 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 	HB_TRY(hb_dalloc_t(m, &dl.d_cres, (size_t)(n + 1) * ncp * esize));
 	HB_TRY(hb_dalloc_t(m, &dl.d_cx, (size_t)(n + 1) * ncp * esize));
 	HB_TRY(hb_dalloc_t(m, &dl.d_spec_args, 1));
-	HB_TRY(hb_dalloc_t(m, &dl.d_spec_stats, 4));
+	HB_TRY(hb_dalloc_t(m, &dl.d_spec_stats, 8));
+	HB_CUDA(ctx, cudaMemsetAsync(dl.d_spec_stats, 0, 64, ctx->stream));
 	const uint32_t g = hb_div_up(n, 256);
 	HB_LAUNCH(ctx, k_spec_prep, g, 256, 0, dl.d_erow, dl.d_first, n, dl.d_kind, dl.d_src);
 	HB_LAUNCH(ctx, k_gather_compact, g, 256, 0, p, dl.d_erow, n, dl.d_cres, esize, ncp);

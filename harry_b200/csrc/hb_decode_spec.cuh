@@ -138,7 +138,7 @@ __device__ __forceinline__ uint32_t block_scan_maps(uint32_t m, int nc, uint32_t
 	if (lane == 31) s_warp[warp] = m;
 	__syncthreads();
 	if (warp == 0) {
-		uint32_t w = s_warp[lane];
+		uint32_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : SPEC_MAP_IDENTITY;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			const uint32_t up = __shfl_up_sync(0xffffffffu, w, d);
@@ -164,7 +164,7 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *s_warp 
 	if (lane == 31) s_warp[warp] = x;
 	__syncthreads();
 	if (warp == 0) {
-		uint32_t w = s_warp[lane];
+		uint32_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0u;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			const uint32_t up = __shfl_up_sync(0xffffffffu, w, d);
@@ -179,9 +179,24 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *s_warp 
 }
 
 // one CTA per vertex list
-template <typename T, int NC, bool FP>
-__global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const SpecArgs *__restrict__ args)
+// shared-memory trajectories: element (slot, k) of thread t lives at [(slot * SPEC_HB + k) * nthreads + t]
+// (slot 0..2 = offset hypotheses, slot 3 = the stored values) -> conflict-free, no local memory
+template <typename Rec> struct SpecTraj {
+	Rec *base;
+	uint32_t nthreads, t;
+	__device__ __forceinline__ Rec &at(int slot, uint32_t k) const { return base[((uint32_t)slot * SPEC_HB + k) * nthreads + t]; }
+};
+
+template <typename T, int NC> __host__ __device__ constexpr int spec_threads()
 {
+	// 4 slots * SPEC_HB records per thread within ~200 KB of shared memory
+	return (int)sizeof(SpecRec<T, NC>) <= 4 ? 1024 : ((int)sizeof(SpecRec<T, NC>) <= 8 ? 768 : 384);
+}
+
+template <typename T, int NC, bool FP>
+__global__ void __launch_bounds__(1024, 1) k_decode_vertex_spec(const SpecArgs *__restrict__ args)
+{
+	extern __shared__ __align__(16) unsigned char s_dyn[];
 	const SpecArgs a = args[blockIdx.x];
 	typedef SpecRec<T, NC> Rec;
 	const Rec *__restrict__ resid = (const Rec *)a.resid;
@@ -190,26 +205,33 @@ __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const Sp
 	const uint32_t t = threadIdx.x;
 	__shared__ uint32_t s_min, s_warp[32], s_excl[SPEC_THREADS], s_incl[SPEC_THREADS];
 	__shared__ uint8_t s_inner[SPEC_THREADS];
-	uint32_t done = 0, B = SPEC_HB;
+	const uint32_t NT = blockDim.x;
+	SpecTraj<Rec> traj;
+	traj.base = (Rec *)s_dyn;
+	traj.nthreads = NT;
+	traj.t = t;
+	uint32_t done = 0, B = FP ? SPEC_HB : 4 * SPEC_HB;
 	bool hyp = !FP;            // hypothesis mode
 	int poor = 0;              // consecutive hypothesis sweeps that advanced by <= 2 chunks
-	unsigned long long sweeps = 0, hsweeps = 0;
+	unsigned long long sweeps = 0, hsweeps = 0, hadv = 0, unk = 0;
+	long long cyc_h = 0, cyc_p = 0;
 	while (done < n) {
 		uint32_t newdone;
+		const long long tc0 = clock64();
+		const bool was_hyp = hyp;
 		if (hyp) {
 			// ---------------- phase 1: three trajectories from the stored state --------------------
 			const unsigned long long start64 = (unsigned long long)done + (unsigned long long)t * SPEC_HB;
 			const bool active = start64 < n;
 			const uint32_t start = active ? (uint32_t)start64 : n;
 			const uint32_t len = active ? ((n - start < SPEC_HB) ? n - start : SPEC_HB) : 0;
-			Rec traj[3][SPEC_HB], old[SPEC_HB];
 			uint32_t minread = 0xffffffffu; // lowest window rank read besides the predecessor rank
 			uint32_t map = SPEC_MAP_IDENTITY;
 			if (active) {
 				Rec pst = resid[0];
 				const bool pred_in_window = start > done; // chunk 0: the predecessor is final
 				if (pred_in_window) pst = x[start - 1];
-				for (uint32_t k = 0; k < len; ++k) old[k] = x[start + k];
+				for (uint32_t k = 0; k < len; ++k) traj.at(3, k) = x[start + k];
 				uint32_t c0 = a.cand_off[start];
 				for (uint32_t k = 0; k < len; ++k) {
 					const uint32_t i = start + k;
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const Sp
 #pragma unroll
 					for (int e = 0; e < 3; ++e) {
 						auto get = [&](uint32_t r) -> Rec {
-							if (r >= start) return traj[e][r - start];
+							if (r >= start) return traj.at(e, r - start);
 							if (pred_in_window && r == start - 1) {
 								Rec v = pst;
 #pragma unroll
@@ -228,9 +250,9 @@ __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const Sp
 							if (r >= done && r < minread) minread = r;
 							return x[r];
 						};
-						if (kind == 1) traj[e][k] = spec_step<T, NC, FP>(a, get, c0, c1 - c0, resid[i]);
-						else if (kind == 2) traj[e][k] = get(a.src[i]);
-						else traj[e][k] = old[k];
+						if (kind == 1) traj.at(e, k) = spec_step<T, NC, FP>(a, get, c0, c1 - c0, resid[i]);
+						else if (kind == 2) traj.at(e, k) = get(a.src[i]);
+						else traj.at(e, k) = traj.at(3, k);
 					}
 					c0 = c1;
 				}
@@ -240,7 +262,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const Sp
 				for (int j = 0; j < NC; ++j)
 #pragma unroll
 					for (int e = 0; e < 3; ++e) {
-						const long long d = (long long)traj[e][len - 1].c[j] - (long long)old[len - 1].c[j] + 1;
+						const long long d = (long long)traj.at(e, len - 1).c[j] - (long long)traj.at(3, len - 1).c[j] + 1;
 						map |= (uint32_t)((d >= 0 && d <= 2) ? d : 3) << (6 * j + 2 * e);
 					}
 			}
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const Sp
 				for (uint32_t k = 0; k < len; ++k) {
 					bool ch = false;
 #pragma unroll
-					for (int j = 0; j < NC; ++j) ch = ch || traj[ein[j]][k].c[j] != old[k].c[j];
+					for (int j = 0; j < NC; ++j) ch = ch || traj.at(ein[j], k).c[j] != traj.at(3, k).c[j];
 					if (k + 1 == len) chg_last = ch;
 					else chg_inner = chg_inner || ch;
 				}
@@ -283,18 +305,25 @@ __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const Sp
 			if (active) {
 				const bool sel = t < first_bad;
 				for (uint32_t k = 0; k < len; ++k) {
-					Rec v = old[k];
+					const Rec o = traj.at(3, k);
+					Rec v = o;
 #pragma unroll
-					for (int j = 0; j < NC; ++j) v.c[j] = traj[sel ? ein[j] : 1][k].c[j];
-					if (!spec_equal<T, NC>(v, old[k])) x[start + k] = v;
+					for (int j = 0; j < NC; ++j) v.c[j] = traj.at(sel ? ein[j] : 1, k).c[j];
+					if (!spec_equal<T, NC>(v, o)) x[start + k] = v;
 				}
 			}
-			const unsigned long long wend = (unsigned long long)done + (unsigned long long)(first_bad == 0xffffffffu ? SPEC_THREADS : first_bad) * SPEC_HB;
+			const unsigned long long wend = (unsigned long long)done + (unsigned long long)(first_bad == 0xffffffffu ? NT : first_bad) * SPEC_HB;
 			newdone = wend < n ? (uint32_t)wend : n;
 			const uint32_t adv = newdone - done;
-			poor = adv <= 2 * SPEC_HB ? poor + 1 : 0;
-			if (poor >= 3) { hyp = false; B = 2 * SPEC_HB; poor = 0; }
+			// policy: hypothesis sweeps are the default.  After 3 poor ones in a row (no contraction
+			// here, e.g. single-candidate predictions at the start of a component) ONE plain sweep
+			// with a long exact chunk 0 carries the progress, then hypotheses get another chance.
+			if (adv <= 2 * SPEC_HB) ++poor;
+			else { poor = 0; B = 4 * SPEC_HB; }
+			if (poor >= 3) hyp = false;
 			++hsweeps;
+			hadv += adv;
+			if (first_bad != 0xffffffffu && t == first_bad && !known) ++unk;
 			__syncthreads();
 		} else {
 			// ---------------- plain mode: in-place recomputation ---------------------------------------
@@ -327,18 +356,23 @@ __global__ void __launch_bounds__(SPEC_THREADS, 1) k_decode_vertex_spec(const Sp
 			if (fc != 0xffffffffu) atomicMin(&s_min, fc);
 			__syncthreads();
 			const uint32_t p = s_min;
-			const unsigned long long wend = (unsigned long long)done + (unsigned long long)SPEC_THREADS * B;
+			const unsigned long long wend = (unsigned long long)done + (unsigned long long)NT * B;
 			newdone = p != 0xffffffffu ? p : (wend < n ? (uint32_t)wend : n);
 			const uint32_t adv = newdone - done;
-			if (adv <= 2 * B && B < SPEC_B_MAX) B <<= 1;
-			else if (adv >= 16 * B) {
-				if (B > 2 * SPEC_HB) B >>= 1;
-				else if (!FP) { hyp = true; poor = 0; } // the window converges again: back to hypotheses
+			if (FP) {
+				if (adv <= 2 * B && B < SPEC_B_MAX) B <<= 1;
+				else if (adv >= 16 * B && B > SPEC_HB) B >>= 1;
+			} else {
+				if (B < SPEC_B_MAX) B <<= 1; // the next fallback uses a longer exact chunk
+				hyp = true;
+				poor = 2;                    // one more poor hypothesis sweep falls back again
 			}
 			__syncthreads();
 		}
 		done = newdone;
 		++sweeps;
+		if (was_hyp) cyc_h += clock64() - tc0; else cyc_p += clock64() - tc0;
 	}
-	if (t == 0 && a.stats) { a.stats[0] = sweeps; a.stats[1] = hsweeps; a.stats[2] = sweeps - hsweeps; }
+	if (t == 0 && a.stats) { a.stats[0] = sweeps; a.stats[1] = hsweeps; a.stats[2] = sweeps - hsweeps; a.stats[3] = hadv; a.stats[5] = (unsigned long long)cyc_h; a.stats[6] = (unsigned long long)cyc_p; }
+	if (unk && a.stats) atomicAdd(&a.stats[4], unk);
 }

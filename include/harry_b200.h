@@ -207,6 +207,8 @@ int hb_dmesh_encode(hb_dmesh *m);                    /* kernels only, streams st
 int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out);
 int hb_dmesh_decode(hb_dmesh *m);                    /* kernels only, rows reconstructed in place */
 int hb_dmesh_fetch_rows(hb_dmesh *m, uint32_t l, void *rows_out); /* nrows * stride bytes */
+/* diagnostics of the speculative vertex reconstruction of list l (8 counters, see hb_api.cu) */
+int hb_dmesh_decode_stats(hb_dmesh *m, uint32_t l, uint64_t *out8);
 /* keep / restore a device copy of all rows + quantization state (stages work in place) */
 int hb_dmesh_snapshot(hb_dmesh *m);
 int hb_dmesh_restore(hb_dmesh *m);
