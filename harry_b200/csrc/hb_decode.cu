@@ -13,6 +13,8 @@
 //     comes from components, lists and -- for batches -- meshes.
 #include "hb_lists.cuh"
 #include "hb_decode_spec.cuh"
+#include "hb_decode_spec2.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
 // VTX: chain walker
@@ -116,6 +118,43 @@ static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args)
 	}
 }
 
+// cluster launch of the hoisted hypothesis kernel (integer lists)
+template <typename T, int NC>
+static int launch_spec2_nc(hb_ctx *ctx, const SpecArgs *d_args, Spec2Scratch *scratch, uint32_t *g_excl, uint8_t *g_inner)
+{
+	const int threads = spec2_threads<T, NC>();
+	const size_t smem = spec2_smem<T, NC>();
+	HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_spec2<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(SPEC2_CLUSTER);
+	cfg.blockDim = dim3(threads);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = ctx->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = SPEC2_CLUSTER;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	cudaEvent_t pa = nullptr, pb = nullptr;
+	if (ctx->profiling) { pa = hb_prof_event(ctx); pb = hb_prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
+	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_decode_vertex_spec2<T, NC>, d_args, scratch, g_excl, g_inner));
+	ctx->launches++;
+	if (pa) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back(hb_ctx::ProfRec{ "k_decode_vertex_spec2", pa, pb }); }
+	return 0;
+}
+template <typename T>
+static int launch_spec2(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, Spec2Scratch *scratch, uint32_t *g_excl, uint8_t *g_inner)
+{
+	switch (ncomp) {
+	case 1: return launch_spec2_nc<T, 1>(ctx, d_args, scratch, g_excl, g_inner);
+	case 2: return launch_spec2_nc<T, 2>(ctx, d_args, scratch, g_excl, g_inner);
+	case 3: return launch_spec2_nc<T, 3>(ctx, d_args, scratch, g_excl, g_inner);
+	default: return launch_spec2_nc<T, 4>(ctx, d_args, scratch, g_excl, g_inner);
+	}
+}
+
 static bool spec_eligible(const ListParams &p)
 {
 	if (p.ncomp < 1 || p.ncomp > 4) return false;
@@ -150,7 +189,16 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 	for (int j = 0; j < 4; ++j) a.bits[j] = j < p.ncomp ? (p.quant[j] ? p.quant[j] : 8 * esize) : 8 * esize;
 	HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_args, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream));
 	HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `a` is a stack object
-	if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args)));
+	static const bool single_cta = getenv("HARRY_B200_SPEC1") != nullptr; // A/B switch: single-CTA kernel
+	if (st != HB_FLOAT && !single_cta) {
+		HB_TRY(hb_dalloc_t(m, &dl.d_spec2_scratch, 1));
+		HB_TRY(hb_dalloc_t(m, &dl.d_spec2_excl, (size_t)SPEC2_CLUSTER * 512));
+		HB_TRY(hb_dalloc_t(m, &dl.d_spec2_inner, (size_t)SPEC2_CLUSTER * 512));
+		HB_CUDA(ctx, cudaMemsetAsync(dl.d_spec2_scratch, 0xff, sizeof(Spec2Scratch), ctx->stream));
+		if (st == HB_UCHAR) HB_TRY(launch_spec2<uint8_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec2_scratch, dl.d_spec2_excl, dl.d_spec2_inner));
+		else if (st == HB_USHORT) HB_TRY(launch_spec2<uint16_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec2_scratch, dl.d_spec2_excl, dl.d_spec2_inner));
+		else HB_TRY(launch_spec2<uint32_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec2_scratch, dl.d_spec2_excl, dl.d_spec2_inner));
+	} else if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args)));
 	else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, p.ncomp, dl.d_spec_args)));
 	else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, p.ncomp, dl.d_spec_args)));
 	else HB_TRY((launch_spec<uint32_t, true>(ctx, p.ncomp, dl.d_spec_args)));

@@ -215,14 +215,19 @@ __global__ void __launch_bounds__(1024, 1) k_decode_vertex_spec(const SpecArgs *
 	int poor = 0;              // consecutive hypothesis sweeps that advanced by <= 2 chunks
 	unsigned long long sweeps = 0, hsweeps = 0, hadv = 0, unk = 0;
 	long long cyc_h = 0, cyc_p = 0;
+	uint32_t est = 0;          // decayed maximum of the recent advance (ranks per sweep) ~ one "ring"
 	while (done < n) {
 		uint32_t newdone;
 		const long long tc0 = clock64();
 		const bool was_hyp = hyp;
 		if (hyp) {
 			// ---------------- phase 1: three trajectories from the stored state --------------------
+			// A rank becomes final two sweeps after the ranks it depends on: recomputing more than
+			// ~2.5x the recent advance is wasted work (and this single SM is instruction bound).
+			uint32_t nact = (5 * est / 2) / SPEC_HB + 48;
+			if (nact > NT) nact = NT;
 			const unsigned long long start64 = (unsigned long long)done + (unsigned long long)t * SPEC_HB;
-			const bool active = start64 < n;
+			const bool active = start64 < n && t < nact;
 			const uint32_t start = active ? (uint32_t)start64 : n;
 			const uint32_t len = active ? ((n - start < SPEC_HB) ? n - start : SPEC_HB) : 0;
 			uint32_t minread = 0xffffffffu; // lowest window rank read besides the predecessor rank
@@ -312,12 +317,13 @@ __global__ void __launch_bounds__(1024, 1) k_decode_vertex_spec(const SpecArgs *
 					if (!spec_equal<T, NC>(v, o)) x[start + k] = v;
 				}
 			}
-			const unsigned long long wend = (unsigned long long)done + (unsigned long long)(first_bad == 0xffffffffu ? NT : first_bad) * SPEC_HB;
+			const unsigned long long wend = (unsigned long long)done + (unsigned long long)(first_bad == 0xffffffffu ? nact : first_bad) * SPEC_HB;
 			newdone = wend < n ? (uint32_t)wend : n;
 			const uint32_t adv = newdone - done;
 			// policy: hypothesis sweeps are the default.  After 3 poor ones in a row (no contraction
 			// here, e.g. single-candidate predictions at the start of a component) ONE plain sweep
 			// with a long exact chunk 0 carries the progress, then hypotheses get another chance.
+			est = adv > est - est / 8 ? adv : est - est / 8;
 			if (adv <= 2 * SPEC_HB) ++poor;
 			else { poor = 0; B = 4 * SPEC_HB; }
 			if (poor >= 3) hyp = false;

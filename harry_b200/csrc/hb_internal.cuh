@@ -40,6 +40,7 @@ struct hb_ctx {
 cudaEvent_t hb_prof_event(hb_ctx *ctx);
 
 struct SpecArgs;
+struct Spec2Scratch;
 struct ListParams {
 	uint8_t *rows;          // AoS rows in HBM (nrows * stride)
 	uint32_t nrows, stride;
@@ -75,6 +76,9 @@ struct DevList {
 	uint8_t *d_cres = nullptr, *d_cx = nullptr; // compact residual / value records
 	struct SpecArgs *d_spec_args = nullptr;
 	unsigned long long *d_spec_stats = nullptr;
+	struct Spec2Scratch *d_spec2_scratch = nullptr;
+	uint32_t *d_spec2_excl = nullptr;
+	uint8_t *d_spec2_inner = nullptr;
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
 	uint8_t *d_rows_backup = nullptr;   // hb_dmesh_snapshot
@@ -221,6 +225,30 @@ template <typename T> struct IntOps {
 		const T d = (T)((U)v1 - (U)v2);
 		const T v = (T)((U)v0 + (U)d);
 		return (v > hi || v < v0) ? hi : v;
+	}
+	// same with the mask precomputed (hot loops)
+	static __device__ __forceinline__ T predict_hi(T v0, T v1, T v2, T hi)
+	{
+		if (v1 < v2) {
+			const T d = (T)((U)v2 - (U)v1);
+			return d > v0 ? (T)0 : (T)((U)v0 - (U)d);
+		}
+		const T d = (T)((U)v1 - (U)v2);
+		const T v = (T)((U)v0 + (U)d);
+		return (v > hi || v < v0) ? hi : v;
+	}
+	static __device__ __forceinline__ T dec_hi(T delta, T pred, T hi)
+	{
+		const T room = (T)((U)hi - (U)pred);
+		if (pred == (T)0) return delta;
+		const T pm1 = (T)((U)pred - (U)1);
+		const T bal = room < pm1 ? room : pm1;
+		const T half = (T)(delta >> 1);
+		if (half > bal) {
+			if (room >= pred) return (T)((U)pred + (U)delta - (U)bal - (U)1);
+			return (T)((U)pred - (U)delta + (U)bal);
+		}
+		return (T)((U)pred + ((U)half ^ ((delta & 1) ? (U) ~(U)0 : (U)0)));
 	}
 	// prediction.h:81-99
 	static __device__ __forceinline__ T enc(T raw, T pred, int bits)

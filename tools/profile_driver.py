@@ -40,4 +40,4 @@ for _ in range(args.reps):
         D.decode()
         D.dequantize(1)
 ctx.sync()
-print("done", ctx.launches(), "decode stats [sweeps, hyp, plain, hyp_adv, unknown, cyc_hyp, cyc_plain]:", D.decode_stats(1)[:7])
+print("done", ctx.launches(), "decode stats [sweeps, hyp, plain, hyp_adv, cyc_load, cyc_traj, cyc_resolve, cyc_write+plain]:", D.decode_stats(1)[:8])
