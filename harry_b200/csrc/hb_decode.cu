@@ -13,7 +13,7 @@
 //     comes from components, lists and -- for batches -- meshes.
 #include "hb_lists.cuh"
 #include "hb_decode_spec.cuh"
-#include "hb_decode_spec2.cuh"
+#include "hb_decode_spec3.cuh"
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
@@ -118,40 +118,40 @@ static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args)
 	}
 }
 
-// cluster launch of the hoisted hypothesis kernel (integer lists)
+// cluster launch of the lane-mapped hypothesis kernel (integer lists)
 template <typename T, int NC>
-static int launch_spec2_nc(hb_ctx *ctx, const SpecArgs *d_args, Spec2Scratch *scratch, uint32_t *g_excl, uint8_t *g_inner)
+static int launch_spec3_nc(hb_ctx *ctx, const SpecArgs *d_args, Spec3Scratch *scratch, uint32_t *g_excl, uint8_t *g_inner)
 {
-	const int threads = spec2_threads<T, NC>();
-	const size_t smem = spec2_smem<T, NC>();
-	HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_spec2<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const int threads = 4 * spec3_cpc<T, NC>();
+	const size_t smem = spec3_smem<T, NC>();
+	HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_spec3<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(SPEC2_CLUSTER);
+	cfg.gridDim = dim3(SPEC3_CLUSTER);
 	cfg.blockDim = dim3(threads);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = ctx->stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeClusterDimension;
-	attr[0].val.clusterDim.x = SPEC2_CLUSTER;
+	attr[0].val.clusterDim.x = SPEC3_CLUSTER;
 	attr[0].val.clusterDim.y = 1;
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
 	cudaEvent_t pa = nullptr, pb = nullptr;
 	if (ctx->profiling) { pa = hb_prof_event(ctx); pb = hb_prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
-	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_decode_vertex_spec2<T, NC>, d_args, scratch, g_excl, g_inner));
+	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_decode_vertex_spec3<T, NC>, d_args, scratch, g_excl, g_inner));
 	ctx->launches++;
-	if (pa) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back(hb_ctx::ProfRec{ "k_decode_vertex_spec2", pa, pb }); }
+	if (pa) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back(hb_ctx::ProfRec{ "k_decode_vertex_spec3", pa, pb }); }
 	return 0;
 }
 template <typename T>
-static int launch_spec2(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, Spec2Scratch *scratch, uint32_t *g_excl, uint8_t *g_inner)
+static int launch_spec3(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, Spec3Scratch *scratch, uint32_t *g_excl, uint8_t *g_inner)
 {
 	switch (ncomp) {
-	case 1: return launch_spec2_nc<T, 1>(ctx, d_args, scratch, g_excl, g_inner);
-	case 2: return launch_spec2_nc<T, 2>(ctx, d_args, scratch, g_excl, g_inner);
-	case 3: return launch_spec2_nc<T, 3>(ctx, d_args, scratch, g_excl, g_inner);
-	default: return launch_spec2_nc<T, 4>(ctx, d_args, scratch, g_excl, g_inner);
+	case 1: return launch_spec3_nc<T, 1>(ctx, d_args, scratch, g_excl, g_inner);
+	case 2: return launch_spec3_nc<T, 2>(ctx, d_args, scratch, g_excl, g_inner);
+	case 3: return launch_spec3_nc<T, 3>(ctx, d_args, scratch, g_excl, g_inner);
+	default: return launch_spec3_nc<T, 4>(ctx, d_args, scratch, g_excl, g_inner);
 	}
 }
 
@@ -191,13 +191,13 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 	HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `a` is a stack object
 	static const bool single_cta = getenv("HARRY_B200_SPEC1") != nullptr; // A/B switch: single-CTA kernel
 	if (st != HB_FLOAT && !single_cta) {
-		HB_TRY(hb_dalloc_t(m, &dl.d_spec2_scratch, 1));
-		HB_TRY(hb_dalloc_t(m, &dl.d_spec2_excl, (size_t)SPEC2_CLUSTER * 512));
-		HB_TRY(hb_dalloc_t(m, &dl.d_spec2_inner, (size_t)SPEC2_CLUSTER * 512));
-		HB_CUDA(ctx, cudaMemsetAsync(dl.d_spec2_scratch, 0xff, sizeof(Spec2Scratch), ctx->stream));
-		if (st == HB_UCHAR) HB_TRY(launch_spec2<uint8_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec2_scratch, dl.d_spec2_excl, dl.d_spec2_inner));
-		else if (st == HB_USHORT) HB_TRY(launch_spec2<uint16_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec2_scratch, dl.d_spec2_excl, dl.d_spec2_inner));
-		else HB_TRY(launch_spec2<uint32_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec2_scratch, dl.d_spec2_excl, dl.d_spec2_inner));
+		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_scratch, 1));
+		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_excl, (size_t)SPEC3_CLUSTER * SPEC3_MAXCPC));
+		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_inner, (size_t)SPEC3_CLUSTER * SPEC3_MAXCPC));
+		HB_CUDA(ctx, cudaMemsetAsync(dl.d_spec3_scratch, 0xff, 128, ctx->stream));
+		if (st == HB_UCHAR) HB_TRY(launch_spec3<uint8_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec3_scratch, dl.d_spec3_excl, dl.d_spec3_inner));
+		else if (st == HB_USHORT) HB_TRY(launch_spec3<uint16_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec3_scratch, dl.d_spec3_excl, dl.d_spec3_inner));
+		else HB_TRY(launch_spec3<uint32_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec3_scratch, dl.d_spec3_excl, dl.d_spec3_inner));
 	} else if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args)));
 	else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, p.ncomp, dl.d_spec_args)));
 	else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, p.ncomp, dl.d_spec_args)));

@@ -40,7 +40,7 @@ struct hb_ctx {
 cudaEvent_t hb_prof_event(hb_ctx *ctx);
 
 struct SpecArgs;
-struct Spec2Scratch;
+struct Spec3Scratch;
 struct ListParams {
 	uint8_t *rows;          // AoS rows in HBM (nrows * stride)
 	uint32_t nrows, stride;
@@ -76,9 +76,9 @@ struct DevList {
 	uint8_t *d_cres = nullptr, *d_cx = nullptr; // compact residual / value records
 	struct SpecArgs *d_spec_args = nullptr;
 	unsigned long long *d_spec_stats = nullptr;
-	struct Spec2Scratch *d_spec2_scratch = nullptr;
-	uint32_t *d_spec2_excl = nullptr;
-	uint8_t *d_spec2_inner = nullptr;
+	struct Spec3Scratch *d_spec3_scratch = nullptr;
+	uint32_t *d_spec3_excl = nullptr;
+	uint8_t *d_spec3_inner = nullptr;
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
 	uint8_t *d_rows_backup = nullptr;   // hb_dmesh_snapshot
