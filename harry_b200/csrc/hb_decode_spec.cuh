@@ -116,12 +116,21 @@ __device__ __forceinline__ bool spec_equal(const SpecRec<T, NC> &a, const SpecRe
 // per component 3 entries (offset-in -1, 0, +1 -> index 0, 1, 2) of 2 bits: offset-out index, 3 = unknown.
 // component j occupies bits [6j, 6j + 6).
 __device__ __forceinline__ uint32_t map_get(uint32_t m, int j, uint32_t e) { return e == 3 ? 3u : (m >> (6 * j + 2 * e)) & 3u; }
-// apply a first, then b
+// apply a first, then b.  Per component: c[e] = a[e] == unknown ? unknown : b[a[e]]; with b extended
+// by a fourth entry "unknown -> unknown" this is one table lookup per entry.
 __device__ __forceinline__ uint32_t map_compose(uint32_t a, uint32_t b, int nc)
 {
 	uint32_t c = 0;
-	for (int j = 0; j < nc; ++j)
-		for (uint32_t e = 0; e < 3; ++e) c |= map_get(b, j, map_get(a, j, e)) << (6 * j + 2 * e);
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		if (j >= nc) break;
+		const uint32_t tab = ((b >> (6 * j)) & 0x3fu) | 0xc0u; // 4 entries of 2 bits
+		const uint32_t aj = (a >> (6 * j)) & 0x3fu;
+		const uint32_t c0 = (tab >> (2 * (aj & 3u))) & 3u;
+		const uint32_t c1 = (tab >> (2 * ((aj >> 2) & 3u))) & 3u;
+		const uint32_t c2 = (tab >> (2 * ((aj >> 4) & 3u))) & 3u;
+		c |= (c0 | (c1 << 2) | (c2 << 4)) << (6 * j);
+	}
 	return c;
 }
 #define SPEC_MAP_IDENTITY 0x00924924u // every component: 0 -> 0, 1 -> 1, 2 -> 2  (binary 100100 repeated)

@@ -25,6 +25,9 @@ namespace cg3 = cooperative_groups;
 #define SPEC3_CLUSTER 8
 #define SPEC3_OPS (SPEC_HB * SPEC3_KCAP * 3)
 #define SPEC3_MAXCPC 256    // chunks per CTA (upper bound)
+#ifndef SPEC3_CPC_SMALL
+#define SPEC3_CPC_SMALL 128
+#endif
 
 #define SPEC3_MAXCHUNKS (SPEC3_CLUSTER * SPEC3_MAXCPC)
 struct Spec3Scratch {
@@ -32,37 +35,93 @@ struct Spec3Scratch {
 	uint32_t plain_first[2];
 	uint32_t pad[28];
 	uint32_t map[SPEC3_MAXCHUNKS];   // offset map of every window chunk
-	uint32_t cnt[SPEC3_MAXCHUNKS];   // changed ranks (inner + last) | inner << 8
+	uint32_t flg[SPEC3_MAXCHUNKS];   // per component j, hypothesis e: bit (6j + 2e) inner changed, bit (6j + 2e + 1) last changed
+	uint32_t dep[SPEC3_MAXCHUNKS];   // chunk of the lowest other-window rank read, or 0xffffffff
 };
 
-// in-place inclusive scan of 2 * blockDim.x maps in shared memory (composition in index order)
-__device__ __forceinline__ void block_scan_maps_x2(uint32_t *s_all, int nc, uint32_t *s_warp, uint32_t *s_prev /* blockDim.x words */)
+// In-place inclusive scan of the first `nvalid` of 2 * blockDim.x maps in shared memory (composition
+// in index order).  Entries beyond nvalid are identities; warps that only hold such entries skip the
+// arithmetic (they still join the barriers).
+__device__ __forceinline__ void block_scan_maps_x2(uint32_t *s_all, int nc, uint32_t *s_warp, uint32_t *s_prev /* blockDim.x words */, uint32_t nvalid)
 {
 	const uint32_t t = threadIdx.x;
-	const uint32_t a0 = s_all[2 * t], a1 = map_compose(a0, s_all[2 * t + 1], nc);
-	const uint32_t incl = block_scan_maps(a1, nc, s_warp);       // inclusive over thread totals
-	// exclusive prefix of this thread = inclusive of the previous thread
-	s_prev[t] = incl;
+	const int lane = t & 31, warp = t >> 5;
+	const bool warp_live = (uint32_t)(warp * 64) < nvalid;
+	uint32_t a0 = SPEC_MAP_IDENTITY, m = SPEC_MAP_IDENTITY;
+	if (warp_live) {
+		a0 = s_all[2 * t];
+		m = map_compose(a0, s_all[2 * t + 1], nc);
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, m, d);
+			if (lane >= d) m = map_compose(up, m, nc);
+		}
+	}
+	if (lane == 31) s_warp[warp] = m;
 	__syncthreads();
-	const uint32_t pre = t ? s_prev[t - 1] : SPEC_MAP_IDENTITY;
-	s_all[2 * t] = map_compose(pre, a0, nc);
-	s_all[2 * t + 1] = incl;
+	if (warp == 0) {
+		uint32_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : SPEC_MAP_IDENTITY;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, w, d);
+			if (lane >= d) w = map_compose(up, w, nc);
+		}
+		s_warp[lane] = w;
+	}
+	__syncthreads();
+	if (warp_live) {
+		if (warp > 0) m = map_compose(s_warp[warp - 1], m, nc);
+		s_prev[t] = m;
+	}
+	__syncthreads();
+	if (warp_live) {
+		const uint32_t pre = t ? s_prev[t - 1] : SPEC_MAP_IDENTITY;
+		s_all[2 * t] = map_compose(pre, a0, nc);
+		s_all[2 * t + 1] = m;
+	}
 	__syncthreads();
 }
-// in-place exclusive scan of 2 * blockDim.x counts
-__device__ __forceinline__ void block_scan_u32_x2(uint32_t *s_all, uint32_t *s_warp)
+// in-place exclusive scan of the first `nvalid` of 2 * blockDim.x counts (the rest are zero and are
+// not needed: range queries only touch indices below nvalid)
+__device__ __forceinline__ void block_scan_u32_x2(uint32_t *s_all, uint32_t *s_warp, uint32_t nvalid)
 {
 	const uint32_t t = threadIdx.x;
-	const uint32_t a0 = s_all[2 * t], a1 = s_all[2 * t + 1];
-	const uint32_t ex = block_scan_u32(a0 + a1, s_warp);
-	s_all[2 * t] = ex;
-	s_all[2 * t + 1] = ex + a0;
+	const int lane = t & 31, warp = t >> 5;
+	const bool warp_live = (uint32_t)(warp * 64) < nvalid;
+	uint32_t a0 = 0, v = 0, x = 0;
+	if (warp_live) {
+		a0 = s_all[2 * t];
+		v = a0 + s_all[2 * t + 1];
+		x = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, x, d);
+			if (lane >= d) x += up;
+		}
+	}
+	if (lane == 31) s_warp[warp] = x;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0u;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, w, d);
+			if (lane >= d) w += up;
+		}
+		s_warp[lane] = w;
+	}
+	__syncthreads();
+	if (warp_live) {
+		const uint32_t ex = x - v + (warp ? s_warp[warp - 1] : 0u);
+		s_all[2 * t] = ex;
+		s_all[2 * t + 1] = ex + a0;
+	}
 	__syncthreads();
 }
 
 template <typename T, int NC> __host__ __device__ constexpr int spec3_cpc()
 {
-	return (int)sizeof(SpecRec<T, NC>) <= 8 ? 256 : 128;
+	return (int)sizeof(SpecRec<T, NC>) <= 8 ? SPEC3_CPC_SMALL : 128;
 }
 // per chunk: 3 trajectories + stored + residual (5 * HB records), OPS operand records, OPS codes,
 // HB candidate counts, HB kinds, HB candidate offsets
@@ -106,6 +165,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 	uint8_t *s_kind = s_K + (size_t)SPEC_HB * CPC;                 // [k * CPC + q]
 	__shared__ uint32_t s_warp[32], s_all[SPEC3_MAXCHUNKS], s_excl[SPEC3_MAXCHUNKS];
 	__shared__ uint8_t s_inner[SPEC3_MAXCHUNKS];
+	__shared__ uint32_t s_first;
 	const uint32_t NCH = C * CPC; // window chunks = 2 * blockDim.x
 
 	auto TR = [&](uint32_t e, uint32_t k) -> Rec & { return s_traj[(k * CPC + q) * 3 + e]; };
@@ -233,7 +293,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 			__syncwarp();
 			const long long tB = clock64();
 			// ------------------------------------------------------------------ phase 1: lane e walks the chunk under hypothesis e
-			uint32_t mybits = 0;
+			uint32_t mybits = 0, myflags = 0;
 			if (active && L < 3) {
 				const uint32_t e = L;
 #pragma unroll 1
@@ -300,67 +360,98 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 					}
 					TR(e, k) = out;
 				}
-				// my entries of the offset map: end value under hypothesis e relative to the stored end value
+				// my entries of the offset map (end value under hypothesis e relative to the stored end
+				// value) and my change flags (which of my ranks differ from the stored ones), per component
 				const Rec last = TR(e, len - 1), olast = s_old[(len - 1) * CPC + q];
 #pragma unroll
 				for (int j = 0; j < NC; ++j) {
 					const long long d = (long long)last.c[j] - (long long)olast.c[j] + 1;
 					mybits |= (uint32_t)((d >= 0 && d <= 2) ? d : 3) << (6 * j + 2 * e);
 				}
-			}
-			uint32_t map = mybits;
-			map |= __shfl_xor_sync(0xffffffffu, map, 1);
-			map |= __shfl_xor_sync(0xffffffffu, map, 2);
-			if (!active) map = SPEC_MAP_IDENTITY;
-			if (L == 0) sc->map[g] = map;
-			if (rank == 0 && t == 0) sc->first_bad[parity ^ 1] = 0xffffffffu;
-			const long long tC = clock64();
-			// ------------------------------------------------------------------ phase 2: resolve across the cluster
-			// every CTA scans the whole window redundantly (2 entries per thread) from global scratch;
-			// barrier.cluster has release / acquire semantics at cluster scope
-			cluster.sync(); // [B] maps visible
-			s_all[2 * t] = __ldcg(&sc->map[2 * t]);
-			s_all[2 * t + 1] = __ldcg(&sc->map[2 * t + 1]);
-			__syncthreads();
-			block_scan_maps_x2(s_all, NC, s_warp, s_excl);
-			const uint32_t before = g == 0 ? SPEC_MAP_IDENTITY : s_all[g - 1];
-			uint32_t ein[NC];
-			bool known = true;
-#pragma unroll
-			for (int j = 0; j < NC; ++j) { ein[j] = map_get(before, j, 1u); known = known && ein[j] != 3u; }
-			// change flags of the selected trajectories: lane e checks the components that selected e
-			uint32_t flags = 0; // bit 0: inner rank changed, bit 1: last rank changed
-			if (active && known && L < 3) {
 				for (uint32_t k = 0; k < len; ++k) {
-					const Rec v = TR(L, k), o = s_old[k * CPC + q];
-					bool ch = false;
+					const Rec v = TR(e, k), o = s_old[k * CPC + q];
 #pragma unroll
-					for (int j = 0; j < NC; ++j) ch = ch || (ein[j] == L && v.c[j] != o.c[j]);
-					if (ch) flags |= (k + 1 == len) ? 2u : 1u;
+					for (int j = 0; j < NC; ++j)
+						if (v.c[j] != o.c[j]) myflags |= ((k + 1 == len) ? 2u : 1u) << (6 * j + 2 * e);
 				}
 			}
-			flags |= __shfl_xor_sync(0xffffffffu, flags, 1);
-			flags |= __shfl_xor_sync(0xffffffffu, flags, 2);
-			if (L == 0) sc->cnt[g] = (flags & 1u) + ((flags >> 1) & 1u) + ((flags & 1u) << 8);
-			cluster.sync(); // [C] counts visible
+			uint32_t map = mybits, flg = myflags;
+			map |= __shfl_xor_sync(0xffffffffu, map, 1);
+			map |= __shfl_xor_sync(0xffffffffu, map, 2);
+			flg |= __shfl_xor_sync(0xffffffffu, flg, 1);
+			flg |= __shfl_xor_sync(0xffffffffu, flg, 2);
+			if (!active) { map = SPEC_MAP_IDENTITY; flg = 0; }
+			if (L == 0) {
+				sc->map[g] = map;
+				sc->flg[g] = flg;
+				sc->dep[g] = (active && minread != 0xffffffffu) ? (minread - done) / SPEC_HB : 0xffffffffu;
+			}
+			if (t == 0) s_first = 0xffffffffu;
+			const long long tC = clock64();
+			// ------------------------------------------------------------------ phase 2: resolve
+			// One cluster barrier (release / acquire at cluster scope) publishes every chunk's record;
+			// then every CTA redundantly derives the offsets, the change counts, the validity of every
+			// chunk and the first invalid one -- identical results, no further exchange.
+			cluster.sync(); // [B]
+			uint32_t f0 = 0, f1 = 0, d0 = 0xffffffffu, d1 = 0xffffffffu;
 			{
-				const uint32_t c0 = __ldcg(&sc->cnt[2 * t]), c1 = __ldcg(&sc->cnt[2 * t + 1]);
-				s_excl[2 * t] = c0 & 0xffu;
-				s_excl[2 * t + 1] = c1 & 0xffu;
-				s_inner[2 * t] = (uint8_t)(c0 >> 8);
-				s_inner[2 * t + 1] = (uint8_t)(c1 >> 8);
+				const bool ld = 2 * t < nact;
+				s_all[2 * t] = ld ? __ldcg(&sc->map[2 * t]) : SPEC_MAP_IDENTITY;
+				s_all[2 * t + 1] = ld ? __ldcg(&sc->map[2 * t + 1]) : SPEC_MAP_IDENTITY;
+				if (ld) { f0 = __ldcg(&sc->flg[2 * t]); f1 = __ldcg(&sc->flg[2 * t + 1]); d0 = __ldcg(&sc->dep[2 * t]); d1 = __ldcg(&sc->dep[2 * t + 1]); }
 			}
 			__syncthreads();
-			block_scan_u32_x2(s_excl, s_warp);
-			bool valid = !active || known;
-			if (L == 0 && active && known && minread != 0xffffffffu && g > 0) {
-				const uint32_t dep = (minread - done) / SPEC_HB;
-				const uint32_t changed_before = s_excl[g - 1] - s_excl[dep]; // chunks [dep, g-2]
-				if (changed_before != 0 || s_inner[g - 1]) valid = false;
+			block_scan_maps_x2(s_all, NC, s_warp, s_excl, nact);
+			// per window chunk i (two per thread): true offsets -> selected change flags
+			bool kn[2] = { true, true };
+			uint32_t cntv[2] = { 0, 0 };
+			uint8_t inn[2] = { 0, 0 };
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const uint32_t i = 2 * t + h;
+				if (i >= nact) continue;
+				const uint32_t bf = i == 0 ? SPEC_MAP_IDENTITY : s_all[i - 1];
+				const uint32_t fl = h ? f1 : f0;
+				uint32_t inner = 0, lastc = 0;
+#pragma unroll
+				for (int j = 0; j < NC; ++j) {
+					const uint32_t ej = map_get(bf, j, 1u);
+					if (ej == 3u) { kn[h] = false; continue; }
+					const uint32_t two = (fl >> (6 * j + 2 * ej)) & 3u;
+					inner |= two & 1u;
+					lastc |= two >> 1;
+				}
+				if (kn[h]) { cntv[h] = inner + lastc; inn[h] = (uint8_t)inner; }
 			}
-			if (L == 0 && !valid) atomicMin(&sc->first_bad[parity], g);
-			cluster.sync(); // [E] first invalid chunk known
-			const uint32_t first_bad = __ldcg(&sc->first_bad[parity]);
+			__syncthreads(); // all reads of s_all[i - 1] done before s_excl (scratch of the scan above) is reused
+			s_excl[2 * t] = cntv[0];
+			s_excl[2 * t + 1] = cntv[1];
+			s_inner[2 * t] = inn[0];
+			s_inner[2 * t + 1] = inn[1];
+			__syncthreads();
+			block_scan_u32_x2(s_excl, s_warp, nact);
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const uint32_t i = 2 * t + h;
+				if (i >= nact) continue;
+				bool valid = kn[h];
+				const uint32_t dp = h ? d1 : d0;
+				if (valid && dp != 0xffffffffu && i > 0) {
+					// other window reads: chunks [dep, i-2] entirely unchanged, chunk i-1 unchanged except
+					// (possibly) its last rank, which the offset hypothesis accounts for
+					if (s_excl[i - 1] - s_excl[dp] != 0 || s_inner[i - 1]) valid = false;
+				}
+				if (!valid) atomicMin(&s_first, i);
+			}
+			__syncthreads();
+			const uint32_t first_bad = s_first;
+			// my chunk's true offsets
+			uint32_t ein[NC];
+			{
+				const uint32_t before = g == 0 ? SPEC_MAP_IDENTITY : (g < nact ? s_all[g - 1] : SPEC_MAP_IDENTITY);
+#pragma unroll
+				for (int j = 0; j < NC; ++j) ein[j] = map_get(before, j, 1u);
+			}
 			const long long tD = clock64();
 			// ------------------------------------------------------------------ phase 3: write (lane L: ranks L, L + 4)
 			if (active) {
