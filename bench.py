@@ -184,6 +184,7 @@ def algorithmic_bytes(w: Workload) -> dict:
         "k_encode_main<CLS_VTX>": k5,
         "k_decode_vertex_chain": k5,
         "k_decode_vertex_spec3": k5,
+        "(k_decode_vertex_spec<T, NC, FP>)": k5,
         "k_flatten_halfedges": 12.0 * ne + 16.0 * ne,
         "k_gather_rp": A * wd * 2,
         "k_scatter_rp": A * wd * 2,

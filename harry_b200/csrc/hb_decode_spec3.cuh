@@ -22,6 +22,7 @@
 namespace cg3 = cooperative_groups;
 
 #define SPEC3_KCAP 2        // candidates per rank cached in shared memory
+#define SPEC3_WIDE 48       // ranks with more candidates block speculation and are evaluated by a whole warp
 #define SPEC3_CLUSTER 8
 #define SPEC3_OPS (SPEC_HB * SPEC3_KCAP * 3)
 #define SPEC3_MAXCPC 256    // chunks per CTA (upper bound)
@@ -205,12 +206,25 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 						s_res[k * CPC + q] = resid[start + k];
 						s_kind[k * CPC + q] = a.kind[start + k];
 						s_coff[k * CPC + q] = b;
-						s_K[k * CPC + q] = (uint8_t)(e2 - b > SPEC3_KCAP ? 255 : e2 - b);
+						s_K[k * CPC + q] = (uint8_t)(e2 - b > SPEC3_WIDE ? 254 : (e2 - b > SPEC3_KCAP ? 255 : e2 - b));
 					}
 				}
 			}
 			__syncwarp();
+			// a chunk holding a wide rank is not speculated on: it blocks the exact prefix until `done`
+			// reaches the wide rank, which is then evaluated by a whole warp (plain branch below)
+			uint32_t blocked = 0;
 			if (active) {
+#pragma unroll
+				for (int h = 0; h < SPEC_HB / 4; ++h) {
+					const uint32_t k = L + 4 * h;
+					if (k < len && s_kind[k * CPC + q] == 1 && s_K[k * CPC + q] == 254) blocked = 1;
+				}
+			}
+			blocked |= __shfl_xor_sync(0xffffffffu, blocked, 1);
+			blocked |= __shfl_xor_sync(0xffffffffu, blocked, 2);
+			const bool compute = active && !blocked;
+			if (compute) {
 				// waves 1 + 2: lane L owns operands op = L * 12 .. L * 12 + 11 (= ranks 2L, 2L + 1)
 #pragma unroll
 				for (int half = 0; half < 2; ++half) {
@@ -266,7 +280,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 				}
 			}
 			__syncwarp();
-			if (active) {
+			if (compute) {
 				// candidates whose three operands are all outside the chunk do not depend on the
 				// hypothesis: predict them once (lane L: candidates 4L .. 4L + 3)
 #pragma unroll
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 			const long long tB = clock64();
 			// ------------------------------------------------------------------ phase 1: lane e walks the chunk under hypothesis e
 			uint32_t mybits = 0, myflags = 0;
-			if (active && L < 3) {
+			if (compute && L < 3) {
 				const uint32_t e = L;
 #pragma unroll 1
 				for (uint32_t k = 0; k < len; ++k) {
@@ -381,6 +395,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 			flg |= __shfl_xor_sync(0xffffffffu, flg, 1);
 			flg |= __shfl_xor_sync(0xffffffffu, flg, 2);
 			if (!active) { map = SPEC_MAP_IDENTITY; flg = 0; }
+			if (blocked) { map = 0x00ffffffu; flg = 0x80000000u; } // every offset unknown; bit 31: never valid
 			if (L == 0) {
 				sc->map[g] = map;
 				sc->flg[g] = flg;
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 			for (int h = 0; h < 2; ++h) {
 				const uint32_t i = 2 * t + h;
 				if (i >= nact) continue;
-				bool valid = kn[h];
+				bool valid = kn[h] && !((h ? f1 : f0) >> 31);
 				const uint32_t dp = h ? d1 : d0;
 				if (valid && dp != 0xffffffffu && i > 0) {
 					// other window reads: chunks [dep, i-2] entirely unchanged, chunk i-1 unchanged except
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 			}
 			const long long tD = clock64();
 			// ------------------------------------------------------------------ phase 3: write (lane L: ranks L, L + 4)
-			if (active) {
+			if (compute) {
 				const bool sel = g < first_bad;
 #pragma unroll
 				for (int h = 0; h < SPEC_HB / 4; ++h) {
@@ -473,7 +488,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 			est = adv > est - est / 8 ? adv : est - est / 8;
 			if (adv <= 2 * SPEC_HB) ++poor;
 			else { poor = 0; Bp = 4 * SPEC_HB; }
-			if (poor >= 3) hyp = false;
+			if (poor >= 3 || adv == 0) hyp = false;
 			++hsweeps;
 			hadv += adv;
 			parity ^= 1;
@@ -484,17 +499,51 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 			// no contraction here; a long exact chunk 0 carries the progress, a few speculative chunks ride along
 			if (rank == 0 && t == 0) sc->plain_first[pparity ^ 1] = 0xffffffffu; // for the next plain sweep
 			const uint32_t B = Bp;
-			if (rank == 0 && t < 32) {
+			const uint32_t K0 = a.cand_off[done + 1] - a.cand_off[done];
+			const bool wide0 = a.kind[done] == 1 && K0 > SPEC3_WIDE;
+			if (rank == 0 && t < 32 && wide0) {
+				// rank `done` is a wide vertex (pole / huge fan): all its operands are final; the warp
+				// sums the candidate predictions with a strided loop + shuffle reduction (integer sums
+				// are order independent, so this equals the sequential result)
+				const uint32_t c0 = a.cand_off[done];
+				long long sum[NC];
+#pragma unroll
+				for (int c = 0; c < NC; ++c) sum[c] = 0;
+				for (uint32_t k = t; k < K0; k += 32) {
+					const uint32_t *tr = a.cand + 3 * (size_t)(c0 + k);
+					const Rec v0 = x[tr[0]], v1 = x[tr[1]], v2 = x[tr[2]];
+#pragma unroll
+					for (int c = 0; c < NC; ++c) sum[c] += (long long)IntOps<T>::predict_hi(v0.c[c], v1.c[c], v2.c[c], hi[c]);
+				}
+#pragma unroll
+				for (int c = 0; c < NC; ++c)
+#pragma unroll
+					for (int d = 16; d > 0; d >>= 1) sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], d);
+				if (t == 0) {
+					const Rec res = resid[done];
+					Rec out = res;
+#pragma unroll
+					for (int c = 0; c < NC; ++c) out.c[c] = IntOps<T>::dec_hi(res.c[c], (T)hb_divround_i64(sum[c], (int)K0), hi[c]);
+					x[done] = out;
+					atomicMin(&sc->plain_first[pparity], done + 1);
+				}
+			} else if (rank == 0 && t < 32) {
 				const unsigned long long start64 = (unsigned long long)done + (unsigned long long)t * B;
 				uint32_t fc = 0xffffffffu;
 				if (start64 < n) {
 					const uint32_t start = (uint32_t)start64;
 					const uint32_t end = (n - start < B) ? n : start + B;
 					uint32_t c0 = a.cand_off[start];
+					uint32_t stop = end;
 					auto get = [&](uint32_t r) -> Rec { return x[r]; };
 					for (uint32_t i = start; i < end; ++i) {
 						const uint32_t c1 = a.cand_off[i + 1];
 						const int kd = a.kind[i];
+						if (kd == 1 && c1 - c0 > SPEC3_WIDE) { // not recomputed here: nothing from here on is validated
+							stop = i;
+							if (fc == 0xffffffffu) fc = i;
+							break;
+						}
 						if (kd) {
 							const Rec old = x[i];
 							const Rec nw = kd == 2 ? x[a.src[i]] : spec_step<T, NC, false>(a, get, c0, c1 - c0, resid[i]);
@@ -505,7 +554,7 @@ __global__ void __launch_bounds__((4 * spec3_cpc<T, NC>()), 1) k_decode_vertex_s
 						}
 						c0 = c1;
 					}
-					if (t == 0 && fc != 0xffffffffu) fc = end; // chunk 0 is exact after the sweep
+					if (t == 0 && fc != 0xffffffffu) fc = stop; // chunk 0 is exact up to where it stopped
 				}
 				if (fc != 0xffffffffu) atomicMin(&sc->plain_first[pparity], fc);
 			}

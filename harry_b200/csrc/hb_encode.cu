@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(128) k_lhist(const uint4 *__restrict__ he, con
 // ------------------------------------------------------------------------------------------------
 #define ENC_THREADS 256
 #define HIST_SMEM_CTX 24 // contexts histogrammed in shared memory; the rest goes to global atomics
+#define ENC_WIDE_K 48     // vertices with more candidates (poles, huge fans) are coded by a whole warp
 
 struct EncodeArgs {
 	const uint32_t *erow, *ek, *first, *dord; // ek == nullptr: emission index == element index
@@ -185,6 +186,8 @@ struct EncodeArgs {
 	unsigned long long *hist, *type_hist;
 	uint32_t n;
 	int l;
+	uint32_t *wide;       // [0] = count, [1..] = element indices whose candidate count exceeds ENC_WIDE_K
+	uint32_t wide_cap;
 };
 
 template <int CLS>
@@ -220,6 +223,10 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 		}
 		a.type[k] = (uint8_t)t;
 		a.aux[k] = aux;
+		if (t == HB_DATA && CLS == CLS_VTX && a.wide && a.cand_off[i + 1] - a.cand_off[i] > ENC_WIDE_K) {
+			const uint32_t slot = atomicAdd(&a.wide[0], 1u);
+			if (slot < a.wide_cap) { a.wide[1 + slot] = i; t = -2; } // residual + histogram by k_encode_wide
+		}
 		if (t == HB_DATA) {
 			const uint32_t d = a.dord[i];
 			uint8_t *out = a.sym + (size_t)d * p.sym_stride;
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 		}
 		// emission-type counts: one shared-memory atomic per warp and type
 		for (int ty = 0; ty < 3; ++ty) {
-			const unsigned m = __ballot_sync(0xffffffffu, t == ty);
+			const unsigned m = __ballot_sync(0xffffffffu, t == ty || (ty == HB_DATA && t == -2));
 			if (m && (threadIdx.x & 31u) == 0) atomicAdd(&s_type[ty], (uint32_t)__popc(m));
 		}
 	}
@@ -284,6 +291,53 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 	for (int k = threadIdx.x; k < nctx_s * 256; k += ENC_THREADS)
 		if (s_hist[k]) atomicAdd(&a.hist[k], (unsigned long long)s_hist[k]);
 	if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&a.type_hist[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+}
+
+// One warp per wide vertex element: the candidate predictions are summed with a warp-strided loop
+// and a shuffle reduction.  Integer storage types only add in int64 (order independent, so this is
+// exact); a float component keeps the reference's in-order double accumulation on lane 0.
+__global__ void __launch_bounds__(128) k_encode_wide(ListParams p, EncodeArgs a)
+{
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t nw = a.wide[0] < a.wide_cap ? a.wide[0] : a.wide_cap;
+	if (w >= nw) return;
+	const uint32_t i = a.wide[1 + w];
+	const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
+	uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+	for (int j = 0; j < p.ncomp; ++j) {
+		const int st = p.stype[j], q = p.quant[j];
+		unsigned long long pred;
+		if (st == HB_FLOAT) {
+			pred = 0;
+			if (lane == 0)
+				pred = combine_candidates(st, K, [&](uint32_t kk) {
+					const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
+					return hb_predict(st, a.rp[(size_t)tr[0] * p.ncomp + j], a.rp[(size_t)tr[1] * p.ncomp + j], a.rp[(size_t)tr[2] * p.ncomp + j], q);
+				});
+		} else {
+			unsigned long long sum = 0;
+			for (uint32_t kk = lane; kk < K; kk += 32) {
+				const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
+				const unsigned long long v = hb_predict(st, a.rp[(size_t)tr[0] * p.ncomp + j], a.rp[(size_t)tr[1] * p.ncomp + j], a.rp[(size_t)tr[2] * p.ncomp + j], q);
+				sum += st == HB_ULONG ? v : (unsigned long long)hb_bits_to_i64(v, st);
+			}
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+			if (st == HB_ULONG) {
+				pred = (sum + ((unsigned long long)K >> 1)) / (unsigned long long)K;
+			} else {
+				pred = (unsigned long long)hb_divround_i64((long long)sum, (int)K);
+				const int size = hb_type_size(st);
+				if (size < 8) pred &= (1ull << (8 * size)) - 1ull;
+			}
+		}
+		if (lane == 0) {
+			const unsigned long long r = hb_enc(st, a.rp[(size_t)i * p.ncomp + j], pred, q);
+			hb_st_bits(out + p.sym_off[j], p.size[j], r);
+			for (int b = 0; b < p.size[j]; ++b)
+				atomicAdd(&a.hist[(size_t)(p.sym_off[j] + b) * 256 + ((uint32_t)(r >> (8 * b)) & 0xffu)], 1ull);
+		}
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,10 +471,20 @@ int hb_encode_lists(hb_dmesh *m)
 		a.celem_h = m->d_celem_h; a.he = m->d_he;
 		a.type = dl.d_type; a.aux = dl.d_aux; a.sym = dl.d_sym; a.hist = dl.d_hist; a.type_hist = dl.d_type_hist;
 		a.n = n; a.l = l;
+		a.wide = nullptr; a.wide_cap = 0;
+		if (cls == CLS_VTX && p.ncomp) {
+			a.wide_cap = 4096;
+			HB_TRY(hb_dalloc_t(m, &dl.d_wide, (size_t)a.wide_cap + 1));
+			HB_CUDA(ctx, cudaMemsetAsync(dl.d_wide, 0, sizeof(uint32_t), ctx->stream));
+			a.wide = dl.d_wide;
+		}
 		const int nctx_s = (int)(p.sym_stride < HIST_SMEM_CTX ? p.sym_stride : HIST_SMEM_CTX);
 		const size_t smem = sizeof(uint32_t) * ((size_t)nctx_s * 256 + 4);
 		const uint32_t g = hb_div_up(n, ENC_THREADS);
-		if (cls == CLS_VTX) HB_LAUNCH(ctx, k_encode_main<CLS_VTX>, g, ENC_THREADS, smem, p, a);
+		if (cls == CLS_VTX) {
+			HB_LAUNCH(ctx, k_encode_main<CLS_VTX>, g, ENC_THREADS, smem, p, a);
+			if (a.wide) HB_LAUNCH(ctx, k_encode_wide, hb_div_up((uint64_t)a.wide_cap * 32, 128), 128, 0, p, a);
+		}
 		else if (cls == CLS_FACE) HB_LAUNCH(ctx, k_encode_main<CLS_FACE>, g, ENC_THREADS, smem, p, a);
 		else HB_LAUNCH(ctx, k_encode_main<CLS_CORNER>, g, ENC_THREADS, smem, p, a);
 	}
