@@ -29,17 +29,28 @@ def build_edges(face_off: np.ndarray, face_idx: np.ndarray) -> np.ndarray:
     a = face_idx.astype(np.int64)
     b = a[nxt]
     twin = np.arange(ne, dtype=np.int64)
-    # sequential first-come matching (exact for any input, O(ne) dict operations)
-    pending = {}
-    al, bl = a.tolist(), b.tolist()
-    for h in range(ne):
-        key = (bl[h], al[h])
-        t = pending.pop(key, None)
-        if t is not None:
-            twin[h] = t
-            twin[t] = h
-        else:
-            pending.setdefault((al[h], bl[h]), h)
+    nv = int(a.max()) + 1 if ne else 0
+    key = a * nv + b
+    rev = b * nv + a
+    order = np.argsort(key, kind="stable")
+    skey = key[order]
+    if ne == 0 or np.all(skey[1:] != skey[:-1]):
+        # every directed edge is unique (manifold orientation): vectorized matching
+        pos = np.searchsorted(skey, rev)
+        pos_c = np.minimum(pos, ne - 1)
+        hit = skey[pos_c] == rev
+        twin[hit] = order[pos_c[hit]]
+    else:
+        # duplicates: sequential first-come matching (exact for any input, O(ne) dict operations)
+        pending = {}
+        al, bl = a.tolist(), b.tolist()
+        for h in range(ne):
+            t = pending.pop((bl[h], al[h]), None)
+            if t is not None:
+                twin[h] = t
+                twin[t] = h
+            else:
+                pending.setdefault((al[h], bl[h]), h)
     edges = np.empty((ne, 3), dtype=np.uint32)
     edges[:, 0] = face_idx
     edges[:, 1] = hface[twin]
