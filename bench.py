@@ -403,6 +403,18 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         else:
             cpu = port_measure(SAMPLE if not args.nr else (args.nr, args.ns))
 
+    E.close()
+    D.close()
+    ctx.close()
+    batch = None
+    if args.batch_meshes > 0 and world == 1:
+        import oracle_lib as ol
+        if ol.have_ref():
+            try:
+                batch = run_batch(local_rank, args.batch_meshes, args.batch_threads, 2, workdir)
+            except Exception as e:  # the headline line must survive a failure of the extra measurement
+                batch = {"error": repr(e)}
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -416,12 +428,101 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             "encode_M_attrs_per_s": world * w.n_attrs / (enc_ms / args.steps * 1e-3) / 1e6 if enc_ms else None,
             "decode_M_attrs_per_s": world * w.n_attrs / (dec_ms / args.steps * 1e-3) / 1e6 if dec_ms else None,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "kernels": kernels,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "batch100k": batch,
         }
         print(json.dumps(out), flush=True)
-    E.close()
-    D.close()
-    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE configs[4]: batch of independent 100K-vertex meshes on one GPU (device resident)
+# ----------------------------------------------------------------------------------------------
+def run_batch(local_rank: int, n_meshes: int, n_threads: int, reps: int, workdir: str):
+    """Many independent meshes keep the whole GPU busy even though one mesh's vertex chain only
+    occupies one 8-SM cluster: one hb_ctx (= one CUDA stream) per host thread, meshes dealt round
+    robin to the threads (harry_b200/shard.py), no exchange of any kind."""
+    import concurrent.futures as cf
+    from harry_b200 import shard
+    distinct = min(n_meshes, 8)
+    loads = []
+    for k in range(distinct):
+        loads.append(BatchMesh(225, 447, 100 + k, workdir))
+    plan = shard.shard_plan(n_meshes, n_threads)
+    n_attrs = sum(loads[i % distinct].n_attrs for i in range(n_meshes))
+
+    def worker(tid):
+        ctx = capi.Context(local_rank)
+        mine = []
+        for i in plan[tid]:
+            bm = loads[i % distinct]
+            E = capi.DeviceMesh(ctx, bm.raw)
+            E.snapshot()
+            D = capi.DeviceMesh(ctx, bm.dec)
+            D.set_bounds(1, *bm.dec_bounds)
+            D.snapshot()
+            mine.append((bm, E, D))
+        ctx.sync()
+        return ctx, mine
+
+    with cf.ThreadPoolExecutor(n_threads) as pool:
+        states = list(pool.map(worker, range(n_threads)))
+
+        def run(st):
+            ctx, mine = st
+            for bm, E, D in mine:
+                E.restore()
+                D.restore()
+                E.quantize(1, bm.new_quant, bm.groups)
+                E.encode()
+                D.decode()
+                D.dequantize(1)
+            ctx.sync()
+
+        list(pool.map(run, states))              # warm-up
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            list(pool.map(run, states))
+        dt = (time.perf_counter() - t0) / reps
+    launches = sum(st[0].launches() for st in states)
+    for ctx, mine in states:
+        for _, E, D in mine:
+            E.close()
+            D.close()
+        ctx.close()
+    return {"value": n_attrs / dt / 1e6, "unit": UNIT, "meshes": n_meshes, "vertices_per_mesh": loads[0].nv, "host_threads": n_threads,
+            "ms_per_batch": dt * 1e3, "ms_per_mesh_amortized": dt * 1e3 / n_meshes, "distinct_meshes": distinct, "gpu_launches_total": int(launches),
+            "workload": "configs[4] shape: UV spheres 225x447 (100 130 vertices) with per-mesh seeded radial noise, -l1 -q14, encode+decode, device resident, "
+                        "timer: host wall clock around all threads + stream syncs"}
+
+
+class BatchMesh:
+    def __init__(self, nr, ns, seed, workdir):
+        import oracle_lib as ol
+        ply = os.path.join(workdir, f"b_{seed}.ply")
+        meshgen.write_ply(ply, meshgen.uv_sphere(nr, ns, noise_seed=seed))
+        rm = ol.RefMesh(ply)
+        self.raw = rm.arrays()
+        rm.requant([(1, -1, QBITS)])
+        rm.traverse()
+        enc = rm.arrays()
+        self.new_quant = enc.lists[1].quants
+        self.groups = self.raw.lists[1].groups
+        self.raw.order, self.raw.order_f, self.raw.edges = enc.order, enc.order_f, enc.edges
+        hry = ply + ".hry"
+        rm.write(hry)
+        rm.close()
+        rd = ol.RefMesh(hry)
+        dec = rd.arrays()
+        st = rd.logged_streams()
+        rd.set_scale(1)
+        self.dec_bounds = tuple(rd.bounds_row(1, w, dec.lists[1].stride) for w in (0, 1, 2))
+        rd.close()
+        self.dec = dec.copy()
+        self.dec.lists = capi.residual_rows_from_streams(dec, st)
+        self.dec.emit_types = [ls.type for ls in st.lists]
+        self.n_attrs = self.raw.n_attrs()
+        self.nv = self.raw.nv
+        os.remove(ply)
+        os.remove(hry)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -539,6 +640,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--batch-meshes", type=int, default=64, help="extra measurement: batch of independent 100K-vertex meshes (0 = skip)")
+    ap.add_argument("--batch-threads", type=int, default=16)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -14,6 +14,8 @@
 #include "hb_lists.cuh"
 #include "hb_decode_spec.cuh"
 #include "hb_decode_spec3.cuh"
+#include "hb_decode_scan.cuh"
+#include <math.h>
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
@@ -155,6 +157,52 @@ static int launch_spec3(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, Spec3Scr
 	}
 }
 
+// cluster launch of the verified-scan kernel (integer lists)
+template <typename T, int NC>
+static int launch_scan_nc(hb_ctx *ctx, const SpecArgs *d_args, int cluster)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(cluster);
+	cfg.blockDim = dim3(SCAN_NTB);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = ctx->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = cluster;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	if (cluster > 8) HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_scan<T, NC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	cudaEvent_t pa = nullptr, pb = nullptr;
+	if (ctx->profiling) { pa = hb_prof_event(ctx); pb = hb_prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
+	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_decode_vertex_scan<T, NC>, d_args));
+	ctx->launches++;
+	if (pa) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back(hb_ctx::ProfRec{ "k_decode_vertex_scan", pa, pb }); }
+	return 0;
+}
+template <typename T>
+static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster)
+{
+	switch (ncomp) {
+	case 1: return launch_scan_nc<T, 1>(ctx, d_args, cluster);
+	case 2: return launch_scan_nc<T, 2>(ctx, d_args, cluster);
+	case 3: return launch_scan_nc<T, 3>(ctx, d_args, cluster);
+	default: return launch_scan_nc<T, 4>(ctx, d_args, cluster);
+	}
+}
+// CTAs per cluster: the window is about one cut-border length (~ sqrt(2 n) on a regular mesh);
+// two ranks per thread
+static int scan_cluster_size(uint32_t n, int ncomp)
+{
+	static const char *env = getenv("HARRY_B200_SCAN_CLUSTER");
+	if (env && atoi(env) > 0) return atoi(env) > SCAN_MAXC ? SCAN_MAXC : atoi(env);
+	const double need = 1.2 * sqrt(2.0 * (double)n) / (double)(SCAN_NWARP * (32 / ncomp));
+	int c = 1;
+	while (c < SCAN_MAXC && (double)c < need) c <<= 1;
+	return c;
+}
+
 static bool spec_eligible(const ListParams &p)
 {
 	if (p.ncomp < 1 || p.ncomp > 4) return false;
@@ -183,14 +231,27 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 	HB_LAUNCH(ctx, k_spec_prep, g, 256, 0, dl.d_erow, dl.d_first, n, dl.d_kind, dl.d_src);
 	HB_LAUNCH(ctx, k_gather_compact, g, 256, 0, p, dl.d_erow, n, dl.d_cres, esize, ncp);
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_cx, 0, (size_t)(n + 1) * ncp * esize, ctx->stream));
+	ScanRec *srec = nullptr;
+	if (st != HB_FLOAT) {
+		HB_TRY(hb_dalloc_t(m, &srec, (size_t)n + 1));
+		dl.d_srec = srec;
+		HB_LAUNCH(ctx, k_scan_prep, g, 256, 0, dl.d_kind, dl.d_src, m->d_vc_off, m->d_vc_tri, n, srec);
+	}
 	SpecArgs a;
+	a.srec = srec;
 	a.kind = dl.d_kind; a.src = dl.d_src; a.cand_off = m->d_vc_off; a.cand = m->d_vc_tri;
 	a.resid = dl.d_cres; a.x = dl.d_cx; a.n = n; a.stats = dl.d_spec_stats;
 	for (int j = 0; j < 4; ++j) a.bits[j] = j < p.ncomp ? (p.quant[j] ? p.quant[j] : 8 * esize) : 8 * esize;
 	HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_args, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream));
 	HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `a` is a stack object
 	static const bool single_cta = getenv("HARRY_B200_SPEC1") != nullptr; // A/B switch: single-CTA kernel
-	if (st != HB_FLOAT && !single_cta) {
+	static const bool use_spec3 = getenv("HARRY_B200_SPEC3") != nullptr;  // A/B switch: hypothesis kernel
+	if (st != HB_FLOAT && !single_cta && !use_spec3) {
+		const int cl = scan_cluster_size(n, p.ncomp);
+		if (st == HB_UCHAR) HB_TRY(launch_scan<uint8_t>(ctx, p.ncomp, dl.d_spec_args, cl));
+		else if (st == HB_USHORT) HB_TRY(launch_scan<uint16_t>(ctx, p.ncomp, dl.d_spec_args, cl));
+		else HB_TRY(launch_scan<uint32_t>(ctx, p.ncomp, dl.d_spec_args, cl));
+	} else if (st != HB_FLOAT && !single_cta) {
 		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_scratch, 1));
 		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_excl, (size_t)SPEC3_CLUSTER * SPEC3_MAXCPC));
 		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_inner, (size_t)SPEC3_CLUSTER * SPEC3_MAXCPC));

@@ -1,0 +1,752 @@
+// hb_decode_scan.cuh -- vertex reconstruction as a verified prefix scan of floor-affine maps.
+//
+// Problem (AttrDecoder::vtx_post, formats/hry/attrcode.h:443-470): in traversal order
+//   x[i] = decodeDelta(residual[i], divround(sum_k predict(x[a_k], x[b_k], x[c_k]), K))
+// and one operand of (almost) every rank i is rank i-1, so the dependency DAG is a chain of depth N.
+// The other operands lie about one cut-border length behind (the previous "ring" of the traversal).
+//
+// Observation: with all other operands known, rank i is a function of x[i-1] alone, and in its
+// regular regime (no saturation in predict(), no escape in decodeDelta()) that function is
+//   f_i(x) = floor((x + A_i) / M_i) + B_i          M_i = K (number of parallelograms)
+// The family  x -> floor((x + A) / M) + B  is closed under composition:
+//   f2(f1(x)) = floor((x + A1 + M1 * r) / (M1 * M2)) + B2 + q,   B1 + A2 = q * M2 + r, 0 <= r < M2
+// and once M exceeds the value range the map degenerates to a step  B + [x >= T]  (kept as M == CAP).
+// Saturated / escaped regimes are CONSTANT maps (decodeDelta returns delta or hi - delta there,
+// prediction.h:46-63), which are in the family as well.  So a window of ranks whose other operands are
+// final can be reconstructed by a parallel prefix composition instead of a sequential walk.
+//
+// Exactness does not rest on that algebra.  Every sweep:
+//   A. window = ranks [done, done + nact * R), R consecutive ranks per thread.  Each thread loads the
+//      operands of its ranks, notes the first rank E that reads a window rank other than its
+//      predecessor (window values are not final: nothing at or after E can be validated this sweep),
+//      and builds the map of each rank: the regular floor-affine form, or -- when a previous sweep
+//      left a guess g for x[i-1] and the exact step disagrees with the regular form at g -- the
+//      constant f_i(g).
+//   B. inclusive composition scan over threads (warp shuffles, shared memory, cluster totals through
+//      distributed shared memory) -> the presumed value of every thread's predecessor rank.
+//   C. every thread walks its R ranks with the EXACT reference step (IntOps::predict_hi / dec_hi)
+//      from that presumed value.
+//   D. verification: thread t is "good" iff the exact end value of thread t equals the presumed start
+//      value of thread t + 1.  Thread 0 starts from x[done - 1], which is final; by induction every
+//      rank up to the first bad boundary is the sequential result.  done = min(that boundary, E).
+// Machine mapping: one thread-block cluster per list; a group of NC adjacent lanes owns ONE rank of
+// the window and every lane of the group carries one component (R = 1 in the description above) --
+// instruction issue on the cluster's SMs is what bounds a sweep, so the per-rank classification is
+// done once, in the prep kernel, and components run side by side in lanes.
+// Progress is at least one rank per sweep for ANY input (group 0 is always exact); the algebra only
+// decides how far `done` moves.  Ranks with more than SCAN_WIDE candidates (sphere poles) end the
+// window and are evaluated by a whole CTA when `done` reaches them (integer sums commute).
+#pragma once
+#include <cooperative_groups.h>
+#include "hb_decode_spec.cuh"
+
+namespace cgs = cooperative_groups;
+
+#define SCAN_NTB 1024
+#define SCAN_NWARP (SCAN_NTB / 32)
+#define SCAN_KIN 4            // candidates held inline in a ScanRec
+#define SCAN_WIDE 32          // more candidates: evaluated cooperatively when first in the window
+#define SCAN_MAXC 16
+#define SCAN_SEQ_TRIGGER 48   // a sweep that advances by fewer ranks hands over to the sequential walker
+#define SCAN_SEQ_MIN 256
+#define SCAN_SEQ_MAX 2048
+
+// Per rank, written once by k_scan_prep (connectivity only, shared by all sweeps): everything a sweep
+// needs besides values, in one 64-byte line.  Which operand is the predecessor rank i - 1 is structural,
+// so the classification happens here and not in the sweeps.
+struct alignas(16) ScanRec {
+	uint32_t hdr;               // bits 0..1 kind (SpecArgs::kind); bits 2..9: per inline candidate 0 = no operand is rank i-1,
+	                            // 1 = v0 is, 2 = v1 is, 3 = other pattern; bit 10: not a regular rank; bits 11..: K
+	uint32_t aux;               // kind 1: CSR offset of the first candidate; kind 2: source rank
+	uint32_t farp1;             // 1 + highest operand rank other than i - 1 (0: none)
+	uint32_t tri[3 * SCAN_KIN]; // the first four candidates (rank triples)
+	uint32_t pad;
+};
+#define SCAN_HDR_IRREGULAR 0x400u
+
+__global__ void __launch_bounds__(256) k_scan_prep(const uint8_t *__restrict__ kind, const uint32_t *__restrict__ src, const uint32_t *__restrict__ cand_off,
+                                                   const uint32_t *__restrict__ cand, uint32_t n, ScanRec *__restrict__ out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t kd = kind[i];
+	const uint32_t c0 = cand_off[i], K = cand_off[i + 1] - c0;
+	const uint32_t pr = i - 1; // 0xffffffff for i == 0: never equal to an operand
+	uint32_t hdr = kd | (K << 11), farp1 = 0, npred = 0;
+	uint32_t tri[3 * SCAN_KIN];
+#pragma unroll
+	for (int w = 0; w < 3 * SCAN_KIN; ++w) tri[w] = 0;
+	if (kd == 2) {
+		if (src[i] != pr) farp1 = src[i] + 1;
+	} else if (kd == 1) {
+		for (uint32_t j = 0; j < K; ++j) {
+			const uint32_t r0 = cand[3 * (size_t)(c0 + j)], r1 = cand[3 * (size_t)(c0 + j) + 1], r2 = cand[3 * (size_t)(c0 + j) + 2];
+			const uint32_t nv = (uint32_t)(r0 == pr) + (uint32_t)(r1 == pr) + (uint32_t)(r2 == pr);
+			if (r0 != pr) farp1 = max(farp1, r0 + 1);
+			if (r1 != pr) farp1 = max(farp1, r1 + 1);
+			if (r2 != pr) farp1 = max(farp1, r2 + 1);
+			uint32_t code = 0;
+			if (nv == 1 && r0 == pr) code = 1;
+			else if (nv == 1 && r1 == pr) code = 2;
+			else if (nv) code = 3;
+			if (code) ++npred;
+			if (code == 3) hdr |= SCAN_HDR_IRREGULAR;
+			if (j < SCAN_KIN) {
+				hdr |= code << (2 + 2 * j);
+				tri[3 * j] = r0; tri[3 * j + 1] = r1; tri[3 * j + 2] = r2;
+			}
+		}
+		if (npred > 1 || (K > SCAN_KIN && K <= SCAN_WIDE)) hdr |= SCAN_HDR_IRREGULAR;
+	}
+	uint4 *o = (uint4 *)(out + i);
+	o[0] = make_uint4(hdr, kd == 2 ? src[i] : c0, farp1, tri[0]);
+	o[1] = make_uint4(tri[1], tri[2], tri[3], tri[4]);
+	o[2] = make_uint4(tri[5], tri[6], tri[7], tri[8]);
+	o[3] = make_uint4(tri[9], tri[10], tri[11], 0u);
+}
+
+// ---- floor-affine maps --------------------------------------------------------------------------
+// floor(c / m), m > 0
+template <typename SW, typename W> __device__ __noinline__ SW scan_floordiv_slow(SW c, W m)
+{
+	return c >= 0 ? (SW)((W)c / m) : -(SW)(((W)(-c) + m - 1) / m);
+}
+
+// x -> floor((x + A) / M) + B with 0 <= A < M <= CAP = 2^width, for 0 <= x < CAP.  M == CAP is the
+// degenerate step B + [x + A >= CAP]; a constant is (CAP, 0, c).
+// 8/16-bit storage types: M = 2^sm when sm < 32 (the common case: 1, 2 or 4 parallelograms, constants,
+// steps -- shifts only); other divisors keep M in sm >> 8 with 0xff in the low byte.
+template <typename T> struct FMap {
+	typedef uint32_t W;
+	typedef int32_t SW;
+	static constexpr int CB = 8 * (int)sizeof(T);
+	uint32_t sm, A;
+	int32_t B;
+	static __device__ __forceinline__ FMap identity() { FMap f; f.sm = 0; f.A = 0; f.B = 0; return f; }
+	static __device__ __forceinline__ FMap constant(SW c, int cb) { FMap f; f.sm = (uint32_t)cb; f.A = 0; f.B = c; return f; }
+	__device__ __forceinline__ uint32_t divisor() const { return sm < 32u ? 1u << sm : sm >> 8; }
+	static __device__ __forceinline__ FMap make(uint32_t M, uint32_t A, SW B) // M <= CAP
+	{
+		FMap f;
+		f.sm = (M & (M - 1u)) == 0u ? (uint32_t)(31 - __clz((int)M)) : ((M << 8) | 0xffu);
+		f.A = A;
+		f.B = B;
+		return f;
+	}
+	// regular form of one rank: floor((x + araw) / K) + b
+	static __device__ __forceinline__ FMap affine(uint32_t K, SW araw, SW b)
+	{
+		FMap f;
+		if ((K & (K - 1u)) == 0u) {
+			const int s = 31 - __clz((int)K);
+			f.sm = (uint32_t)s;
+			f.A = (uint32_t)araw & (K - 1u);
+			f.B = b + (araw >> s);
+		} else {
+			const SW q = scan_floordiv_slow<SW, W>(araw, K);
+			f.sm = (K << 8) | 0xffu;
+			f.A = (uint32_t)(araw - q * (SW)K);
+			f.B = b + q;
+		}
+		return f;
+	}
+	__device__ __forceinline__ SW eval(SW x) const
+	{
+		if (sm < 32u) return ((x + (SW)A) >> sm) + B; // arithmetic shift == floor
+		return scan_floordiv_slow<SW, W>(x + (SW)A, sm >> 8) + B;
+	}
+};
+// 32-bit storage types: general form only (64-bit parameters, 128-bit products)
+template <> struct FMap<uint32_t> {
+	typedef unsigned long long W;
+	typedef long long SW;
+	W M, A;
+	SW B;
+	static __device__ __forceinline__ W cap() { return (W)1 << 32; }
+	static __device__ __forceinline__ FMap identity() { FMap f; f.M = 1; f.A = 0; f.B = 0; return f; }
+	static __device__ __forceinline__ FMap constant(SW c, int) { FMap f; f.M = cap(); f.A = 0; f.B = c; return f; }
+	static __device__ __forceinline__ SW floordiv(SW c, W m)
+	{
+		if ((m & (m - 1)) == 0) return c >> (63 - __clzll((long long)m));
+		return scan_floordiv_slow<SW, W>(c, m);
+	}
+	static __device__ __forceinline__ FMap affine(uint32_t K, SW araw, SW b)
+	{
+		FMap f;
+		const SW q = floordiv(araw, (W)K);
+		f.M = K;
+		f.A = (W)(araw - q * (SW)K);
+		f.B = b + q;
+		return f;
+	}
+	__device__ __forceinline__ SW eval(SW x) const { return floordiv(x + (SW)A, M) + B; }
+};
+
+// apply f1 first, then f2:  floor((floor((x + A1) / M1) + B1 + A2) / M2) + B2
+//   = floor((x + A1 + M1 * r) / (M1 * M2)) + B2 + q   with B1 + A2 = q * M2 + r, 0 <= r < M2;
+// a product M >= CAP is folded back to the step form (x + A < 2 M there, so the quotient is 0 or 1).
+// cb = quantization bits of the component: every value is < 2^cb, so divisors fold at 2^cb
+template <typename T> __device__ __forceinline__ FMap<T> scan_compose(const FMap<T> &f1, const FMap<T> &f2, int cb)
+{
+	const uint32_t CAPV = 1u << cb;
+	FMap<T> f;
+	if (f1.sm == (uint32_t)cb && f2.sm == (uint32_t)cb) {
+		// step after step (all that is left once ~cb halvings have been composed): f1 takes the
+		// values B1 and B1 + 1
+		const uint32_t y0 = f1.B + (int)f2.A >= (int)CAPV ? 1u : 0u;
+		const uint32_t y1 = f1.B + 1 + (int)f2.A >= (int)CAPV ? 1u : 0u;
+		f.sm = (uint32_t)cb;
+		f.A = y1 != y0 ? f1.A : 0u;
+		f.B = f2.B + (int)y0;
+		return f;
+	}
+	const int Cc = f1.B + (int)f2.A;
+	if ((f1.sm | f2.sm) < 32u) {
+		// both divisors are powers of two (1, 2, 4 parallelograms; constants; steps): shifts only
+		const uint32_t r = (uint32_t)Cc & ((1u << f2.sm) - 1u);
+		const uint32_t s = f1.sm + f2.sm;
+		f.B = f2.B + (Cc >> f2.sm);
+		f.sm = s;
+		f.A = f1.A + (r << f1.sm);
+		if (s > (uint32_t)cb) {
+			const unsigned long long thr = (1ull << s) - ((unsigned long long)f1.A + ((unsigned long long)r << f1.sm));
+			f.sm = (uint32_t)cb;
+			f.A = thr >= CAPV ? 0u : CAPV - (uint32_t)thr;
+		}
+		return f;
+	}
+	const uint32_t M1 = f1.divisor(), M2 = f2.divisor();
+	const int q = Cc >= 0 ? (int)((uint32_t)Cc / M2) : -(int)(((uint32_t)(-Cc) + M2 - 1u) / M2);
+	const uint32_t r = (uint32_t)(Cc - q * (int)M2);
+	const unsigned long long M = (unsigned long long)M1 * M2;
+	const unsigned long long A = (unsigned long long)f1.A + (unsigned long long)M1 * r;
+	f.B = f2.B + q;
+	if (M >= CAPV) {
+		const unsigned long long thr = M - A; // >= 1
+		f.sm = (uint32_t)cb;
+		f.A = thr >= CAPV ? 0u : CAPV - (uint32_t)thr;
+	} else {
+		const uint32_t m = (uint32_t)M;
+		f.sm = (m & (m - 1u)) == 0u ? (uint32_t)(31 - __clz((int)m)) : ((m << 8) | 0xffu);
+		f.A = (uint32_t)A;
+	}
+	return f;
+}
+template <> __device__ __noinline__ FMap<uint32_t> scan_compose<uint32_t>(const FMap<uint32_t> &f1, const FMap<uint32_t> &f2, int)
+{
+	typedef unsigned long long W;
+	typedef long long SW;
+	typedef unsigned __int128 WW;
+	const W CAP = FMap<uint32_t>::cap();
+	const SW Cc = f1.B + (SW)f2.A;
+	const SW q = FMap<uint32_t>::floordiv(Cc, f2.M);
+	const W r = (W)(Cc - q * (SW)f2.M);
+	const WW M = (WW)f1.M * (WW)f2.M;
+	const WW A = (WW)f1.A + (WW)f1.M * (WW)r;
+	FMap<uint32_t> f;
+	f.B = f2.B + q;
+	if (M >= (WW)CAP) {
+		const WW thr = M - A;
+		f.M = CAP;
+		f.A = thr >= (WW)CAP ? (W)0 : (W)((WW)CAP - thr);
+	} else {
+		f.M = (W)M;
+		f.A = (W)A;
+	}
+	return f;
+}
+
+template <typename T> __device__ __forceinline__ FMap<T> scan_shfl_up(const FMap<T> &m, int d)
+{
+	FMap<T> r;
+	r.sm = __shfl_up_sync(0xffffffffu, m.sm, d);
+	r.A = __shfl_up_sync(0xffffffffu, m.A, d);
+	r.B = __shfl_up_sync(0xffffffffu, m.B, d);
+	return r;
+}
+template <> __device__ __forceinline__ FMap<uint32_t> scan_shfl_up<uint32_t>(const FMap<uint32_t> &m, int d)
+{
+	FMap<uint32_t> r;
+	r.M = __shfl_up_sync(0xffffffffu, m.M, d);
+	r.A = __shfl_up_sync(0xffffffffu, m.A, d);
+	r.B = __shfl_up_sync(0xffffffffu, m.B, d);
+	return r;
+}
+template <typename T> __device__ __forceinline__ FMap<T> scan_shfl(const FMap<T> &m, int lane)
+{
+	FMap<T> r;
+	r.sm = __shfl_sync(0xffffffffu, m.sm, lane);
+	r.A = __shfl_sync(0xffffffffu, m.A, lane);
+	r.B = __shfl_sync(0xffffffffu, m.B, lane);
+	return r;
+}
+template <> __device__ __forceinline__ FMap<uint32_t> scan_shfl<uint32_t>(const FMap<uint32_t> &m, int lane)
+{
+	FMap<uint32_t> r;
+	r.M = __shfl_sync(0xffffffffu, m.M, lane);
+	r.A = __shfl_sync(0xffffffffu, m.A, lane);
+	r.B = __shfl_sync(0xffffffffu, m.B, lane);
+	return r;
+}
+
+// L2-coherent scalar load (values are rewritten between sweeps by other SMs of the cluster)
+__device__ __forceinline__ uint32_t scan_ld(const uint8_t *p) { return __ldcg((const unsigned char *)p); }
+__device__ __forceinline__ uint32_t scan_ld(const uint16_t *p) { return __ldcg((const unsigned short *)p); }
+__device__ __forceinline__ uint32_t scan_ld(const uint32_t *p) { return __ldcg((const unsigned int *)p); }
+
+// Values travel as 32-bit words inside the kernel.  For 8/16-bit storage types the reference's
+// modulo-2^width arithmetic (prediction.h:46-63,121-137) is restated on 32-bit words -- the native
+// narrow types cost a byte-permute after every operation:
+//   predict: v1 < v2 ? max(v0 - (v2 - v1), 0) : min(v0 + (v1 - v2), hi)   (the wrapped sum of the
+//            reference is < v0 exactly when the true sum exceeds the type, which also selects hi)
+//   dec:     the reference expression with every intermediate reduced modulo 2^width
+template <typename T> struct ScanOps {
+	static constexpr uint32_t TM = (1u << (8 * sizeof(T))) - 1u;
+	static __device__ __forceinline__ uint32_t predict(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t hi)
+	{
+		const int s = (int)v0 + (int)v1 - (int)v2;
+		return v1 < v2 ? (uint32_t)max(s, 0) : (uint32_t)min(s, (int)hi);
+	}
+	static __device__ __forceinline__ uint32_t dec(uint32_t delta, uint32_t pred, uint32_t hi)
+	{
+		const uint32_t room = (hi - pred) & TM;
+		const uint32_t pm1 = (pred - 1u) & TM;
+		const uint32_t bal = min(room, pm1);
+		const uint32_t half = delta >> 1;
+		uint32_t r = (delta & 1u) ? pred + ~half : pred + half;
+		if (half > bal) r = room >= pred ? pred + delta - bal - 1u : pred - delta + bal;
+		if (pred == 0u) r = delta;
+		return r & TM;
+	}
+};
+template <> struct ScanOps<uint32_t> {
+	static __device__ __forceinline__ uint32_t predict(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t hi) { return IntOps<uint32_t>::predict_hi(v0, v1, v2, hi); }
+	static __device__ __forceinline__ uint32_t dec(uint32_t delta, uint32_t pred, uint32_t hi) { return IntOps<uint32_t>::dec_hi(delta, pred, hi); }
+};
+
+// (sum + K / 2) / K of transform.h:90-91 for K > 2
+template <typename W> __device__ __noinline__ W scan_divk(W sum, uint32_t K) { return (sum + (W)(K >> 1)) / (W)K; }
+template <typename T> __device__ __forceinline__ uint32_t scan_mean(typename FMap<T>::W sum, uint32_t K)
+{
+	typedef typename FMap<T>::W W;
+	if (K == 2) return (uint32_t)(T)((sum + 1) >> 1);
+	if (K <= 1) return (uint32_t)(T)sum; // K == 0: sum == 0
+	if (K == 4) return (uint32_t)(T)((sum + 2) >> 2);
+	return (uint32_t)(T)scan_divk<W>(sum, K);
+}
+
+enum { SCAN_NONE = 0, SCAN_CONST = 1, SCAN_COPY = 2, SCAN_STD = 3, SCAN_OPAQUE = 4 };
+
+// the exact step of a regular rank for one component: one candidate reads the predecessor value `cur`
+// at operand position varpos (0: v0, 1: v1); S = sum of the other candidates' predictions
+template <typename T>
+__device__ __forceinline__ uint32_t scan_std_step(uint32_t cur, uint32_t va, uint32_t vb, uint32_t delta, typename FMap<T>::W S, uint32_t K, uint32_t varpos, uint32_t hi)
+{
+	typedef typename FMap<T>::W W;
+	const uint32_t p = varpos ? ScanOps<T>::predict(va, cur, vb, hi) : ScanOps<T>::predict(cur, va, vb, hi);
+	return ScanOps<T>::dec(delta, scan_mean<T>(S + (W)p, K), hi);
+}
+
+// One component of the generic step (any number of candidates, any operand pattern).  Operand r:
+// rank `predrank` reads pv; ranks >= lo come from the stretch buffer `sq` (sequential mode, else
+// lo = 0xffffffff); everything else from the value array.
+template <typename T>
+__device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ cand, const T *xc, uint32_t cs, uint32_t predrank, uint32_t pv, const T *sq, uint32_t lo,
+                                                   uint32_t c0, uint32_t K, uint32_t delta, uint32_t hi)
+{
+	typedef typename FMap<T>::W W;
+	W sum = 0;
+	for (uint32_t k = 0; k < K; ++k) {
+		const uint32_t *tr = cand + 3 * (size_t)(c0 + k);
+		uint32_t v[3];
+#pragma unroll
+		for (int o = 0; o < 3; ++o) {
+			const uint32_t r = __ldg(tr + o);
+			v[o] = r == predrank ? pv : (r >= lo ? (uint32_t)sq[(size_t)(r - lo) * cs] : scan_ld(xc + (size_t)r * cs));
+		}
+		sum += (W)ScanOps<T>::predict(v[0], v[1], v[2], hi);
+	}
+	return ScanOps<T>::dec(delta, scan_mean<T>(sum, K), hi);
+}
+
+#ifdef SCAN_DEBUG
+#define SCAN_CLK(v) const long long v = clock64()
+#define SCAN_PROBE(i, ta, tb) pr[i] += (tb) - (ta)
+#else
+#define SCAN_CLK(v)
+#define SCAN_PROBE(i, ta, tb)
+#endif
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecArgs *__restrict__ args)
+{
+	typedef FMap<T> Map;
+	typedef typename Map::W W;
+	typedef typename Map::SW SW;
+	constexpr uint32_t RS = NC == 3 ? 4 : NC;          // elements per value record
+	constexpr uint32_t G = 32 / NC;                    // groups (ranks) per warp; lanes >= G * NC idle
+	constexpr uint32_t NSEG = SCAN_NWARP * G;          // ranks per CTA and sweep
+	cgs::cluster_group cluster = cgs::this_cluster();
+	const uint32_t C = cluster.num_blocks();
+	const uint32_t crank = cluster.block_rank();
+	const uint32_t list = blockIdx.x / C;
+	const SpecArgs a = args[list];
+	const ScanRec *__restrict__ srec = (const ScanRec *)a.srec;
+	const uint32_t n = a.n;
+	const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const uint32_t grp = lane / NC;                     // my group within the warp
+	const bool live = grp < G;                          // lanes beyond the last full group only join shuffles
+	const uint32_t c = live ? lane % NC : 0;            // my component
+	const uint32_t q = warp * G + (live ? grp : G - 1); // my rank slot within the CTA
+	const T *__restrict__ rc = (const T *)a.resid + c;  // component views: element r at [r * RS]
+	T *xc = (T *)a.x + c;
+	const uint32_t NSEGT = C * NSEG;                    // ranks per window
+
+	__shared__ Map s_wtot[SCAN_NWARP][NC];      // inclusive warp totals of this CTA
+	__shared__ Map s_ctot[SCAN_MAXC][NC];       // CTA totals of the whole cluster (pushed by their owners)
+	__shared__ uint32_t s_ndE[SCAN_MAXC];       // per CTA: first rank that reads a non-final window value
+	__shared__ uint32_t s_ndF[SCAN_MAXC];       // per CTA: first rank behind a failed boundary check
+	__shared__ uint32_t s_start[NSEG + 1][NC];  // presumed start value of every slot (+ of the next CTA's first slot)
+	__shared__ uint32_t s_vcta[NC];             // start value of this CTA's first slot
+	__shared__ uint32_t s_minE, s_minF;
+	__shared__ unsigned long long s_sum[4];
+	__shared__ T s_seq[SCAN_SEQ_MAX * RS];      // values of a sequential stretch
+
+	const uint32_t hi = (uint32_t)IntOps<T>::mask(a.bits[c]);
+	const int cb = a.bits[c];
+	const int cbw = a.bits[warp < (uint32_t)NC ? warp : 0]; // warps 0 .. NC-1 scan the totals of component `warp`
+	const int lgC = 31 - __clz((int)C);
+
+	uint32_t done = 0, gend = 0, est = NSEGT;
+	bool widehead = false, seqmode = false, lastseq = false;
+	uint32_t seqlen = SCAN_SEQ_MIN;
+	unsigned long long sweeps = 0, fails = 0, wides = 0, capped = 0, nseq = 0;
+	long long cyA = 0, cyB = 0, cyC = 0, cyD = 0;
+#ifdef SCAN_DEBUG
+	long long pr[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+#endif
+	auto csync = [&]() { if (C > 1) cluster.sync(); else __syncthreads(); };
+
+	while (done < n) {
+		const long long tA = clock64();
+		// ---------------------------------------------------------------- wide rank at the head of the window
+		// (a sweep that cannot move `done` has found one: see phase A)
+		if (widehead) {
+			const uint32_t K0 = __ldg(&srec[done].hdr) >> 11;
+			if (crank == 0) {
+				if (t < 4) s_sum[t] = 0ull;
+				__syncthreads();
+				const uint32_t c0 = __ldg(&srec[done].aux);
+				unsigned long long sum = 0ull;
+				if (live) {
+					for (uint32_t k = q; k < K0; k += NSEG) {
+						const uint32_t *tr = a.cand + 3 * (size_t)(c0 + k);
+						const uint32_t v0 = scan_ld(xc + (size_t)tr[0] * RS), v1 = scan_ld(xc + (size_t)tr[1] * RS), v2 = scan_ld(xc + (size_t)tr[2] * RS);
+						sum += (unsigned long long)ScanOps<T>::predict(v0, v1, v2, hi);
+					}
+					atomicAdd(&s_sum[c], sum);
+				}
+				__syncthreads();
+				if (t < (uint32_t)NC) xc[(size_t)done * RS] = (T)ScanOps<T>::dec(rc[(size_t)done * RS], (uint32_t)(T)hb_divround_i64((long long)s_sum[c], (int)K0), hi);
+			}
+			csync();
+			++done;
+			if (gend < done) gend = done;
+			widehead = false;
+			++wides;
+			++sweeps;
+			cyD += clock64() - tA;
+			continue;
+		}
+		// ---------------------------------------------------------------- sequential stretch (one warp)
+		// The window was cut after a few ranks (E-limit: e.g. the first ring of a sphere, where every
+		// vertex is predicted from the two before it).  Warp 0 of CTA 0 walks the next `seqlen`
+		// ranks in order: its lane groups prefetch the records and the final operands of G ranks,
+		// then take turns; values produced inside the stretch travel through shared memory.
+		if (seqmode) {
+			const uint32_t len = n - done < seqlen ? n - done : seqlen;
+			if (crank == 0 && warp == 0) {
+				uint32_t stop = len;
+				for (uint32_t b0 = 0; b0 < len; b0 += G) {
+					const uint32_t k0 = b0 + grp;
+					const bool valid = live && k0 < len;
+					const uint32_t i = done + (valid ? k0 : 0);
+					const uint4 *sr = (const uint4 *)(srec + i);
+					const uint4 q0 = __ldg(sr), q1 = __ldg(sr + 1);
+					const uint32_t tri[6] = { q0.w, q1.x, q1.y, q1.z, q1.w, __ldg(&srec[i].tri[5]) };
+					const uint32_t kd = q0.x & 3u, K = q0.x >> 11, aux = q0.y;
+					const uint32_t res = rc[(size_t)i * RS];
+					const unsigned wm = __ballot_sync(0xffffffffu, valid && kd == 1 && K > SCAN_WIDE);
+					const uint32_t nl = wm ? ((uint32_t)__ffs((int)wm) - 1u) / NC : G;
+					uint32_t ov[6];
+#pragma unroll
+					for (int w = 0; w < 6; ++w) {
+						ov[w] = 0;
+						if (valid && kd == 1 && K <= 2 && (uint32_t)(w / 3) < K && tri[w] < done) ov[w] = scan_ld(xc + (size_t)tri[w] * RS);
+					}
+					uint32_t cv = 0;
+					if (valid && kd == 0) cv = scan_ld(xc + (size_t)i * RS);
+					if (valid && kd == 2 && aux < done) cv = scan_ld(xc + (size_t)aux * RS);
+#pragma unroll 1
+					for (uint32_t j = 0; j < nl; ++j) {
+						if (grp == j && valid) {
+							uint32_t val = cv;
+							if (kd == 2 && aux >= done) val = s_seq[(aux - done) * RS + c];
+							if (kd == 1 && K <= 2) {
+								W sum = 0;
+#pragma unroll
+								for (int cj = 0; cj < 2; ++cj) {
+									if ((uint32_t)cj >= K) continue;
+									uint32_t v[3];
+#pragma unroll
+									for (int o = 0; o < 3; ++o) v[o] = tri[3 * cj + o] < done ? ov[3 * cj + o] : (uint32_t)s_seq[(tri[3 * cj + o] - done) * RS + c];
+									sum += (W)ScanOps<T>::predict(v[0], v[1], v[2], hi);
+								}
+								val = ScanOps<T>::dec(res, scan_mean<T>(sum, K), hi);
+							} else if (kd == 1) {
+								val = scan_generic_step<T>(a.cand, xc, RS, 0xffffffffu, 0u, s_seq + c, done, aux, K, res, hi);
+							}
+							s_seq[k0 * RS + c] = (T)val;
+						}
+						__syncwarp();
+					}
+					if (wm) { stop = b0 + nl; break; }
+				}
+				if (live)
+					for (uint32_t k = grp; k < stop; k += G) xc[(size_t)(done + k) * RS] = s_seq[k * RS + c];
+				if (lane < C) {
+					uint32_t *dst = C > 1 ? cluster.map_shared_rank(&s_ndE[0], lane) : &s_ndE[0];
+					*dst = stop;
+				}
+			}
+			csync();
+			const uint32_t stop = s_ndE[0];
+			csync(); // s_ndE is rewritten by the next sweep
+			if (stop == 0) widehead = true;
+			done += stop;
+			if (gend < done) gend = done;
+			seqmode = false;
+			++nseq;
+			++sweeps;
+			cyD += clock64() - tA;
+			continue;
+		}
+		// ---------------------------------------------------------------- phase A: operands and the map of my rank
+		// the window is dealt evenly to the CTAs of the cluster, whole warps each (instruction issue
+		// per SM is what bounds a sweep); warps beyond `wpc` sit the sweep out
+		uint32_t wpc = (((est + est / 8 + 8 + G * C - 1) >> lgC)) / G; // active warps per CTA
+		if (wpc > SCAN_NWARP) wpc = SCAN_NWARP;
+		const uint32_t per = wpc * G;                       // slots per CTA
+		const uint32_t nact = per << lgC;                   // slots of the window
+		const uint32_t gs = crank * per + q;                // my slot in the window
+		const unsigned long long i64 = (unsigned long long)done + gs;
+		const bool active = live && warp < wpc && i64 < n;
+		const uint32_t i = active ? (uint32_t)i64 : n;
+		const unsigned long long wend64 = (unsigned long long)done + nact;
+		const uint32_t wend = wend64 < n ? (uint32_t)wend64 : n;
+		const uint32_t x0 = done ? scan_ld(xc + (size_t)(done - 1) * RS) : 0u;
+		// warps 0 .. NC-1 later push x[done - 1] of component `warp` through the CTA totals
+		const uint32_t x0w = (done && warp < (uint32_t)NC) ? scan_ld((const T *)a.x + (size_t)(done - 1) * RS + warp) : 0u;
+
+		uint32_t mode = SCAN_NONE, Kk = 0, vpos = 0, ra = 0, rb = 0, rd = 0;
+		bool wr = false;
+		W S = 0;
+		uint32_t Ecand = 0xffffffffu;
+		Map tm = Map::identity();
+		if (active) {
+			const uint4 *sr = (const uint4 *)(srec + i);
+			const uint4 q0 = __ldg(sr), q1 = __ldg(sr + 1), q2 = __ldg(sr + 2), q3 = __ldg(sr + 3);
+			const uint32_t tri[3 * SCAN_KIN] = { q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
+			const uint32_t hdr = q0.x, kd = hdr & 3u, K = hdr >> 11, aux = q0.y, farp1 = q0.z;
+			const uint32_t res = rc[(size_t)i * RS];
+			// operand values of the inline candidates: all loads are issued before any is used
+			// (the slot of the predecessor rank is loaded too and ignored)
+			uint32_t ov[3 * SCAN_KIN];
+#pragma unroll
+			for (int w = 0; w < 3 * SCAN_KIN; ++w) {
+				ov[w] = 0;
+				if (kd == 1 && (uint32_t)(w / 3) < K) ov[w] = scan_ld(xc + (size_t)tri[w] * RS);
+			}
+			// a guess for x[i - 1] exists if a previous sweep computed it with all operands final
+			const bool have_guess = i == done || i - 1 < gend;
+			uint32_t g = 0;
+			if (i == done) g = x0;
+			else if (have_guess) g = scan_ld(xc + (size_t)(i - 1) * RS);
+			rd = res;
+			Kk = K;
+			wr = kd != 0;
+			if (farp1 > done || (kd == 1 && K > SCAN_WIDE)) {
+				// reads a window value that is not final (or is a wide rank, evaluated when `done`
+				// reaches it): nothing from here on can be validated in this sweep
+				Ecand = i;
+				mode = SCAN_CONST;
+				wr = false;
+				tm = Map::constant(0, cb);
+			} else if (kd == 0) {
+				mode = SCAN_CONST;
+				ra = scan_ld(xc + (size_t)i * RS);
+				tm = Map::constant((SW)ra, cb);
+			} else if (kd == 2) {
+				if (i > 0 && aux == i - 1) {
+					mode = SCAN_COPY;
+				} else {
+					mode = SCAN_CONST;
+					ra = scan_ld(xc + (size_t)aux * RS);
+					tm = Map::constant((SW)ra, cb);
+				}
+			} else if (hdr & SCAN_HDR_IRREGULAR) {
+				mode = SCAN_OPAQUE;
+				S = (W)aux;
+				tm = Map::constant((SW)scan_generic_step<T>(a.cand, xc, RS, i - 1, g, xc, 0xffffffffu, aux, K, res, hi), cb);
+			} else {
+				W Sacc = 0;
+				uint32_t va = 0, vb = 0, vp = 0;
+				bool var = false;
+#pragma unroll
+				for (int j = 0; j < SCAN_KIN; ++j) {
+					if ((uint32_t)j >= K) continue;
+					const uint32_t code = (hdr >> (2 + 2 * j)) & 3u;
+					if (code == 0) {
+						Sacc += (W)ScanOps<T>::predict(ov[3 * j], ov[3 * j + 1], ov[3 * j + 2], hi);
+					} else {
+						var = true;
+						vp = code - 1u;
+						va = code == 1 ? ov[3 * j + 1] : ov[3 * j];
+						vb = ov[3 * j + 2];
+					}
+				}
+				if (!var) {
+					mode = SCAN_CONST;
+					ra = ScanOps<T>::dec(res, scan_mean<T>(Sacc, K), hi);
+					tm = Map::constant((SW)ra, cb);
+				} else {
+					mode = SCAN_STD;
+					vpos = vp;
+					ra = va;
+					rb = vb;
+					S = Sacc;
+					const SW half = (SW)(res >> 1);
+					const SW sb = (res & 1) ? -(half + 1) : half;
+					tm = Map::affine(K, (SW)va - (SW)vb + (SW)Sacc + (SW)(K >> 1), sb);
+					if (have_guess) {
+						const uint32_t yg = scan_std_step<T>(g, va, vb, res, Sacc, K, vp, hi);
+						if ((uint32_t)(T)tm.eval((SW)g) != yg) tm = Map::constant((SW)yg, cb);
+					}
+				}
+			}
+		}
+		const long long tB = clock64();
+		// ---------------------------------------------------------------- phase B: composition scan
+		Map inc = tm;
+		if (warp < wpc) {
+#pragma unroll 1
+			for (uint32_t d = 1; d < G; d <<= 1) {
+				const Map up = scan_shfl_up<T>(inc, (int)(d * NC));
+				if (grp >= d) inc = scan_compose<T>(up, inc, cb);
+			}
+		}
+		SCAN_CLK(p1);
+		if (live && grp == G - 1) s_wtot[warp][c] = inc;
+		if (t == 0) { s_minE = 0xffffffffu; s_minF = 0xffffffffu; }
+		__syncthreads();
+		SCAN_CLK(p2);
+		if (warp < (uint32_t)NC) {
+			// warp w scans the warp totals of component w
+			Map w = s_wtot[lane][warp];
+#pragma unroll 1
+			for (int d = 1; d < SCAN_NWARP; d <<= 1) {
+				const Map up = scan_shfl_up<T>(w, d);
+				if ((int)lane >= d) w = scan_compose<T>(up, w, cbw);
+			}
+			s_wtot[lane][warp] = w;
+			const Map tot = scan_shfl<T>(w, SCAN_NWARP - 1);
+			if (lane < C) {
+				Map *dst = C > 1 ? cluster.map_shared_rank(&s_ctot[crank][warp], lane) : &s_ctot[crank][warp];
+				*dst = tot;
+			}
+		}
+		SCAN_CLK(p3);
+		csync(); // [1] warp totals (this CTA) and CTA totals (cluster) visible
+		SCAN_CLK(p4);
+		if (warp < (uint32_t)NC) {
+			// start value of this CTA and of the next one: x0 pushed through the totals of the CTAs
+			// before (inclusive scan over the cluster, then one evaluation per lane)
+			Map w = lane < C ? s_ctot[lane][warp] : Map::identity();
+#pragma unroll 1
+			for (int d = 1; d < SCAN_MAXC; d <<= 1) {
+				const Map up = scan_shfl_up<T>(w, d);
+				if ((int)lane >= d && (uint32_t)d < C) w = scan_compose<T>(up, w, cbw);
+			}
+			const uint32_t v = (uint32_t)(T)w.eval((SW)x0w);
+			if (lane + 1 == crank) s_vcta[warp] = v;
+			if (crank == 0 && lane == 0) s_vcta[warp] = x0w;
+			if (lane == crank) s_start[per][warp] = v;
+		}
+		Map ex = scan_shfl_up<T>(inc, NC);
+		if (grp == 0) ex = Map::identity();
+		if (warp > 0 && live) ex = scan_compose<T>(s_wtot[warp - 1][c], ex, cb);
+		__syncthreads();
+		uint32_t start = (uint32_t)(T)ex.eval((SW)s_vcta[c]);
+		if (gs == 0) start = x0; // final by construction
+		if (live) s_start[q][c] = start;
+		__syncthreads();
+		const long long tC = clock64();
+		// ---------------------------------------------------------------- phase C: the exact step
+		uint32_t cur = start;
+		if (mode == SCAN_CONST) cur = ra;
+		else if (mode == SCAN_STD) cur = scan_std_step<T>(start, ra, rb, rd, S, Kk, vpos, hi);
+		else if (mode == SCAN_OPAQUE) cur = scan_generic_step<T>(a.cand, xc, RS, i - 1, start, xc, 0xffffffffu, (uint32_t)S, Kk, rd, hi);
+		const long long tD = clock64();
+		// ---------------------------------------------------------------- phase D: verify, publish, write
+		uint32_t ndE = Ecand, ndF = 0xffffffffu;
+		if (active) {
+			const uint32_t nxt = s_start[q + 1][c];
+			const bool last = gs + 1 >= nact; // nothing after me in this window
+			if (!last && cur != nxt) ndF = i + 1;
+			if (wr) xc[(size_t)i * RS] = (T)cur;
+		}
+		ndE = __reduce_min_sync(0xffffffffu, ndE);
+		ndF = __reduce_min_sync(0xffffffffu, ndF);
+		if (lane == 0) {
+			if (ndE != 0xffffffffu) atomicMin(&s_minE, ndE);
+			if (ndF != 0xffffffffu) atomicMin(&s_minF, ndF);
+		}
+		SCAN_CLK(p5);
+		__syncthreads();
+		SCAN_CLK(p6);
+		if (t < C) {
+			uint32_t *dE = C > 1 ? cluster.map_shared_rank(&s_ndE[crank], t) : &s_ndE[crank];
+			uint32_t *dF = C > 1 ? cluster.map_shared_rank(&s_ndF[crank], t) : &s_ndF[crank];
+			*dE = s_minE;
+			*dF = s_minF;
+		}
+		csync(); // [2] values and the two limits visible
+		SCAN_CLK(p7);
+		uint32_t E = wend, F = 0xffffffffu;
+		for (uint32_t r = 0; r < C; ++r) { E = min(E, s_ndE[r]); F = min(F, s_ndF[r]); }
+		const uint32_t newdone = min(E, F);
+		if (F < E) ++fails;
+		else if (newdone == wend && wend < n) ++capped;
+		if (gend < E) gend = E;            // [newdone, E) now holds this sweep's values: guesses for the next one
+		if (newdone == done) widehead = true; // only a wide head rank stops slot 0
+		else if (newdone - done < SCAN_SEQ_TRIGGER && newdone < n && !(F < E)) {
+			seqmode = true;                   // dependency-limited window: walk a stretch sequentially
+			seqlen = lastseq ? (seqlen * 2 < SCAN_SEQ_MAX ? seqlen * 2 : SCAN_SEQ_MAX) : SCAN_SEQ_MIN;
+			lastseq = true;
+		} else lastseq = false;
+		const uint32_t adv = newdone - done;
+		if (newdone == wend && wend < n) est = est * 2 < NSEGT ? est * 2 : NSEGT;
+		else est = adv > est - est / 8 ? adv : est - est / 8;
+		done = newdone;
+		++sweeps;
+		SCAN_PROBE(0, tB, p1); SCAN_PROBE(1, p1, p2); SCAN_PROBE(2, p2, p3); SCAN_PROBE(3, p3, p4); SCAN_PROBE(4, p4, tC); SCAN_PROBE(5, tD, p5); SCAN_PROBE(6, p5, p6); SCAN_PROBE(7, p6, p7);
+		{ const long long tE = clock64(); cyA += tB - tA; cyB += tC - tB; cyC += tD - tC; cyD += tE - tD; }
+	}
+#ifdef SCAN_DEBUG
+	if (t == 0) printf("cta %u A %lld probes: warpscan %lld sync %lld lvl2 %lld csync1 %lld start %lld walk %lld | verify+write %lld sync %lld push+csync2 %lld (per sweep, %llu sweeps)\n", crank, cyA / (long long)sweeps, pr[0] / (long long)sweeps, pr[1] / (long long)sweeps, pr[2] / (long long)sweeps, pr[3] / (long long)sweeps, pr[4] / (long long)sweeps, cyC / (long long)sweeps, pr[5] / (long long)sweeps, pr[6] / (long long)sweeps, pr[7] / (long long)sweeps, sweeps);
+#endif
+	if (crank == 0 && t == 0 && a.stats) {
+		a.stats[0] = sweeps; a.stats[1] = fails | (capped << 32); a.stats[2] = (wides << 32) | (nseq << 40); a.stats[3] = n;
+		a.stats[4] = (unsigned long long)cyA; a.stats[5] = (unsigned long long)cyB; a.stats[6] = (unsigned long long)cyC; a.stats[7] = (unsigned long long)cyD;
+	}
+}

@@ -52,6 +52,7 @@ struct SpecArgs {
 	uint32_t n;
 	int bits[4];              // quantization bits per component (prediction.h:22-25)
 	unsigned long long *stats; // [0] sweeps, [1] hypothesis sweeps, [2] plain sweeps
+	const void *srec;         // hb_decode_scan.cuh: one ScanRec per rank
 };
 
 // one reconstruction step for all components of a rank.  `get(r)` returns the record of rank r.

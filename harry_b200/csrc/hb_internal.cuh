@@ -79,6 +79,7 @@ struct DevList {
 	struct Spec3Scratch *d_spec3_scratch = nullptr;
 	uint32_t *d_spec3_excl = nullptr;
 	uint8_t *d_spec3_inner = nullptr;
+	void *d_srec = nullptr;             // hb_decode_scan.cuh records
 	uint32_t *d_wide = nullptr;         // encode: elements deferred to the warp-per-element kernel
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
