@@ -218,8 +218,10 @@ def algorithmic_bytes(w: Workload) -> dict:
     return {
         "k_bounds_reduce": A * s,
         "k_requant": A * (s + wd),
-        "k_vertex_candidates<false>": conn + 4.0 * nv,
-        "k_vertex_candidates<true>": conn + 12.0 * P * nv,
+        "k_vertex_candidates_stage": conn + 4.0 * nv + 12.0 * P * nv,
+        "k_vertex_candidates_compact": 2 * 12.0 * P * nv + 4.0 * nv,
+        "k_decode_vertex_scan": k5,
+        "k_scan_prep": 12.0 * P * nv + 9.0 * nv + 64.0 * nv,
         "k_encode_main<CLS_VTX>": k5,
         "k_decode_vertex_chain": k5,
         "k_decode_vertex_spec3": k5,

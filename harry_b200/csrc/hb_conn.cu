@@ -257,25 +257,277 @@ __device__ __forceinline__ void paral_visit(const uint4 *__restrict__ he, uint32
 	if (deg > 4) sink.offer(v0, v1, v1); // second "parallelogram" of an n-gon degenerates (Appendix C.3)
 }
 
-template <bool FILL>
-__global__ void __launch_bounds__(256) k_vertex_candidates(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ ord_v,
-                                                            const uint32_t *__restrict__ vrank, const uint16_t *__restrict__ vtx_regs, uint32_t n, uint32_t ne,
-                                                            uint32_t *__restrict__ cnt_or_off, uint32_t *__restrict__ tri, int *err)
+// Pass 1 (MODE_STAGE): one fan walk per traversed vertex; the first VC_STAGE accepted
+// parallelograms are parked in a fixed-size staging slot, the count goes to cnt[].  After the scan
+// of the counts k_vertex_candidates_compact streams the staged triples into the CSR; only vertices
+// with more than VC_STAGE parallelograms (poles, closing vertices) walk their fan a second time
+// (MODE_FILL, restricted to those vertices).
+#define VC_STAGE 4
+struct ParalStageSink {
+	const uint32_t *vrank;
+	const uint16_t *vtx_regs;
+	uint32_t self;
+	uint16_t reg;
+	uint32_t count;
+	uint32_t *stage; // VC_STAGE triples
+	__device__ __forceinline__ void offer(uint32_t v0, uint32_t v1, uint32_t vo)
+	{
+		const uint32_t r0 = vrank[v0], r1 = vrank[v1], ro = vrank[vo];
+		if (r0 >= self || r1 >= self || ro >= self) return;
+		if (vtx_regs[v0] != reg || vtx_regs[v1] != reg || vtx_regs[vo] != reg) return;
+		if (count < VC_STAGE) {
+			stage[3 * count] = r0;
+			stage[3 * count + 1] = r1;
+			stage[3 * count + 2] = ro;
+		}
+		++count;
+	}
+};
+template <typename Sink>
+__device__ __forceinline__ void paral_visit_t(const uint4 *__restrict__ he, uint32_t e, const uint4 &rec, Sink &sink)
+{
+	const uint32_t deg = rec.z >> 16;
+	if (deg == 3) {
+		const uint32_t e1 = he_next(e, rec.z);
+		const uint32_t t = he[e1].y;
+		if (t == e1) return;
+		const uint4 rt = he[t];
+		const uint32_t tn = he_next(t, rt.z);
+		const uint4 rtn = he[tn];
+		const uint32_t tnn = he_next(tn, rtn.z);
+		sink.offer(rt.x, rtn.x, he[tnn].x);
+		return;
+	}
+	const uint32_t e0 = he_next(e, rec.z), e1 = he_prev(e, rec.z);
+	const uint4 r0 = he[e0];
+	const uint32_t v0 = r0.x, v1 = he[e1].x;
+	sink.offer(v0, v1, he[he_next(e0, r0.z)].x);
+	if (deg > 4) sink.offer(v0, v1, v1); // second "parallelogram" of an n-gon degenerates (Appendix C.3)
+}
+
+// Wide fans.  A fan is a linked list (e -> next(twin(e))): a thread that has not closed it after
+// VC_WALK_CAP steps hands the vertex over to the wide path, which collects the vertex's half-edges
+// with one streaming pass, ranks the list by pointer doubling and evaluates the parallelograms of
+// all fan positions in parallel -- a 4472-face sphere pole costs one thread ~5 ms, the wide path
+// well under a millisecond.  More than VC_MAXWIDE such vertices: the rest walk sequentially.
+#define VC_WALK_CAP 64
+#define VC_MAXWIDE 64
+#define VC_WIDE_MARK 0xffffffffu
+struct WideCtl {
+	uint32_t n;                    // wide vertices registered (may exceed VC_MAXWIDE)
+	uint32_t vtx[VC_MAXWIDE], rank[VC_MAXWIDE], deg[VC_MAXWIDE], base[VC_MAXWIDE + 1], fill[VC_MAXWIDE], ncand[VC_MAXWIDE];
+};
+
+__global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ ord_v,
+                                                                  const uint32_t *__restrict__ vrank, const uint16_t *__restrict__ vtx_regs, uint32_t n, uint32_t ne,
+                                                                  uint32_t *__restrict__ cnt, uint32_t *__restrict__ stage, WideCtl *__restrict__ wide, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
+	// a parallelogram needs three vertices coded earlier (two for the degenerate n-gon case): the
+	// first two traversal positions cannot have any, whatever their fan looks like
+	if (i < 2) { cnt[i] = 0; return; }
+	ParalStageSink sink;
+	sink.vrank = vrank;
+	sink.vtx_regs = vtx_regs;
+	sink.self = i;
+	sink.reg = vtx_regs[ord_v[i]];
+	sink.count = 0;
+	uint32_t st[3 * VC_STAGE];
+	sink.stage = st;
+	bool ok = fan_walk(he, ord_h[i], VC_WALK_CAP, [&](uint32_t e, const uint4 &rec) { paral_visit_t(he, e, rec, sink); });
+	if (!ok) {
+		const uint32_t slot = atomicAdd(&wide->n, 1u);
+		if (slot < VC_MAXWIDE) {
+			wide->vtx[slot] = ord_v[i];
+			wide->rank[slot] = i;
+			cnt[i] = 0; // set by k_wide_rank
+			stage[(size_t)i * 3 * VC_STAGE] = VC_WIDE_MARK;
+			return;
+		}
+		sink.count = 0;
+		ok = fan_walk(he, ord_h[i], ne + 2, [&](uint32_t e, const uint4 &rec) { paral_visit_t(he, e, rec, sink); });
+		if (!ok) atomicExch(err, 5);
+	}
+	cnt[i] = sink.count;
+	if (sink.count) {
+		uint4 *o = (uint4 *)(stage + (size_t)i * 3 * VC_STAGE);
+		o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+		if (sink.count > 1) o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+		if (sink.count > 2) o[2] = make_uint4(st[8], st[9], st[10], st[11]);
+	}
+}
+
+// Pass 2: staged triples -> CSR (streaming); vertices that overflowed the staging slot walk again
+__global__ void __launch_bounds__(256) k_vertex_candidates_compact(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ ord_v,
+                                                                    const uint32_t *__restrict__ vrank, const uint16_t *__restrict__ vtx_regs, uint32_t n, uint32_t ne,
+                                                                    const uint32_t *__restrict__ off, const uint32_t *__restrict__ stage, uint32_t *__restrict__ tri, int *err)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t o0 = off[i], K = off[i + 1] - o0;
+	if (K == 0) return;
+	if (stage[(size_t)i * 3 * VC_STAGE] == VC_WIDE_MARK) return; // written by k_wide_copy
+	if (K <= VC_STAGE) {
+		const uint32_t *st = stage + (size_t)i * 3 * VC_STAGE;
+		for (uint32_t w = 0; w < 3 * K; ++w) tri[3 * (size_t)o0 + w] = st[w];
+		return;
+	}
 	ParalSink sink;
 	sink.vrank = vrank;
 	sink.vtx_regs = vtx_regs;
 	sink.self = i;
 	sink.reg = vtx_regs[ord_v[i]];
 	sink.count = 0;
-	sink.out = FILL ? tri + 3 * (size_t)cnt_or_off[i] : nullptr;
-	// a vertex visited twice would see itself as coded the second time; the reference marks a
-	// vertex coded after its first visit (attrcode.h:218), which vrank (first visit) reproduces.
+	sink.out = tri + 3 * (size_t)o0;
 	const bool ok = fan_walk(he, ord_h[i], ne + 2, [&](uint32_t e, const uint4 &rec) { paral_visit(he, e, rec, sink); });
 	if (!ok) atomicExch(err, 5);
-	if (!FILL) cnt_or_off[i] = sink.count;
+}
+
+// ---- wide fans ---------------------------------------------------------------------------------
+// half-edges whose origin is a wide vertex: count per vertex (SCATTER = false), then scatter into
+// contiguous node lists and note every node's index (SCATTER = true)
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ he, uint32_t ne, WideCtl *__restrict__ wide, uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos)
+{
+	__shared__ uint32_t s_v[VC_MAXWIDE];
+	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
+	if (threadIdx.x < nw) s_v[threadIdx.x] = wide->vtx[threadIdx.x];
+	__syncthreads();
+	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
+		const uint32_t org = he[e].x;
+		for (uint32_t w = 0; w < nw; ++w) {
+			if (org != s_v[w]) continue;
+			if (!SCATTER) atomicAdd(&wide->deg[w], 1u);
+			else {
+				const uint32_t idx = wide->base[w] + atomicAdd(&wide->fill[w], 1u);
+				nodes[idx] = e;
+				pos[e] = idx;
+			}
+		}
+	}
+}
+__global__ void k_wide_bases(WideCtl *wide)
+{
+	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
+	uint32_t acc = 0;
+	for (uint32_t w = 0; w < nw; ++w) { wide->base[w] = acc; acc += wide->deg[w]; wide->fill[w] = 0; }
+	wide->base[nw] = acc;
+}
+
+// One CTA per wide vertex: rank its fan by pointer doubling (distance to the tail of the
+// e -> next(twin(e)) path, the path cut in front of the gate half-edge when the fan is closed),
+// turn the ranks into the visiting order of fan_walk (forward from the gate, then backward from
+// the gate's predecessor), and evaluate paral() for every position in parallel.  Triples go to
+// `arena` (two per node at most) in visiting order; the count goes to cnt[rank].
+#define WIDE_T 1024
+__global__ void __launch_bounds__(WIDE_T) k_wide_rank(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ vrank,
+                                                      const uint16_t *__restrict__ vtx_regs, WideCtl *__restrict__ wide, const uint32_t *__restrict__ nodes,
+                                                      const uint32_t *__restrict__ pos, uint32_t *nxtA, uint32_t *nxtB, uint32_t *dA, uint32_t *dB, uint32_t *lastA, uint32_t *lastB,
+                                                      uint32_t *__restrict__ order, uint32_t *__restrict__ arena, uint32_t *__restrict__ cnt, int *err)
+{
+	const uint32_t NIL = 0xffffffffu;
+	const uint32_t slot = blockIdx.x, t = threadIdx.x;
+	const uint32_t b = wide->base[slot], d = wide->deg[slot], self = wide->rank[slot];
+	const uint32_t ein = ord_h[self];
+	const uint16_t reg = vtx_regs[wide->vtx[slot]];
+	__shared__ uint32_t s_warp[32], s_carry, s_total;
+	for (uint32_t k = t; k < d; k += WIDE_T) {
+		const uint32_t e = nodes[b + k];
+		const uint4 rec = he[e];
+		uint32_t sidx = NIL;
+		if (rec.y != e) {
+			const uint32_t e2 = he_next(rec.y, he[rec.y].z);
+			if (e2 != ein) sidx = pos[e2] - b;
+		}
+		nxtA[b + k] = sidx;
+		dA[b + k] = sidx == NIL ? 0u : 1u;
+		lastA[b + k] = k;
+		order[b + k] = NIL;
+	}
+	__syncthreads();
+	for (uint32_t span = 1; span < d; span <<= 1) {
+		for (uint32_t k = t; k < d; k += WIDE_T) {
+			const uint32_t sidx = nxtA[b + k];
+			if (sidx != NIL && sidx < d) {
+				dB[b + k] = dA[b + k] + dA[b + sidx];
+				nxtB[b + k] = nxtA[b + sidx];
+				lastB[b + k] = lastA[b + sidx];
+			} else {
+				dB[b + k] = dA[b + k];
+				nxtB[b + k] = NIL;
+				lastB[b + k] = lastA[b + k];
+			}
+		}
+		__syncthreads();
+		uint32_t *tp;
+		tp = nxtA; nxtA = nxtB; nxtB = tp;
+		tp = dA; dA = dB; dB = tp;
+		tp = lastA; lastA = lastB; lastB = tp;
+	}
+	const uint32_t kin = pos[ein] - b;
+	if (kin >= d || nxtA[b + kin] != NIL) { if (t == 0) atomicExch(err, 5); return; } // the gate's path does not end: inconsistent twins
+	const uint32_t D = dA[b + kin], tail = lastA[b + kin];
+	// visiting position: nodes behind the gate D - dtail, nodes in front of it (open fan) dtail
+	for (uint32_t k = t; k < d; k += WIDE_T) {
+		if (lastA[b + k] != tail) continue; // another fan of a non-manifold vertex
+		const uint32_t dt = dA[b + k];
+		const uint32_t p = dt <= D ? D - dt : dt;
+		if (p < d) order[b + p] = nodes[b + k];
+	}
+	if (t == 0) s_carry = 0;
+	__syncthreads();
+	for (uint32_t p0 = 0; p0 < d; p0 += WIDE_T) {
+		const uint32_t p = p0 + t;
+		ParalStageSink sink;
+		sink.vrank = vrank;
+		sink.vtx_regs = vtx_regs;
+		sink.self = self;
+		sink.reg = reg;
+		sink.count = 0;
+		uint32_t st[3 * VC_STAGE];
+		sink.stage = st;
+		if (p < d) {
+			const uint32_t e = order[b + p];
+			if (e != NIL) paral_visit_t(he, e, he[e], sink);
+		}
+		// exclusive scan of the per-position counts (0..2)
+		const uint32_t c = sink.count;
+		uint32_t x = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, x, o);
+			if ((int)(t & 31) >= o) x += up;
+		}
+		if ((t & 31) == 31) s_warp[t >> 5] = x;
+		__syncthreads();
+		if (t < 32) {
+			uint32_t w = s_warp[t];
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t up = __shfl_up_sync(0xffffffffu, w, o);
+				if ((int)t >= o) w += up;
+			}
+			s_warp[t] = w;
+			if (t == 31) s_total = w;
+		}
+		__syncthreads();
+		const uint32_t excl = s_carry + x - c + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+		for (uint32_t j = 0; j < c; ++j) {
+			uint32_t *o = arena + 3 * (size_t)(2 * b + excl + j);
+			o[0] = st[3 * j]; o[1] = st[3 * j + 1]; o[2] = st[3 * j + 2];
+		}
+		__syncthreads();
+		if (t == 0) s_carry += s_total;
+		__syncthreads();
+	}
+	if (t == 0) { wide->ncand[slot] = s_carry; cnt[self] = s_carry; }
+}
+__global__ void __launch_bounds__(256) k_wide_copy(const WideCtl *__restrict__ wide, const uint32_t *__restrict__ off, const uint32_t *__restrict__ arena, uint32_t *__restrict__ tri)
+{
+	const uint32_t slot = blockIdx.x;
+	const uint32_t nc = wide->ncand[slot], b = wide->base[slot], o0 = off[wide->rank[slot]];
+	for (uint32_t w = threadIdx.x; w < 3 * nc; w += blockDim.x) tri[3 * (size_t)o0 + w] = arena[3 * (size_t)(2 * b) + w];
 }
 
 // corner candidates: fan faces coded earlier (face rank smaller) in the same face region
@@ -355,13 +607,48 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 	HB_TRY(hb_dalloc_t(m, &m->d_vc_off, (size_t)n + 2));
 	m->vc_total = 0;
 	if (n) {
-		HB_LAUNCH(ctx, k_vertex_candidates<false>, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, (uint32_t *)nullptr, ctx->d_err);
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_stage, (size_t)n * 3 * VC_STAGE + 4));
+		uint32_t *stage = m->d_vc_stage;
+		WideCtl *wide = nullptr;
+		HB_TRY(hb_dalloc(m, &m->d_vc_wide, sizeof(WideCtl)));
+		wide = (WideCtl *)m->d_vc_wide;
+		HB_CUDA(ctx, cudaMemsetAsync(wide, 0, sizeof(WideCtl), ctx->stream));
+		HB_LAUNCH(ctx, k_vertex_candidates_stage, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, wide, ctx->d_err);
+		uint32_t nwide = 0;
+		HB_CUDA(ctx, cudaMemcpyAsync(&nwide, &wide->n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (nwide > VC_MAXWIDE) nwide = VC_MAXWIDE;
+		uint32_t *arena = nullptr;
+		if (nwide) {
+			const uint32_t grid = (uint32_t)ctx->sm_count * 8;
+			HB_LAUNCH(ctx, k_wide_collect<false>, grid, 256, 0, m->d_he, m->ne, wide, (uint32_t *)nullptr, (uint32_t *)nullptr);
+			HB_LAUNCH(ctx, k_wide_bases, 1, 1, 0, wide);
+			uint32_t total = 0;
+			HB_CUDA(ctx, cudaMemcpyAsync(&total, &wide->base[nwide], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+			HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			// scratch of the wide path: sized by this mesh's wide fans, released with the mesh
+			uint32_t *nodes = nullptr, *pos = nullptr, *work = nullptr, *order = nullptr;
+			if (total > m->vc_wide_cap) {
+				m->d_vc_wnodes = m->d_vc_wwork = m->d_vc_worder = m->d_vc_warena = nullptr; // the old ones stay in m->allocs until the mesh is freed
+				m->vc_wide_cap = total;
+			}
+			HB_TRY(hb_dalloc_t(m, &m->d_vc_wnodes, (size_t)total + 1));
+			HB_TRY(hb_dalloc_t(m, &m->d_vc_wpos, (size_t)m->ne + 1));
+			HB_TRY(hb_dalloc_t(m, &m->d_vc_wwork, 6 * (size_t)total + 6));
+			HB_TRY(hb_dalloc_t(m, &m->d_vc_worder, (size_t)total + 1));
+			HB_TRY(hb_dalloc_t(m, &m->d_vc_warena, 6 * (size_t)total + 6));
+			nodes = m->d_vc_wnodes; pos = m->d_vc_wpos; work = m->d_vc_wwork; order = m->d_vc_worder; arena = m->d_vc_warena;
+			HB_LAUNCH(ctx, k_wide_collect<true>, grid, 256, 0, m->d_he, m->ne, wide, nodes, pos);
+			HB_LAUNCH(ctx, k_wide_rank, nwide, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + total, work + 2 * (size_t)total, work + 3 * (size_t)total,
+			          work + 4 * (size_t)total, work + 5 * (size_t)total, order, arena, m->d_vc_off, ctx->d_err);
+		}
 		HB_TRY(hb_scan_exclusive_u32(ctx, m->d_vc_off, m->d_vc_off, n, nullptr));
 		HB_CUDA(ctx, cudaMemcpyAsync(&m->vc_total, m->d_vc_off + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 		HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		HB_TRY(hb_check_device_error(ctx, "vertex fan walk"));
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_tri, 3 * (size_t)m->vc_total + 3));
-		HB_LAUNCH(ctx, k_vertex_candidates<true>, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, m->d_vc_tri, ctx->d_err);
+		HB_LAUNCH(ctx, k_vertex_candidates_compact, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, m->d_vc_tri, ctx->d_err);
+		if (nwide) HB_LAUNCH(ctx, k_wide_copy, nwide, 256, 0, wide, m->d_vc_off, arena, m->d_vc_tri);
 	} else {
 		HB_CUDA(ctx, cudaMemsetAsync(m->d_vc_off, 0, sizeof(uint32_t) * 2, ctx->stream));
 	}

@@ -233,8 +233,8 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_cx, 0, (size_t)(n + 1) * ncp * esize, ctx->stream));
 	ScanRec *srec = nullptr;
 	if (st != HB_FLOAT) {
-		HB_TRY(hb_dalloc_t(m, &srec, (size_t)n + 1));
-		dl.d_srec = srec;
+		HB_TRY(hb_dalloc(m, &dl.d_srec, sizeof(ScanRec) * ((size_t)n + 1)));
+		srec = (ScanRec *)dl.d_srec;
 		HB_LAUNCH(ctx, k_scan_prep, g, 256, 0, dl.d_kind, dl.d_src, m->d_vc_off, m->d_vc_tri, n, srec);
 	}
 	SpecArgs a;
