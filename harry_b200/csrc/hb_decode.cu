@@ -157,12 +157,12 @@ static int launch_spec3(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, Spec3Scr
 	}
 }
 
-// cluster launch of the verified-scan kernel (integer lists)
-template <typename T, int NC>
-static int launch_scan_nc(hb_ctx *ctx, const SpecArgs *d_args, int cluster)
+// cluster launch of the verified-scan kernel (integer lists): one cluster per component
+template <typename T>
+static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster)
 {
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(cluster);
+	cfg.gridDim = dim3(cluster * ncomp);
 	cfg.blockDim = dim3(SCAN_NTB);
 	cfg.dynamicSmemBytes = 0;
 	cfg.stream = ctx->stream;
@@ -173,23 +173,13 @@ static int launch_scan_nc(hb_ctx *ctx, const SpecArgs *d_args, int cluster)
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	if (cluster > 8) HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_scan<T, NC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	if (cluster > 8) HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_scan<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 	cudaEvent_t pa = nullptr, pb = nullptr;
 	if (ctx->profiling) { pa = hb_prof_event(ctx); pb = hb_prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
-	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_decode_vertex_scan<T, NC>, d_args));
+	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_decode_vertex_scan<T>, d_args, (uint32_t)ncomp));
 	ctx->launches++;
 	if (pa) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back(hb_ctx::ProfRec{ "k_decode_vertex_scan", pa, pb }); }
 	return 0;
-}
-template <typename T>
-static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster)
-{
-	switch (ncomp) {
-	case 1: return launch_scan_nc<T, 1>(ctx, d_args, cluster);
-	case 2: return launch_scan_nc<T, 2>(ctx, d_args, cluster);
-	case 3: return launch_scan_nc<T, 3>(ctx, d_args, cluster);
-	default: return launch_scan_nc<T, 4>(ctx, d_args, cluster);
-	}
 }
 // CTAs per cluster: the window is about one cut-border length (~ sqrt(2 n) on a regular mesh);
 // two ranks per thread
@@ -197,7 +187,8 @@ static int scan_cluster_size(uint32_t n, int ncomp)
 {
 	static const char *env = getenv("HARRY_B200_SCAN_CLUSTER");
 	if (env && atoi(env) > 0) return atoi(env) > SCAN_MAXC ? SCAN_MAXC : atoi(env);
-	const double need = 1.2 * sqrt(2.0 * (double)n) / (double)(SCAN_NWARP * (32 / ncomp));
+	(void)ncomp;
+	const double need = 1.2 * sqrt(2.0 * (double)n) / (double)SCAN_NTB;
 	int c = 1;
 	while (c < SCAN_MAXC && (double)c < need) c <<= 1;
 	return c;

@@ -29,10 +29,11 @@
 //   D. verification: thread t is "good" iff the exact end value of thread t equals the presumed start
 //      value of thread t + 1.  Thread 0 starts from x[done - 1], which is final; by induction every
 //      rank up to the first bad boundary is the sequential result.  done = min(that boundary, E).
-// Machine mapping: one thread-block cluster per list; a group of NC adjacent lanes owns ONE rank of
-// the window and every lane of the group carries one component (R = 1 in the description above) --
-// instruction issue on the cluster's SMs is what bounds a sweep, so the per-rank classification is
-// done once, in the prep kernel, and components run side by side in lanes.
+// Machine mapping: one thread-block cluster per (list, component) -- the components of an integer list
+// are independent chains, so they run on different SMs -- and one thread per rank of the window
+// (R = 1 in the description above).  A sweep is bounded by dependent-instruction latency and by the
+// two cluster barriers, not by bandwidth: the per-rank classification is done once, in the prep
+// kernel, and the cluster is sized so that an SM holds only a few active warps.
 // Progress is at least one rank per sweep for ANY input (group 0 is always exact); the algebra only
 // decides how far `done` moves.  Ranks with more than SCAN_WIDE candidates (sphere poles) end the
 // window and are evaluated by a whole CTA when `done` reaches them (integer sums commute).
@@ -42,7 +43,7 @@
 
 namespace cgs = cooperative_groups;
 
-#define SCAN_NTB 1024
+#define SCAN_NTB 512
 #define SCAN_NWARP (SCAN_NTB / 32)
 #define SCAN_KIN 4            // candidates held inline in a ScanRec
 #define SCAN_WIDE 32          // more candidates: evaluated cooperatively when first in the window
@@ -116,15 +117,17 @@ template <typename SW, typename W> __device__ __noinline__ SW scan_floordiv_slow
 // degenerate step B + [x + A >= CAP]; a constant is (CAP, 0, c).
 // 8/16-bit storage types: M = 2^sm when sm < 32 (the common case: 1, 2 or 4 parallelograms, constants,
 // steps -- shifts only); other divisors keep M in sm >> 8 with 0xff in the low byte.
-template <typename T> struct FMap {
+template <typename T> struct alignas(16) FMap {
 	typedef uint32_t W;
 	typedef int32_t SW;
 	static constexpr int CB = 8 * (int)sizeof(T);
 	uint32_t sm, A;
 	int32_t B;
+	uint32_t pad_;
 	static __device__ __forceinline__ FMap identity() { FMap f; f.sm = 0; f.A = 0; f.B = 0; return f; }
 	static __device__ __forceinline__ FMap constant(SW c, int cb) { FMap f; f.sm = (uint32_t)cb; f.A = 0; f.B = c; return f; }
 	__device__ __forceinline__ uint32_t divisor() const { return sm < 32u ? 1u << sm : sm >> 8; }
+	__device__ __forceinline__ bool is_step(int cb) const { return sm == (uint32_t)cb; } // takes the values B and B + 1 only
 	static __device__ __forceinline__ FMap make(uint32_t M, uint32_t A, SW B) // M <= CAP
 	{
 		FMap f;
@@ -157,12 +160,14 @@ template <typename T> struct FMap {
 	}
 };
 // 32-bit storage types: general form only (64-bit parameters, 128-bit products)
-template <> struct FMap<uint32_t> {
+template <> struct alignas(16) FMap<uint32_t> {
 	typedef unsigned long long W;
 	typedef long long SW;
 	W M, A;
 	SW B;
+	unsigned long long pad_;
 	static __device__ __forceinline__ W cap() { return (W)1 << 32; }
+	__device__ __forceinline__ bool is_step(int) const { return M == cap(); }
 	static __device__ __forceinline__ FMap identity() { FMap f; f.M = 1; f.A = 0; f.B = 0; return f; }
 	static __device__ __forceinline__ FMap constant(SW c, int) { FMap f; f.M = cap(); f.A = 0; f.B = c; return f; }
 	static __device__ __forceinline__ SW floordiv(SW c, W m)
@@ -215,9 +220,15 @@ template <typename T> __device__ __forceinline__ FMap<T> scan_compose(const FMap
 		}
 		return f;
 	}
+	// some divisor is not a power of two (3, 5, 6, 7 .. parallelograms).  |Cc| < 2^24 and M2 <= 2^16
+	// for in-range data: a float quotient with one correction step is exact there, and for anything
+	// else the map is garbage that the verification discards anyway.
 	const uint32_t M1 = f1.divisor(), M2 = f2.divisor();
-	const int q = Cc >= 0 ? (int)((uint32_t)Cc / M2) : -(int)(((uint32_t)(-Cc) + M2 - 1u) / M2);
-	const uint32_t r = (uint32_t)(Cc - q * (int)M2);
+	int q = __float2int_rd(__fdividef((float)Cc, (float)M2));
+	int rr = Cc - q * (int)M2;
+	if (rr < 0) { --q; rr += (int)M2; }
+	if (rr >= (int)M2) { ++q; rr -= (int)M2; }
+	const uint32_t r = (uint32_t)rr;
 	const unsigned long long M = (unsigned long long)M1 * M2;
 	const unsigned long long A = (unsigned long long)f1.A + (unsigned long long)M1 * r;
 	f.B = f2.B + q;
@@ -289,6 +300,32 @@ template <> __device__ __forceinline__ FMap<uint32_t> scan_shfl<uint32_t>(const 
 	return r;
 }
 
+// ---- cluster plumbing: asynchronous remote shared-memory stores that complete a transaction barrier
+// in the destination CTA (st.async + mbarrier complete_tx) -- a consumer warp waits for exactly the
+// bytes it was promised instead of for a barrier over the whole cluster
+__device__ __forceinline__ uint32_t scan_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t scan_mapa(uint32_t addr, uint32_t cta)
+{
+	uint32_t r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+	return r;
+}
+__device__ __forceinline__ void scan_st_async_v4(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void scan_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void scan_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.release.cta.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool scan_mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred P_OUT;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P_OUT, [%1], %2;\n\tselp.b32 %0, 1, 0, P_OUT;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	return ok != 0;
+}
+
 // L2-coherent scalar load (values are rewritten between sweeps by other SMs of the cluster)
 __device__ __forceinline__ uint32_t scan_ld(const uint8_t *p) { return __ldcg((const unsigned char *)p); }
 __device__ __forceinline__ uint32_t scan_ld(const uint16_t *p) { return __ldcg((const unsigned short *)p); }
@@ -351,7 +388,7 @@ __device__ __forceinline__ uint32_t scan_std_step(uint32_t cur, uint32_t va, uin
 // rank `predrank` reads pv; ranks >= lo come from the stretch buffer `sq` (sequential mode, else
 // lo = 0xffffffff); everything else from the value array.
 template <typename T>
-__device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ cand, const T *xc, uint32_t cs, uint32_t predrank, uint32_t pv, const T *sq, uint32_t lo,
+__device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ cand, const T *xc, uint32_t cs, uint32_t predrank, uint32_t pv, const T *sq, uint32_t sqs, uint32_t lo,
                                                    uint32_t c0, uint32_t K, uint32_t delta, uint32_t hi)
 {
 	typedef typename FMap<T>::W W;
@@ -362,7 +399,7 @@ __device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ 
 #pragma unroll
 		for (int o = 0; o < 3; ++o) {
 			const uint32_t r = __ldg(tr + o);
-			v[o] = r == predrank ? pv : (r >= lo ? (uint32_t)sq[(size_t)(r - lo) * cs] : scan_ld(xc + (size_t)r * cs));
+			v[o] = r == predrank ? pv : (r >= lo ? (uint32_t)sq[(size_t)(r - lo) * sqs] : scan_ld(xc + (size_t)r * cs));
 		}
 		sum += (W)ScanOps<T>::predict(v[0], v[1], v[2], hi);
 	}
@@ -377,55 +414,63 @@ __device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ 
 #define SCAN_PROBE(i, ta, tb)
 #endif
 
-template <typename T, int NC>
-__global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecArgs *__restrict__ args)
+template <typename T>
+__global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecArgs *__restrict__ args, uint32_t ncomp)
 {
 	typedef FMap<T> Map;
 	typedef typename Map::W W;
 	typedef typename Map::SW SW;
-	constexpr uint32_t RS = NC == 3 ? 4 : NC;          // elements per value record
-	constexpr uint32_t G = 32 / NC;                    // groups (ranks) per warp; lanes >= G * NC idle
+	constexpr int NC = 1;                              // components per thread group (one cluster per component)
+	constexpr uint32_t G = 32;                         // ranks per warp
 	constexpr uint32_t NSEG = SCAN_NWARP * G;          // ranks per CTA and sweep
 	cgs::cluster_group cluster = cgs::this_cluster();
 	const uint32_t C = cluster.num_blocks();
 	const uint32_t crank = cluster.block_rank();
-	const uint32_t list = blockIdx.x / C;
+	const uint32_t job = blockIdx.x / C;               // (list, component)
+	const uint32_t list = job / ncomp;
+	const uint32_t c = job % ncomp;                    // my component
 	const SpecArgs a = args[list];
+	const uint32_t RS = ncomp == 3 ? 4 : ncomp;        // elements per value record
 	const ScanRec *__restrict__ srec = (const ScanRec *)a.srec;
 	const uint32_t n = a.n;
 	const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	const uint32_t grp = lane / NC;                     // my group within the warp
-	const bool live = grp < G;                          // lanes beyond the last full group only join shuffles
-	const uint32_t c = live ? lane % NC : 0;            // my component
-	const uint32_t q = warp * G + (live ? grp : G - 1); // my rank slot within the CTA
+	const uint32_t grp = lane;
+	constexpr bool live = true;
+	const uint32_t q = t;                               // my rank slot within the CTA
 	const T *__restrict__ rc = (const T *)a.resid + c;  // component views: element r at [r * RS]
 	T *xc = (T *)a.x + c;
 	const uint32_t NSEGT = C * NSEG;                    // ranks per window
 
-	__shared__ Map s_wtot[SCAN_NWARP][NC];      // inclusive warp totals of this CTA
-	__shared__ Map s_ctot[SCAN_MAXC][NC];       // CTA totals of the whole cluster (pushed by their owners)
+	__shared__ Map s_all[SCAN_MAXC * SCAN_NWARP]; // warp totals of the whole cluster (pushed by their owners), active warps only
+	__shared__ __align__(8) unsigned long long s_bar; // transaction barrier of the incoming totals
 	__shared__ uint32_t s_ndE[SCAN_MAXC];       // per CTA: first rank that reads a non-final window value
 	__shared__ uint32_t s_ndF[SCAN_MAXC];       // per CTA: first rank behind a failed boundary check
 	__shared__ uint32_t s_start[NSEG + 1][NC];  // presumed start value of every slot (+ of the next CTA's first slot)
-	__shared__ uint32_t s_vcta[NC];             // start value of this CTA's first slot
 	__shared__ uint32_t s_minE, s_minF;
 	__shared__ unsigned long long s_sum[4];
-	__shared__ T s_seq[SCAN_SEQ_MAX * RS];      // values of a sequential stretch
+	__shared__ T s_seq[SCAN_SEQ_MAX + 6 * 32];  // values of a sequential stretch + the final operands of the current batch
 
 	const uint32_t hi = (uint32_t)IntOps<T>::mask(a.bits[c]);
 	const int cb = a.bits[c];
-	const int cbw = a.bits[warp < (uint32_t)NC ? warp : 0]; // warps 0 .. NC-1 scan the totals of component `warp`
+	const int cbw = cb;
 	const int lgC = 31 - __clz((int)C);
 
 	uint32_t done = 0, gend = 0, est = NSEGT;
 	bool widehead = false, seqmode = false, lastseq = false;
-	uint32_t seqlen = SCAN_SEQ_MIN;
-	unsigned long long sweeps = 0, fails = 0, wides = 0, capped = 0, nseq = 0;
+	uint32_t seqlen = SCAN_SEQ_MIN, smallrun = 0;
+	unsigned long long sweeps = 0, fails = 0, wides = 0, capped = 0, nseq = 0, nfallback = 0;
 	long long cyA = 0, cyB = 0, cyC = 0, cyD = 0;
 #ifdef SCAN_DEBUG
 	long long pr[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #endif
 	auto csync = [&]() { if (C > 1) cluster.sync(); else __syncthreads(); };
+	const uint32_t bar = scan_smem_u32(&s_bar);
+	uint32_t bar_parity = 0;
+	if (t == 0) {
+		scan_mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	cluster.sync();
 
 	while (done < n) {
 		const long long tA = clock64();
@@ -444,10 +489,10 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 						const uint32_t v0 = scan_ld(xc + (size_t)tr[0] * RS), v1 = scan_ld(xc + (size_t)tr[1] * RS), v2 = scan_ld(xc + (size_t)tr[2] * RS);
 						sum += (unsigned long long)ScanOps<T>::predict(v0, v1, v2, hi);
 					}
-					atomicAdd(&s_sum[c], sum);
+					atomicAdd(&s_sum[0], sum);
 				}
 				__syncthreads();
-				if (t < (uint32_t)NC) xc[(size_t)done * RS] = (T)ScanOps<T>::dec(rc[(size_t)done * RS], (uint32_t)(T)hb_divround_i64((long long)s_sum[c], (int)K0), hi);
+				if (t == 0) xc[(size_t)done * RS] = (T)ScanOps<T>::dec(rc[(size_t)done * RS], (uint32_t)(T)hb_divround_i64((long long)s_sum[0], (int)K0), hi);
 			}
 			csync();
 			++done;
@@ -478,42 +523,45 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 					const uint32_t res = rc[(size_t)i * RS];
 					const unsigned wm = __ballot_sync(0xffffffffu, valid && kd == 1 && K > SCAN_WIDE);
 					const uint32_t nl = wm ? ((uint32_t)__ffs((int)wm) - 1u) / NC : G;
-					uint32_t ov[6];
+					// operands of the (up to two) inline candidates: final ones are fetched now and parked
+					// behind the stretch buffer, so that the serial step reads all six through one
+					// precomputed shared-memory index each
+					uint32_t oi[6];
 #pragma unroll
 					for (int w = 0; w < 6; ++w) {
-						ov[w] = 0;
-						if (valid && kd == 1 && K <= 2 && (uint32_t)(w / 3) < K && tri[w] < done) ov[w] = scan_ld(xc + (size_t)tri[w] * RS);
+						oi[w] = SCAN_SEQ_MAX + 6 * lane + w;
+						uint32_t cvw = 0;
+						if (valid && kd == 1 && K <= 2 && (uint32_t)(w / 3) < K) {
+							if (tri[w] < done) cvw = scan_ld(xc + (size_t)tri[w] * RS);
+							else oi[w] = tri[w] - done;
+						}
+						s_seq[SCAN_SEQ_MAX + 6 * lane + w] = (T)cvw;
 					}
 					uint32_t cv = 0;
 					if (valid && kd == 0) cv = scan_ld(xc + (size_t)i * RS);
 					if (valid && kd == 2 && aux < done) cv = scan_ld(xc + (size_t)aux * RS);
+					__syncwarp();
 #pragma unroll 1
 					for (uint32_t j = 0; j < nl; ++j) {
 						if (grp == j && valid) {
 							uint32_t val = cv;
-							if (kd == 2 && aux >= done) val = s_seq[(aux - done) * RS + c];
+							if (kd == 2 && aux >= done) val = s_seq[aux - done];
 							if (kd == 1 && K <= 2) {
-								W sum = 0;
-#pragma unroll
-								for (int cj = 0; cj < 2; ++cj) {
-									if ((uint32_t)cj >= K) continue;
-									uint32_t v[3];
-#pragma unroll
-									for (int o = 0; o < 3; ++o) v[o] = tri[3 * cj + o] < done ? ov[3 * cj + o] : (uint32_t)s_seq[(tri[3 * cj + o] - done) * RS + c];
-									sum += (W)ScanOps<T>::predict(v[0], v[1], v[2], hi);
-								}
-								val = ScanOps<T>::dec(res, scan_mean<T>(sum, K), hi);
+								const uint32_t p0 = ScanOps<T>::predict(s_seq[oi[0]], s_seq[oi[1]], s_seq[oi[2]], hi);
+								const uint32_t p1 = ScanOps<T>::predict(s_seq[oi[3]], s_seq[oi[4]], s_seq[oi[5]], hi);
+								const uint32_t pred = K == 2 ? (uint32_t)(T)(((W)p0 + (W)p1 + 1) >> 1) : (K == 1 ? p0 : 0u);
+								val = ScanOps<T>::dec(res, pred, hi);
 							} else if (kd == 1) {
-								val = scan_generic_step<T>(a.cand, xc, RS, 0xffffffffu, 0u, s_seq + c, done, aux, K, res, hi);
+								val = scan_generic_step<T>(a.cand, xc, RS, 0xffffffffu, 0u, s_seq, 1u, done, aux, K, res, hi);
 							}
-							s_seq[k0 * RS + c] = (T)val;
+							s_seq[k0] = (T)val;
 						}
 						__syncwarp();
 					}
 					if (wm) { stop = b0 + nl; break; }
 				}
 				if (live)
-					for (uint32_t k = grp; k < stop; k += G) xc[(size_t)(done + k) * RS] = s_seq[k * RS + c];
+					for (uint32_t k = grp; k < stop; k += G) xc[(size_t)(done + k) * RS] = s_seq[k];
 				if (lane < C) {
 					uint32_t *dst = C > 1 ? cluster.map_shared_rank(&s_ndE[0], lane) : &s_ndE[0];
 					*dst = stop;
@@ -537,6 +585,9 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		uint32_t wpc = (((est + est / 8 + 8 + G * C - 1) >> lgC)) / G; // active warps per CTA
 		if (wpc > SCAN_NWARP) wpc = SCAN_NWARP;
 		const uint32_t per = wpc * G;                       // slots per CTA
+		// warp totals travel to the CTA that owns them and to every CTA behind it; thread 0 announces
+		// how many bytes this CTA is going to receive in this sweep
+		if (t == 0) scan_mbar_arrive_expect_tx(bar, (crank + 1u) * wpc * (uint32_t)sizeof(Map));
 		const uint32_t nact = per << lgC;                   // slots of the window
 		const uint32_t gs = crank * per + q;                // my slot in the window
 		const unsigned long long i64 = (unsigned long long)done + gs;
@@ -545,8 +596,12 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		const unsigned long long wend64 = (unsigned long long)done + nact;
 		const uint32_t wend = wend64 < n ? (uint32_t)wend64 : n;
 		const uint32_t x0 = done ? scan_ld(xc + (size_t)(done - 1) * RS) : 0u;
-		// warps 0 .. NC-1 later push x[done - 1] of component `warp` through the CTA totals
-		const uint32_t x0w = (done && warp < (uint32_t)NC) ? scan_ld((const T *)a.x + (size_t)(done - 1) * RS + warp) : 0u;
+		if (active && (unsigned long long)i + est < n) {
+			// the record and residual this slot will most likely need in the next sweep: pull them into L2 now
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(srec + i + est));
+			if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(rc + (size_t)(i + est) * RS));
+		}
+		const uint32_t x0w = x0;
 
 		uint32_t mode = SCAN_NONE, Kk = 0, vpos = 0, ra = 0, rb = 0, rd = 0;
 		bool wr = false;
@@ -597,7 +652,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 			} else if (hdr & SCAN_HDR_IRREGULAR) {
 				mode = SCAN_OPAQUE;
 				S = (W)aux;
-				tm = Map::constant((SW)scan_generic_step<T>(a.cand, xc, RS, i - 1, g, xc, 0xffffffffu, aux, K, res, hi), cb);
+				tm = Map::constant((SW)scan_generic_step<T>(a.cand, xc, RS, i - 1, g, xc, RS, 0xffffffffu, aux, K, res, hi), cb);
 			} else {
 				W Sacc = 0;
 				uint32_t va = 0, vb = 0, vp = 0;
@@ -629,78 +684,123 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 					const SW sb = (res & 1) ? -(half + 1) : half;
 					tm = Map::affine(K, (SW)va - (SW)vb + (SW)Sacc + (SW)(K >> 1), sb);
 					if (have_guess) {
+						// the head of the window knows its predecessor exactly: a constant, exactly
 						const uint32_t yg = scan_std_step<T>(g, va, vb, res, Sacc, K, vp, hi);
-						if ((uint32_t)(T)tm.eval((SW)g) != yg) tm = Map::constant((SW)yg, cb);
+						if (i == done || (uint32_t)(T)tm.eval((SW)g) != yg) tm = Map::constant((SW)yg, cb);
 					}
 				}
 			}
 		}
 		const long long tB = clock64();
-		// ---------------------------------------------------------------- phase B: composition scan
+		// ---------------------------------------------------------------- phase B: presumed start values
+		// B1. inclusive composition scan inside every active warp; the warp totals go to every CTA
+		//     of the cluster (distributed shared memory), element index = cta * wpc + warp.
 		Map inc = tm;
 		if (warp < wpc) {
 #pragma unroll 1
-			for (uint32_t d = 1; d < G; d <<= 1) {
-				const Map up = scan_shfl_up<T>(inc, (int)(d * NC));
-				if (grp >= d) inc = scan_compose<T>(up, inc, cb);
+			for (uint32_t d = 1; d < 32; d <<= 1) {
+				const Map up = scan_shfl_up<T>(inc, (int)d);
+				if (lane >= d) inc = scan_compose<T>(up, inc, cb);
+			}
+			const Map tot = scan_shfl<T>(inc, 31);
+			if (crank + lane < C) {
+				static_assert(sizeof(Map) % 16 == 0, "totals travel as 16-byte vectors");
+				const uint32_t *w = (const uint32_t *)&tot;
+				const uint32_t dst = scan_mapa(scan_smem_u32(&s_all[crank * wpc + warp]), crank + lane), dbar = scan_mapa(bar, crank + lane);
+#pragma unroll
+				for (int v = 0; v < (int)(sizeof(Map) / 16); ++v) scan_st_async_v4(dst + 16 * v, dbar, w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
 			}
 		}
 		SCAN_CLK(p1);
-		if (live && grp == G - 1) s_wtot[warp][c] = inc;
 		if (t == 0) { s_minE = 0xffffffffu; s_minF = 0xffffffffu; }
-		__syncthreads();
 		SCAN_CLK(p2);
-		if (warp < (uint32_t)NC) {
-			// warp w scans the warp totals of component w
-			Map w = s_wtot[lane][warp];
-#pragma unroll 1
-			for (int d = 1; d < SCAN_NWARP; d <<= 1) {
-				const Map up = scan_shfl_up<T>(w, d);
-				if ((int)lane >= d) w = scan_compose<T>(up, w, cbw);
-			}
-			s_wtot[lane][warp] = w;
-			const Map tot = scan_shfl<T>(w, SCAN_NWARP - 1);
-			if (lane < C) {
-				Map *dst = C > 1 ? cluster.map_shared_rank(&s_ctot[crank][warp], lane) : &s_ctot[crank][warp];
-				*dst = tot;
-			}
-		}
 		SCAN_CLK(p3);
-		csync(); // [1] warp totals (this CTA) and CTA totals (cluster) visible
-		SCAN_CLK(p4);
-		if (warp < (uint32_t)NC) {
-			// start value of this CTA and of the next one: x0 pushed through the totals of the CTAs
-			// before (inclusive scan over the cluster, then one evaluation per lane)
-			Map w = lane < C ? s_ctot[lane][warp] : Map::identity();
-#pragma unroll 1
-			for (int d = 1; d < SCAN_MAXC; d <<= 1) {
-				const Map up = scan_shfl_up<T>(w, d);
-				if ((int)lane >= d && (uint32_t)d < C) w = scan_compose<T>(up, w, cbw);
-			}
-			const uint32_t v = (uint32_t)(T)w.eval((SW)x0w);
-			if (lane + 1 == crank) s_vcta[warp] = v;
-			if (crank == 0 && lane == 0) s_vcta[warp] = x0w;
-			if (lane == crank) s_start[per][warp] = v;
+		// [1] wait for the totals promised to this CTA (no barrier: the producers complete the
+		// transaction count that thread 0 armed at the top of the sweep)
+		if (warp < wpc) {
+			while (!scan_mbar_try_wait(bar, bar_parity)) { }
 		}
-		Map ex = scan_shfl_up<T>(inc, NC);
-		if (grp == 0) ex = Map::identity();
-		if (warp > 0 && live) ex = scan_compose<T>(s_wtot[warp - 1][c], ex, cb);
-		__syncthreads();
-		uint32_t start = (uint32_t)(T)ex.eval((SW)s_vcta[c]);
+		bar_parity ^= 1u;
+		SCAN_CLK(p4);
+		// B2. the value in front of my warp: out[j], out[k] = value after warp total k, j = my element
+		//     - 1.  Once ~cb halvings are composed a total is a step: it outputs B or B + 1.  Lane l
+		//     looks at element k = base - l: fed with the two possible outputs of its predecessor
+		//     it yields a (pred said B) or b (pred said B + 1).  a == b anchors the chain (so does a
+		//     total that is constant over the whole value range, and element 0, whose input
+		//     x[done - 1] is known); b == a + 1 copies the predecessor's choice.  The nearest anchor
+		//     at or before element j decides -- a ballot per 32 elements instead of a scan over the
+		//     cluster.  An element whose predecessor is not a step yet (long runs of single-
+		//     parallelogram vertices) breaks the shortcut: the totals from the anchor on are then
+		//     evaluated one after the other.
+		uint32_t vstart = x0;
+		if (warp < wpc) {
+			const int j = (int)(crank * wpc + warp) - 1;
+			if (j >= 0) {
+				int base = j, anchor_k = -1;
+				uint32_t a_target = 0, anchor_out = x0;
+				bool first = true, broken = false, direct = false;
+				for (;;) {
+					const int k = base - (int)lane;
+					uint32_t va = 0, kB = 0;
+					bool anch = false, bad = false;
+					if (k >= 0) {
+						const Map f = s_all[k];
+						kB = (uint32_t)f.B;
+						if (k == 0) {
+							va = (uint32_t)(T)f.eval((SW)x0);
+							anch = true;
+						} else {
+							const Map pf = s_all[k - 1];
+							const bool ps = pf.is_step(cb);
+							const uint32_t c0 = (uint32_t)(T)f.eval(0), c1 = (uint32_t)(T)f.eval((SW)hi);
+							va = (uint32_t)(T)f.eval(pf.B);
+							const uint32_t vb = (uint32_t)(T)f.eval(pf.B + 1);
+							if (c0 == c1) { va = c0; anch = true; }
+							else if (ps && va == vb) anch = true;
+							else bad = !ps || vb != va + 1u;
+						}
+					}
+					if (first) { a_target = __shfl_sync(0xffffffffu, va, 0); first = false; }
+					const uint32_t AM = __ballot_sync(0xffffffffu, anch), BM = __ballot_sync(0xffffffffu, bad);
+					if (AM) {
+						const int La = __ffs((int)AM) - 1;
+						if (BM & ((1u << La) - 1u)) broken = true;
+						const uint32_t aLa = __shfl_sync(0xffffffffu, va, La), bLa = __shfl_sync(0xffffffffu, kB, La);
+						anchor_k = base - La;
+						anchor_out = aLa;
+						if (!broken) { vstart = anchor_k == j ? aLa : a_target + (aLa - bLa); direct = true; }
+						break;
+					}
+					if (BM) broken = true;
+					base -= 32;
+				}
+				if (!direct) {
+					SW v = (SW)anchor_out;
+					for (int kk = anchor_k + 1; kk <= j; ++kk) v = (SW)(uint32_t)(T)s_all[kk].eval(v);
+					vstart = (uint32_t)(T)v;
+					if (lane == 0) ++nfallback;
+				}
+			}
+		}
+		const uint32_t vend = (uint32_t)(T)scan_shfl<T>(inc, 31).eval((SW)vstart);
+		Map ex = scan_shfl_up<T>(inc, 1);
+		if (lane == 0) ex = Map::identity();
+		uint32_t start = (uint32_t)(T)ex.eval((SW)vstart);
 		if (gs == 0) start = x0; // final by construction
-		if (live) s_start[q][c] = start;
+		s_start[q][0] = start;
+		if (warp + 1 == wpc && lane == 0) s_start[per][0] = vend;
 		__syncthreads();
 		const long long tC = clock64();
 		// ---------------------------------------------------------------- phase C: the exact step
 		uint32_t cur = start;
 		if (mode == SCAN_CONST) cur = ra;
 		else if (mode == SCAN_STD) cur = scan_std_step<T>(start, ra, rb, rd, S, Kk, vpos, hi);
-		else if (mode == SCAN_OPAQUE) cur = scan_generic_step<T>(a.cand, xc, RS, i - 1, start, xc, 0xffffffffu, (uint32_t)S, Kk, rd, hi);
+		else if (mode == SCAN_OPAQUE) cur = scan_generic_step<T>(a.cand, xc, RS, i - 1, start, xc, RS, 0xffffffffu, (uint32_t)S, Kk, rd, hi);
 		const long long tD = clock64();
 		// ---------------------------------------------------------------- phase D: verify, publish, write
 		uint32_t ndE = Ecand, ndF = 0xffffffffu;
 		if (active) {
-			const uint32_t nxt = s_start[q + 1][c];
+			const uint32_t nxt = s_start[q + 1][0];
 			const bool last = gs + 1 >= nact; // nothing after me in this window
 			if (!last && cur != nxt) ndF = i + 1;
 			if (wr) xc[(size_t)i * RS] = (T)cur;
@@ -729,11 +829,15 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		else if (newdone == wend && wend < n) ++capped;
 		if (gend < E) gend = E;            // [newdone, E) now holds this sweep's values: guesses for the next one
 		if (newdone == done) widehead = true; // only a wide head rank stops slot 0
-		else if (newdone - done < SCAN_SEQ_TRIGGER && newdone < n && !(F < E)) {
-			seqmode = true;                   // dependency-limited window: walk a stretch sequentially
-			seqlen = lastseq ? (seqlen * 2 < SCAN_SEQ_MAX ? seqlen * 2 : SCAN_SEQ_MAX) : SCAN_SEQ_MIN;
-			lastseq = true;
-		} else lastseq = false;
+		else if (E - done < SCAN_SEQ_TRIGGER && newdone < n) {
+			// the window itself is short (not a verification failure): the second time in a row a
+			// stretch is walked sequentially, twice as long as the previous one if that was one too
+			if (++smallrun >= 2) {
+				seqmode = true;
+				seqlen = lastseq ? (seqlen * 2 < SCAN_SEQ_MAX ? seqlen * 2 : SCAN_SEQ_MAX) : SCAN_SEQ_MIN;
+				lastseq = true;
+			}
+		} else { smallrun = 0; lastseq = false; }
 		const uint32_t adv = newdone - done;
 		if (newdone == wend && wend < n) est = est * 2 < NSEGT ? est * 2 : NSEGT;
 		else est = adv > est - est / 8 ? adv : est - est / 8;
@@ -745,8 +849,11 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 #ifdef SCAN_DEBUG
 	if (t == 0) printf("cta %u A %lld probes: warpscan %lld sync %lld lvl2 %lld csync1 %lld start %lld walk %lld | verify+write %lld sync %lld push+csync2 %lld (per sweep, %llu sweeps)\n", crank, cyA / (long long)sweeps, pr[0] / (long long)sweeps, pr[1] / (long long)sweeps, pr[2] / (long long)sweeps, pr[3] / (long long)sweeps, pr[4] / (long long)sweeps, cyC / (long long)sweeps, pr[5] / (long long)sweeps, pr[6] / (long long)sweeps, pr[7] / (long long)sweeps, sweeps);
 #endif
-	if (crank == 0 && t == 0 && a.stats) {
-		a.stats[0] = sweeps; a.stats[1] = fails | (capped << 32); a.stats[2] = (wides << 32) | (nseq << 40); a.stats[3] = n;
+#ifdef SCAN_DEBUG
+	if (crank == 0 && t == 0) printf("comp %u: sweeps %llu fails %llu capped %llu fallback %llu nseq %llu cycles %lld\n", c, sweeps, fails, capped, nfallback, nseq, cyA + cyB + cyC + cyD);
+#endif
+	if (crank == 0 && t == 0 && a.stats && c == 0) {
+		a.stats[0] = sweeps; a.stats[1] = fails | (capped << 32); a.stats[2] = nfallback | (wides << 32) | (nseq << 40); a.stats[3] = n;
 		a.stats[4] = (unsigned long long)cyA; a.stats[5] = (unsigned long long)cyB; a.stats[6] = (unsigned long long)cyC; a.stats[7] = (unsigned long long)cyD;
 	}
 }
