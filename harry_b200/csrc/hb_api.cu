@@ -1,6 +1,9 @@
 // hb_api.cu -- the C ABI (include/harry_b200.h): context, device-resident mesh, and the
 // host-buffer entry points that replace the reference's calls.
 #include "hb_internal.cuh"
+#include <mutex>
+#include <unordered_map>
+#include <utility>
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -478,15 +481,72 @@ extern "C" int hb_dmesh_decode(hb_dmesh *m)
 // ------------------------------------------------------------------------------------------------
 // stream download
 // ------------------------------------------------------------------------------------------------
+// Output streams live in page-locked host memory (device -> host copies into pageable memory run at
+// a fraction of the link rate).  Page-locking is expensive, so blocks are recycled through a small
+// process-wide cache: hb_streams_free() parks them, the next fetch of a similar size reuses them.
+namespace {
+struct PinnedCache {
+	std::mutex mu;
+	std::vector<std::pair<void *, size_t>> free_blocks;
+	std::unordered_map<void *, std::pair<size_t, bool>> live; // ptr -> (capacity, pinned)
+	size_t cached_bytes = 0;
+	static constexpr size_t kMaxCached = (size_t)8 << 30;
+	void *alloc(size_t bytes)
+	{
+		if (bytes == 0) bytes = 1;
+		bytes = (bytes + 4095) & ~(size_t)4095;
+		{
+			std::lock_guard<std::mutex> g(mu);
+			size_t best = free_blocks.size();
+			for (size_t k = 0; k < free_blocks.size(); ++k)
+				if (free_blocks[k].second >= bytes && free_blocks[k].second <= 2 * bytes + (1 << 20) && (best == free_blocks.size() || free_blocks[k].second < free_blocks[best].second)) best = k;
+			if (best != free_blocks.size()) {
+				void *p = free_blocks[best].first;
+				const size_t cap = free_blocks[best].second;
+				free_blocks.erase(free_blocks.begin() + (long)best);
+				cached_bytes -= cap;
+				live[p] = { cap, true };
+				return p;
+			}
+		}
+		void *p = nullptr;
+		bool pinned = cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess;
+		if (!pinned) { cudaGetLastError(); p = malloc(bytes); }
+		if (!p) return nullptr;
+		std::lock_guard<std::mutex> g(mu);
+		live[p] = { bytes, pinned };
+		return p;
+	}
+	void release(void *p)
+	{
+		if (!p) return;
+		std::unique_lock<std::mutex> g(mu);
+		auto it = live.find(p);
+		if (it == live.end()) { g.unlock(); free(p); return; }
+		const size_t cap = it->second.first;
+		const bool pinned = it->second.second;
+		live.erase(it);
+		if (pinned && cached_bytes + cap <= kMaxCached) {
+			free_blocks.emplace_back(p, cap);
+			cached_bytes += cap;
+			return;
+		}
+		g.unlock();
+		if (pinned) cudaFreeHost(p); else free(p);
+	}
+};
+PinnedCache g_pinned;
+} // namespace
+
 extern "C" void hb_streams_free(hb_streams *s)
 {
 	if (!s) return;
 	if (s->lists) {
-		for (int l = 0; l < s->nlists; ++l) { free(s->lists[l].type); free(s->lists[l].aux); free(s->lists[l].symbols); free(s->lists[l].hist); }
+		for (int l = 0; l < s->nlists; ++l) { g_pinned.release(s->lists[l].type); g_pinned.release(s->lists[l].aux); g_pinned.release(s->lists[l].symbols); g_pinned.release(s->lists[l].hist); }
 		free(s->lists);
 	}
-	free(s->reg_vtx);
-	free(s->reg_face);
+	g_pinned.release(s->reg_vtx);
+	g_pinned.release(s->reg_face);
 	free(s);
 }
 
@@ -509,8 +569,8 @@ extern "C" int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out)
 	s->n_vtx = m->norder;
 	s->n_face = m->norder_f;
 	s->nlists = m->nlists;
-	s->reg_vtx = (uint16_t *)malloc(sizeof(uint16_t) * ((size_t)m->norder + 1));
-	s->reg_face = (uint16_t *)malloc(sizeof(uint16_t) * ((size_t)m->norder_f + 1));
+	s->reg_vtx = (uint16_t *)g_pinned.alloc(sizeof(uint16_t) * ((size_t)m->norder + 1));
+	s->reg_face = (uint16_t *)g_pinned.alloc(sizeof(uint16_t) * ((size_t)m->norder_f + 1));
 	s->lists = (hb_list_streams *)calloc((size_t)m->nlists + 1, sizeof(hb_list_streams));
 	int rc = 0;
 	uint16_t *d_reg = nullptr;
@@ -546,11 +606,12 @@ extern "C" int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out)
 	for (int l = 0; l < m->nlists; ++l) {
 		DevList &dl = m->lists[l];
 		hb_list_streams &ls = s->lists[l];
-		ls.type = (uint8_t *)malloc((size_t)ls.n_emit + 1);
-		ls.aux = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)ls.n_emit + 1));
-		ls.symbols = (uint8_t *)malloc((size_t)ls.n_data * ls.sym_stride + 1);
-		ls.hist = (uint64_t *)calloc((size_t)ls.sym_stride * 256 + 4, sizeof(uint64_t));
+		ls.type = (uint8_t *)g_pinned.alloc((size_t)ls.n_emit + 1);
+		ls.aux = (uint32_t *)g_pinned.alloc(sizeof(uint32_t) * ((size_t)ls.n_emit + 1));
+		ls.symbols = (uint8_t *)g_pinned.alloc((size_t)ls.n_data * ls.sym_stride + 1);
+		ls.hist = (uint64_t *)g_pinned.alloc(sizeof(uint64_t) * ((size_t)ls.sym_stride * 256 + 4));
 		if (!ls.type || !ls.aux || !ls.symbols || !ls.hist) { rc = hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); goto fail; }
+		memset(ls.hist, 0, sizeof(uint64_t) * ((size_t)ls.sym_stride * 256 + 4));
 		if (!dl.n_elems) continue;
 		if (ls.n_emit) {
 			FETCH_CUDA(cudaMemcpyAsync(ls.type, dl.d_type, ls.n_emit, cudaMemcpyDeviceToHost, ctx->stream));
