@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	__shared__ uint32_t s_start[NSEG + 1][NC];  // presumed start value of every slot (+ of the next CTA's first slot)
 	__shared__ uint32_t s_minE, s_minF;
 	__shared__ unsigned long long s_sum[4];
-	__shared__ T s_seq[SCAN_SEQ_MAX + 6 * 32];  // values of a sequential stretch + the final operands of the current batch
+	__shared__ T s_seq[SCAN_SEQ_MAX];           // values of a sequential stretch
 
 	const uint32_t hi = (uint32_t)IntOps<T>::mask(a.bits[c]);
 	const int cb = a.bits[c];
@@ -504,10 +504,13 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 			continue;
 		}
 		// ---------------------------------------------------------------- sequential stretch (one warp)
-		// The window was cut after a few ranks (E-limit: e.g. the first ring of a sphere, where every
-		// vertex is predicted from the two before it).  Warp 0 of CTA 0 walks the next `seqlen`
-		// ranks in order: its lane groups prefetch the records and the final operands of G ranks,
-		// then take turns; values produced inside the stretch travel through shared memory.
+		// The window was cut after a few ranks: some operand other than rank i - 1 is a few ranks old
+		// (the first ring of a sphere -- every vertex predicted from the two before it -- and most
+		// vertices of an irregular triangulation).  Warp 0 of CTA 0 then walks the next `seqlen`
+		// ranks in order, 32 at a time: (P) in parallel, every lane fetches the record of its rank
+		// and every operand that is already known -- final values from L2, values of earlier batches
+		// of this stretch from shared memory -- and sums the candidates that are complete;
+		// (S) the lanes take turns: a turn only reads the operands produced inside the batch.
 		if (seqmode) {
 			const uint32_t len = n - done < seqlen ? n - done : seqlen;
 			if (crank == 0 && warp == 0) {
@@ -517,39 +520,56 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 					const bool valid = live && k0 < len;
 					const uint32_t i = done + (valid ? k0 : 0);
 					const uint4 *sr = (const uint4 *)(srec + i);
-					const uint4 q0 = __ldg(sr), q1 = __ldg(sr + 1);
-					const uint32_t tri[6] = { q0.w, q1.x, q1.y, q1.z, q1.w, __ldg(&srec[i].tri[5]) };
+					const uint4 q0 = __ldg(sr), q1 = __ldg(sr + 1), q2 = __ldg(sr + 2), q3 = __ldg(sr + 3);
+					const uint32_t tri[3 * SCAN_KIN] = { q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
 					const uint32_t kd = q0.x & 3u, K = q0.x >> 11, aux = q0.y;
 					const uint32_t res = rc[(size_t)i * RS];
 					const unsigned wm = __ballot_sync(0xffffffffu, valid && kd == 1 && K > SCAN_WIDE);
-					const uint32_t nl = wm ? ((uint32_t)__ffs((int)wm) - 1u) / NC : G;
-					// operands of the (up to two) inline candidates: final ones are fetched now and parked
-					// behind the stretch buffer, so that the serial step reads all six through one
-					// precomputed shared-memory index each
-					uint32_t oi[6];
+					const uint32_t nl = wm ? (uint32_t)__ffs((int)wm) - 1u : G;
+					const bool inl = valid && kd == 1 && K <= SCAN_KIN;
+					// operand values known now; the others (produced in this batch) are picked up in the turn
+					uint32_t ov[3 * SCAN_KIN];
+					uint32_t late = 0; // bit w: operand w comes from this batch
 #pragma unroll
-					for (int w = 0; w < 6; ++w) {
-						oi[w] = SCAN_SEQ_MAX + 6 * lane + w;
-						uint32_t cvw = 0;
-						if (valid && kd == 1 && K <= 2 && (uint32_t)(w / 3) < K) {
-							if (tri[w] < done) cvw = scan_ld(xc + (size_t)tri[w] * RS);
-							else oi[w] = tri[w] - done;
+					for (int w = 0; w < 3 * SCAN_KIN; ++w) {
+						ov[w] = 0;
+						if (inl && (uint32_t)(w / 3) < K) {
+							const uint32_t r = tri[w];
+							if (r < done) ov[w] = scan_ld(xc + (size_t)r * RS);
+							else if (r < done + b0) ov[w] = s_seq[r - done];
+							else late |= 1u << w;
 						}
-						s_seq[SCAN_SEQ_MAX + 6 * lane + w] = (T)cvw;
 					}
+					W sknown = 0;
+#pragma unroll
+					for (int cj = 0; cj < SCAN_KIN; ++cj)
+						if (inl && (uint32_t)cj < K && ((late >> (3 * cj)) & 7u) == 0) sknown += (W)ScanOps<T>::predict(ov[3 * cj], ov[3 * cj + 1], ov[3 * cj + 2], hi);
 					uint32_t cv = 0;
 					if (valid && kd == 0) cv = scan_ld(xc + (size_t)i * RS);
 					if (valid && kd == 2 && aux < done) cv = scan_ld(xc + (size_t)aux * RS);
-					__syncwarp();
+					// (sum + K / 2) / K as a multiplication: exact for sum < 2^27, K <= 32
+					const uint32_t kinv = K > 2 ? (uint32_t)((0x100000000ull + K - 1) / K) : 0u;
 #pragma unroll 1
 					for (uint32_t j = 0; j < nl; ++j) {
 						if (grp == j && valid) {
 							uint32_t val = cv;
 							if (kd == 2 && aux >= done) val = s_seq[aux - done];
-							if (kd == 1 && K <= 2) {
-								const uint32_t p0 = ScanOps<T>::predict(s_seq[oi[0]], s_seq[oi[1]], s_seq[oi[2]], hi);
-								const uint32_t p1 = ScanOps<T>::predict(s_seq[oi[3]], s_seq[oi[4]], s_seq[oi[5]], hi);
-								const uint32_t pred = K == 2 ? (uint32_t)(T)(((W)p0 + (W)p1 + 1) >> 1) : (K == 1 ? p0 : 0u);
+							if (inl) {
+								W sum = sknown;
+#pragma unroll
+								for (int cj = 0; cj < SCAN_KIN; ++cj) {
+									const uint32_t lm = (late >> (3 * cj)) & 7u;
+									if (lm == 0) continue;
+									const uint32_t v0 = (lm & 1u) ? (uint32_t)s_seq[tri[3 * cj] - done] : ov[3 * cj];
+									const uint32_t v1 = (lm & 2u) ? (uint32_t)s_seq[tri[3 * cj + 1] - done] : ov[3 * cj + 1];
+									const uint32_t v2 = (lm & 4u) ? (uint32_t)s_seq[tri[3 * cj + 2] - done] : ov[3 * cj + 2];
+									sum += (W)ScanOps<T>::predict(v0, v1, v2, hi);
+								}
+								uint32_t pred;
+								if (K == 2) pred = (uint32_t)(T)((sum + 1) >> 1);
+								else if (K <= 1) pred = (uint32_t)(T)sum;
+								else if (sizeof(T) < 4) pred = __umulhi((uint32_t)sum + (K >> 1), kinv);
+								else pred = scan_mean<T>(sum, K);
 								val = ScanOps<T>::dec(res, pred, hi);
 							} else if (kd == 1) {
 								val = scan_generic_step<T>(a.cand, xc, RS, 0xffffffffu, 0u, s_seq, 1u, done, aux, K, res, hi);

@@ -145,6 +145,42 @@ def poly_grid(n: int = 60, seed: int = 7) -> PolyMesh:
                     vtx_props={"quality": quality}, face_props={"area": area})
 
 
+def tri_irregular(n: int = 48, seed: int = 11, holes: bool = True) -> PolyMesh:
+    """Irregular triangulation: a jittered (n+1)^2 height field, every cell split along a random
+    diagonal (vertex valences 3..8, vertices with 1, 2, 3 and more parallelograms), a few cells
+    removed (interior borders), rough z so that residuals are large and hit the escape branch of
+    the residual mapping near the range limits.  Exercises the irregular paths of the vertex decoder."""
+    rng = np.random.default_rng(seed)
+    ys, xs = np.mgrid[0:n + 1, 0:n + 1]
+    pos = np.empty(((n + 1) * (n + 1), 3), dtype=np.float64)
+    pos[:, 0] = xs.ravel() + 0.35 * rng.standard_normal(xs.size) * ((xs.ravel() > 0) & (xs.ravel() < n))
+    pos[:, 1] = ys.ravel() + 0.35 * rng.standard_normal(ys.size) * ((ys.ravel() > 0) & (ys.ravel() < n))
+    pos[:, 2] = np.sin(0.4 * xs.ravel()) * np.cos(0.3 * ys.ravel()) + 0.3 * rng.standard_normal(xs.size)
+    # a band of exactly flat, exactly extreme z (escape / saturation regimes, constant runs)
+    pos[(ys.ravel() % 7) == 3, 2] = pos[:, 2].min()
+
+    def vid(x, y):
+        return y * (n + 1) + x
+
+    flip = rng.random((n, n)) < 0.5
+    drop = (rng.random((n, n)) < 0.02) if holes else np.zeros((n, n), dtype=bool)
+    faces = []
+    for y in range(n):
+        for x in range(n):
+            if drop[y, x]:
+                continue
+            a, b, c, d = vid(x, y), vid(x + 1, y), vid(x + 1, y + 1), vid(x, y + 1)
+            if flip[y, x]:
+                faces.append((a, b, d))
+                faces.append((b, c, d))
+            else:
+                faces.append((a, b, c))
+                faces.append((a, c, d))
+    faces = np.asarray(faces, dtype=np.uint32)
+    face_off = (3 * np.arange(faces.shape[0] + 1)).astype(np.uint32)
+    return PolyMesh(pos=pos.astype(np.float32), face_off=face_off, face_idx=faces.ravel())
+
+
 # ----------------------------------------------------------------------------------------------
 # PLY writer (binary little endian)
 # ----------------------------------------------------------------------------------------------

@@ -21,6 +21,13 @@ CASES = {
     "obj_q14_q10": (lambda d: _obj(d, "o.obj", False), [(0, -1, 14), (2, -1, 10)]),
     "obj_lossless": (lambda d: _obj(d, "o.obj", False), []),
     "obj_multi_q14": (lambda d: _obj(d, "om.obj", True), [(0, -1, 14)]),
+    # the integer storage types of the vertex decoder's scan kernel (u8 / u16 / u32), regular and irregular meshes
+    "sphere_q8": (lambda d: _ply(d, "sn8.ply", meshgen.uv_sphere(33, 51, noise_seed=4)), [(1, -1, 8)]),
+    "sphere_q20": (lambda d: _ply(d, "sn20.ply", meshgen.uv_sphere(29, 47, noise_seed=6)), [(1, -1, 20)]),
+    "irr_q14": (lambda d: _ply(d, "irr.ply", meshgen.tri_irregular(48, 11)), [(1, -1, 14)]),
+    "irr_q7": (lambda d: _ply(d, "irr.ply", meshgen.tri_irregular(48, 11)), [(1, -1, 7)]),
+    "irr_q24": (lambda d: _ply(d, "irr.ply", meshgen.tri_irregular(48, 11)), [(1, -1, 24)]),
+    "irr_big_q12": (lambda d: _ply(d, "irrb.ply", meshgen.tri_irregular(160, 5)), [(1, -1, 12)]),
     "obj_multi_all": (lambda d: _obj(d, "om.obj", True), [(0, -1, 12), (1, -1, 9), (2, -1, 10), (3, -1, 11)]),
 }
 CONFIG1 = ("sphere35k_lossless", lambda d: _ply(d, "s35k.ply", meshgen.uv_sphere(133, 264)), [])
