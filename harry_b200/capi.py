@@ -357,7 +357,9 @@ class StreamsPy:
         return True, ""
 
 
-def streams_to_py(sp) -> StreamsPy:
+def streams_to_py(sp, copy: bool = True) -> StreamsPy:
+    """hb_streams -> numpy.  copy=False returns views of the library's (page-locked) buffers: valid
+    until hb_streams_free is called on `sp` -- what a C++ caller of the ABI sees, no extra pass."""
     s = sp.contents
 
     def arr(ptr, n, dtype):
@@ -365,7 +367,8 @@ def streams_to_py(sp) -> StreamsPy:
             return np.zeros(0, dtype=dtype)
         addr = C.cast(ptr, C.c_void_p).value
         buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(addr)
-        return np.frombuffer(buf, dtype=dtype).copy()
+        a = np.frombuffer(buf, dtype=dtype)
+        return a.copy() if copy else a
 
     lists = []
     for l in range(s.nlists):
@@ -615,6 +618,13 @@ class Context:
             return streams_to_py(sp)
         finally:
             self.lib.hb_streams_free(sp)
+
+    def attr_encode_view(self, mesh: MeshArrays):
+        """Same call, zero-copy: returns (streams viewing the library's buffers, release callable)."""
+        d = mesh.to_desc()
+        sp = C.POINTER(Streams)()
+        self._check(self.lib.hb_attr_encode(self.h, C.byref(d), C.byref(sp)), "hb_attr_encode")
+        return streams_to_py(sp, copy=False), (lambda: self.lib.hb_streams_free(sp))
 
     # AttrDecoder::decode (value reconstruction)
     def attr_decode(self, mesh: MeshArrays) -> None:

@@ -326,6 +326,25 @@ __device__ __forceinline__ bool scan_mbar_try_wait(uint32_t bar, uint32_t parity
 	return ok != 0;
 }
 
+// Shared-memory accesses by 32-bit shared-window address.  (In a cluster kernel nvcc derives the
+// address of a dynamically indexed shared array that is captured by a lambda through the cluster
+// window -- an S2R SR_CgaCtaId in front of every access; the sequential walker cannot afford that.)
+template <int BYTES> __device__ __forceinline__ uint32_t scan_lds(uint32_t addr);
+template <> __device__ __forceinline__ uint32_t scan_lds<1>(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+template <> __device__ __forceinline__ uint32_t scan_lds<2>(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+template <> __device__ __forceinline__ uint32_t scan_lds<4>(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+template <int BYTES> __device__ __forceinline__ void scan_sts(uint32_t addr, uint32_t v);
+template <> __device__ __forceinline__ void scan_sts<1>(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+template <> __device__ __forceinline__ void scan_sts<2>(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+template <> __device__ __forceinline__ void scan_sts<4>(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 scan_lds_v4(uint32_t addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void scan_sts_v4(uint32_t addr, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
 // L2-coherent scalar load (values are rewritten between sweeps by other SMs of the cluster)
 __device__ __forceinline__ uint32_t scan_ld(const uint8_t *p) { return __ldcg((const unsigned char *)p); }
 __device__ __forceinline__ uint32_t scan_ld(const uint16_t *p) { return __ldcg((const unsigned short *)p); }
@@ -385,10 +404,9 @@ __device__ __forceinline__ uint32_t scan_std_step(uint32_t cur, uint32_t va, uin
 }
 
 // One component of the generic step (any number of candidates, any operand pattern).  Operand r:
-// rank `predrank` reads pv; ranks >= lo come from the stretch buffer `sq` (sequential mode, else
-// lo = 0xffffffff); everything else from the value array.
+// rank `predrank` reads pv, everything else comes from the value array.
 template <typename T>
-__device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ cand, const T *xc, uint32_t cs, uint32_t predrank, uint32_t pv, const T *sq, uint32_t sqs, uint32_t lo,
+__device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ cand, const T *xc, uint32_t cs, uint32_t predrank, uint32_t pv,
                                                    uint32_t c0, uint32_t K, uint32_t delta, uint32_t hi)
 {
 	typedef typename FMap<T>::W W;
@@ -399,7 +417,7 @@ __device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ 
 #pragma unroll
 		for (int o = 0; o < 3; ++o) {
 			const uint32_t r = __ldg(tr + o);
-			v[o] = r == predrank ? pv : (r >= lo ? (uint32_t)sq[(size_t)(r - lo) * sqs] : scan_ld(xc + (size_t)r * cs));
+			v[o] = r == predrank ? pv : scan_ld(xc + (size_t)r * cs);
 		}
 		sum += (W)ScanOps<T>::predict(v[0], v[1], v[2], hi);
 	}
@@ -449,6 +467,8 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	__shared__ uint32_t s_minE, s_minF;
 	__shared__ unsigned long long s_sum[4];
 	__shared__ T s_seq[SCAN_SEQ_MAX];           // values of a sequential stretch
+	__shared__ __align__(16) uint32_t s_item[2][32][16]; // work items of the sequential stretch (two batches)
+	__shared__ __align__(16) uint4 s_pref[SCAN_NTB][3];  // record of the rank this thread will most likely own in the next sweep
 
 	const uint32_t hi = (uint32_t)IntOps<T>::mask(a.bits[c]);
 	const int cb = a.bits[c];
@@ -458,6 +478,9 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	uint32_t done = 0, gend = 0, est = NSEGT;
 	bool widehead = false, seqmode = false, lastseq = false;
 	uint32_t seqlen = SCAN_SEQ_MIN, smallrun = 0;
+	uint32_t lastadv = 0, pref_i = 0xffffffffu; // advance of the last sweep; rank whose record sits in s_pref[t]
+	uint32_t prefb;
+	asm volatile("mov.u32 %0, %1;" : "=r"(prefb) : "r"(scan_smem_u32(&s_pref[threadIdx.x][0])));
 	unsigned long long sweeps = 0, fails = 0, wides = 0, capped = 0, nseq = 0, nfallback = 0;
 	long long cyA = 0, cyB = 0, cyC = 0, cyD = 0;
 #ifdef SCAN_DEBUG
@@ -465,6 +488,11 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 #endif
 	auto csync = [&]() { if (C > 1) cluster.sync(); else __syncthreads(); };
 	const uint32_t bar = scan_smem_u32(&s_bar);
+	// shared-window addresses of the sequential walker's buffers, pinned in registers (an opaque move keeps
+	// the compiler from re-deriving them in front of every access)
+	uint32_t seqb, itemb;
+	asm volatile("mov.u32 %0, %1;" : "=r"(seqb) : "r"(scan_smem_u32(s_seq)));
+	asm volatile("mov.u32 %0, %1;" : "=r"(itemb) : "r"(scan_smem_u32(s_item)));
 	uint32_t bar_parity = 0;
 	if (t == 0) {
 		scan_mbar_init(bar, 1);
@@ -514,74 +542,134 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		if (seqmode) {
 			const uint32_t len = n - done < seqlen ? n - done : seqlen;
 			if (crank == 0 && warp == 0) {
+				// Two roles in one warp.  PREPARE (all lanes, one rank each, one batch ahead): fetch
+				// the record, every operand that is already known (final values from L2, values of
+				// earlier batches from the stretch buffer), sum the complete candidates, and park a
+				// 64-byte work item in shared memory.  EXECUTE (lane 0): walk the 32 items of the
+				// current batch in order; only operands produced inside the last two batches are
+				// read at that point.  The loads of PREPARE are in flight while lane 0 executes.
 				uint32_t stop = len;
-				for (uint32_t b0 = 0; b0 < len; b0 += G) {
-					const uint32_t k0 = b0 + grp;
-					const bool valid = live && k0 < len;
-					const uint32_t i = done + (valid ? k0 : 0);
+				constexpr int TB = (int)sizeof(T);
+				// item words: 0 kind | K << 2 | late mask << 8, 1 residual, 2 known sum (or the value for kinds 0 / 2),
+				// 3 aux, 4..15 operands: the value if known, else the index into the stretch buffer
+				// PREPARE is split in two so that its second wave of loads (operand values) is in
+				// flight while lane 0 executes: issue() reads the record (prefetched into L2 two
+				// batches ahead) and starts the operand loads, finish() turns them into the item.
+				uint32_t p_tri[3 * SCAN_KIN], p_ov[3 * SCAN_KIN], p_kd = 0, p_K = 0, p_aux = 0, p_res = 0, p_late = 0, p_cv = 0;
+				bool p_valid = false, p_inl = false;
+				auto issue = [&](uint32_t b0) -> bool {
+					const uint32_t k0 = b0 + lane;
+					p_valid = k0 < len;
+					const uint32_t i = done + (p_valid ? k0 : 0);
 					const uint4 *sr = (const uint4 *)(srec + i);
 					const uint4 q0 = __ldg(sr), q1 = __ldg(sr + 1), q2 = __ldg(sr + 2), q3 = __ldg(sr + 3);
-					const uint32_t tri[3 * SCAN_KIN] = { q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
-					const uint32_t kd = q0.x & 3u, K = q0.x >> 11, aux = q0.y;
-					const uint32_t res = rc[(size_t)i * RS];
-					const unsigned wm = __ballot_sync(0xffffffffu, valid && kd == 1 && K > SCAN_WIDE);
-					const uint32_t nl = wm ? (uint32_t)__ffs((int)wm) - 1u : G;
-					const bool inl = valid && kd == 1 && K <= SCAN_KIN;
-					// operand values known now; the others (produced in this batch) are picked up in the turn
-					uint32_t ov[3 * SCAN_KIN];
-					uint32_t late = 0; // bit w: operand w comes from this batch
+					if ((unsigned long long)i + 64 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(srec + i + 64));
+					p_tri[0] = q0.w; p_tri[1] = q1.x; p_tri[2] = q1.y; p_tri[3] = q1.z; p_tri[4] = q1.w; p_tri[5] = q2.x;
+					p_tri[6] = q2.y; p_tri[7] = q2.z; p_tri[8] = q2.w; p_tri[9] = q3.x; p_tri[10] = q3.y; p_tri[11] = q3.z;
+					p_kd = q0.x & 3u; p_K = q0.x >> 11; p_aux = q0.y;
+					p_res = rc[(size_t)i * RS];
+					p_inl = p_valid && p_kd == 1 && p_K <= SCAN_KIN;
+					p_late = 0;
 #pragma unroll
 					for (int w = 0; w < 3 * SCAN_KIN; ++w) {
-						ov[w] = 0;
-						if (inl && (uint32_t)(w / 3) < K) {
-							const uint32_t r = tri[w];
-							if (r < done) ov[w] = scan_ld(xc + (size_t)r * RS);
-							else if (r < done + b0) ov[w] = s_seq[r - done];
-							else late |= 1u << w;
+						p_ov[w] = 0;
+						if (p_inl && (uint32_t)(w / 3) < p_K) {
+							const uint32_t r = p_tri[w];
+							if (r < done) p_ov[w] = scan_ld(xc + (size_t)r * RS);
+							else if (r + 32 < done + b0) p_ov[w] = scan_lds<TB>(seqb + TB * (r - done)); // produced at least a batch before the one executing now
+							else { p_late |= 1u << w; p_ov[w] = r - done; }
 						}
 					}
+					p_cv = 0;
+					if (p_valid && p_kd == 0) p_cv = scan_ld(xc + (size_t)i * RS);
+					if (p_valid && p_kd == 2 && p_aux < done) p_cv = scan_ld(xc + (size_t)p_aux * RS);
+					return p_valid && p_kd == 1 && p_K > SCAN_WIDE;
+				};
+				// item (48 bytes): word 0 = kind | K << 2 | slot-0 late mask << 8 | slot-1 late mask << 11 | slot-1 used << 14,
+				// 1 residual, 2 sum of the complete candidates (or the value / stretch index for kinds 0 / 2),
+				// 3 reciprocal of K, 4..6 operands of slot 0, 7..9 operands of slot 1 (the value if known, else the
+				// stretch index).  Kinds: 0 value known, 1 regular (at most two candidates read this or the
+				// previous batch), 2 copy of a stretch value, 3 generic step.
+				auto finish = [&](uint32_t buf, bool wide) {
 					W sknown = 0;
+					uint32_t nl2 = 0, m0 = 0, m1 = 0, s0[3] = { 0, 0, 0 }, s1[3] = { 0, 0, 0 };
 #pragma unroll
-					for (int cj = 0; cj < SCAN_KIN; ++cj)
-						if (inl && (uint32_t)cj < K && ((late >> (3 * cj)) & 7u) == 0) sknown += (W)ScanOps<T>::predict(ov[3 * cj], ov[3 * cj + 1], ov[3 * cj + 2], hi);
-					uint32_t cv = 0;
-					if (valid && kd == 0) cv = scan_ld(xc + (size_t)i * RS);
-					if (valid && kd == 2 && aux < done) cv = scan_ld(xc + (size_t)aux * RS);
-					// (sum + K / 2) / K as a multiplication: exact for sum < 2^27, K <= 32
-					const uint32_t kinv = K > 2 ? (uint32_t)((0x100000000ull + K - 1) / K) : 0u;
-#pragma unroll 1
-					for (uint32_t j = 0; j < nl; ++j) {
-						if (grp == j && valid) {
-							uint32_t val = cv;
-							if (kd == 2 && aux >= done) val = s_seq[aux - done];
-							if (inl) {
-								W sum = sknown;
-#pragma unroll
-								for (int cj = 0; cj < SCAN_KIN; ++cj) {
-									const uint32_t lm = (late >> (3 * cj)) & 7u;
-									if (lm == 0) continue;
-									const uint32_t v0 = (lm & 1u) ? (uint32_t)s_seq[tri[3 * cj] - done] : ov[3 * cj];
-									const uint32_t v1 = (lm & 2u) ? (uint32_t)s_seq[tri[3 * cj + 1] - done] : ov[3 * cj + 1];
-									const uint32_t v2 = (lm & 4u) ? (uint32_t)s_seq[tri[3 * cj + 2] - done] : ov[3 * cj + 2];
-									sum += (W)ScanOps<T>::predict(v0, v1, v2, hi);
-								}
-								uint32_t pred;
-								if (K == 2) pred = (uint32_t)(T)((sum + 1) >> 1);
-								else if (K <= 1) pred = (uint32_t)(T)sum;
-								else if (sizeof(T) < 4) pred = __umulhi((uint32_t)sum + (K >> 1), kinv);
-								else pred = scan_mean<T>(sum, K);
-								val = ScanOps<T>::dec(res, pred, hi);
-							} else if (kd == 1) {
-								val = scan_generic_step<T>(a.cand, xc, RS, 0xffffffffu, 0u, s_seq, 1u, done, aux, K, res, hi);
-							}
-							s_seq[k0] = (T)val;
+					for (int cj = 0; cj < SCAN_KIN; ++cj) {
+						if (!(p_inl && (uint32_t)cj < p_K)) continue;
+						const uint32_t lm = (p_late >> (3 * cj)) & 7u;
+						if (lm == 0) sknown += (W)ScanOps<T>::predict(p_ov[3 * cj], p_ov[3 * cj + 1], p_ov[3 * cj + 2], hi);
+						else {
+							if (nl2 == 0) { m0 = lm; s0[0] = p_ov[3 * cj]; s0[1] = p_ov[3 * cj + 1]; s0[2] = p_ov[3 * cj + 2]; }
+							else if (nl2 == 1) { m1 = lm; s1[0] = p_ov[3 * cj]; s1[1] = p_ov[3 * cj + 1]; s1[2] = p_ov[3 * cj + 2]; }
+							++nl2;
 						}
-						__syncwarp();
 					}
+					// (sum + K / 2) / K as a multiplication: exact for sum < 2^27, K <= 32 (K == 2: a shift by one)
+					uint32_t w2 = (uint32_t)sknown, w3 = p_K > 1 ? (uint32_t)((0x100000000ull + p_K - 1) / p_K) : 0u, kind = p_kd;
+					if (p_valid && p_kd == 0) w2 = p_cv;
+					if (p_valid && p_kd == 2) {
+						if (p_aux < done) { w2 = p_cv; kind = 0; }      // a known value
+						else w2 = p_aux - done;                           // stretch index
+					}
+					if (p_valid && p_kd == 1 && (!p_inl || nl2 > 2 || sknown > (W)0xffffffffu)) { kind = 3; w3 = p_aux; } // generic step
+					if (!p_valid) kind = 0;
+					const uint32_t o = itemb + 64 * (buf * 32 + lane);
+					scan_sts_v4(o, make_uint4(kind | (p_K << 2) | (m0 << 8) | (m1 << 11) | ((nl2 > 1 ? 1u : 0u) << 14) | (wide ? 0x80000000u : 0u), p_res, w2, w3));
+					scan_sts_v4(o + 16, make_uint4(s0[0], s0[1], s0[2], s1[0]));
+					scan_sts_v4(o + 32, make_uint4(s1[1], s1[2], 0u, 0u));
+				};
+				bool wide_next = issue(0);
+				finish(0, wide_next);
+				__syncwarp();
+				for (uint32_t b0 = 0; b0 < len; b0 += 32) {
+					const uint32_t buf = (b0 >> 5) & 1u;
+					const unsigned wm = __ballot_sync(0xffffffffu, wide_next);
+					const uint32_t nl = wm ? (uint32_t)__ffs((int)wm) - 1u : min(32u, len - b0);
+					const bool more = b0 + 32 < len && !wm;
+					SCAN_CLK(q0c);
+					if (more) wide_next = issue(b0 + 32);
+					SCAN_CLK(q1c);
+					if (lane == 0) {
+#pragma unroll 1
+						for (uint32_t j = 0; j < nl; ++j) {
+							const uint32_t it = itemb + 64 * (buf * 32 + j);
+							const uint4 h = scan_lds_v4(it), oa = scan_lds_v4(it + 16), ob = scan_lds_v4(it + 32);
+							const uint32_t kind = h.x & 3u, K = (h.x >> 2) & 0x3fu;
+							uint32_t val = h.z;
+							if (kind == 1) {
+								// branch-free: slot 0 always holds a candidate here (a rank without late
+								// operands was folded into kind 0 ... or has K == 0), slot 1 is masked
+								const uint32_t m = h.x >> 8;
+								const uint32_t v0 = (m & 1u) ? scan_lds<TB>(seqb + TB * oa.x) : oa.x;
+								const uint32_t v1 = (m & 2u) ? scan_lds<TB>(seqb + TB * oa.y) : oa.y;
+								const uint32_t v2 = (m & 4u) ? scan_lds<TB>(seqb + TB * oa.z) : oa.z;
+								const uint32_t u0 = (m & 8u) ? scan_lds<TB>(seqb + TB * oa.w) : oa.w;
+								const uint32_t u1 = (m & 16u) ? scan_lds<TB>(seqb + TB * ob.x) : ob.x;
+								const uint32_t u2 = (m & 32u) ? scan_lds<TB>(seqb + TB * ob.y) : ob.y;
+								W sum = (W)h.z;
+								if (m & 7u) sum += (W)ScanOps<T>::predict(v0, v1, v2, hi);
+								if (m & 64u) sum += (W)ScanOps<T>::predict(u0, u1, u2, hi);
+								uint32_t pred;
+								if constexpr (sizeof(T) < 4) pred = K <= 1 ? (uint32_t)sum : __umulhi((uint32_t)sum + (K >> 1), h.w);
+								else pred = scan_mean<T>(sum, K);
+								val = ScanOps<T>::dec(h.y, pred, hi);
+							} else if (kind == 2) {
+								val = scan_lds<TB>(seqb + TB * h.z);
+							} else if (kind == 3) {
+								val = scan_generic_step<T>(a.cand, xc, RS, 0xffffffffu, 0u, h.w, K, h.y, hi); // earlier ranks of the stretch are in the value array already
+							}
+							scan_sts<TB>(seqb + TB * (b0 + j), val);
+							xc[(size_t)(done + b0 + j) * RS] = (T)val;
+						}
+					}
+					__syncwarp();
+					SCAN_CLK(q2c);
+					if (more) finish(buf ^ 1u, wide_next);
+					__syncwarp();
+					SCAN_CLK(q3c);
+					SCAN_PROBE(0, q0c, q1c); SCAN_PROBE(1, q1c, q2c); SCAN_PROBE(2, q2c, q3c);
 					if (wm) { stop = b0 + nl; break; }
 				}
-				if (live)
-					for (uint32_t k = grp; k < stop; k += G) xc[(size_t)(done + k) * RS] = s_seq[k];
 				if (lane < C) {
 					uint32_t *dst = C > 1 ? cluster.map_shared_rank(&s_ndE[0], lane) : &s_ndE[0];
 					*dst = stop;
@@ -629,8 +717,18 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		uint32_t Ecand = 0xffffffffu;
 		Map tm = Map::identity();
 		if (active) {
-			const uint4 *sr = (const uint4 *)(srec + i);
-			const uint4 q0 = __ldg(sr), q1 = __ldg(sr + 1), q2 = __ldg(sr + 2), q3 = __ldg(sr + 3);
+			// the record: copied into shared memory during the previous sweep's barrier if this thread
+			// owns the rank it expected to own (cp.async below), else from L2 now
+			uint4 q0, q1, q2, q3;
+			if (i == pref_i) {
+				asm volatile("cp.async.wait_all;" ::: "memory");
+				q0 = scan_lds_v4(prefb); q1 = scan_lds_v4(prefb + 16); q2 = scan_lds_v4(prefb + 32);
+				q3 = make_uint4(0u, 0u, 0u, 0u);
+				if ((q0.x >> 11) > 3u) q3 = __ldg((const uint4 *)(srec + i) + 3); // only a fourth candidate lives there
+			} else {
+				const uint4 *sr = (const uint4 *)(srec + i);
+				q0 = __ldg(sr); q1 = __ldg(sr + 1); q2 = __ldg(sr + 2); q3 = __ldg(sr + 3);
+			}
 			const uint32_t tri[3 * SCAN_KIN] = { q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
 			const uint32_t hdr = q0.x, kd = hdr & 3u, K = hdr >> 11, aux = q0.y, farp1 = q0.z;
 			const uint32_t res = rc[(size_t)i * RS];
@@ -672,7 +770,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 			} else if (hdr & SCAN_HDR_IRREGULAR) {
 				mode = SCAN_OPAQUE;
 				S = (W)aux;
-				tm = Map::constant((SW)scan_generic_step<T>(a.cand, xc, RS, i - 1, g, xc, RS, 0xffffffffu, aux, K, res, hi), cb);
+				tm = Map::constant((SW)scan_generic_step<T>(a.cand, xc, RS, i - 1, g, aux, K, res, hi), cb);
 			} else {
 				W Sacc = 0;
 				uint32_t va = 0, vb = 0, vp = 0;
@@ -815,7 +913,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		uint32_t cur = start;
 		if (mode == SCAN_CONST) cur = ra;
 		else if (mode == SCAN_STD) cur = scan_std_step<T>(start, ra, rb, rd, S, Kk, vpos, hi);
-		else if (mode == SCAN_OPAQUE) cur = scan_generic_step<T>(a.cand, xc, RS, i - 1, start, xc, RS, 0xffffffffu, (uint32_t)S, Kk, rd, hi);
+		else if (mode == SCAN_OPAQUE) cur = scan_generic_step<T>(a.cand, xc, RS, i - 1, start, (uint32_t)S, Kk, rd, hi);
 		const long long tD = clock64();
 		// ---------------------------------------------------------------- phase D: verify, publish, write
 		uint32_t ndE = Ecand, ndF = 0xffffffffu;
@@ -830,6 +928,17 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		if (lane == 0) {
 			if (ndE != 0xffffffffu) atomicMin(&s_minE, ndE);
 			if (ndF != 0xffffffffu) atomicMin(&s_minF, ndF);
+		}
+		// next sweep: if it advances like the last one did, this thread owns rank i + lastadv -- start
+		// copying that record into shared memory now, behind the barrier
+		asm volatile("cp.async.wait_all;" ::: "memory");
+		pref_i = 0xffffffffu;
+		if (active && lastadv && (unsigned long long)i + lastadv < n) {
+			pref_i = i + lastadv;
+			const ScanRec *src = srec + pref_i;
+#pragma unroll
+			for (int v = 0; v < 3; ++v) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(prefb + 16 * v), "l"((const uint4 *)src + v) : "memory");
+			asm volatile("cp.async.commit_group;" ::: "memory");
 		}
 		SCAN_CLK(p5);
 		__syncthreads();
@@ -859,6 +968,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 			}
 		} else { smallrun = 0; lastseq = false; }
 		const uint32_t adv = newdone - done;
+		lastadv = adv;
 		if (newdone == wend && wend < n) est = est * 2 < NSEGT ? est * 2 : NSEGT;
 		else est = adv > est - est / 8 ? adv : est - est / 8;
 		done = newdone;
@@ -867,7 +977,8 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		{ const long long tE = clock64(); cyA += tB - tA; cyB += tC - tB; cyC += tD - tC; cyD += tE - tD; }
 	}
 #ifdef SCAN_DEBUG
-	if (t == 0) printf("cta %u A %lld probes: warpscan %lld sync %lld lvl2 %lld csync1 %lld start %lld walk %lld | verify+write %lld sync %lld push+csync2 %lld (per sweep, %llu sweeps)\n", crank, cyA / (long long)sweeps, pr[0] / (long long)sweeps, pr[1] / (long long)sweeps, pr[2] / (long long)sweeps, pr[3] / (long long)sweeps, pr[4] / (long long)sweeps, cyC / (long long)sweeps, pr[5] / (long long)sweeps, pr[6] / (long long)sweeps, pr[7] / (long long)sweeps, sweeps);
+	if (t == 0 && crank == 0 && nseq > 20) printf("seq probes: issue %lld exec %lld finish %lld total cycles over %llu stretches\n", pr[0], pr[1], pr[2], nseq);
+	if (t == 0 && nseq <= 20) printf("cta %u A %lld probes: warpscan %lld sync %lld lvl2 %lld csync1 %lld start %lld walk %lld | verify+write %lld sync %lld push+csync2 %lld (per sweep, %llu sweeps)\n", crank, cyA / (long long)sweeps, pr[0] / (long long)sweeps, pr[1] / (long long)sweeps, pr[2] / (long long)sweeps, pr[3] / (long long)sweeps, pr[4] / (long long)sweeps, cyC / (long long)sweeps, pr[5] / (long long)sweeps, pr[6] / (long long)sweeps, pr[7] / (long long)sweeps, sweeps);
 #endif
 #ifdef SCAN_DEBUG
 	if (crank == 0 && t == 0) printf("comp %u: sweeps %llu fails %llu capped %llu fallback %llu nseq %llu cycles %lld\n", c, sweeps, fails, capped, nfallback, nseq, cyA + cyB + cyC + cyD);

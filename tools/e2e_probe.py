@@ -39,7 +39,7 @@ for it in range(args.reps):
     sc = bench.float_scale_row(la, mn, mx); T.append(time.perf_counter())
     ctx.requant(la, w.new_quant[vl], mn, sc); T.append(time.perf_counter())
     km0 = ctx.last_timing() if hasattr(ctx, "last_timing") else None
-    streams = ctx.attr_encode(hraw); T.append(time.perf_counter())
+    streams, release = ctx.attr_encode_view(hraw); T.append(time.perf_counter())
     km1 = ctx.last_timing() if hasattr(ctx, "last_timing") else None
     ctx.attr_decode(hdec); T.append(time.perf_counter())
     km2 = ctx.last_timing() if hasattr(ctx, "last_timing") else None
@@ -49,3 +49,4 @@ for it in range(args.reps):
     print("iter", it, " ".join(f"{n}={1e3 * (b - a):.1f}ms" for n, a, b in zip(names, T[:-1], T[1:])), f"total={1e3 * (T[-1] - T[0]):.1f}ms",
           "enc(kernel,copy)=", km1, "dec(kernel,copy)=", km2, flush=True)
     del streams
+    release()
