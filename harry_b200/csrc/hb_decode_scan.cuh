@@ -461,6 +461,8 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 
 	__shared__ Map s_all[SCAN_MAXC * SCAN_NWARP]; // warp totals of the whole cluster (pushed by their owners), active warps only
 	__shared__ __align__(8) unsigned long long s_bar; // transaction barrier of the incoming totals
+	__shared__ uint32_t s_eva[SCAN_MAXC * SCAN_NWARP];  // per element: its output if the predecessor says B
+	__shared__ uint32_t s_eam[SCAN_MAXC * SCAN_NWARP / 32], s_ebm[SCAN_MAXC * SCAN_NWARP / 32]; // anchor / broken-shortcut bit masks
 	__shared__ uint32_t s_ndE[SCAN_MAXC];       // per CTA: first rank that reads a non-final window value
 	__shared__ uint32_t s_ndF[SCAN_MAXC];       // per CTA: first rank behind a failed boundary check
 	__shared__ uint32_t s_start[NSEG + 1][NC];  // presumed start value of every slot (+ of the next CTA's first slot)
@@ -835,66 +837,70 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		SCAN_CLK(p3);
 		// [1] wait for the totals promised to this CTA (no barrier: the producers complete the
 		// transaction count that thread 0 armed at the top of the sweep)
-		if (warp < wpc) {
-			while (!scan_mbar_try_wait(bar, bar_parity)) { }
-		}
+		while (!scan_mbar_try_wait(bar, bar_parity)) { }
 		bar_parity ^= 1u;
 		SCAN_CLK(p4);
 		// B2. the value in front of my warp: out[j], out[k] = value after warp total k, j = my element
-		//     - 1.  Once ~cb halvings are composed a total is a step: it outputs B or B + 1.  Lane l
-		//     looks at element k = base - l: fed with the two possible outputs of its predecessor
-		//     it yields a (pred said B) or b (pred said B + 1).  a == b anchors the chain (so does a
-		//     total that is constant over the whole value range, and element 0, whose input
-		//     x[done - 1] is known); b == a + 1 copies the predecessor's choice.  The nearest anchor
-		//     at or before element j decides -- a ballot per 32 elements instead of a scan over the
-		//     cluster.  An element whose predecessor is not a step yet (long runs of single-
-		//     parallelogram vertices) breaks the shortcut: the totals from the anchor on are then
-		//     evaluated one after the other.
+		//     - 1.  Once ~cb halvings are composed a total is a step: it outputs B or B + 1.  Fed
+		//     with the two possible outputs of its predecessor, element k yields a (pred said B) or b
+		//     (pred said B + 1).  a == b anchors the chain (so does a total that is constant over the
+		//     whole value range, and element 0, whose input x[done - 1] is known); b == a + 1 copies
+		//     the predecessor's choice.  The nearest anchor at or before element j decides.  Every
+		//     CTA classifies the elements in front of its last warp once, one element per thread, and
+		//     publishes two bit masks; a warp then finds its anchor with a few bit operations instead
+		//     of a scan over the cluster.  An element whose predecessor is not a step yet (long runs
+		//     of single-parallelogram vertices) breaks the shortcut: the totals from the anchor on
+		//     are then evaluated one after the other.
+		const uint32_t nW = (crank + 1u) * wpc;             // elements that reached this CTA
+		{
+			uint32_t va = 0;
+			bool anch = false, bad = false;
+			if (t < nW) {
+				const Map f = s_all[t];
+				if (t == 0) {
+					va = (uint32_t)(T)f.eval((SW)x0);
+					anch = true;
+				} else {
+					const Map pf = s_all[t - 1];
+					const bool ps = pf.is_step(cb);
+					const uint32_t c0 = (uint32_t)(T)f.eval(0), c1 = (uint32_t)(T)f.eval((SW)hi);
+					va = (uint32_t)(T)f.eval(pf.B);
+					const uint32_t vb = (uint32_t)(T)f.eval(pf.B + 1);
+					if (c0 == c1) { va = c0; anch = true; }
+					else if (ps && va == vb) anch = true;
+					else bad = !ps || vb != va + 1u;
+				}
+				s_eva[t] = va;
+			}
+			if (t < SCAN_MAXC * SCAN_NWARP) {
+				const uint32_t am = __ballot_sync(0xffffffffu, anch), bm = __ballot_sync(0xffffffffu, bad);
+				if (lane == 0) { s_eam[warp] = am; s_ebm[warp] = bm; }
+			}
+		}
+		__syncthreads();
 		uint32_t vstart = x0;
 		if (warp < wpc) {
 			const int j = (int)(crank * wpc + warp) - 1;
 			if (j >= 0) {
-				int base = j, anchor_k = -1;
-				uint32_t a_target = 0, anchor_out = x0;
-				bool first = true, broken = false, direct = false;
-				for (;;) {
-					const int k = base - (int)lane;
-					uint32_t va = 0, kB = 0;
-					bool anch = false, bad = false;
-					if (k >= 0) {
-						const Map f = s_all[k];
-						kB = (uint32_t)f.B;
-						if (k == 0) {
-							va = (uint32_t)(T)f.eval((SW)x0);
-							anch = true;
-						} else {
-							const Map pf = s_all[k - 1];
-							const bool ps = pf.is_step(cb);
-							const uint32_t c0 = (uint32_t)(T)f.eval(0), c1 = (uint32_t)(T)f.eval((SW)hi);
-							va = (uint32_t)(T)f.eval(pf.B);
-							const uint32_t vb = (uint32_t)(T)f.eval(pf.B + 1);
-							if (c0 == c1) { va = c0; anch = true; }
-							else if (ps && va == vb) anch = true;
-							else bad = !ps || vb != va + 1u;
-						}
-					}
-					if (first) { a_target = __shfl_sync(0xffffffffu, va, 0); first = false; }
-					const uint32_t AM = __ballot_sync(0xffffffffu, anch), BM = __ballot_sync(0xffffffffu, bad);
-					if (AM) {
-						const int La = __ffs((int)AM) - 1;
-						if (BM & ((1u << La) - 1u)) broken = true;
-						const uint32_t aLa = __shfl_sync(0xffffffffu, va, La), bLa = __shfl_sync(0xffffffffu, kB, La);
-						anchor_k = base - La;
-						anchor_out = aLa;
-						if (!broken) { vstart = anchor_k == j ? aLa : a_target + (aLa - bLa); direct = true; }
-						break;
-					}
-					if (BM) broken = true;
-					base -= 32;
+				// nearest anchor at or before element j; any bad element in (anchor, j]
+				int wd = j >> 5;
+				uint32_t am = s_eam[wd] & (0xffffffffu >> (31 - (j & 31)));
+				uint32_t badbits = 0, bmask = 0xffffffffu >> (31 - (j & 31));
+				while (am == 0) { // element 0 is always an anchor
+					badbits |= s_ebm[wd] & bmask;
+					--wd;
+					am = s_eam[wd];
+					bmask = 0xffffffffu;
 				}
-				if (!direct) {
-					SW v = (SW)anchor_out;
-					for (int kk = anchor_k + 1; kk <= j; ++kk) v = (SW)(uint32_t)(T)s_all[kk].eval(v);
+				const int hb = 31 - __clz((int)am);
+				const int ka = (wd << 5) + hb;
+				badbits |= s_ebm[wd] & bmask & ~(0xffffffffu >> (31 - hb));
+				const uint32_t aka = s_eva[ka];
+				if (!badbits) {
+					vstart = ka == j ? aka : s_eva[j] + (aka - (uint32_t)s_all[ka].B);
+				} else {
+					SW v = (SW)aka;
+					for (int kk = ka + 1; kk <= j; ++kk) v = (SW)(uint32_t)(T)s_all[kk].eval(v);
 					vstart = (uint32_t)(T)v;
 					if (lane == 0) ++nfallback;
 				}
