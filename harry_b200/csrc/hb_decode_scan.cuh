@@ -811,6 +811,14 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 				}
 			}
 		}
+		// A map only serves the presumed inputs of LATER ranks (a rank's own value comes from the exact
+		// step).  A general-divisor map (3, 5, 6.. parallelograms: the closing vertex of a ring) drags
+		// its warp onto the slow composition path; if the window is cut one or two ranks behind it
+		// anyway, it is not composed -- the repair turn of phase C fixes the one rank in between.
+		if constexpr (sizeof(T) < 4) {
+			const uint32_t cutmask = __ballot_sync(0xffffffffu, Ecand != 0xffffffffu);
+			if (active && mode == SCAN_STD && tm.sm >= 32u && ((cutmask >> lane) & 6u)) tm = Map::constant(0, cb);
+		}
 		const long long tB = clock64();
 		// ---------------------------------------------------------------- phase B: presumed start values
 		// B1. inclusive composition scan inside every active warp; the warp totals go to every CTA
@@ -916,18 +924,36 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		__syncthreads();
 		const long long tC = clock64();
 		// ---------------------------------------------------------------- phase C: the exact step
-		uint32_t cur = start;
-		if (mode == SCAN_CONST) cur = ra;
-		else if (mode == SCAN_STD) cur = scan_std_step<T>(start, ra, rb, rd, S, Kk, vpos, hi);
-		else if (mode == SCAN_OPAQUE) cur = scan_generic_step<T>(a.cand, xc, RS, i - 1, start, (uint32_t)S, Kk, rd, hi);
+		auto exact = [&](uint32_t from) -> uint32_t {
+			if (mode == SCAN_CONST) return ra;
+			if (mode == SCAN_STD) return scan_std_step<T>(from, ra, rb, rd, S, Kk, vpos, hi);
+			if (mode == SCAN_OPAQUE) return scan_generic_step<T>(a.cand, xc, RS, i - 1, from, (uint32_t)S, Kk, rd, hi);
+			return from;
+		};
+		uint32_t cur = exact(start);
+		// one repair turn inside the warp: a thread whose presumed input differs from what its left
+		// neighbour actually produced redoes its step from that value (an isolated bad map -- a rank
+		// whose map was not composed, see phase A -- then costs nothing)
+		{
+			const uint32_t pc = __shfl_up_sync(0xffffffffu, cur, 1);
+			if (active && lane > 0 && pc != start) {
+				start = pc;
+				cur = exact(pc);
+			}
+		}
 		const long long tD = clock64();
 		// ---------------------------------------------------------------- phase D: verify, publish, write
+		// the boundary in front of a thread is good iff its left neighbour's final result is the
+		// input the thread used; across warps: the presumed start of the next warp's first thread
 		uint32_t ndE = Ecand, ndF = 0xffffffffu;
-		if (active) {
-			const uint32_t nxt = s_start[q + 1][0];
-			const bool last = gs + 1 >= nact; // nothing after me in this window
-			if (!last && cur != nxt) ndF = i + 1;
-			if (wr) xc[(size_t)i * RS] = (T)cur;
+		{
+			const uint32_t pc = __shfl_up_sync(0xffffffffu, cur, 1);
+			if (active) {
+				if (lane > 0 && pc != start) ndF = i;
+				const bool last = gs + 1 >= nact; // nothing after me in this window
+				if (lane == 31 && !last && cur != s_start[q + 1][0]) ndF = min(ndF, i + 1);
+				if (wr) xc[(size_t)i * RS] = (T)cur;
+			}
 		}
 		ndE = __reduce_min_sync(0xffffffffu, ndE);
 		ndF = __reduce_min_sync(0xffffffffu, ndF);
