@@ -232,6 +232,30 @@ def algorithmic_bytes(w: Workload) -> dict:
     }
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` per launch, from the committed summary of the
+    last `ncu --set full` capture of this workload (profiles/r01b_*_ncu_full.txt); None if not captured."""
+    import glob
+    import re
+    units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01b_*_ncu_full.txt"))):
+        cur, rd, wr = None, None, None
+        for line in open(path):
+            if line.startswith("## "):
+                cur, rd, wr = line[3:], None, None
+                continue
+            m = re.match(r"dram__bytes_(read|write)\.sum = ([0-9.]+) (\w+)", line)
+            if m and cur is not None and kernel.split("<")[0].strip("() ") in cur:
+                v = float(m.group(2)) * units.get(m.group(3), 1.0)
+                if m.group(1) == "read":
+                    rd = v
+                else:
+                    wr = v
+                if rd is not None and wr is not None:
+                    return rd + wr
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -333,7 +357,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     bytes_launch = alg.get(tname)
     roof = {"bound": "hbm", "kernel": tname, "launches_per_step": tn / args.steps, "ms_per_launch": per_launch_ms,
             "share_of_step": tms / total_ms if total_ms else None, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-            "traffic": None}
+            "traffic": ncu_traffic(tname)}
     if bytes_launch:
         roof["achieved"] = bytes_launch / (per_launch_ms * 1e-3) / 1e9
         roof["frac"] = roof["achieved"] / peak
