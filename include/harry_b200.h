@@ -184,6 +184,8 @@ int hb_requant(hb_ctx *ctx, hb_list_desc *list, const uint8_t *new_quant, const 
                const void *scale_row);
 
 /* ---- attribute coder (host buffers) ------------------------------------------------------ */
+/* *out: library-allocated streams in page-locked host memory; hb_streams_free parks the buffers in
+ * a process-wide cache for the next call ("Ownership"). */
 int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams **out);
 void hb_streams_free(hb_streams *s);
 /* In: lists[l].rows[k] holds the residual of the k-th DATA emission of list l, binding tables
