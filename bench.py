@@ -217,7 +217,10 @@ def algorithmic_bytes(w: Workload) -> dict:
     conn = 16.0 * ne + 4.0 * nv          # every half-edge record once + the rank table
     return {
         "k_bounds_reduce": A * s,
+        "k_bounds_reduce_f32<3>": A * s,
         "k_requant": A * (s + wd),
+        "k_requant_f32": A * (s + s),          # in place: the 4-byte slot is read and written (the quantized value sits in its low bytes)
+        "(k_encode_vtx_packed<T, NC>)": k5,
         "k_vertex_candidates_stage": conn + 4.0 * nv + 12.0 * P * nv,
         "k_vertex_candidates_compact": 2 * 12.0 * P * nv + 4.0 * nv,
         "k_decode_vertex_scan": k5,

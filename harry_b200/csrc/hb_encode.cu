@@ -8,6 +8,8 @@
 //   K5 encode_main prediction from the fan candidates, residual (pred::encodeDelta), byte-plane
 //                  symbol rows, per-context 256-bin histograms, type / history-offset streams
 #include "hb_lists.cuh"
+#include <type_traits>
+#include "hb_decode_spec.cuh" // SpecRec: packed rank-space records
 
 // ------------------------------------------------------------------------------------------------
 template <int CLS>
@@ -341,6 +343,177 @@ __global__ void __launch_bounds__(128) k_encode_wide(ListParams p, EncodeArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5, packed fast path: vertex lists whose components share one integer storage type (every quantized
+// list).  Values live in rank space as one aligned record per vertex (8 bytes for three 16-bit
+// components), so a parallelogram operand is ONE load instead of one 8-byte container per component,
+// and the arithmetic runs in T instead of runtime-typed u64 containers.  Same results as
+// k_encode_main<CLS_VTX>.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) k_gather_packed(ListParams p, const uint32_t *__restrict__ erow, uint32_t n, SpecRec<T, NC> *__restrict__ out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	SpecRec<T, NC> r;
+#pragma unroll
+	for (int j = 0; j < (int)(sizeof(r.c) / sizeof(T)); ++j) r.c[j] = 0;
+	if (row != HB_NONE) {
+		const uint8_t *src = p.rows + (size_t)row * p.stride;
+#pragma unroll
+		for (int j = 0; j < NC; ++j) r.c[j] = (T)hb_ld_bits(src + p.offset[j], (int)sizeof(T));
+	}
+	out[i] = r;
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p, EncodeArgs a, const SpecRec<T, NC> *__restrict__ rec)
+{
+	typedef SpecRec<T, NC> Rec;
+	typedef typename std::conditional<(sizeof(T) <= 2), uint32_t, unsigned long long>::type Acc;
+	extern __shared__ uint32_t s_hist[]; // [NC * sizeof(T)][256] + 4 type counters
+	constexpr int NCTX = NC * (int)sizeof(T);
+	for (int k = threadIdx.x; k < NCTX * 256 + 4; k += ENC_THREADS) s_hist[k] = 0;
+	__syncthreads();
+	uint32_t *s_type = s_hist + NCTX * 256;
+
+	const uint32_t i = blockIdx.x * ENC_THREADS + threadIdx.x;
+	const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
+	int t = -1;
+	T res[NC];
+#pragma unroll
+	for (int j = 0; j < NC; ++j) res[j] = 0;
+	if (row != HB_NONE) {
+		const uint32_t k = a.ek ? a.ek[i] : i;
+		const uint32_t fi = a.first[row];
+		t = HB_DATA;
+		uint32_t aux = 0;
+		if (fi != i) {
+			t = HB_HIST;
+			aux = a.dord[i] - 1u - a.dord[fi]; // tidx - 1 - g, attrcode.h:43-52
+		}
+		a.type[k] = (uint8_t)t;
+		a.aux[k] = aux;
+		const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
+		if (t == HB_DATA && a.wide && K > ENC_WIDE_K) {
+			const uint32_t slot = atomicAdd(&a.wide[0], 1u);
+			if (slot < a.wide_cap) { a.wide[1 + slot] = i; t = -2; } // residual + histogram by k_encode_wide_packed
+		}
+		if (t == HB_DATA) {
+			const Rec raw = rec[i];
+			Acc sum[NC];
+#pragma unroll
+			for (int j = 0; j < NC; ++j) sum[j] = 0;
+			for (uint32_t kk = 0; kk < K; ++kk) {
+				const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
+				const Rec v0 = rec[tr[0]], v1 = rec[tr[1]], v2 = rec[tr[2]];
+#pragma unroll
+				for (int j = 0; j < NC; ++j) sum[j] += (Acc)IntOps<T>::predict(v0.c[j], v1.c[j], v2.c[j], hb_stype_bits(p.stype[j], p.quant[j]));
+			}
+			uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+#pragma unroll
+			for (int j = 0; j < NC; ++j) {
+				const T pred = K == 0 ? (T)0 : (K == 1 ? (T)sum[j] : (K == 2 ? (T)((sum[j] + 1) >> 1) : (T)hb_divround_i64((long long)sum[j], (int)K)));
+				res[j] = IntOps<T>::enc(raw.c[j], pred, hb_stype_bits(p.stype[j], p.quant[j]));
+				hb_st_bits(out + p.sym_off[j], (int)sizeof(T), res[j]);
+			}
+		}
+	}
+	// warp-aggregated histogram update (see k_encode_main)
+	{
+		const bool is_data = t == HB_DATA;
+#pragma unroll
+		for (int j = 0; j < NC; ++j) {
+#pragma unroll
+			for (int b = 0; b < (int)sizeof(T); ++b) {
+				const uint32_t ctx = p.sym_off[j] + b;
+				const uint32_t s = is_data ? ((uint32_t)res[j] >> (8 * b)) & 0xffu : 0x100u + (threadIdx.x & 31u);
+				const unsigned grp = __match_any_sync(0xffffffffu, s);
+				if (is_data && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31u)) atomicAdd(&s_hist[ctx * 256 + s], (uint32_t)__popc(grp));
+			}
+		}
+		for (int ty = 0; ty < 3; ++ty) {
+			const unsigned m = __ballot_sync(0xffffffffu, t == ty || (ty == HB_DATA && t == -2));
+			if (m && (threadIdx.x & 31u) == 0) atomicAdd(&s_type[ty], (uint32_t)__popc(m));
+		}
+	}
+	__syncthreads();
+	for (int k = threadIdx.x; k < NCTX * 256; k += ENC_THREADS)
+		if (s_hist[k]) atomicAdd(&a.hist[k], (unsigned long long)s_hist[k]);
+	if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&a.type_hist[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+}
+
+// one warp per wide vertex (integer sums are order independent)
+template <typename T, int NC>
+__global__ void __launch_bounds__(128) k_encode_wide_packed(ListParams p, EncodeArgs a, const SpecRec<T, NC> *__restrict__ rec)
+{
+	typedef SpecRec<T, NC> Rec;
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t nw = a.wide[0] < a.wide_cap ? a.wide[0] : a.wide_cap;
+	if (w >= nw) return;
+	const uint32_t i = a.wide[1 + w];
+	const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
+	unsigned long long sum[NC];
+#pragma unroll
+	for (int j = 0; j < NC; ++j) sum[j] = 0;
+	for (uint32_t kk = lane; kk < K; kk += 32) {
+		const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
+		const Rec v0 = rec[tr[0]], v1 = rec[tr[1]], v2 = rec[tr[2]];
+#pragma unroll
+		for (int j = 0; j < NC; ++j) sum[j] += (unsigned long long)IntOps<T>::predict(v0.c[j], v1.c[j], v2.c[j], hb_stype_bits(p.stype[j], p.quant[j]));
+	}
+#pragma unroll
+	for (int j = 0; j < NC; ++j)
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], d);
+	if (lane == 0) {
+		const Rec raw = rec[i];
+		uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+#pragma unroll
+		for (int j = 0; j < NC; ++j) {
+			const T pred = (T)hb_divround_i64((long long)sum[j], (int)K);
+			const T r = IntOps<T>::enc(raw.c[j], pred, hb_stype_bits(p.stype[j], p.quant[j]));
+			hb_st_bits(out + p.sym_off[j], (int)sizeof(T), r);
+			for (int b = 0; b < (int)sizeof(T); ++b)
+				atomicAdd(&a.hist[(size_t)(p.sym_off[j] + b) * 256 + (((uint32_t)r >> (8 * b)) & 0xffu)], 1ull);
+		}
+	}
+}
+
+template <typename T, int NC>
+static int encode_vtx_packed_nc(hb_dmesh *m, DevList &dl, const EncodeArgs &a)
+{
+	hb_ctx *ctx = m->ctx;
+	const uint32_t n = dl.n_elems;
+	HB_TRY(hb_dalloc(m, (void **)&dl.d_cx, sizeof(SpecRec<T, NC>) * ((size_t)n + 1)));
+	SpecRec<T, NC> *rec = (SpecRec<T, NC> *)dl.d_cx;
+	HB_LAUNCH(ctx, (k_gather_packed<T, NC>), hb_div_up(n, 256), 256, 0, dl.p, dl.d_erow, n, rec);
+	const size_t smem = sizeof(uint32_t) * ((size_t)NC * sizeof(T) * 256 + 4);
+	HB_LAUNCH(ctx, (k_encode_vtx_packed<T, NC>), hb_div_up(n, ENC_THREADS), ENC_THREADS, smem, dl.p, a, rec);
+	if (a.wide) HB_LAUNCH(ctx, (k_encode_wide_packed<T, NC>), hb_div_up((uint64_t)a.wide_cap * 32, 128), 128, 0, dl.p, a, rec);
+	return 0;
+}
+template <typename T>
+static int encode_vtx_packed(hb_dmesh *m, DevList &dl, const EncodeArgs &a)
+{
+	switch (dl.p.ncomp) {
+	case 1: return encode_vtx_packed_nc<T, 1>(m, dl, a);
+	case 2: return encode_vtx_packed_nc<T, 2>(m, dl, a);
+	case 3: return encode_vtx_packed_nc<T, 3>(m, dl, a);
+	default: return encode_vtx_packed_nc<T, 4>(m, dl, a);
+	}
+}
+static bool packed_eligible(const ListParams &p)
+{
+	if (p.ncomp < 1 || p.ncomp > 4 || p.target != CLS_VTX) return false;
+	const int st = p.uniform_stype;
+	if (st != HB_UCHAR && st != HB_USHORT && st != HB_UINT) return false;
+	for (int j = 0; j < p.ncomp; ++j)
+		if (p.sym_off[j] != j * hb_type_size(st)) return false;
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
 static ElemCtx make_elem_ctx(hb_dmesh *m, int cls)
@@ -452,7 +625,8 @@ int hb_encode_lists(hb_dmesh *m)
 		const int cls = p.target;
 		if (cls != CLS_VTX && cls != CLS_FACE && cls != CLS_CORNER) { dl.n_elems = 0; continue; }
 		if (cls == CLS_CORNER && !m->any_corner) { dl.n_elems = 0; continue; }
-		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE, false));
+		const bool packed = cls == CLS_VTX && packed_eligible(p);
+		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE && !packed, false));
 		const uint32_t n = dl.n_elems;
 		HB_TRY(hb_dalloc_t(m, &dl.d_type, (size_t)n + 1));
 		HB_TRY(hb_dalloc_t(m, &dl.d_aux, (size_t)n + 1));
@@ -481,7 +655,11 @@ int hb_encode_lists(hb_dmesh *m)
 		const int nctx_s = (int)(p.sym_stride < HIST_SMEM_CTX ? p.sym_stride : HIST_SMEM_CTX);
 		const size_t smem = sizeof(uint32_t) * ((size_t)nctx_s * 256 + 4);
 		const uint32_t g = hb_div_up(n, ENC_THREADS);
-		if (cls == CLS_VTX) {
+		if (packed) {
+			if (p.uniform_stype == HB_UCHAR) HB_TRY(encode_vtx_packed<uint8_t>(m, dl, a));
+			else if (p.uniform_stype == HB_USHORT) HB_TRY(encode_vtx_packed<uint16_t>(m, dl, a));
+			else HB_TRY(encode_vtx_packed<uint32_t>(m, dl, a));
+		} else if (cls == CLS_VTX) {
 			HB_LAUNCH(ctx, k_encode_main<CLS_VTX>, g, ENC_THREADS, smem, p, a);
 			if (a.wide) HB_LAUNCH(ctx, k_encode_wide, hb_div_up((uint64_t)a.wide_cap * 32, 128), 128, 0, p, a);
 		}

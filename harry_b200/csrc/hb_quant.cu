@@ -10,6 +10,7 @@
 #include "hb_internal.cuh"
 
 #include <float.h>
+#include <string.h>
 
 // monotone u64 sort keys: unsigned order of the key == numeric order of the value
 __device__ __forceinline__ unsigned long long key_of(unsigned long long bits, int type)
@@ -250,6 +251,165 @@ __global__ void __launch_bounds__(256) k_requant(ListParams p, RequantParams rq,
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast paths for the usual list: every component float32, rows tightly packed (stride == 4 * ncomp),
+// unquantized or at most 16 / 32 bits.  The AoS buffer is then one flat float array: 128-bit loads
+// and stores, four scalars per thread per step; the grid is a multiple of ncomp threads, so the
+// component of each of a thread's four lanes never changes.  Same arithmetic as the generic kernels.
+// ------------------------------------------------------------------------------------------------
+static bool flat_f32(const ListParams &p)
+{
+	if (p.ncomp < 1 || p.ncomp > 4 || p.stride != 4u * (uint32_t)p.ncomp || (((size_t)p.rows) & 15u)) return false;
+	for (int j = 0; j < p.ncomp; ++j)
+		if (p.type[j] != HB_FLOAT || p.offset[j] != 4 * j) return false;
+	return true;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) k_bounds_reduce_f32(const uint4 *__restrict__ rows4, const uint32_t *__restrict__ rows1, uint32_t nscal,
+                                                           unsigned long long *__restrict__ scratch)
+{
+	constexpr uint32_t ncomp = NC;
+	const uint32_t G = gridDim.x * blockDim.x; // a multiple of ncomp
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t nvec = nscal >> 2;
+	uint32_t kmin[4], kmax[4], zneg[4], zpos[4], comp[4];
+#pragma unroll
+	for (int m = 0; m < 4; ++m) {
+		kmin[m] = 0x7f7fffffu ^ 0x80000000u;   // key of numeric_limits<float>::max()
+		kmax[m] = 0x00800000u ^ 0x80000000u;   // key of numeric_limits<float>::min() (quant.h:33)
+		zneg[m] = zpos[m] = 0xffffffffu;
+		comp[m] = (4u * tid + (uint32_t)m) % ncomp;
+	}
+	auto take = [&](int m, uint32_t bits, uint32_t e) {
+		if ((bits & 0x7fffffffu) > 0x7f800000u) return; // NaN never replaces a bound
+		if ((bits & 0x7fffffffu) == 0u) { // remember which zero came first in row order
+			const uint32_t row = e / ncomp;
+			if (bits >> 31) zneg[m] = min(zneg[m], row);
+			else zpos[m] = min(zpos[m], row);
+		}
+		const uint32_t k = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
+		kmin[m] = min(kmin[m], k);
+		kmax[m] = max(kmax[m], k);
+	};
+	// two vectors in flight per thread and step
+	uint32_t v = tid;
+	for (; v + G < nvec; v += 2 * G) {
+		const uint4 q = rows4[v], q2 = rows4[v + G];
+		take(0, q.x, 4u * v); take(1, q.y, 4u * v + 1u); take(2, q.z, 4u * v + 2u); take(3, q.w, 4u * v + 3u);
+		const uint32_t e2 = 4u * (v + G);
+		take(0, q2.x, e2); take(1, q2.y, e2 + 1u); take(2, q2.z, e2 + 2u); take(3, q2.w, e2 + 3u);
+	}
+	if (v < nvec) {
+		const uint4 q = rows4[v];
+		take(0, q.x, 4u * v); take(1, q.y, 4u * v + 1u); take(2, q.z, 4u * v + 2u); take(3, q.w, 4u * v + 3u);
+	}
+	__shared__ unsigned long long s_red[4 * 4];
+	if (threadIdx.x < 16) s_red[threadIdx.x] = (threadIdx.x & 3) == 1 ? 0ull : ~0ull;
+	__syncthreads();
+	// the up to three scalars behind the last full vector: one thread, component = index % ncomp
+	if (tid == 0) {
+		for (uint32_t e = nvec << 2; e < nscal; ++e) {
+			const uint32_t bits = rows1[e], j = e % ncomp, row = e / ncomp;
+			if ((bits & 0x7fffffffu) > 0x7f800000u) continue;
+			if ((bits & 0x7fffffffu) == 0u) atomicMin(&s_red[4 * j + ((bits >> 31) ? 2 : 3)], (unsigned long long)row);
+			const uint32_t k = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
+			atomicMin(&s_red[4 * j + 0], (unsigned long long)k);
+			atomicMax(&s_red[4 * j + 1], (unsigned long long)k);
+		}
+	}
+	// warp-level combine first: lanes l and l + ncomp * x hold the same components only if 4 * 32 is a
+	// multiple of ncomp; keep it simple -- shared-memory atomics, 16 per thread at most, once per kernel
+#pragma unroll
+	for (int m = 0; m < 4; ++m) {
+		const uint32_t j = comp[m];
+		atomicMin(&s_red[4 * j + 0], (unsigned long long)kmin[m]);
+		atomicMax(&s_red[4 * j + 1], (unsigned long long)kmax[m]);
+		if (zneg[m] != 0xffffffffu) atomicMin(&s_red[4 * j + 2], (unsigned long long)zneg[m]);
+		if (zpos[m] != 0xffffffffu) atomicMin(&s_red[4 * j + 3], (unsigned long long)zpos[m]);
+	}
+	__syncthreads();
+	if (threadIdx.x < 4 * ncomp) {
+		const uint32_t k = threadIdx.x;
+		if ((k & 3) == 1) atomicMax(&scratch[k], s_red[k]);
+		else if (s_red[k] != ~0ull) atomicMin(&scratch[k], s_red[k]);
+	}
+}
+
+struct FlatRequant {
+	float mn[4], sc[4], m_src[4], m_dst[4];
+	uint32_t smask[4], dmask[4]; // low-byte masks of the source / destination storage type (0: the float itself)
+	uint8_t sq[4], dq[4];
+};
+// one scalar: quant.h:135 (float -> fixed), :167-169 (fixed -> fixed), :182 (fixed -> float); the bytes of the
+// slot above the destination storage type keep their old contents
+__device__ __forceinline__ uint32_t requant_f32_one(uint32_t bits, const FlatRequant &r, int j)
+{
+	if (r.sq[j] == 0 && r.dq[j] == 0) return bits;
+	unsigned long long q;
+	if (r.sq[j]) q = bits & r.smask[j];
+	else q = (unsigned long long)__fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__uint_as_float(bits), r.mn[j]), r.sc[j]), r.m_dst[j]), 0.5f);
+	if (r.sq[j] && r.dq[j]) {
+		const unsigned long long ms = (unsigned long long)(long long)(int32_t)((1u << r.sq[j]) - 1u), md = (unsigned long long)(long long)(int32_t)((1u << r.dq[j]) - 1u);
+		q = q / ms * md + q % ms * md / ms;
+	}
+	if (r.dq[j]) return (bits & ~r.dmask[j]) | ((uint32_t)q & r.dmask[j]);
+	return __float_as_uint(__fadd_rn(__fmul_rn(__fdiv_rn((float)q, r.m_src[j]), r.sc[j]), r.mn[j]));
+}
+struct FlatLane { float mn, sc, m_src, m_dst; uint32_t smask, dmask, sq, dq; };
+__device__ __forceinline__ uint32_t requant_f32_lane(uint32_t bits, const FlatLane &r)
+{
+	if (r.sq == 0 && r.dq == 0) return bits;
+	unsigned long long q;
+	if (r.sq) q = bits & r.smask;
+	else q = (unsigned long long)__fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__uint_as_float(bits), r.mn), r.sc), r.m_dst), 0.5f);
+	if (r.sq && r.dq) {
+		const unsigned long long ms = (unsigned long long)(long long)(int32_t)((1u << r.sq) - 1u), md = (unsigned long long)(long long)(int32_t)((1u << r.dq) - 1u);
+		q = q / ms * md + q % ms * md / ms;
+	}
+	if (r.dq) return (bits & ~r.dmask) | ((uint32_t)q & r.dmask);
+	return __float_as_uint(__fadd_rn(__fmul_rn(__fdiv_rn((float)q, r.m_src), r.sc), r.mn));
+}
+__global__ void __launch_bounds__(256) k_requant_f32(uint4 *__restrict__ rows4, uint32_t *__restrict__ rows1, uint32_t nscal, uint32_t ncomp, FlatRequant r, const float *__restrict__ bounds)
+{
+	// bounds rows (k_bounds_finish / k_scale): min at row 0, scale at row 2, `ncomp` floats each
+	for (uint32_t j = 0; j < ncomp; ++j) { r.mn[j] = bounds[j]; r.sc[j] = bounds[2 * ncomp + j]; }
+	const uint32_t G = gridDim.x * blockDim.x; // a multiple of ncomp
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t nvec = nscal >> 2;
+	FlatLane L[4];
+#pragma unroll
+	for (int m = 0; m < 4; ++m) {
+		const int j = (int)((4u * tid + (uint32_t)m) % ncomp);
+		L[m].mn = r.mn[j]; L[m].sc = r.sc[j]; L[m].m_src = r.m_src[j]; L[m].m_dst = r.m_dst[j];
+		L[m].smask = r.smask[j]; L[m].dmask = r.dmask[j]; L[m].sq = r.sq[j]; L[m].dq = r.dq[j];
+	}
+	uint32_t v = tid;
+	for (; v + G < nvec; v += 2 * G) {
+		uint4 q = rows4[v], q2 = rows4[v + G];
+		q.x = requant_f32_lane(q.x, L[0]); q.y = requant_f32_lane(q.y, L[1]); q.z = requant_f32_lane(q.z, L[2]); q.w = requant_f32_lane(q.w, L[3]);
+		q2.x = requant_f32_lane(q2.x, L[0]); q2.y = requant_f32_lane(q2.y, L[1]); q2.z = requant_f32_lane(q2.z, L[2]); q2.w = requant_f32_lane(q2.w, L[3]);
+		rows4[v] = q;
+		rows4[v + G] = q2;
+	}
+	if (v < nvec) {
+		uint4 q = rows4[v];
+		q.x = requant_f32_lane(q.x, L[0]); q.y = requant_f32_lane(q.y, L[1]); q.z = requant_f32_lane(q.z, L[2]); q.w = requant_f32_lane(q.w, L[3]);
+		rows4[v] = q;
+	}
+	if (tid == 0)
+		for (uint32_t e = nvec << 2; e < nscal; ++e) rows1[e] = requant_f32_one(rows1[e], r, (int)(e % ncomp));
+}
+// threads of a flat kernel: ~8 blocks of 256 per SM, a multiple of 256 * ncomp, not more than the work
+static uint32_t flat_blocks(hb_ctx *ctx, uint32_t nvec, uint32_t ncomp)
+{
+	uint32_t blocks = (uint32_t)ctx->sm_count * 8;
+	const uint32_t need = hb_div_up(nvec ? nvec : 1, 256);
+	if (blocks > need) blocks = need;
+	blocks = (blocks + ncomp - 1) / ncomp * ncomp;
+	return blocks;
+}
+
 static uint32_t pick_rows_per_step(hb_ctx *ctx, const ListParams &p)
 {
 	// ~8 resident blocks of 256 threads per SM, rounded so that threads = rows_per_step * ncomp
@@ -271,7 +431,23 @@ int hb_list_bounds(hb_dmesh *m, uint32_t l)
 	unsigned long long *scratch = nullptr;
 	HB_CUDA(ctx, cudaMallocAsync((void **)&scratch, sizeof(unsigned long long) * 4 * HB_MAX_COMP, ctx->stream));
 	HB_LAUNCH(ctx, k_bounds_init, 1, HB_MAX_COMP, 0, p, scratch);
-	if (p.nrows) {
+	if (p.nrows && flat_f32(p) && (uint64_t)p.nrows * p.ncomp < 0xffffffffull) {
+		bool unq = true;
+		for (int j = 0; j < p.ncomp; ++j) unq = unq && p.quant[j] == 0;
+		if (unq) {
+			const uint32_t nscal = p.nrows * (uint32_t)p.ncomp;
+			const uint32_t fb = flat_blocks(ctx, nscal >> 2, (uint32_t)p.ncomp);
+			switch (p.ncomp) {
+			case 1: HB_LAUNCH(ctx, k_bounds_reduce_f32<1>, fb, 256, 0, (const uint4 *)p.rows, (const uint32_t *)p.rows, nscal, scratch); break;
+			case 2: HB_LAUNCH(ctx, k_bounds_reduce_f32<2>, fb, 256, 0, (const uint4 *)p.rows, (const uint32_t *)p.rows, nscal, scratch); break;
+			case 3: HB_LAUNCH(ctx, k_bounds_reduce_f32<3>, fb, 256, 0, (const uint4 *)p.rows, (const uint32_t *)p.rows, nscal, scratch); break;
+			default: HB_LAUNCH(ctx, k_bounds_reduce_f32<4>, fb, 256, 0, (const uint4 *)p.rows, (const uint32_t *)p.rows, nscal, scratch); break;
+			}
+		} else {
+			const uint32_t rps = pick_rows_per_step(ctx, p);
+			HB_LAUNCH(ctx, k_bounds_reduce, hb_div_up((uint64_t)rps * p.ncomp, 256), 256, 0, p, scratch, rps);
+		}
+	} else if (p.nrows) {
 		const uint32_t rps = pick_rows_per_step(ctx, p);
 		HB_LAUNCH(ctx, k_bounds_reduce, hb_div_up((uint64_t)rps * p.ncomp, 256), 256, 0, p, scratch, rps);
 	}
@@ -309,7 +485,22 @@ int hb_list_requant(hb_dmesh *m, uint32_t l, const uint8_t *new_quant)
 		if (p.type[j] == HB_DOUBLE) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "requant: double lists (the reference shifts an int by >= 32 bits, undefined)");
 		if (p.quant[j] > 31 || new_quant[j] > 31) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "requant: more than 31 bits (the reference computes 1 << q in int, undefined)");
 	}
-	if (any && p.nrows) {
+	bool flat = any && p.nrows && flat_f32(p) && (uint64_t)p.nrows * p.ncomp < 0xffffffffull;
+	for (int j = 0; flat && j < p.ncomp; ++j) flat = p.quant[j] <= 31 && new_quant[j] <= 31;
+	if (flat) {
+		FlatRequant fr;
+		memset(&fr, 0, sizeof fr);
+		for (int j = 0; j < p.ncomp; ++j) {
+			const int sq = p.quant[j], dq = new_quant[j];
+			fr.sq[j] = (uint8_t)sq; fr.dq[j] = (uint8_t)dq;
+			fr.m_src[j] = sq ? (float)(int32_t)((1u << sq) - 1u) : 0.f;
+			fr.m_dst[j] = dq ? (float)(int32_t)((1u << dq) - 1u) : 0.f;
+			fr.smask[j] = sq ? (sq <= 8 ? 0xffu : sq <= 16 ? 0xffffu : 0xffffffffu) : 0u;
+			fr.dmask[j] = dq ? (dq <= 8 ? 0xffu : dq <= 16 ? 0xffffu : 0xffffffffu) : 0u;
+		}
+		const uint32_t nscal = p.nrows * (uint32_t)p.ncomp;
+		HB_LAUNCH(ctx, k_requant_f32, flat_blocks(ctx, nscal >> 2, (uint32_t)p.ncomp), 256, 0, (uint4 *)p.rows, (uint32_t *)p.rows, nscal, (uint32_t)p.ncomp, fr, (const float *)dl.d_bounds);
+	} else if (any && p.nrows) {
 		const uint32_t rps = pick_rows_per_step(ctx, p);
 		HB_LAUNCH(ctx, k_requant, hb_div_up((uint64_t)rps * p.ncomp, 256), 256, 0, p, rq, dl.d_bounds, rps);
 	}
