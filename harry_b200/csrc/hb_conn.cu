@@ -9,7 +9,7 @@
 #include "hb_internal.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// exclusive scan (3-phase), out[n] receives the total
+// exclusive scan (single pass, decoupled look-back), out[n] receives the total
 // ------------------------------------------------------------------------------------------------
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 8
@@ -43,61 +43,111 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
 	return base + x - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t *__restrict__ tile_sums, uint32_t n)
+// Single pass with decoupled look-back: a tile publishes its aggregate, looks back over the status
+// words of its predecessors until it meets an inclusive prefix, and publishes its own.  Tiles are
+// numbered by an atomic ticket (a tile never waits for one that has not started).  Status word:
+// bits 62..63 = 0 empty / 1 aggregate / 2 inclusive prefix, low 32 bits = value.
+#define SCAN_VEC (SCAN_ITEMS / 4)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, unsigned long long *__restrict__ status,
+                                                               uint32_t *__restrict__ ticket, uint32_t n, uint32_t ntiles, uint32_t *__restrict__ out_total2)
 {
-	const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	__shared__ uint32_t s_tile, s_prefix;
+	if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
 	uint32_t v[SCAN_ITEMS], s = 0;
+	if (base + SCAN_ITEMS <= n && ((((size_t)in) & 15u) == 0)) {
 #pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; ++k) {
-		v[k] = base + k < n ? in[base + k] : 0;
-		s += v[k];
+		for (int q = 0; q < SCAN_VEC; ++q) {
+			const uint4 w = ((const uint4 *)(in + base))[q];
+			v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = base + k < n ? in[base + k] : 0;
 	}
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
 	uint32_t total;
 	uint32_t ex = block_exclusive_scan(s, &total);
-#pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; ++k) {
-		if (base + k < n) out[base + k] = ex;
-		ex += v[k];
-	}
-	if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t *__restrict__ tile_sums, uint32_t ntiles, uint32_t *__restrict__ out_total, uint32_t *__restrict__ out_total2)
-{
-	uint32_t carry = 0;
-	for (uint32_t base = 0; base < ntiles; base += SCAN_THREADS) {
-		const uint32_t i = base + threadIdx.x;
-		const uint32_t v = i < ntiles ? tile_sums[i] : 0;
-		uint32_t total;
-		const uint32_t ex = block_exclusive_scan(v, &total);
-		if (i < ntiles) tile_sums[i] = carry + ex;
-		carry += total;
-	}
 	if (threadIdx.x == 0) {
-		*out_total = carry;
-		if (out_total2) *out_total2 = carry;
+		volatile unsigned long long *st = status;
+		if (tile == 0) {
+			st[0] = (2ull << 62) | total;
+			s_prefix = 0;
+		} else {
+			st[tile] = (1ull << 62) | total;
+		}
+	}
+	if (tile > 0 && threadIdx.x < 32) {
+		// warp 0 looks back 32 tiles at a time
+		volatile unsigned long long *st = status;
+		uint32_t acc = 0;
+		int j = (int)tile - 1;
+		for (;;) {
+			const int k = j - (int)threadIdx.x;
+			unsigned long long w = k >= 0 ? st[k] : (2ull << 62);
+			// wait until every word of this window is published
+			while (__any_sync(0xffffffffu, (w >> 62) == 0)) w = k >= 0 ? st[k] : (2ull << 62);
+			const unsigned incl = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+			const int first = incl ? __ffs((int)incl) - 1 : 32; // nearest inclusive prefix in the window
+			uint32_t part = (int)threadIdx.x <= first ? (uint32_t)w : 0u;
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+			acc += part;
+			if (incl) break;
+			j -= 32;
+		}
+		if (threadIdx.x == 0) {
+			s_prefix = acc;
+			__threadfence();
+			st[tile] = (2ull << 62) | (unsigned long long)(acc + total);
+		}
+	}
+	__syncthreads();
+	ex += s_prefix;
+	if (base + SCAN_ITEMS <= n && ((((size_t)out) & 15u) == 0)) {
+#pragma unroll
+		for (int q = 0; q < SCAN_VEC; ++q) {
+			uint4 w;
+			w.x = ex; ex += v[4 * q];
+			w.y = ex; ex += v[4 * q + 1];
+			w.z = ex; ex += v[4 * q + 2];
+			w.w = ex; ex += v[4 * q + 3];
+			((uint4 *)(out + base))[q] = w;
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SCAN_ITEMS; ++k) {
+			if (base + k < n) out[base + k] = ex;
+			ex += v[k];
+		}
+	}
+	if (tile == ntiles - 1 && threadIdx.x == 0) {
+		out[n] = s_prefix + total;
+		if (out_total2) *out_total2 = s_prefix + total;
 	}
 }
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ tile_sums, uint32_t n)
+__global__ void k_scan_empty(uint32_t *out, uint32_t *out_total2)
 {
-	const uint32_t add = tile_sums[blockIdx.x];
-	const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; ++k)
-		if (base + k < n) out[base + k] += add;
+	out[0] = 0;
+	if (out_total2) *out_total2 = 0;
 }
 
 // d_out must hold n + 1 entries; d_out[n] = total.  in == out is allowed.
 int hb_scan_exclusive_u32(hb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint32_t n, uint32_t *d_total)
 {
 	const uint32_t ntiles = n ? hb_div_up(n, SCAN_TILE) : 0;
-	uint32_t *d_sums = nullptr;
-	HB_CUDA(ctx, cudaMallocAsync((void **)&d_sums, sizeof(uint32_t) * (ntiles + 1), ctx->stream));
-	if (ntiles) HB_LAUNCH(ctx, k_scan_tiles, ntiles, SCAN_THREADS, 0, d_in, d_out, d_sums, n);
-	HB_LAUNCH(ctx, k_scan_sums, 1, SCAN_THREADS, 0, d_sums, ntiles, d_out + n, d_total);
-	if (ntiles > 1) HB_LAUNCH(ctx, k_scan_add, ntiles, SCAN_THREADS, 0, d_out, d_sums, n);
-	HB_CUDA(ctx, cudaFreeAsync(d_sums, ctx->stream));
+	if (!ntiles) {
+		HB_LAUNCH(ctx, k_scan_empty, 1, 1, 0, d_out, d_total);
+		return 0;
+	}
+	unsigned long long *d_status = nullptr;
+	HB_CUDA(ctx, cudaMallocAsync((void **)&d_status, sizeof(unsigned long long) * ((size_t)ntiles + 1), ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(unsigned long long) * ((size_t)ntiles + 1), ctx->stream));
+	HB_LAUNCH(ctx, k_scan_lookback, ntiles, SCAN_THREADS, 0, d_in, d_out, d_status, (uint32_t *)(d_status + ntiles), n, ntiles, d_total);
+	HB_CUDA(ctx, cudaFreeAsync(d_status, ctx->stream));
 	return 0;
 }
 

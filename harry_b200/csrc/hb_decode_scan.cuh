@@ -68,8 +68,8 @@ struct alignas(16) ScanRec {
 __global__ void __launch_bounds__(256) k_scan_prep(const uint8_t *__restrict__ kind, const uint32_t *__restrict__ src, const uint32_t *__restrict__ cand_off,
                                                    const uint32_t *__restrict__ cand, uint32_t n, ScanRec *__restrict__ out)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+	const uint32_t iraw = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = iraw < n ? iraw : n - 1; // threads behind the end redo the last rank (their words are not stored)
 	const uint32_t kd = kind[i];
 	const uint32_t c0 = cand_off[i], K = cand_off[i + 1] - c0;
 	const uint32_t pr = i - 1; // 0xffffffff for i == 0: never equal to an operand
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(256) k_scan_prep(const uint8_t *__restrict__ k
 		}
 		if (npred > 1 || (K > SCAN_KIN && K <= SCAN_WIDE)) hdr |= SCAN_HDR_IRREGULAR;
 	}
+	if (iraw >= n) return;
 	uint4 *o = (uint4 *)(out + i);
 	o[0] = make_uint4(hdr, kd == 2 ? src[i] : c0, farp1, tri[0]);
 	o[1] = make_uint4(tri[1], tri[2], tri[3], tri[4]);
