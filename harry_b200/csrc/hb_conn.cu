@@ -438,7 +438,8 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_compact(const uint4 *
 // half-edges whose origin is a wide vertex: count per vertex (SCATTER = false), then scatter into
 // contiguous node lists and note every node's index (SCATTER = true)
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ he, uint32_t ne, WideCtl *__restrict__ wide, uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos)
+__global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ he, uint32_t ne, WideCtl *__restrict__ wide, uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos,
+                                                      uint32_t cap_per_slot)
 {
 	__shared__ uint32_t s_v[VC_MAXWIDE];
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
@@ -450,12 +451,32 @@ __global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ 
 			if (org != s_v[w]) continue;
 			if (!SCATTER) atomicAdd(&wide->deg[w], 1u);
 			else {
-				const uint32_t idx = wide->base[w] + atomicAdd(&wide->fill[w], 1u);
+				const uint32_t k = atomicAdd(&wide->fill[w], 1u);
+				if (k >= cap_per_slot) continue; // evenly split arena too small: the host falls back to exact slots
+				const uint32_t idx = wide->base[w] + k;
 				nodes[idx] = e;
 				pos[e] = idx;
 			}
 		}
 	}
+}
+// evenly split arena: slot w owns [w * per, (w + 1) * per); base[VC_MAXWIDE] doubles as the overflow flag
+__global__ void k_wide_even_bases(WideCtl *wide, uint32_t per)
+{
+	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
+	for (uint32_t w = 0; w <= nw; ++w) wide->base[w] = w * per;
+	for (uint32_t w = 0; w < nw; ++w) wide->fill[w] = 0;
+	wide->base[VC_MAXWIDE] = 0;
+}
+__global__ void k_wide_fill_to_deg(WideCtl *wide, uint32_t per)
+{
+	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
+	uint32_t overflow = 0;
+	for (uint32_t w = 0; w < nw; ++w) {
+		wide->deg[w] = wide->fill[w];
+		if (wide->fill[w] > per) overflow = 1;
+	}
+	wide->base[VC_MAXWIDE] = overflow;
 }
 __global__ void k_wide_bases(WideCtl *wide)
 {
@@ -671,26 +692,46 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 		uint32_t *arena = nullptr;
 		if (nwide) {
 			const uint32_t grid = (uint32_t)ctx->sm_count * 8;
-			HB_LAUNCH(ctx, k_wide_collect<false>, grid, 256, 0, m->d_he, m->ne, wide, (uint32_t *)nullptr, (uint32_t *)nullptr);
-			HB_LAUNCH(ctx, k_wide_bases, 1, 1, 0, wide);
-			uint32_t total = 0;
-			HB_CUDA(ctx, cudaMemcpyAsync(&total, &wide->base[nwide], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-			HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-			// scratch of the wide path: sized by this mesh's wide fans, released with the mesh
-			uint32_t *nodes = nullptr, *pos = nullptr, *work = nullptr, *order = nullptr;
-			if (total > m->vc_wide_cap) {
-				m->d_vc_wnodes = m->d_vc_wwork = m->d_vc_worder = m->d_vc_warena = nullptr; // the old ones stay in m->allocs until the mesh is freed
-				m->vc_wide_cap = total;
-			}
-			HB_TRY(hb_dalloc_t(m, &m->d_vc_wnodes, (size_t)total + 1));
+			// One streaming pass when the fans fit an evenly split arena (WIDE_ARENA nodes in all: a
+			// sphere pole has a few thousand); otherwise count first, then scatter into exact slots.
+			const uint32_t WIDE_ARENA = 1u << 20;
+			const uint32_t per = WIDE_ARENA / nwide;
+			uint32_t total = per * nwide;
 			HB_TRY(hb_dalloc_t(m, &m->d_vc_wpos, (size_t)m->ne + 1));
-			HB_TRY(hb_dalloc_t(m, &m->d_vc_wwork, 6 * (size_t)total + 6));
-			HB_TRY(hb_dalloc_t(m, &m->d_vc_worder, (size_t)total + 1));
-			HB_TRY(hb_dalloc_t(m, &m->d_vc_warena, 6 * (size_t)total + 6));
-			nodes = m->d_vc_wnodes; pos = m->d_vc_wpos; work = m->d_vc_wwork; order = m->d_vc_worder; arena = m->d_vc_warena;
-			HB_LAUNCH(ctx, k_wide_collect<true>, grid, 256, 0, m->d_he, m->ne, wide, nodes, pos);
-			HB_LAUNCH(ctx, k_wide_rank, nwide, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + total, work + 2 * (size_t)total, work + 3 * (size_t)total,
-			          work + 4 * (size_t)total, work + 5 * (size_t)total, order, arena, m->d_vc_off, ctx->d_err);
+			bool exact = m->vc_wide_cap > WIDE_ARENA; // a previous run over this mesh already needed exact slots
+			if (!exact) {
+				if (m->vc_wide_cap < total) { m->d_vc_wnodes = m->d_vc_wwork = m->d_vc_worder = m->d_vc_warena = nullptr; m->vc_wide_cap = total; }
+				HB_TRY(hb_dalloc_t(m, &m->d_vc_wnodes, (size_t)m->vc_wide_cap + 1));
+				HB_LAUNCH(ctx, k_wide_even_bases, 1, 1, 0, wide, per);
+				HB_LAUNCH(ctx, k_wide_collect<true>, grid, 256, 0, m->d_he, m->ne, wide, m->d_vc_wnodes, m->d_vc_wpos, per);
+				HB_LAUNCH(ctx, k_wide_fill_to_deg, 1, 1, 0, wide, per);
+				uint32_t overflow = 0;
+				HB_CUDA(ctx, cudaMemcpyAsync(&overflow, &wide->base[VC_MAXWIDE], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+				HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				exact = overflow != 0;
+			}
+			if (exact) {
+				HB_CUDA(ctx, cudaMemsetAsync(wide->deg, 0, sizeof(wide->deg), ctx->stream));
+				HB_LAUNCH(ctx, k_wide_collect<false>, grid, 256, 0, m->d_he, m->ne, wide, (uint32_t *)nullptr, (uint32_t *)nullptr, 0u);
+				HB_LAUNCH(ctx, k_wide_bases, 1, 1, 0, wide);
+				HB_CUDA(ctx, cudaMemcpyAsync(&total, &wide->base[nwide], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+				HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				if (total > m->vc_wide_cap || m->vc_wide_cap <= WIDE_ARENA) {
+					m->d_vc_wnodes = m->d_vc_wwork = m->d_vc_worder = m->d_vc_warena = nullptr; // the old ones stay in m->allocs until the mesh is freed
+					m->vc_wide_cap = total > WIDE_ARENA ? total : WIDE_ARENA + 1;
+				}
+				HB_TRY(hb_dalloc_t(m, &m->d_vc_wnodes, (size_t)m->vc_wide_cap + 1));
+				HB_LAUNCH(ctx, k_wide_collect<true>, grid, 256, 0, m->d_he, m->ne, wide, m->d_vc_wnodes, m->d_vc_wpos, 0xffffffffu);
+			}
+			// scratch of the ranking: sized like the node arena, released with the mesh
+			const size_t cap = m->vc_wide_cap;
+			HB_TRY(hb_dalloc_t(m, &m->d_vc_wwork, 6 * cap + 6));
+			HB_TRY(hb_dalloc_t(m, &m->d_vc_worder, cap + 1));
+			HB_TRY(hb_dalloc_t(m, &m->d_vc_warena, 6 * cap + 6));
+			uint32_t *nodes = m->d_vc_wnodes, *pos = m->d_vc_wpos, *work = m->d_vc_wwork, *order = m->d_vc_worder;
+			arena = m->d_vc_warena;
+			HB_LAUNCH(ctx, k_wide_rank, nwide, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + cap, work + 2 * cap, work + 3 * cap,
+			          work + 4 * cap, work + 5 * cap, order, arena, m->d_vc_off, ctx->d_err);
 		}
 		HB_TRY(hb_scan_exclusive_u32(ctx, m->d_vc_off, m->d_vc_off, n, nullptr));
 		HB_CUDA(ctx, cudaMemcpyAsync(&m->vc_total, m->d_vc_off + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
