@@ -15,28 +15,34 @@
 // prediction.h:46-63), which are in the family as well.  So a window of ranks whose other operands are
 // final can be reconstructed by a parallel prefix composition instead of a sequential walk.
 //
-// Exactness does not rest on that algebra.  Every sweep:
-//   A. window = ranks [done, done + nact * R), R consecutive ranks per thread.  Each thread loads the
-//      operands of its ranks, notes the first rank E that reads a window rank other than its
-//      predecessor (window values are not final: nothing at or after E can be validated this sweep),
-//      and builds the map of each rank: the regular floor-affine form, or -- when a previous sweep
-//      left a guess g for x[i-1] and the exact step disagrees with the regular form at g -- the
-//      constant f_i(g).
-//   B. inclusive composition scan over threads (warp shuffles, shared memory, cluster totals through
-//      distributed shared memory) -> the presumed value of every thread's predecessor rank.
-//   C. every thread walks its R ranks with the EXACT reference step (IntOps::predict_hi / dec_hi)
-//      from that presumed value.
-//   D. verification: thread t is "good" iff the exact end value of thread t equals the presumed start
-//      value of thread t + 1.  Thread 0 starts from x[done - 1], which is final; by induction every
-//      rank up to the first bad boundary is the sequential result.  done = min(that boundary, E).
+// Exactness does not rest on that algebra.  Every sweep (one thread per rank of the window):
+//   A. window = ranks [done, done + slots).  Each thread reads the record of its rank (k_scan_prep:
+//      which operand is rank i - 1, the highest other operand) and the operand values, notes whether
+//      its rank reads a window rank other than its predecessor (the first such rank E cuts the window:
+//      nothing at or after E can be validated this sweep), and builds the map of its rank: the regular
+//      floor-affine form, or -- when a previous sweep left a guess g for x[i-1] and the exact step
+//      disagrees with the regular form at g -- the constant f_i(g).
+//   B. inclusive composition scan inside each warp; the warp totals travel to the other CTAs of the
+//      cluster (st.async completing a transaction barrier); every CTA classifies the totals -- a total
+//      is a step, so fed with the two possible outputs of its predecessor it either gives one value
+//      (anchor) or copies the predecessor's choice -- and a warp finds the value in front of it from the
+//      nearest anchor with a few bit operations -> the presumed input of every thread.
+//   C. every thread runs the EXACT reference step (ScanOps::predict / dec == IntOps, prediction.h)
+//      from its presumed input; one repair turn inside the warp redoes the step of a thread whose left
+//      neighbour produced something else.
+//   D. verification: the boundary in front of a thread is good iff its left neighbour's exact result
+//      is the input the thread used.  Thread 0 starts from x[done - 1], which is final; by induction
+//      every rank up to the first bad boundary is the sequential result.  done = min(that, E).
 // Machine mapping: one thread-block cluster per (list, component) -- the components of an integer list
-// are independent chains, so they run on different SMs -- and one thread per rank of the window
-// (R = 1 in the description above).  A sweep is bounded by dependent-instruction latency and by the
-// two cluster barriers, not by bandwidth: the per-rank classification is done once, in the prep
-// kernel, and the cluster is sized so that an SM holds only a few active warps.
-// Progress is at least one rank per sweep for ANY input (group 0 is always exact); the algebra only
+// are independent chains, so they run on different SMs.  A sweep is bounded by dependent-instruction
+// latency and by the two hand-offs (warp totals; values + limits through a cluster barrier), not by
+// bandwidth: the window is dealt evenly to the CTAs so that an SM holds only a few active warps, the
+// record of the next sweep is copied into shared memory behind the barrier (cp.async).
+// Progress is at least one rank per sweep for ANY input (thread 0 is always exact); the algebra only
 // decides how far `done` moves.  Ranks with more than SCAN_WIDE candidates (sphere poles) end the
-// window and are evaluated by a whole CTA when `done` reaches them (integer sums commute).
+// window and are evaluated by a whole CTA when `done` reaches them (integer sums commute); windows
+// of a few ranks (higher-order dependence on the chain: the first ring of a sphere, irregular
+// triangulations) are handed to a sequential walker (one warp: prepare 32 ranks ahead / execute).
 #pragma once
 #include <cooperative_groups.h>
 #include "hb_decode_spec.cuh"
