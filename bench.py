@@ -411,8 +411,11 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             if it == 1:
                 rows_b = la.rows.nbytes
                 conn_b = sum(getattr(hraw, n).nbytes for n in ("edges", "face_off", "order", "order_f", "vtx_regs", "face_regs", "bind_face", "bind_vtx"))
-                dconn_b = sum(getattr(hdec, n).nbytes for n in ("edges", "face_off", "order", "vtx_regs", "face_regs", "bind_face", "bind_vtx")) + \
-                    (hdec.order_f.nbytes if hdec.order_f is not None else 0)
+                # hb_attr_decode of a mesh whose face / corner lists carry no components uploads no face-side arrays (target 1 == HB_VTX)
+                vertex_only = all(l.ncomp == 0 or l.nrows == 0 or l.target == 1 for l in hdec.lists)
+                dnames = ("edges", "face_off", "order", "vtx_regs", "bind_vtx") if vertex_only else ("edges", "face_off", "order", "vtx_regs", "face_regs", "bind_face", "bind_vtx")
+                dconn_b = sum(getattr(hdec, n).nbytes for n in dnames) + \
+                    (hdec.order_f.nbytes if hdec.order_f is not None and not vertex_only else 0)
                 h2d = rows_b * 2 + conn_b + rows_b + dconn_b + ld.rows.nbytes * 2 + sum(len(t) for t in w.dec.emit_types)
                 d2h = rows_b + ld.rows.nbytes * 2 + streams.reg_vtx.nbytes + streams.reg_face.nbytes + \
                     sum(x.type.nbytes + x.aux.nbytes + x.symbols.nbytes + x.hist.nbytes for x in streams.lists)

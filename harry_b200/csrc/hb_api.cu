@@ -298,13 +298,16 @@ static int build_slot_table(hb_ctx *ctx, const int32_t *off, const uint16_t *lis
 	return 0;
 }
 
-static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh *m)
+// vertex_only: the caller will only reconstruct vertex lists (hb_attr_decode of a mesh whose face and
+// corner lists carry no components): the face-side arrays (order_f, face regions, face / corner bindings --
+// 280 MB on the 10M-vertex mesh) are then neither uploaded nor ranked
+static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh *m, bool vertex_only = false)
 {
 	m->ctx = ctx;
 	m->nv = d->nv; m->nf = d->nf; m->ne = d->ne;
 	m->norder = d->norder;
-	m->has_order_f = d->order_f != nullptr;
-	m->norder_f = d->order_f ? d->norder_f : d->nf;
+	m->has_order_f = d->order_f != nullptr && !vertex_only;
+	m->norder_f = vertex_only ? 0 : (d->order_f ? d->norder_f : d->nf);
 	m->nb_face = d->nb_face; m->nb_vtx = d->nb_vtx; m->nb_corner = d->nb_corner;
 	m->nregs_face = d->nregs_face; m->nregs_vtx = d->nregs_vtx; m->nlists = d->nlists;
 	if (d->ne && (!d->edges || !d->face_off)) return hb_fail(ctx, HB_ERR_INVALID, "mesh: edges / face_off == NULL");
@@ -330,12 +333,15 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh *m)
 	HB_TRY(upload(m, (void **)&m->d_edges_raw, d->edges, 12 * (size_t)d->ne));
 	HB_TRY(upload(m, (void **)&m->d_face_off, d->face_off, sizeof(uint32_t) * ((size_t)d->nf + 1)));
 	HB_TRY(upload(m, (void **)&m->d_order, d->order, 8 * (size_t)d->norder));
-	if (d->order_f) HB_TRY(upload(m, (void **)&m->d_order_f, d->order_f, 8 * (size_t)d->norder_f));
+	if (d->order_f && !vertex_only) HB_TRY(upload(m, (void **)&m->d_order_f, d->order_f, 8 * (size_t)d->norder_f));
 	HB_TRY(upload(m, (void **)&m->d_vtx_regs, d->vtx_regs, sizeof(uint16_t) * (size_t)d->nv));
-	HB_TRY(upload(m, (void **)&m->d_face_regs, d->face_regs, sizeof(uint16_t) * (size_t)d->nf));
-	HB_TRY(upload(m, (void **)&m->d_bind_face, d->bind_face_attr, sizeof(uint32_t) * (size_t)d->nf * d->nb_face));
+	if (!vertex_only) {
+		HB_TRY(upload(m, (void **)&m->d_face_regs, d->face_regs, sizeof(uint16_t) * (size_t)d->nf));
+		HB_TRY(upload(m, (void **)&m->d_bind_face, d->bind_face_attr, sizeof(uint32_t) * (size_t)d->nf * d->nb_face));
+	}
 	HB_TRY(upload(m, (void **)&m->d_bind_vtx, d->bind_vtx_attr, sizeof(uint32_t) * (size_t)d->nv * d->nb_vtx));
-	HB_TRY(upload(m, (void **)&m->d_bind_corner, d->bind_corner_attr, sizeof(uint32_t) * (size_t)d->ne * d->nb_corner));
+	if (!vertex_only) HB_TRY(upload(m, (void **)&m->d_bind_corner, d->bind_corner_attr, sizeof(uint32_t) * (size_t)d->ne * d->nb_corner));
+	if (vertex_only) m->any_corner = false;
 	HB_TRY(upload(m, (void **)&m->d_slot_vtx, m->h_slot_vtx.data(), sizeof(int16_t) * m->h_slot_vtx.size()));
 	HB_TRY(upload(m, (void **)&m->d_slot_face, m->h_slot_face.data(), sizeof(int16_t) * m->h_slot_face.size()));
 	HB_TRY(upload(m, (void **)&m->d_slot_corner, m->h_slot_corner.data(), sizeof(int16_t) * m->h_slot_corner.size()));
@@ -723,7 +729,10 @@ extern "C" int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh)
 	hb_dmesh *m = new hb_dmesh();
 	PhaseTimer t(ctx);
 	t.mark(0);
-	int rc = dmesh_upload_impl(ctx, mesh, m);
+	bool vertex_only = true;
+	for (int l = 0; l < mesh->nlists; ++l)
+		if (mesh->lists[l].target != HB_VTX && mesh->lists[l].ncomp && mesh->lists[l].nrows) vertex_only = false;
+	int rc = dmesh_upload_impl(ctx, mesh, m, vertex_only);
 	t.mark(1);
 	if (rc == 0) rc = hb_decode_lists(m);
 	t.mark(2);

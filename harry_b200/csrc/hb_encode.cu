@@ -443,40 +443,48 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p,
 	if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&a.type_hist[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
 }
 
-// one warp per wide vertex (integer sums are order independent)
+// one CTA per wide vertex (integer sums are order independent)
+#define ENC_WIDE_T 256
 template <typename T, int NC>
-__global__ void __launch_bounds__(128) k_encode_wide_packed(ListParams p, EncodeArgs a, const SpecRec<T, NC> *__restrict__ rec)
+__global__ void __launch_bounds__(ENC_WIDE_T) k_encode_wide_packed(ListParams p, EncodeArgs a, const SpecRec<T, NC> *__restrict__ rec)
 {
 	typedef SpecRec<T, NC> Rec;
-	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	const uint32_t nw = a.wide[0] < a.wide_cap ? a.wide[0] : a.wide_cap;
-	if (w >= nw) return;
-	const uint32_t i = a.wide[1 + w];
-	const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
-	unsigned long long sum[NC];
+	__shared__ unsigned long long s_sum[NC];
+	for (uint32_t w = blockIdx.x; w < nw; w += gridDim.x) {
+		if (threadIdx.x < NC) s_sum[threadIdx.x] = 0ull;
+		__syncthreads();
+		const uint32_t i = a.wide[1 + w];
+		const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
+		unsigned long long sum[NC];
 #pragma unroll
-	for (int j = 0; j < NC; ++j) sum[j] = 0;
-	for (uint32_t kk = lane; kk < K; kk += 32) {
-		const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
-		const Rec v0 = rec[tr[0]], v1 = rec[tr[1]], v2 = rec[tr[2]];
+		for (int j = 0; j < NC; ++j) sum[j] = 0;
+		for (uint32_t kk = threadIdx.x; kk < K; kk += ENC_WIDE_T) {
+			const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
+			const Rec v0 = rec[tr[0]], v1 = rec[tr[1]], v2 = rec[tr[2]];
 #pragma unroll
-		for (int j = 0; j < NC; ++j) sum[j] += (unsigned long long)IntOps<T>::predict(v0.c[j], v1.c[j], v2.c[j], hb_stype_bits(p.stype[j], p.quant[j]));
-	}
-#pragma unroll
-	for (int j = 0; j < NC; ++j)
-#pragma unroll
-		for (int d = 16; d > 0; d >>= 1) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], d);
-	if (lane == 0) {
-		const Rec raw = rec[i];
-		uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+			for (int j = 0; j < NC; ++j) sum[j] += (unsigned long long)IntOps<T>::predict(v0.c[j], v1.c[j], v2.c[j], hb_stype_bits(p.stype[j], p.quant[j]));
+		}
 #pragma unroll
 		for (int j = 0; j < NC; ++j) {
-			const T pred = (T)hb_divround_i64((long long)sum[j], (int)K);
-			const T r = IntOps<T>::enc(raw.c[j], pred, hb_stype_bits(p.stype[j], p.quant[j]));
-			hb_st_bits(out + p.sym_off[j], (int)sizeof(T), r);
-			for (int b = 0; b < (int)sizeof(T); ++b)
-				atomicAdd(&a.hist[(size_t)(p.sym_off[j] + b) * 256 + (((uint32_t)r >> (8 * b)) & 0xffu)], 1ull);
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], d);
+			if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum[j], sum[j]);
 		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			const Rec raw = rec[i];
+			uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+#pragma unroll
+			for (int j = 0; j < NC; ++j) {
+				const T pred = (T)hb_divround_i64((long long)s_sum[j], (int)K);
+				const T r = IntOps<T>::enc(raw.c[j], pred, hb_stype_bits(p.stype[j], p.quant[j]));
+				hb_st_bits(out + p.sym_off[j], (int)sizeof(T), r);
+				for (int b = 0; b < (int)sizeof(T); ++b)
+					atomicAdd(&a.hist[(size_t)(p.sym_off[j] + b) * 256 + (((uint32_t)r >> (8 * b)) & 0xffu)], 1ull);
+			}
+		}
+		__syncthreads();
 	}
 }
 
@@ -490,7 +498,7 @@ static int encode_vtx_packed_nc(hb_dmesh *m, DevList &dl, const EncodeArgs &a)
 	HB_LAUNCH(ctx, (k_gather_packed<T, NC>), hb_div_up(n, 256), 256, 0, dl.p, dl.d_erow, n, rec);
 	const size_t smem = sizeof(uint32_t) * ((size_t)NC * sizeof(T) * 256 + 4);
 	HB_LAUNCH(ctx, (k_encode_vtx_packed<T, NC>), hb_div_up(n, ENC_THREADS), ENC_THREADS, smem, dl.p, a, rec);
-	if (a.wide) HB_LAUNCH(ctx, (k_encode_wide_packed<T, NC>), hb_div_up((uint64_t)a.wide_cap * 32, 128), 128, 0, dl.p, a, rec);
+	if (a.wide) HB_LAUNCH(ctx, (k_encode_wide_packed<T, NC>), 64, ENC_WIDE_T, 0, dl.p, a, rec);
 	return 0;
 }
 template <typename T>

@@ -181,6 +181,27 @@ def tri_irregular(n: int = 48, seed: int = 11, holes: bool = True) -> PolyMesh:
     return PolyMesh(pos=pos.astype(np.float32), face_off=face_off, face_idx=faces.ravel())
 
 
+def cones(k: int = 80, valence: int = 90, seed: int = 2) -> PolyMesh:
+    """k separate cones: an apex joined to a closed ring of `valence` vertices.  Every apex is a wide
+    fan for the fan gather (more than 64 steps); more cones than the wide path takes (64) make the
+    surplus fall back to one-thread walks.  Noisy positions."""
+    rng = np.random.default_rng(seed)
+    pos, faces = [], []
+    for c in range(k):
+        base = len(pos)
+        cx, cy = 3.0 * (c % 10), 3.0 * (c // 10)
+        pos.append((cx, cy, 1.0 + 0.1 * rng.standard_normal()))
+        for j in range(valence):
+            a = 2.0 * np.pi * j / valence
+            r = 1.0 + 0.05 * rng.standard_normal()
+            pos.append((cx + r * np.cos(a), cy + r * np.sin(a), 0.05 * rng.standard_normal()))
+        for j in range(valence):
+            faces.append((base, base + 1 + j, base + 1 + (j + 1) % valence))
+    faces = np.asarray(faces, dtype=np.uint32)
+    face_off = (3 * np.arange(faces.shape[0] + 1)).astype(np.uint32)
+    return PolyMesh(pos=np.asarray(pos, dtype=np.float32), face_off=face_off, face_idx=faces.ravel())
+
+
 # ----------------------------------------------------------------------------------------------
 # PLY writer (binary little endian)
 # ----------------------------------------------------------------------------------------------

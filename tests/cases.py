@@ -27,6 +27,9 @@ CASES = {
     "irr_q14": (lambda d: _ply(d, "irr.ply", meshgen.tri_irregular(48, 11)), [(1, -1, 14)]),
     "irr_q7": (lambda d: _ply(d, "irr.ply", meshgen.tri_irregular(48, 11)), [(1, -1, 7)]),
     "irr_q24": (lambda d: _ply(d, "irr.ply", meshgen.tri_irregular(48, 11)), [(1, -1, 24)]),
+    # 80 wide fans (more than the 64 the wide-fan path takes at once), quantized and lossless float
+    "cones_q12": (lambda d: _ply(d, "cones.ply", meshgen.cones(80, 90)), [(1, -1, 12)]),
+    "cones_lossless": (lambda d: _ply(d, "cones.ply", meshgen.cones(80, 90)), []),
     "irr_big_q12": (lambda d: _ply(d, "irrb.ply", meshgen.tri_irregular(160, 5)), [(1, -1, 12)]),
     "obj_multi_all": (lambda d: _obj(d, "om.obj", True), [(0, -1, 12), (1, -1, 9), (2, -1, 10), (3, -1, 11)]),
 }
