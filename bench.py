@@ -677,7 +677,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--batch-meshes", type=int, default=64, help="extra measurement: batch of independent 100K-vertex meshes (0 = skip)")
-    ap.add_argument("--batch-threads", type=int, default=16)
+    ap.add_argument("--batch-threads", type=int, default=8)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
