@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	__shared__ uint32_t s_ndF[SCAN_MAXC];       // per CTA: first rank behind a failed boundary check
 	__shared__ uint32_t s_start[NSEG + 1][NC];  // presumed start value of every slot (+ of the next CTA's first slot)
 	__shared__ uint32_t s_minE, s_minF;
+	__shared__ uint32_t s_stop;                 // length of the sequential stretch just walked (pushed by CTA 0)
 	__shared__ unsigned long long s_sum[4];
 	__shared__ T s_seq[SCAN_SEQ_MAX];           // values of a sequential stretch
 	__shared__ __align__(16) uint32_t s_item[2][32][16]; // work items of the sequential stretch (two batches)
@@ -680,13 +681,13 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 					if (wm) { stop = b0 + nl; break; }
 				}
 				if (lane < C) {
-					uint32_t *dst = C > 1 ? cluster.map_shared_rank(&s_ndE[0], lane) : &s_ndE[0];
+					uint32_t *dst = C > 1 ? cluster.map_shared_rank(&s_stop, lane) : &s_stop;
 					*dst = stop;
 				}
 			}
 			csync();
-			const uint32_t stop = s_ndE[0];
-			csync(); // s_ndE is rewritten by the next sweep
+			const uint32_t stop = s_stop;
+			csync(); // s_stop may be rewritten by the next stretch
 			if (stop == 0) widehead = true;
 			done += stop;
 			if (gend < done) gend = done;
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		const uint32_t per = wpc * G;                       // slots per CTA
 		// warp totals travel to the CTA that owns them and to every CTA behind it; thread 0 announces
 		// how many bytes this CTA is going to receive in this sweep
-		if (t == 0) scan_mbar_arrive_expect_tx(bar, (crank + 1u) * wpc * (uint32_t)sizeof(Map));
+		if (t == 0 && C > 1) scan_mbar_arrive_expect_tx(bar, (crank + 1u) * wpc * (uint32_t)sizeof(Map));
 		const uint32_t nact = per << lgC;                   // slots of the window
 		const uint32_t gs = crank * per + q;                // my slot in the window
 		const unsigned long long i64 = (unsigned long long)done + gs;
@@ -838,7 +839,9 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 				if (lane >= d) inc = scan_compose<T>(up, inc, cb);
 			}
 			const Map tot = scan_shfl<T>(inc, 31);
-			if (crank + lane < C) {
+			if (C == 1) {
+				if (lane == 0) s_all[warp] = tot; // a single CTA: plain shared memory, block barrier below
+			} else if (crank + lane < C) {
 				static_assert(sizeof(Map) % 16 == 0, "totals travel as 16-byte vectors");
 				const uint32_t *w = (const uint32_t *)&tot;
 				const uint32_t dst = scan_mapa(scan_smem_u32(&s_all[crank * wpc + warp]), crank + lane), dbar = scan_mapa(bar, crank + lane);
@@ -852,8 +855,12 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		SCAN_CLK(p3);
 		// [1] wait for the totals promised to this CTA (no barrier: the producers complete the
 		// transaction count that thread 0 armed at the top of the sweep)
-		while (!scan_mbar_try_wait(bar, bar_parity)) { }
-		bar_parity ^= 1u;
+		if (C == 1) {
+			__syncthreads();
+		} else {
+			while (!scan_mbar_try_wait(bar, bar_parity)) { }
+			bar_parity ^= 1u;
+		}
 		SCAN_CLK(p4);
 		// B2. the value in front of my warp: out[j], out[k] = value after warp total k, j = my element
 		//     - 1.  Once ~cb halvings are composed a total is a step: it outputs B or B + 1.  Fed
@@ -926,7 +933,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		if (lane == 0) ex = Map::identity();
 		uint32_t start = (uint32_t)(T)ex.eval((SW)vstart);
 		if (gs == 0) start = x0; // final by construction
-		s_start[q][0] = start;
+		if (warp < wpc) s_start[q][0] = start; // (slot `per` belongs to the line below)
 		if (warp + 1 == wpc && lane == 0) s_start[per][0] = vend;
 		__syncthreads();
 		const long long tC = clock64();
