@@ -62,7 +62,7 @@ def log(*a):
 class Workload:
     source = "reference host code (oracle/_ref: PLY reader, cbm::encode / cbm::decode, .hry writer/reader)"
 
-    def __init__(self, nr: int, ns: int, workdir: str, keep_ref: bool = False):
+    def __init__(self, nr: int, ns: int, workdir: str, keep_ref: bool = False, keep_expected: bool = False):
         import oracle_lib as ol  # input preparation + CPU baseline only
         if not ol.have_ref() or (os.environ.get("HARRY_BENCH_FALLBACK") and not keep_ref):
             if keep_ref:
@@ -86,6 +86,7 @@ class Workload:
         enc = rm.arrays()
         self.new_quant = [la.quants for la in enc.lists]
         self.raw.order, self.raw.order_f, self.raw.edges = enc.order, enc.order_f, enc.edges
+        self.enc_expected = rm.attr_encode() if keep_expected else None   # the reference's own AttrCoder on this mesh
         self.hry = os.path.join(workdir, f"sphere_{nr}x{ns}.hry")
         rm.write(self.hry)
         rm.close()
@@ -101,6 +102,7 @@ class Workload:
             rd.set_scale(l)
             self.dec_bounds.append(tuple(rd.bounds_row(l, w, la.stride) for w in (0, 1, 2)))
         rd.close()
+        self.dec_expected = [la.rows.copy() for la in dec.lists] if keep_expected else None   # rows the reference decoded
         self.dec = dec.copy()
         self.dec.lists = capi.residual_rows_from_streams(dec, st)
         self.dec.emit_types = [ls.type for ls in st.lists]
@@ -552,6 +554,7 @@ class BatchMesh:
         rd.set_scale(1)
         self.dec_bounds = tuple(rd.bounds_row(1, w, dec.lists[1].stride) for w in (0, 1, 2))
         rd.close()
+        self.dec_expected = [la.rows.copy() for la in dec.lists] if keep_expected else None   # rows the reference decoded
         self.dec = dec.copy()
         self.dec.lists = capi.residual_rows_from_streams(dec, st)
         self.dec.emit_types = [ls.type for ls in st.lists]

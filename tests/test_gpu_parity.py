@@ -142,3 +142,29 @@ def test_roundtrip_property_large(ctx):
     ctx.attr_decode(dec)
     cols = [0, 1, 4, 5, 8, 9]
     assert np.array_equal(dec.lists[1].rows[:, cols], mesh.lists[1].rows[:, cols])
+
+
+# ---- BASELINE configs[1] at its full size -----------------------------------------------------------
+@needs_ref
+def test_config2_full_size(ctx, workdir):
+    """The 10M-vertex mesh bench.py measures: encode streams and decoded rows equal the reference's own
+    AttrCoder / AttrDecoder output (about a minute, most of it the reference preparing the inputs)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    w = bench.Workload(*bench.FULL, workdir, keep_expected=True)
+    E = capi.DeviceMesh(ctx, w.raw)
+    E.quantize(1, w.new_quant[1], w.raw.lists[1].groups)
+    E.encode()
+    ok, why = E.fetch_streams().equal(w.enc_expected)
+    E.close()
+    assert ok, why
+    D = capi.DeviceMesh(ctx, w.dec)
+    for l, (mn, mx, sc) in enumerate(w.dec_bounds):
+        if w.dec.lists[l].ncomp:
+            D.set_bounds(l, mn, mx, sc)
+    D.decode()
+    for l, exp in enumerate(w.dec_expected):
+        if w.dec.lists[l].ncomp:
+            assert np.array_equal(D.fetch_rows(l), exp), f"list {l}"
+    D.close()

@@ -21,8 +21,9 @@ ap.add_argument("--nr", type=int, default=708)
 ap.add_argument("--ns", type=int, default=1412)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--no-decode", action="store_true")
+ap.add_argument("--verify", action="store_true", help="compare the encode streams and the decoded rows with the reference's at this size")
 args = ap.parse_args()
-w = bench.Workload(args.nr, args.ns, tempfile.mkdtemp(prefix="harry_prof_"))
+w = bench.Workload(args.nr, args.ns, tempfile.mkdtemp(prefix="harry_prof_"), keep_expected=args.verify)
 ctx = capi.Context(0)
 E = capi.DeviceMesh(ctx, w.raw)
 E.snapshot()
@@ -36,8 +37,15 @@ for _ in range(args.reps):
     D.restore()
     E.quantize(1, w.new_quant[1], w.raw.lists[1].groups)
     E.encode()
+    if args.verify:
+        ok, why = E.fetch_streams().equal(w.enc_expected)
+        print("verify: encode streams (types, history offsets, residual symbols, histograms) == reference:", ok, why, flush=True)
     if not args.no_decode:
         D.decode()
+        if args.verify:
+            import numpy as np
+            good = all(np.array_equal(D.fetch_rows(l), exp) for l, exp in enumerate(w.dec_expected) if w.dec.lists[l].ncomp)
+            print("verify: decoded rows == reference decoder output:", good, flush=True)
         D.dequantize(1)
 ctx.sync()
 print("done", ctx.launches(), "decode stats [sweeps, hyp, plain, hyp_adv, cyc_load, cyc_traj, cyc_resolve, cyc_write+plain]:", D.decode_stats(1)[:8])
