@@ -554,7 +554,6 @@ class BatchMesh:
         rd.set_scale(1)
         self.dec_bounds = tuple(rd.bounds_row(1, w, dec.lists[1].stride) for w in (0, 1, 2))
         rd.close()
-        self.dec_expected = [la.rows.copy() for la in dec.lists] if keep_expected else None   # rows the reference decoded
         self.dec = dec.copy()
         self.dec.lists = capi.residual_rows_from_streams(dec, st)
         self.dec.emit_types = [ls.type for ls in st.lists]
