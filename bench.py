@@ -419,8 +419,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
                 dconn_b = sum(getattr(hdec, n).nbytes for n in dnames) + \
                     (hdec.order_f.nbytes if hdec.order_f is not None and not vertex_only else 0)
                 h2d = rows_b * 2 + conn_b + rows_b + dconn_b + ld.rows.nbytes * 2 + sum(len(t) for t in w.dec.emit_types)
-                d2h = rows_b + ld.rows.nbytes * 2 + streams.reg_vtx.nbytes + streams.reg_face.nbytes + \
-                    sum(x.type.nbytes + x.aux.nbytes + x.symbols.nbytes + x.hist.nbytes for x in streams.lists)
+                d2h = rows_b + ld.rows.nbytes * 2 + streams.nbytes_copied   # all-zero streams come back as NULL, not copied
             del streams
             release()
         t_step = t_e2e / n_e2e

@@ -363,23 +363,34 @@ def streams_to_py(sp, copy: bool = True) -> StreamsPy:
     s = sp.contents
 
     def arr(ptr, n, dtype):
-        if n == 0 or not ptr:
+        if n == 0:
             return np.zeros(0, dtype=dtype)
+        if not ptr:   # an all-zero stream is returned as NULL (harry_b200.h, hb_attr_encode): a zero-stride view
+            return np.broadcast_to(np.zeros(1, dtype=dtype), (n,))
         addr = C.cast(ptr, C.c_void_p).value
         buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(addr)
         a = np.frombuffer(buf, dtype=dtype)
         return a.copy() if copy else a
 
+    copied = 0   # bytes the library actually copied device -> host (NULL streams are not)
+
+    def nb(ptr, n, itemsize):
+        return n * itemsize if ptr and n else 0
+
     lists = []
     for l in range(s.nlists):
         ls = s.lists[l]
+        copied += nb(ls.type, ls.n_emit, 1) + nb(ls.aux, ls.n_emit, 4) + nb(ls.symbols, ls.n_data * ls.sym_stride, 1) + (ls.sym_stride * 256 + 4) * 8
         lists.append(ListStreamsPy(
             type=arr(ls.type, ls.n_emit, np.uint8),
             aux=arr(ls.aux, ls.n_emit, np.uint32),
             symbols=arr(ls.symbols, ls.n_data * ls.sym_stride, np.uint8).reshape(ls.n_data, ls.sym_stride),
             hist=arr(ls.hist, ls.sym_stride * 256, np.uint64).reshape(ls.sym_stride, 256),
             type_hist=np.array([ls.type_hist[k] for k in range(4)], dtype=np.uint64)))
-    return StreamsPy(arr(s.reg_vtx, s.n_vtx, np.uint16), arr(s.reg_face, s.n_face, np.uint16), lists)
+    copied += nb(s.reg_vtx, s.n_vtx, 2) + nb(s.reg_face, s.n_face, 2)
+    out = StreamsPy(arr(s.reg_vtx, s.n_vtx, np.uint16), arr(s.reg_face, s.n_face, np.uint16), lists)
+    out.nbytes_copied = copied
+    return out
 
 
 def residual_rows_from_streams(mesh: MeshArrays, st: StreamsPy) -> list:

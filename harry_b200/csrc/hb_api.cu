@@ -575,22 +575,24 @@ extern "C" int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out)
 	s->n_vtx = m->norder;
 	s->n_face = m->norder_f;
 	s->nlists = m->nlists;
-	s->reg_vtx = (uint16_t *)g_pinned.alloc(sizeof(uint16_t) * ((size_t)m->norder + 1));
-	s->reg_face = (uint16_t *)g_pinned.alloc(sizeof(uint16_t) * ((size_t)m->norder_f + 1));
+	// a mesh with a single vertex (face) region has an all-zero region stream: NULL stands for it
+	const bool reg_v = m->nregs_vtx > 1, reg_f = m->nregs_face > 1;
+	s->reg_vtx = reg_v ? (uint16_t *)g_pinned.alloc(sizeof(uint16_t) * ((size_t)m->norder + 1)) : nullptr;
+	s->reg_face = reg_f ? (uint16_t *)g_pinned.alloc(sizeof(uint16_t) * ((size_t)m->norder_f + 1)) : nullptr;
 	s->lists = (hb_list_streams *)calloc((size_t)m->nlists + 1, sizeof(hb_list_streams));
 	int rc = 0;
 	uint16_t *d_reg = nullptr;
 	const uint32_t nmax = m->norder > m->norder_f ? m->norder : m->norder_f;
 #define FETCH_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = hb_fail(ctx, HB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); goto fail; } } while (0)
-	if (!s->reg_vtx || !s->reg_face || !s->lists) { rc = hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); goto fail; }
+	if ((reg_v && !s->reg_vtx) || (reg_f && !s->reg_face) || !s->lists) { rc = hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); goto fail; }
 	// region symbol streams (io.h:109-116): region of every traversed vertex / face
 	FETCH_CUDA(cudaMallocAsync((void **)&d_reg, sizeof(uint16_t) * ((size_t)nmax + 1), ctx->stream));
-	if (m->norder) {
+	if (m->norder && reg_v) {
 		k_region_stream<<<hb_div_up(m->norder, 256), 256, 0, ctx->stream>>>(m->d_ord_v, m->d_he, m->d_vtx_regs, m->norder, 0, d_reg);
 		ctx->launches++;
 		FETCH_CUDA(cudaMemcpyAsync(s->reg_vtx, d_reg, sizeof(uint16_t) * m->norder, cudaMemcpyDeviceToHost, ctx->stream));
 	}
-	if (m->norder_f) {
+	if (m->norder_f && reg_f) {
 		k_region_stream<<<hb_div_up(m->norder_f, 256), 256, 0, ctx->stream>>>(m->d_ford_h, m->d_he, m->d_face_regs, m->norder_f, 1, d_reg);
 		ctx->launches++;
 		FETCH_CUDA(cudaMemcpyAsync(s->reg_face, d_reg, sizeof(uint16_t) * m->norder_f, cudaMemcpyDeviceToHost, ctx->stream));
@@ -607,19 +609,23 @@ extern "C" int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out)
 		if (dl.d_ek) FETCH_CUDA(cudaMemcpyAsync(&ls.n_emit, dl.d_ek + dl.n_elems, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 		else ls.n_emit = dl.n_elems;
 		FETCH_CUDA(cudaMemcpyAsync(&ls.n_data, dl.d_dord + dl.n_elems, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		FETCH_CUDA(cudaMemcpyAsync(ls.type_hist, dl.d_type_hist, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	FETCH_CUDA(cudaStreamSynchronize(ctx->stream));
 	for (int l = 0; l < m->nlists; ++l) {
 		DevList &dl = m->lists[l];
 		hb_list_streams &ls = s->lists[l];
-		ls.type = (uint8_t *)g_pinned.alloc((size_t)ls.n_emit + 1);
-		ls.aux = (uint32_t *)g_pinned.alloc(sizeof(uint32_t) * ((size_t)ls.n_emit + 1));
+		// every emission is a DATA row (no shared attribute rows): the type and history-offset streams are
+		// all zero -- NULL stands for them, nothing is copied
+		const bool all_data = ls.type_hist[HB_HIST] + ls.type_hist[HB_LHIST] == 0;
+		ls.type = all_data ? nullptr : (uint8_t *)g_pinned.alloc((size_t)ls.n_emit + 1);
+		ls.aux = all_data ? nullptr : (uint32_t *)g_pinned.alloc(sizeof(uint32_t) * ((size_t)ls.n_emit + 1));
 		ls.symbols = (uint8_t *)g_pinned.alloc((size_t)ls.n_data * ls.sym_stride + 1);
 		ls.hist = (uint64_t *)g_pinned.alloc(sizeof(uint64_t) * ((size_t)ls.sym_stride * 256 + 4));
-		if (!ls.type || !ls.aux || !ls.symbols || !ls.hist) { rc = hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); goto fail; }
+		if ((!all_data && (!ls.type || !ls.aux)) || !ls.symbols || !ls.hist) { rc = hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); goto fail; }
 		memset(ls.hist, 0, sizeof(uint64_t) * ((size_t)ls.sym_stride * 256 + 4));
 		if (!dl.n_elems) continue;
-		if (ls.n_emit) {
+		if (ls.n_emit && !all_data) {
 			FETCH_CUDA(cudaMemcpyAsync(ls.type, dl.d_type, ls.n_emit, cudaMemcpyDeviceToHost, ctx->stream));
 			FETCH_CUDA(cudaMemcpyAsync(ls.aux, dl.d_aux, sizeof(uint32_t) * ls.n_emit, cudaMemcpyDeviceToHost, ctx->stream));
 		}

@@ -34,7 +34,7 @@ void AttrCoder<io::writer>::encode<progress::handle>(progress::handle &prog)
 	auto emit_one = [&](mesh::listidx_t l) {
 		const hb_list_streams &ls = s->lists[l];
 		const uint32_t k = emit[l]++;
-		switch (ls.type[k]) {
+		switch (ls.type ? ls.type[k] : (uint8_t)HB_DATA) { // NULL: every emission is a DATA row
 		case HB_DATA: {
 			const mixing::Fmt &fmt = mesh.attrs[l].fmt();
 			const uint8_t *src = ls.symbols + (size_t)data[l]++ * ls.sym_stride;
@@ -53,13 +53,13 @@ void AttrCoder<io::writer>::encode<progress::handle>(progress::handle &prog)
 
 	prog.start(order.size());
 	for (size_t i = 0; i < order.size(); ++i) { // attrcode.h:399-404, vtx_post :321-344
-		const mesh::regidx_t r = s->reg_vtx[i];
+		const mesh::regidx_t r = s->reg_vtx ? s->reg_vtx[i] : 0; // NULL: single region
 		wr.reg_vtx(r);
 		for (mesh::listidx_t a = 0; a < mesh.attrs.num_bindings_vtx_reg(r); ++a) emit_one(mesh.attrs.binding_reg_vtxlist(r, a));
 		prog(i);
 	}
 	for (size_t i = 0; i < order_f.size(); ++i) { // attrcode.h:405-414, face_post :345-365, corner_post :367-393
-		const mesh::regidx_t r = s->reg_face[i];
+		const mesh::regidx_t r = s->reg_face ? s->reg_face[i] : 0;
 		wr.reg_face(r);
 		for (mesh::listidx_t a = 0; a < mesh.attrs.num_bindings_face_reg(r); ++a) emit_one(mesh.attrs.binding_reg_facelist(r, a));
 		const int ne = mesh.conn.num_edges(order_f[i].f());

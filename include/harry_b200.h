@@ -184,7 +184,9 @@ int hb_requant(hb_ctx *ctx, hb_list_desc *list, const uint8_t *new_quant, const 
                const void *scale_row);
 
 /* ---- attribute coder (host buffers) ------------------------------------------------------ */
-/* *out: library-allocated streams in page-locked host memory; hb_streams_free parks the buffers in
+/* A stream that is all zero is returned as NULL and not copied: reg_vtx / reg_face of a mesh with a single
+ * region, type and aux of a list whose emissions are all DATA rows (type_hist[HB_HIST] + type_hist[HB_LHIST] == 0).
+ * *out: library-allocated streams in page-locked host memory; hb_streams_free parks the buffers in
  * a process-wide cache for the next call ("Ownership"). */
 int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams **out);
 void hb_streams_free(hb_streams *s);
