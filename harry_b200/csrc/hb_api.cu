@@ -73,6 +73,10 @@ extern "C" int hb_ctx_create(int device, hb_ctx **out)
 	} while (0)
 	CREATE_TRY(cudaSetDevice(device));
 	CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_up[0], cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_up[1], cudaEventDisableTiming));
 	for (int i = 0; i < 6; ++i) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
 	CREATE_TRY(cudaMalloc((void **)&ctx->d_err, sizeof(int)));
 	CREATE_TRY(cudaMemset(ctx->d_err, 0, sizeof(int)));
@@ -97,6 +101,10 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+	if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
+	for (int i = 0; i < 2; ++i)
+		if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
 	for (int i = 0; i < 6; ++i)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -250,7 +258,17 @@ static int validate_list(hb_ctx *ctx, const hb_list_desc &L, bool for_coder)
 static int upload(hb_dmesh *m, void **dst, const void *src, size_t bytes)
 {
 	HB_TRY(hb_dalloc(m, dst, bytes));
-	if (bytes && src) HB_CUDA(m->ctx, cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, m->ctx->stream));
+	if (!(bytes && src)) return 0;
+	hb_ctx *ctx = m->ctx;
+	if (m->async_copy) {
+		// the buffer comes from the stream-ordered pool of ctx->stream: the copy stream may touch it
+		// once it has waited for an event recorded behind the allocation
+		HB_CUDA(ctx, cudaEventRecord(ctx->ev_alloc, ctx->stream));
+		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_alloc, 0));
+		HB_CUDA(ctx, cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+	} else {
+		HB_CUDA(ctx, cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	}
 	return 0;
 }
 
@@ -275,6 +293,7 @@ extern "C" void hb_dmesh_free(hb_dmesh *m)
 {
 	if (!m) return;
 	cudaSetDevice(m->ctx->device);
+	if (m->async_copy) cudaStreamSynchronize(m->ctx->copy_stream); // nothing may still be landing in these buffers
 	for (void *p : m->allocs) cudaFreeAsync(p, m->ctx->stream);
 	cudaStreamSynchronize(m->ctx->stream);
 	delete m;
@@ -335,6 +354,8 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh *m, bo
 	HB_TRY(upload(m, (void **)&m->d_order, d->order, 8 * (size_t)d->norder));
 	if (d->order_f && !vertex_only) HB_TRY(upload(m, (void **)&m->d_order_f, d->order_f, 8 * (size_t)d->norder_f));
 	HB_TRY(upload(m, (void **)&m->d_vtx_regs, d->vtx_regs, sizeof(uint16_t) * (size_t)d->nv));
+	// everything K0 / K3 / K4 read is on its way: first milestone of the copy stream
+	if (m->async_copy) HB_CUDA(ctx, cudaEventRecord(ctx->ev_up[0], ctx->copy_stream));
 	if (!vertex_only) {
 		HB_TRY(upload(m, (void **)&m->d_face_regs, d->face_regs, sizeof(uint16_t) * (size_t)d->nf));
 		HB_TRY(upload(m, (void **)&m->d_bind_face, d->bind_face_attr, sizeof(uint32_t) * (size_t)d->nf * d->nb_face));
@@ -354,6 +375,22 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh *m, bo
 			HB_TRY(upload(m, (void **)&dl.d_emit_type, d->emit_type[l], dl.emit_count));
 		}
 	}
+	if (m->async_copy) HB_CUDA(ctx, cudaEventRecord(ctx->ev_up[1], ctx->copy_stream));
+	return 0;
+}
+
+// host-buffer entry points: connectivity stages under the tail of the upload, everything else behind it
+static int upload_overlapped(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_dmesh *m, bool vertex_only)
+{
+	m->async_copy = true;
+	HB_TRY(dmesh_upload_impl(ctx, mesh, m, vertex_only));
+	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
+	HB_TRY(hb_build_conn(m));
+	bool need_v = false;
+	for (int l = 0; l < m->nlists; ++l)
+		if (m->lists[l].p.target == HB_VTX && m->lists[l].p.ncomp) need_v = true;
+	if (need_v) HB_TRY(hb_build_vertex_candidates(m));
+	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[1], 0));
 	return 0;
 }
 
@@ -718,7 +755,7 @@ extern "C" int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams 
 	hb_dmesh *m = new hb_dmesh();
 	PhaseTimer t(ctx);
 	t.mark(0);
-	int rc = dmesh_upload_impl(ctx, mesh, m);
+	int rc = upload_overlapped(ctx, mesh, m, false);
 	t.mark(1);
 	if (rc == 0) rc = hb_encode_lists(m);
 	t.mark(2);
@@ -738,7 +775,7 @@ extern "C" int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh)
 	bool vertex_only = true;
 	for (int l = 0; l < mesh->nlists; ++l)
 		if (mesh->lists[l].target != HB_VTX && mesh->lists[l].ncomp && mesh->lists[l].nrows) vertex_only = false;
-	int rc = dmesh_upload_impl(ctx, mesh, m, vertex_only);
+	int rc = upload_overlapped(ctx, mesh, m, vertex_only);
 	t.mark(1);
 	if (rc == 0) rc = hb_decode_lists(m);
 	t.mark(2);

@@ -24,6 +24,10 @@
 struct hb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	// host-buffer entry points upload on a second stream: the connectivity stages (K0, K3, K4) start as soon as
+	// their arrays have landed and run under the rest of the upload
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_alloc = nullptr, ev_up[2] = { nullptr, nullptr };
 	cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	std::string err;
 	uint64_t launches = 0;
@@ -92,6 +96,7 @@ struct hb_dmesh {
 	uint32_t nv = 0, nf = 0, ne = 0, norder = 0, norder_f = 0;
 	uint16_t nb_face = 0, nb_vtx = 0, nb_corner = 0, nregs_face = 0, nregs_vtx = 0, nlists = 0;
 	bool has_order_f = false;
+	bool async_copy = false;     // uploads go to ctx->copy_stream (hb_attr_encode / hb_attr_decode)
 	std::vector<void *> allocs;
 	// uploaded
 	uint8_t *d_edges_raw = nullptr;
