@@ -294,6 +294,8 @@ def pin_mesh(m: capi.MeshArrays) -> capi.MeshArrays:
     for la in m.lists:
         if la.rows.size:
             la.rows = pinned_like(np.ascontiguousarray(la.rows))
+    if m.emit_types is not None:   # decode input: the drained type symbols
+        m.emit_types = [pinned_like(np.ascontiguousarray(t)) if t is not None and t.size else t for t in m.emit_types]
     return m
 
 
