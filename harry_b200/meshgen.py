@@ -181,10 +181,12 @@ def tri_irregular(n: int = 48, seed: int = 11, holes: bool = True) -> PolyMesh:
     return PolyMesh(pos=pos.astype(np.float32), face_off=face_off, face_idx=faces.ravel())
 
 
-def cones(k: int = 80, valence: int = 90, seed: int = 2) -> PolyMesh:
+def cones(k: int = 80, valence: int = 90, seed: int = 2, open_every: int = 0) -> PolyMesh:
     """k separate cones: an apex joined to a closed ring of `valence` vertices.  Every apex is a wide
     fan for the fan gather (more than 64 steps); more cones than the wide path takes (64) make the
-    surplus fall back to one-thread walks.  Noisy positions."""
+    surplus fall back to one-thread walks.  Noisy positions.  open_every = n > 0: every n-th cone
+    lacks three of its triangles, so its apex sits on a border (an OPEN wide fan: the walk runs
+    forward from the gate to the border, then backward from the gate's predecessor)."""
     rng = np.random.default_rng(seed)
     pos, faces = [], []
     for c in range(k):
@@ -195,7 +197,10 @@ def cones(k: int = 80, valence: int = 90, seed: int = 2) -> PolyMesh:
             a = 2.0 * np.pi * j / valence
             r = 1.0 + 0.05 * rng.standard_normal()
             pos.append((cx + r * np.cos(a), cy + r * np.sin(a), 0.05 * rng.standard_normal()))
+        gap = open_every > 0 and c % open_every == 0
         for j in range(valence):
+            if gap and valence // 3 <= j < valence // 3 + 3:
+                continue
             faces.append((base, base + 1 + j, base + 1 + (j + 1) % valence))
     faces = np.asarray(faces, dtype=np.uint32)
     face_off = (3 * np.arange(faces.shape[0] + 1)).astype(np.uint32)

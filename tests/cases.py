@@ -30,6 +30,9 @@ CASES = {
     # 80 wide fans (more than the 64 the wide-fan path takes at once), quantized and lossless float
     "cones_q12": (lambda d: _ply(d, "cones.ply", meshgen.cones(80, 90)), [(1, -1, 12)]),
     "cones_lossless": (lambda d: _ply(d, "cones.ply", meshgen.cones(80, 90)), []),
+    # open wide fans (apex on a border): forward part, then backward part of the fan walk
+    "cones_open_q12": (lambda d: _ply(d, "coneso.ply", meshgen.cones(40, 100, seed=4, open_every=2)), [(1, -1, 12)]),
+    "cones_open_lossless": (lambda d: _ply(d, "coneso.ply", meshgen.cones(40, 100, seed=4, open_every=2)), []),
     "irr_big_q12": (lambda d: _ply(d, "irrb.ply", meshgen.tri_irregular(160, 5)), [(1, -1, 12)]),
     "obj_multi_all": (lambda d: _obj(d, "om.obj", True), [(0, -1, 12), (1, -1, 9), (2, -1, 10), (3, -1, 11)]),
 }
