@@ -444,6 +444,12 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
 
     E.close()
     D.close()
+    twin = None
+    if world == 1 and not args.no_twin:
+        try:
+            twin = run_twin(ctx, w, peak, args.no_cpu)
+        except Exception as e:  # the headline line must survive a failure of the extra measurement
+            twin = {"error": repr(e)}
     ctx.close()
     batch = None
     if args.batch_meshes > 0 and world == 1:
@@ -467,9 +473,59 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             "encode_M_attrs_per_s": world * w.n_attrs / (enc_ms / args.steps * 1e-3) / 1e6 if enc_ms else None,
             "decode_M_attrs_per_s": world * w.n_attrs / (dec_ms / args.steps * 1e-3) / 1e6 if dec_ms else None,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "kernels": kernels,
-            "cpu_baseline": cpu, "batch100k": batch,
+            "cpu_baseline": cpu, "batch100k": batch, "twin_match": twin,
         }
         print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# twin matching of the workload's faces (the step in front of the path)
+# ----------------------------------------------------------------------------------------------
+def run_twin(ctx, w, peak: float, no_cpu: bool, reps: int = 3):
+    """hb_twin_match on the connectivity of the N = 1 workload: host buffers in page-locked memory, wall clock
+    around the synchronous call (upload of face_off + origins, three kernels + scan, download of the 12-byte
+    records), kernel time from the library's CUDA events, CPU port on the bounded sample beside it."""
+    face_off = pinned_like(np.ascontiguousarray(w.raw.face_off))
+    org = pinned_like(np.ascontiguousarray(w.raw.edges[:, 0]))
+    out = pinned_like(np.zeros((w.ne, 3), np.uint32))
+    ctx.twin_match(w.nv, face_off, org, out=out)           # warm-up (memory pool, page-locked registration)
+    ctx.profile(True)
+    wall = kern = copy = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        ctx.twin_match(w.nv, face_off, org, out=out)
+        wall += time.perf_counter() - t0
+        k, c = ctx.timing()
+        kern += k
+        copy += c
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    wall, kern, copy = wall / reps * 1e3, kern / reps, copy / reps
+    # algorithmic bytes per half-edge: count reads the origin (4); fill reads it and writes a 16-byte entry (20);
+    # resolve reads the origin, its own entry and its partner's, writes the 12-byte record (48)
+    alg = {"k_twin_scatter<false>": 4, "k_twin_scatter<true>": 20, "k_twin_resolve": 48}
+    kernels = {}
+    for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        k = {"launches_per_call": n / reps, "ms_per_call": ms / reps}
+        if name in alg:
+            k["GBps"] = alg[name] * w.ne / (ms / n * 1e-3) / 1e9
+            k["frac_of_peak"] = k["GBps"] / peak
+        kernels[name] = k
+    res = {"half_edges": int(w.ne), "kernel_ms": kern, "copy_ms": copy, "e2e_ms": wall,
+           "value": w.ne / (kern * 1e-3) / 1e6 if kern else None, "e2e_value": w.ne / (wall * 1e-3) / 1e6, "unit": "M half-edges/s",
+           "h2d_bytes": int(face_off.nbytes + org.nbytes), "d2h_bytes": int(out.nbytes),
+           "algorithmic_bytes_per_half_edge": sum(alg.values()), "kernels": kernels,
+           "timer": "kernel_ms / copy_ms: CUDA events on the library stream; e2e_ms: host wall clock around the synchronous C-ABI call"}
+    del face_off, org, out
+    if not no_cpu:
+        import oracle_lib as ol
+        pm = meshgen.uv_sphere(*SAMPLE)
+        t0 = time.perf_counter()
+        ol.o_twin_match(pm.nv, pm.face_off, pm.face_idx)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": pm.face_idx.shape[0] / dt / 1e6, "unit": "M half-edges/s", "cores": 1, "kind": "port",
+                               "sample": f"UV sphere {SAMPLE[0]}x{SAMPLE[1]} ({pm.face_idx.shape[0]} half-edges), ho_twin_match (open-addressing restatement of the Builder's unordered_map), single thread"}
+    return res
 
 
 # ----------------------------------------------------------------------------------------------
@@ -678,6 +734,7 @@ def main():
     ap.add_argument("--ns", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-twin", action="store_true", help="skip the extra measurement of hb_twin_match (SURVEY 8f row f2)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--batch-meshes", type=int, default=64, help="extra measurement: batch of independent 100K-vertex meshes (0 = skip)")
     ap.add_argument("--batch-threads", type=int, default=8)

@@ -497,6 +497,8 @@ def load_library():
     lib.hb_bounds.restype = C.c_int
     lib.hb_requant.argtypes = [vp, C.POINTER(ListDesc), C.POINTER(C.c_uint8), vp, vp]
     lib.hb_requant.restype = C.c_int
+    lib.hb_twin_match.argtypes = [vp, u32, u32, vp, vp, u32, vp]
+    lib.hb_twin_match.restype = C.c_int
     lib.hb_attr_encode.argtypes = [vp, C.POINTER(MeshDesc), C.POINTER(C.POINTER(Streams))]
     lib.hb_attr_encode.restype = C.c_int
     lib.hb_streams_free.argtypes = [C.POINTER(Streams)]
@@ -538,7 +540,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "hb_ctx_create", "hb_ctx_destroy", "hb_last_error", "hb_last_timing", "hb_kernel_launches",
     "hb_ctx_profile", "hb_ctx_profile_report", "hb_ctx_mark", "hb_ctx_elapsed",
-    "hb_bounds", "hb_requant", "hb_attr_encode", "hb_streams_free", "hb_attr_decode",
+    "hb_bounds", "hb_requant", "hb_attr_encode", "hb_streams_free", "hb_attr_decode", "hb_twin_match",
     "hb_dmesh_upload", "hb_dmesh_free", "hb_dmesh_quantize", "hb_dmesh_dequantize", "hb_dmesh_encode",
     "hb_dmesh_fetch_streams", "hb_dmesh_set_bounds", "hb_dmesh_snapshot", "hb_dmesh_restore", "hb_dmesh_decode", "hb_dmesh_fetch_rows",
     "hb_dmesh_fetch_bounds", "hb_dmesh_decode_stats", "hb_ctx_sync",
@@ -619,6 +621,24 @@ class Context:
         sc = np.ascontiguousarray(scale_row, dtype=np.uint8)
         self._check(self.lib.hb_requant(self.h, C.byref(d), nq, mn.ctypes.data, sc.ctypes.data), "hb_requant")
         la.sync_from_desc(d)
+
+    # mesh::Builder::add_edge over all faces (structs/conn.h:164-214)
+    def twin_match(self, nv: int, face_off: np.ndarray, org: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """org: (ne,) uint32 origins, or (ne, 3) uint32 edge records whose column 0 holds them (matched in place when
+        `out` is the same array).  Returns (ne, 3) uint32 records {org, twin_face, twin_edge}."""
+        face_off = np.ascontiguousarray(face_off, dtype=np.uint32)
+        nf = int(face_off.shape[0]) - 1
+        ne = int(face_off[nf]) if nf > 0 else 0
+        if org.dtype != np.uint32 or not org.flags.c_contiguous:
+            org = np.ascontiguousarray(org, dtype=np.uint32)
+        stride = 12 if org.ndim == 2 else 4
+        if org.shape[0] != ne or (org.ndim == 2 and org.shape[1] != 3):
+            raise HarryError(f"twin_match: org has shape {org.shape}, expected ({ne},) or ({ne}, 3)")
+        if out is None:
+            out = np.zeros((ne, 3), dtype=np.uint32)
+        self._check(self.lib.hb_twin_match(self.h, nv, max(nf, 0), face_off.ctypes.data, org.ctypes.data, stride, out.ctypes.data),
+                    "hb_twin_match")
+        return out
 
     # AttrCoder::encode
     def attr_encode(self, mesh: MeshArrays) -> StreamsPy:

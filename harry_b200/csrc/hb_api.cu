@@ -748,6 +748,42 @@ extern "C" int hb_requant(hb_ctx *ctx, hb_list_desc *list, const uint8_t *new_qu
 	return rc;
 }
 
+extern "C" int hb_twin_match(hb_ctx *ctx, uint32_t nv, uint32_t nf, const uint32_t *face_off, const void *org, uint32_t org_stride,
+                             void *edges_out)
+{
+	if (nf && (!face_off || !org || !edges_out)) return hb_fail(ctx, HB_ERR_INVALID, "twin_match: NULL argument");
+	if (org_stride != 4 && org_stride != 12) return hb_fail(ctx, HB_ERR_INVALID, "twin_match: org_stride must be 4 (packed) or 12 (edge records)");
+	const uint32_t ne = nf ? face_off[nf] : 0;
+	if (nf && face_off[0] != 0) return hb_fail(ctx, HB_ERR_INVALID, "twin_match: face_off[0] != 0");
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	hb_dmesh *m = new hb_dmesh();
+	m->ctx = ctx;
+	PhaseTimer t(ctx);
+	t.mark(0);
+	uint32_t *d_face_off = nullptr, *d_org = nullptr, *d_out = nullptr;
+	int rc = hb_dalloc_t(m, &d_face_off, (size_t)nf + 1);
+	if (rc == 0) rc = hb_dalloc_t(m, &d_out, (size_t)ne * 3);
+	if (rc == 0 && org_stride == 4) rc = hb_dalloc_t(m, &d_org, (size_t)ne);
+	auto up = [&](void *dst, const void *src, size_t bytes) {
+		if (rc != 0 || !bytes) return;
+		if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+			rc = hb_fail(ctx, HB_ERR_CUDA, "twin_match: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+	};
+	up(d_face_off, face_off, sizeof(uint32_t) * ((size_t)nf + 1));
+	if (org_stride == 4) up(d_org, org, sizeof(uint32_t) * (size_t)ne);
+	else up(d_out, org, 12 * (size_t)ne); // the records themselves: org read in place, twin words overwritten
+	t.mark(1);
+	if (rc == 0) rc = hb_twin_build(m, nv, nf, ne, d_face_off, org_stride == 4 ? d_org : d_out, org_stride / 4, d_out);
+	t.mark(2);
+	if (rc == 0 && ne && cudaMemcpyAsync(edges_out, d_out, 12 * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+		rc = hb_fail(ctx, HB_ERR_CUDA, "twin_match: download failed: %s", cudaGetErrorString(cudaGetLastError()));
+	t.mark(3);
+	t.finish(4);
+	if (rc == 0) rc = hb_check_device_error(ctx, "twin matching");
+	hb_dmesh_free(m);
+	return rc;
+}
+
 extern "C" int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams **out)
 {
 	*out = nullptr;

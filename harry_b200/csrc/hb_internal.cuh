@@ -179,6 +179,8 @@ int hb_list_bounds(hb_dmesh *m, uint32_t l);
 int hb_list_scale(hb_dmesh *m, uint32_t l, const uint8_t *groups);
 int hb_list_requant(hb_dmesh *m, uint32_t l, const uint8_t *new_quant);
 void hb_fill_list_params(ListParams &p, const hb_list_desc &L);
+int hb_twin_build(hb_dmesh *m, uint32_t nv, uint32_t nf, uint32_t ne, const uint32_t *d_face_off, const uint32_t *d_org,
+                  uint32_t os, uint32_t *d_out); // hb_twin.cu
 
 // ------------------------------------------------------------------------------------------------
 // device arithmetic

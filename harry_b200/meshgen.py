@@ -207,6 +207,18 @@ def cones(k: int = 80, valence: int = 90, seed: int = 2, open_every: int = 0) ->
     return PolyMesh(pos=np.asarray(pos, dtype=np.float32), face_off=face_off, face_idx=faces.ravel())
 
 
+def soup(nv: int = 30, nf: int = 400, seed: int = 1, min_deg: int = 1, max_deg: int = 6) -> PolyMesh:
+    """Random polygon soup over few vertices: heavily non-manifold (many half-edges per directed edge), with
+    degenerate edges (a, a) and faces of 1 or 2 corners when min_deg allows.  Input for the twin matching only
+    (structs/conn.h:178-190: which half-edges pair up depends on their file order)."""
+    rng = np.random.default_rng(seed)
+    deg = rng.integers(min_deg, max_deg + 1, nf)
+    face_off = np.concatenate([[0], np.cumsum(deg)]).astype(np.uint32)
+    face_idx = rng.integers(0, nv, int(face_off[-1])).astype(np.uint32)
+    face_idx[rng.integers(0, face_idx.shape[0])] = nv - 1   # the reader derives nv from the largest index
+    return PolyMesh(pos=rng.random((nv, 3)).astype(np.float32), face_off=face_off, face_idx=face_idx)
+
+
 # ----------------------------------------------------------------------------------------------
 # PLY writer (binary little endian)
 # ----------------------------------------------------------------------------------------------

@@ -14,6 +14,9 @@
  *   hb_attr_decode   <- attrcode::AttrDecoder<RD>::decode(P&)    formats/hry/attrcode.h:534-550
  *                       (call site formats/hry/reader.cc:192), after the host drained the
  *                       arithmetic-coded symbol stream into residual rows + binding tables
+ *   hb_twin_match    <- mesh::Builder::add_edge / face_end / set_org  structs/conn.h:164-214
+ *                       (the twin hash join the readers run per face corner, formats/ply/reader.cc:349-353,
+ *                       formats/obj/reader.rl; SURVEY.md section 8f row f2 -- the step in front of the path)
  *
  * The same structs are consumed by the CPU oracle (oracle/harry_oracle.h: ho_* functions with
  * identical signatures), which is test infrastructure only.
@@ -193,6 +196,21 @@ void hb_streams_free(hb_streams *s);
 /* In: lists[l].rows[k] holds the residual of the k-th DATA emission of list l, binding tables
  * filled from the HIST/LHIST symbols.  Out: rows hold the reconstructed attribute values. */
 int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh);
+
+/* ---- ingest: twin matching (host buffers) ------------------------------------------------ */
+/* Half-edge (f, e) = global index face_off[f] + e runs from its origin to the origin of the next corner
+ * of f.  Matches half-edges of opposite direction on the same vertex pair exactly like the reference's
+ * Builder does while it reads the faces in file order (first unmatched half-edge of a directed edge
+ * waits, a later opposite one merges with it, a later one of the SAME direction stays a border), so
+ * non-manifold and degenerate input gives the same table.  Borders are their own twin.
+ *   org         origin vertex of every half-edge, one u32 every org_stride bytes: 4 = packed array,
+ *               12 = the org field of Conn::edgeorg records (structs/conn.h:73-76); in that case org
+ *               may be edges_out itself (in place, what a reader with Builder::automerge = false holds)
+ *   edges_out   ne = face_off[nf] records of 12 bytes { u32 org; u32 twin_face; u16 twin_edge; u16 0 },
+ *               the layout hb_mesh_desc.edges takes
+ * nv = number of vertices (every org must be < nv <= 2^31). */
+int hb_twin_match(hb_ctx *ctx, uint32_t nv, uint32_t nf, const uint32_t *face_off, const void *org,
+                  uint32_t org_stride, void *edges_out);
 
 /* ---- device-resident pipeline (inputs stay in HBM between stages; used for batches and by
  *      bench.py's kernel-only timing) ---------------------------------------------------- */

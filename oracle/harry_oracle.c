@@ -1173,3 +1173,102 @@ int ho_debug_vertex_candidates(const hb_mesh_desc *m, uint32_t **off_out, uint32
 	*tri_out = tri.v;
 	return rc;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Twin matching: mesh::Builder, structs/conn.h:164-214.        */
+/*                                                                                             */
+/* The reference keeps an unordered_map from the DIRECTED edge (a, b) to the half-edge that    */
+/* first carried it.  Half-edges arrive in file order (face by face, corner by corner:         */
+/* set_org :203-210 calls add_edge(last, vtx) for corners 1.., face_end :199-202 closes the    */
+/* loop with add_edge(last, start)); half-edge (f, e) runs from org(f, e) to org(f, e+1 mod n). */
+/* add_edge(a, b) :178-190: if (b, a) is in the map, merge with the half-edge stored there and  */
+/* ERASE the entry; otherwise insert (a, b) -- std::unordered_map::insert keeps an existing     */
+/* entry, so a second half-edge with the same direction stays a border (its twin is itself,     */
+/* Conn::add_face :87-91).  Restated here with an open-addressing table (linear probing,        */
+/* tombstones) instead of the node-based map; only the lookup / insert-if-absent / erase        */
+/* semantics matter.                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct tw_slot { uint32_t a, b, he; uint32_t state; } tw_slot; /* state: 0 empty, 1 full, 2 erased */
+
+static uint64_t tw_hash(uint32_t a, uint32_t b)
+{
+	uint64_t x = ((uint64_t)a << 32) | b;
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+	return x;
+}
+static tw_slot *tw_find(tw_slot *tab, uint64_t mask, uint32_t a, uint32_t b)
+{
+	uint64_t i = tw_hash(a, b) & mask;
+	for (;; i = (i + 1) & mask) {
+		if (tab[i].state == 0) return NULL;
+		if (tab[i].state == 1 && tab[i].a == a && tab[i].b == b) return &tab[i];
+	}
+}
+static void tw_insert_absent(tw_slot *tab, uint64_t mask, uint32_t a, uint32_t b, uint32_t he)
+{
+	uint64_t i = tw_hash(a, b) & mask;
+	tw_slot *grave = NULL;
+	for (;; i = (i + 1) & mask) {
+		if (tab[i].state == 0) break;
+		if (tab[i].state == 2) { if (!grave) grave = &tab[i]; continue; }
+		if (tab[i].a == a && tab[i].b == b) return; /* insert() of an existing key is a no-op */
+	}
+	tw_slot *s = grave ? grave : &tab[i];
+	s->a = a; s->b = b; s->he = he; s->state = 1;
+}
+
+int ho_twin_match(uint32_t nv, uint32_t nf, const uint32_t *face_off, const void *org_in, uint32_t org_stride, void *edges_out)
+{
+	if (nf && (!face_off || !edges_out)) FAIL(HB_ERR_INVALID, "twin_match: NULL argument");
+	if (org_stride != 4 && org_stride != 12) FAIL(HB_ERR_INVALID, "twin_match: org_stride must be 4 or 12");
+	uint32_t ne = nf ? face_off[nf] : 0;
+	if (ne && !org_in) FAIL(HB_ERR_INVALID, "twin_match: NULL org");
+	uint8_t *out = (uint8_t *)edges_out;
+	uint32_t *org = (uint32_t *)malloc(sizeof(uint32_t) * (ne ? ne : 1)); /* packed copy (org_in may alias edges_out) */
+	if (!org) FAIL(HB_ERR_NOMEM, "twin_match: out of memory");
+	for (uint32_t h = 0; h < ne; ++h) memcpy(&org[h], (const uint8_t *)org_in + (size_t)h * org_stride, 4);
+	uint32_t *he_face = (uint32_t *)malloc(sizeof(uint32_t) * (ne ? ne : 1));
+	uint32_t *twin = (uint32_t *)malloc(sizeof(uint32_t) * (ne ? ne : 1));
+	uint64_t cap = 16;
+	while (cap < 2 * (uint64_t)ne) cap <<= 1;
+	tw_slot *tab = (tw_slot *)calloc(cap, sizeof(tw_slot));
+	if (!he_face || !twin || !tab) { free(org); free(he_face); free(twin); free(tab); FAIL(HB_ERR_NOMEM, "twin_match: out of memory"); }
+	int rc = 0;
+	for (uint32_t f = 0; f < nf && !rc; ++f) {
+		uint32_t o = face_off[f], n = face_off[f + 1] - o;
+		if (face_off[f + 1] < o || face_off[f + 1] > ne) { rc = HB_ERR_INVALID; break; }
+		for (uint32_t e = 0; e < n; ++e) {
+			uint32_t h = o + e;
+			he_face[h] = f;
+			twin[h] = h; /* Conn::add_face: every half-edge starts as its own twin */
+			if (org[h] >= nv) { rc = HB_ERR_INVALID; break; }
+		}
+	}
+	for (uint32_t f = 0; f < nf && !rc; ++f) {
+		uint32_t o = face_off[f], n = face_off[f + 1] - o;
+		for (uint32_t e = 0; e < n; ++e) {
+			uint32_t h = o + e, a = org[h], b = org[o + (e + 1 == n ? 0 : e + 1)];
+			tw_slot *t = tw_find(tab, cap - 1, b, a);
+			if (t) {
+				twin[t->he] = h; /* Conn::fmerge :154-158 */
+				twin[h] = t->he;
+				t->state = 2;
+			} else {
+				tw_insert_absent(tab, cap - 1, a, b, h);
+			}
+		}
+	}
+	if (!rc) {
+		for (uint32_t h = 0; h < ne; ++h) {
+			uint32_t t = twin[h], tf = he_face[t];
+			uint16_t te = (uint16_t)(t - face_off[tf]), pad = 0;
+			memcpy(out + 12 * (size_t)h, &org[h], 4);
+			memcpy(out + 12 * (size_t)h + 4, &tf, 4);
+			memcpy(out + 12 * (size_t)h + 8, &te, 2);
+			memcpy(out + 12 * (size_t)h + 10, &pad, 2);
+		}
+	}
+	free(org); free(he_face); free(twin); free(tab);
+	if (rc) FAIL(rc, "twin_match: malformed face_off / org (vertex index >= nv)");
+	return 0;
+}

@@ -65,6 +65,7 @@ def oracle():
         lib.ho_predict.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
         lib.ho_encode_delta.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int]
         lib.ho_decode_delta.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int]
+        lib.ho_twin_match.argtypes = [C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, vp]
         lib.ho_msb.argtypes = [C.c_uint32]
         lib.ho_msb.restype = C.c_uint32
         _oracle = lib
@@ -101,6 +102,19 @@ def o_requant(la: capi.ListArrays, new_quant, mn, sc):
     sc = np.ascontiguousarray(sc)
     _ocheck(oracle().ho_requant(C.byref(d), nq, mn.ctypes.data, sc.ctypes.data), "requant")
     la.sync_from_desc(d)
+
+
+def o_twin_match(nv: int, face_off: np.ndarray, org: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """Same contract as capi.Context.twin_match."""
+    face_off = np.ascontiguousarray(face_off, dtype=np.uint32)
+    nf = int(face_off.shape[0]) - 1
+    ne = int(face_off[nf]) if nf > 0 else 0
+    org = np.ascontiguousarray(org, dtype=np.uint32)
+    if out is None:
+        out = np.zeros((ne, 3), dtype=np.uint32)
+    _ocheck(oracle().ho_twin_match(nv, max(nf, 0), face_off.ctypes.data, org.ctypes.data, 12 if org.ndim == 2 else 4, out.ctypes.data),
+            "twin_match")
+    return out
 
 
 def o_attr_encode(mesh: capi.MeshArrays) -> capi.StreamsPy:
