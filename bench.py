@@ -503,7 +503,7 @@ def run_twin(ctx, w, peak: float, no_cpu: bool, reps: int = 3):
     wall, kern, copy = wall / reps * 1e3, kern / reps, copy / reps
     # algorithmic bytes per half-edge: count reads the origin (4); fill reads it and writes a 16-byte entry (20);
     # resolve reads the origin, its own entry and its partner's, writes the 12-byte record (48)
-    alg = {"k_twin_scatter<false>": 4, "k_twin_scatter<true>": 20, "k_twin_resolve": 48}
+    alg = {"k_twin_scatter<false>": 4, "k_twin_scatter<true>": 20, "k_twin_resolve<1>": 48}
     kernels = {}
     for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         k = {"launches_per_call": n / reps, "ms_per_call": ms / reps}
