@@ -98,6 +98,16 @@ void set_bounds_b200(mesh::attr::Attrs &attrs)
 	}
 }
 
+void finish_read_b200(mesh::Mesh &mesh)
+{
+	static_assert(sizeof(mesh::conn::Conn::edgeorg) == 12, "hb_twin_match works in place on 12-byte Conn::edgeorg records");
+	const uint32_t nf = (uint32_t)mesh.faces.size();
+	if (nf && hb_twin_match(b200::context(), (uint32_t)mesh.conn.num_vtx(), nf, mesh.faces.offsets.data(), mesh.conn.edges.data(), 12,
+	                        mesh.conn.edges.data()) != 0)
+		b200::fail("twin_match");
+	set_bounds_b200(mesh.attrs);
+}
+
 // quant::requant(Attrs&, vector<Quant>, clear) (structs/quant.h:222-242): the format bookkeeping
 // (backup_fmt / tmp / restore_fmt) and set_scale stay the reference's; the row conversion
 // requant(Attr&, Fmt) (:215-221) runs on the GPU

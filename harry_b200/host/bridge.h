@@ -35,5 +35,9 @@ void flatten(mesh::Mesh &mesh, const std::vector<mesh::conn::fepair> &order, con
 namespace quant {
 // same signatures as quant::set_bounds (structs/quant.h:39-44) / quant::requant (:222-242)
 void set_bounds_b200(mesh::attr::Attrs &attrs);
+// what a reader does once all faces are in: twin matching of the half-edges on the GPU (replaces the per-corner
+// hash join of mesh::Builder, structs/conn.h:164-214, which the reader TUs switch off with Builder::noautomerge,
+// structs/mesh.h:49-52), then set_bounds
+void finish_read_b200(mesh::Mesh &mesh);
 void requant_b200(mesh::attr::Attrs &attrs, const std::vector<Quant> &quant, bool clear);
 }
