@@ -169,11 +169,14 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []   # (arrival time, line)
+        self.t0 = None
 
     def start(self):
+        """Started well before the timed region (nvidia-smi needs a few hundred ms to come up, a timed region of
+        a few steps is shorter than that); only the samples that arrive inside the region are reported."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -182,18 +185,28 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin_region(self):
+        self.t0 = time.perf_counter()
 
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.perf_counter()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.02]
+        window = "timed region"
+        if not inside:   # region shorter than one sampling period: the warm-up steps right before it ran the same work
+            inside = [ln for (t, ln) in self.lines[-3:]]
+            window = "last samples before the end of the timed region (warm-up steps of the same work)"
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -206,7 +219,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window, "period_ms": 25}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -303,6 +316,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     workdir = tempfile.mkdtemp(prefix="harry_bench_")
     nr, ns = (args.nr, args.ns) if args.nr else FULL
     w = Workload(nr, ns, workdir)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     ctx = capi.Context(local_rank)
     vl = 1
     groups = w.raw.lists[vl].groups
@@ -331,8 +346,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     ctx.sync()
     if dist is not None:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin_region()
     launches0 = ctx.launches()
     ctx.profile(True)
     enc_ms = dec_ms = 0.0
