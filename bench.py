@@ -495,6 +495,24 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
 # ----------------------------------------------------------------------------------------------
 # twin matching of the workload's faces (the step in front of the path)
 # ----------------------------------------------------------------------------------------------
+def twin_cpu_baseline():
+    """Twin matching of the bounded CPU sample on one host core: the reference's own conn::Builder
+    (structs/conn.h:172-233, std::unordered_map) driven through oracle/_ref when it is there, else the oracle port."""
+    import oracle_lib as ol
+    pm = meshgen.uv_sphere(*SAMPLE)
+    ne = int(pm.face_idx.shape[0])
+    if ol.have_ref_twin():
+        _, dt = ol.ref_twin_match(pm.face_off, pm.face_idx)
+        kind, what = "reference", "conn::Builder::face_begin / set_org / face_end over all faces (the readers' loop without the parsing)"
+    else:
+        t0 = time.perf_counter()
+        ol.o_twin_match(pm.nv, pm.face_off, pm.face_idx)
+        dt = time.perf_counter() - t0
+        kind, what = "port", "ho_twin_match (open-addressing restatement of the Builder's unordered_map)"
+    return {"value": ne / dt / 1e6, "unit": "M half-edges/s", "cores": 1, "kind": kind,
+            "sample": f"UV sphere {SAMPLE[0]}x{SAMPLE[1]} ({ne} half-edges), {what}, single thread"}
+
+
 def run_twin(ctx, w, peak: float, no_cpu: bool, reps: int = 3):
     """hb_twin_match on the connectivity of the N = 1 workload: host buffers in page-locked memory, wall clock
     around the synchronous call (upload of face_off + origins, three kernels + scan, download of the 12-byte
@@ -532,13 +550,7 @@ def run_twin(ctx, w, peak: float, no_cpu: bool, reps: int = 3):
            "timer": "kernel_ms / copy_ms: CUDA events on the library stream; e2e_ms: host wall clock around the synchronous C-ABI call"}
     del face_off, org, out
     if not no_cpu:
-        import oracle_lib as ol
-        pm = meshgen.uv_sphere(*SAMPLE)
-        t0 = time.perf_counter()
-        ol.o_twin_match(pm.nv, pm.face_off, pm.face_idx)
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": pm.face_idx.shape[0] / dt / 1e6, "unit": "M half-edges/s", "cores": 1, "kind": "port",
-                               "sample": f"UV sphere {SAMPLE[0]}x{SAMPLE[1]} ({pm.face_idx.shape[0]} half-edges), ho_twin_match (open-addressing restatement of the Builder's unordered_map), single thread"}
+        res["cpu_baseline"] = twin_cpu_baseline()
     return res
 
 

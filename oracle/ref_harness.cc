@@ -520,4 +520,32 @@ int ref_time_decode(const char *hry_path, double *times)
 	return rc;
 }
 
+/* The reference's own twin matching on a face list: conn::Builder (structs/conn.h:172-233) driven the way the
+ * readers drive it -- face_begin, set_org per corner, face_end (formats/ply/reader.cc:349-353).  edges_out receives
+ * Conn::edges (12-byte edgeorg records), *seconds the time of the loop alone. */
+int ref_twin_match(uint32_t nf, const uint32_t *face_off, const uint32_t *org, void *edges_out, double *seconds)
+{
+	try {
+		static_assert(sizeof(mesh::conn::Conn::edgeorg) == 12, "Conn::edgeorg layout");
+		mesh::Faces faces;
+		mesh::conn::Conn conn(faces);
+		mesh::conn::Builder b(conn);
+		b.reserve(nf);
+		double t0 = now_s();
+		for (uint32_t f = 0; f < nf; ++f) {
+			const uint32_t n = face_off[f + 1] - face_off[f];
+			b.face_begin((mesh::ledgeidx_t)n);
+			for (uint32_t e = 0; e < n; ++e) b.set_org(org[face_off[f] + e]);
+			b.face_end();
+		}
+		double t1 = now_s();
+		if (seconds) *seconds = t1 - t0;
+		if (edges_out && !conn.edges.empty()) std::memcpy(edges_out, conn.edges.data(), conn.edges.size() * 12);
+		return 0;
+	} catch (std::exception &e) {
+		g_err = e.what();
+		return -1;
+	}
+}
+
 } // extern "C"

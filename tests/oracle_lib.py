@@ -166,6 +166,8 @@ def ref():
         lib.ref_streams_free.restype = None
         lib.ref_time_path.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         lib.ref_time_decode.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
+        if hasattr(lib, "ref_twin_match"):   # harness builds older than the twin matching row lack it
+            lib.ref_twin_match.argtypes = [C.c_uint32, vp, vp, vp, C.POINTER(C.c_double)]
         _ref = lib
     return _ref
 
@@ -258,6 +260,23 @@ class RefMesh:
             rc = self.lib.ref_time_path(self.h, len(loq), arr, t)
         self._check(rc, "time_path")
         return list(t)
+
+
+def have_ref_twin() -> bool:
+    return have_ref() and hasattr(ref(), "ref_twin_match")
+
+
+def ref_twin_match(face_off: np.ndarray, org: np.ndarray):
+    """The reference's conn::Builder (structs/conn.h:172-233) on a face list: ((ne, 3) uint32 records, seconds)."""
+    face_off = np.ascontiguousarray(face_off, dtype=np.uint32)
+    org = np.ascontiguousarray(org, dtype=np.uint32)
+    nf = int(face_off.shape[0]) - 1
+    out = np.zeros((int(face_off[nf]) if nf > 0 else 0, 3), dtype=np.uint32)
+    sec = C.c_double()
+    if ref().ref_twin_match(max(nf, 0), face_off.ctypes.data, org.ctypes.data, out.ctypes.data, C.byref(sec)) != 0:
+        raise RuntimeError(f"reference twin_match: {ref().ref_last_error().decode()}")
+    out[:, 2] &= 0xFFFF   # the pad bytes of fepair are not initialised by the reference
+    return out, sec.value
 
 
 def ref_time_decode(hry_path: str):

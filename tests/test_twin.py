@@ -116,6 +116,22 @@ def test_oracle_twin_live_reference_soup(workdir, seed):
     assert np.array_equal(ol.o_twin_match(m.nv, m.face_off, np.ascontiguousarray(m.edges[:, 0])), m.edges)
 
 
+@pytest.mark.skipif(not ol.have_ref_twin(), reason="oracle/_ref/libharry_ref.so lacks ref_twin_match")
+@pytest.mark.parametrize("name", list(GENERATED.keys()))
+def test_oracle_twin_vs_reference_builder(name):
+    """the reference's conn::Builder driven directly (no file in between) on the generated inputs of the GPU tests"""
+    pm = GENERATED[name]()
+    want, _ = ol.ref_twin_match(pm.face_off, pm.face_idx)
+    assert np.array_equal(ol.o_twin_match(pm.nv, pm.face_off, pm.face_idx), want)
+
+
+@pytest.mark.skipif(not ol.have_ref_twin(), reason="oracle/_ref/libharry_ref.so lacks ref_twin_match")
+def test_oracle_twin_vs_reference_builder_1m():
+    pm = meshgen.uv_sphere(708, 1412)
+    want, _ = ol.ref_twin_match(pm.face_off, pm.face_idx)
+    assert np.array_equal(ol.o_twin_match(pm.nv, pm.face_off, pm.face_idx), want)
+
+
 # ---- GPU: CUDA path through the C ABI ----------------------------------------------------------
 @pytest.fixture(scope="module")
 def ctx():
@@ -184,6 +200,8 @@ def test_cuda_twin_1m_vs_oracle(ctx):
     want = ol.o_twin_match(pm.nv, pm.face_off, pm.face_idx)
     got = ctx.twin_match(pm.nv, pm.face_off, pm.face_idx)
     assert np.array_equal(got, want)
+    if ol.have_ref_twin():
+        assert np.array_equal(got, ol.ref_twin_match(pm.face_off, pm.face_idx)[0])
     assert check_table_properties(pm.face_off, got) == 0      # closed surface: no border
 
 
