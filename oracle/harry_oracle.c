@@ -1236,7 +1236,7 @@ int ho_twin_match(uint32_t nv, uint32_t nf, const uint32_t *face_off, const void
 	int rc = 0;
 	for (uint32_t f = 0; f < nf && !rc; ++f) {
 		uint32_t o = face_off[f], n = face_off[f + 1] - o;
-		if (face_off[f + 1] < o || face_off[f + 1] > ne) { rc = HB_ERR_INVALID; break; }
+		if (face_off[f + 1] < o || face_off[f + 1] > ne || n > 0xffffu) { rc = HB_ERR_INVALID; break; } /* fepair::e is 16 bits wide (structs/conn.h:22-31) */
 		for (uint32_t e = 0; e < n; ++e) {
 			uint32_t h = o + e;
 			he_face[h] = f;
@@ -1269,6 +1269,6 @@ int ho_twin_match(uint32_t nv, uint32_t nf, const uint32_t *face_off, const void
 		}
 	}
 	free(org); free(he_face); free(twin); free(tab);
-	if (rc) FAIL(rc, "twin_match: malformed face_off / org (vertex index >= nv)");
+	if (rc) FAIL(rc, "twin_match: malformed face_off (decreasing, beyond ne, face with more than 65535 corners) or vertex index >= nv");
 	return 0;
 }

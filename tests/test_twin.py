@@ -94,6 +94,16 @@ def test_oracle_twin_rejects_bad_vertex():
         ol.o_twin_match(3, face_off, np.array([0, 1, 3], np.uint32))
 
 
+def test_oracle_twin_face_size_limit():
+    """a face may have 65535 corners (fepair::e is 16 bits wide), not more"""
+    n = 65535
+    org = np.arange(n, dtype=np.uint32)
+    got = ol.o_twin_match(n, np.array([0, n], np.uint32), org)
+    assert np.array_equal(got[:, 2], np.arange(n, dtype=np.uint32)) and np.all(got[:, 1] == 0)   # all borders
+    with pytest.raises(RuntimeError):
+        ol.o_twin_match(n + 1, np.array([0, n + 1], np.uint32), np.arange(n + 1, dtype=np.uint32))
+
+
 @needs_ref
 @pytest.mark.parametrize("name", list(CASES.keys()) + [CONFIG1[0]])
 def test_oracle_twin_live_reference(workdir, name):
@@ -190,6 +200,9 @@ def test_cuda_twin_empty_and_errors(ctx):
     assert np.array_equal(ctx.twin_match(4, face_off, org), ol.o_twin_match(4, face_off, org))
     with pytest.raises(capi.HarryError):
         ctx.twin_match(3, face_off, org)                      # vertex 3 >= nv
+    n = 65536                                                 # one corner more than fepair::e can address
+    with pytest.raises(capi.HarryError):
+        ctx.twin_match(n, np.array([0, n], np.uint32), np.arange(n, dtype=np.uint32))
     # the context stays usable after a rejected call
     assert np.array_equal(ctx.twin_match(4, face_off, org), ol.o_twin_match(4, face_off, org))
 
