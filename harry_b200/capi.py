@@ -103,6 +103,18 @@ class Streams(C.Structure):
     ]
 
 
+class BatchStreams(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("mesh", C.POINTER(Streams)), ("priv", C.c_void_p)]
+
+
+class QuantReq(C.Structure):
+    _fields_ = [("list", C.c_uint32), ("new_quant", C.c_uint8 * HB_MAX_COMP), ("groups", C.c_uint8 * HB_MAX_COMP)]
+
+
+class DequantReq(C.Structure):
+    _fields_ = [("list", C.c_uint32), ("bounds", C.c_void_p)]
+
+
 # ----------------------------------------------------------------------------------------------
 # numpy containers
 # ----------------------------------------------------------------------------------------------
@@ -360,7 +372,10 @@ class StreamsPy:
 def streams_to_py(sp, copy: bool = True) -> StreamsPy:
     """hb_streams -> numpy.  copy=False returns views of the library's (page-locked) buffers: valid
     until hb_streams_free is called on `sp` -- what a C++ caller of the ABI sees, no extra pass."""
-    s = sp.contents
+    return streams_struct_to_py(sp.contents, copy)
+
+
+def streams_struct_to_py(s, copy: bool = True) -> StreamsPy:
 
     def arr(ptr, n, dtype):
         if n == 0:
@@ -507,6 +522,20 @@ def load_library():
     lib.hb_attr_decode.restype = C.c_int
     lib.hb_dmesh_upload.argtypes = [vp, C.POINTER(MeshDesc), C.POINTER(vp)]
     lib.hb_dmesh_upload.restype = C.c_int
+    lib.hb_dmesh_upload_batch.argtypes = [vp, C.POINTER(MeshDesc), u32, C.POINTER(vp)]
+    lib.hb_dmesh_upload_batch.restype = C.c_int
+    lib.hb_dmesh_segments.argtypes = [vp]
+    lib.hb_dmesh_segments.restype = u32
+    lib.hb_dmesh_fetch_streams_batch.argtypes = [vp, C.POINTER(C.POINTER(BatchStreams))]
+    lib.hb_dmesh_fetch_streams_batch.restype = C.c_int
+    lib.hb_dmesh_fetch_rows_seg.argtypes = [vp, u32, u32, vp]
+    lib.hb_dmesh_fetch_rows_seg.restype = C.c_int
+    lib.hb_batch_streams_free.argtypes = [C.POINTER(BatchStreams)]
+    lib.hb_batch_streams_free.restype = None
+    lib.hb_encode_batch.argtypes = [vp, C.POINTER(MeshDesc), u32, C.POINTER(QuantReq), u32, C.POINTER(vp), C.POINTER(C.POINTER(BatchStreams))]
+    lib.hb_encode_batch.restype = C.c_int
+    lib.hb_decode_batch.argtypes = [vp, C.POINTER(MeshDesc), u32, C.POINTER(DequantReq), u32]
+    lib.hb_decode_batch.restype = C.c_int
     lib.hb_dmesh_free.argtypes = [vp]
     lib.hb_dmesh_free.restype = None
     lib.hb_dmesh_quantize.argtypes = [vp, u32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
@@ -544,7 +573,16 @@ EXPORTED_SYMBOLS = [
     "hb_dmesh_upload", "hb_dmesh_free", "hb_dmesh_quantize", "hb_dmesh_dequantize", "hb_dmesh_encode",
     "hb_dmesh_fetch_streams", "hb_dmesh_set_bounds", "hb_dmesh_snapshot", "hb_dmesh_restore", "hb_dmesh_decode", "hb_dmesh_fetch_rows",
     "hb_dmesh_fetch_bounds", "hb_dmesh_decode_stats", "hb_ctx_sync",
+    "hb_dmesh_upload_batch", "hb_dmesh_segments", "hb_dmesh_fetch_streams_batch", "hb_dmesh_fetch_rows_seg",
+    "hb_encode_batch", "hb_decode_batch", "hb_batch_streams_free",
 ]
+
+
+def _desc_array(meshes):
+    arr = (MeshDesc * len(meshes))()
+    for i, m in enumerate(meshes):
+        arr[i] = m.to_desc()
+    return arr
 
 
 class Context:
@@ -663,15 +701,63 @@ class Context:
         self._check(self.lib.hb_attr_decode(self.h, C.byref(d)), "hb_attr_decode")
 
 
-class DeviceMesh:
-    """Device-resident mesh (hb_dmesh): upload once, run stages as kernels only."""
+    # ---- batches of independent meshes (host buffers, pipelined in groups) ----------------------
+    def encode_batch(self, meshes, quant=(), want_bounds: bool = True, copy: bool = True):
+        """hb_encode_batch: per mesh set_bounds + set_scale + requant of the lists in `quant`
+        [(list, new_quant, groups)], then AttrCoder::encode.  Returns ([StreamsPy per mesh],
+        [bounds array (n, 3, stride) uint8 per request], release callable when copy=False)."""
+        n = len(meshes)
+        descs = _desc_array(meshes)
+        nq = len(quant)
+        reqs = (QuantReq * max(1, nq))()
+        bounds, bptr = [], (C.c_void_p * max(1, nq))()
+        for k, (l, new_quant, groups) in enumerate(quant):
+            reqs[k].list = l
+            for j, v in enumerate(new_quant):
+                reqs[k].new_quant[j] = v
+            for j, v in enumerate(groups):
+                reqs[k].groups[j] = v
+            b = np.zeros((n, 3, max(1, meshes[0].lists[l].stride)), dtype=np.uint8)
+            bounds.append(b)
+            bptr[k] = b.ctypes.data if want_bounds else None
+        bp = C.POINTER(BatchStreams)()
+        self._check(self.lib.hb_encode_batch(self.h, descs, n, reqs, nq, bptr, C.byref(bp)), "hb_encode_batch")
+        out = [streams_struct_to_py(bp.contents.mesh[i], copy) for i in range(n)]
+        if copy:
+            self.lib.hb_batch_streams_free(bp)
+            return out, bounds
+        return out, bounds, (lambda: self.lib.hb_batch_streams_free(bp))
 
-    def __init__(self, ctx: Context, mesh: MeshArrays):
+    def decode_batch(self, meshes, dequant=()):
+        """hb_decode_batch: per mesh AttrDecoder::decode, then requant(clear) of the lists in `dequant`
+        [(list, bounds array (n, 3, stride) uint8)].  Rows of every list are updated in place."""
+        n = len(meshes)
+        descs = _desc_array(meshes)
+        nq = len(dequant)
+        reqs = (DequantReq * max(1, nq))()
+        keep = []
+        for k, (l, b) in enumerate(dequant):
+            b = np.ascontiguousarray(b, dtype=np.uint8)
+            keep.append(b)
+            reqs[k].list = l
+            reqs[k].bounds = b.ctypes.data
+        self._check(self.lib.hb_decode_batch(self.h, descs, n, reqs, nq), "hb_decode_batch")
+        for m in meshes:
+            for l, _ in dequant:
+                m.lists[l].quants = [0] * m.lists[l].ncomp
+
+
+class DeviceMesh:
+    """Device-resident mesh (hb_dmesh): upload once, run stages as kernels only.  With a list of
+    meshes of one schema: a batch -- ONE device mesh whose stages run once over all of them."""
+
+    def __init__(self, ctx: Context, mesh):
         self.ctx = ctx
-        self.mesh = mesh
-        d = mesh.to_desc()
+        self.meshes = list(mesh) if isinstance(mesh, (list, tuple)) else [mesh]
+        self.mesh = self.meshes[0]
+        descs = _desc_array(self.meshes)
         h = C.c_void_p()
-        ctx._check(ctx.lib.hb_dmesh_upload(ctx.h, C.byref(d), C.byref(h)), "hb_dmesh_upload")
+        ctx._check(ctx.lib.hb_dmesh_upload_batch(ctx.h, descs, len(self.meshes), C.byref(h)), "hb_dmesh_upload_batch")
         self.h = h
 
     def close(self):
@@ -704,10 +790,19 @@ class DeviceMesh:
         finally:
             self.ctx.lib.hb_streams_free(sp)
 
+    def fetch_streams_batch(self) -> list:
+        bp = C.POINTER(BatchStreams)()
+        self.ctx._check(self.ctx.lib.hb_dmesh_fetch_streams_batch(self.h, C.byref(bp)), "hb_dmesh_fetch_streams_batch")
+        try:
+            return [streams_struct_to_py(bp.contents.mesh[i]) for i in range(bp.contents.n)]
+        finally:
+            self.ctx.lib.hb_batch_streams_free(bp)
+
     def set_bounds(self, l: int, mn=None, mx=None, sc=None):
-        ptr = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.uint8).ctypes.data
-        keep = [np.ascontiguousarray(a, dtype=np.uint8) for a in (mn, mx, sc) if a is not None]
-        self.ctx._check(self.ctx.lib.hb_dmesh_set_bounds(self.h, l, ptr(mn), ptr(mx), ptr(sc)), "hb_dmesh_set_bounds")
+        """Rows of all meshes back to back for a batch: arrays of shape (n, stride)."""
+        keep = [None if a is None else np.ascontiguousarray(a, dtype=np.uint8) for a in (mn, mx, sc)]
+        ptr = lambda a: None if a is None else a.ctypes.data
+        self.ctx._check(self.ctx.lib.hb_dmesh_set_bounds(self.h, l, ptr(keep[0]), ptr(keep[1]), ptr(keep[2])), "hb_dmesh_set_bounds")
         del keep
 
     def snapshot(self):
@@ -719,10 +814,10 @@ class DeviceMesh:
     def decode(self):
         self.ctx._check(self.ctx.lib.hb_dmesh_decode(self.h), "hb_dmesh_decode")
 
-    def fetch_rows(self, l: int) -> np.ndarray:
-        la = self.mesh.lists[l]
+    def fetch_rows(self, l: int, seg: int = 0) -> np.ndarray:
+        la = self.meshes[seg].lists[l]
         out = np.zeros((la.nrows, la.stride), dtype=np.uint8)
-        self.ctx._check(self.ctx.lib.hb_dmesh_fetch_rows(self.h, l, out.ctypes.data), "hb_dmesh_fetch_rows")
+        self.ctx._check(self.ctx.lib.hb_dmesh_fetch_rows_seg(self.h, seg, l, out.ctypes.data), "hb_dmesh_fetch_rows_seg")
         return out
 
     def decode_stats(self, l: int) -> list:
@@ -731,9 +826,12 @@ class DeviceMesh:
         return [int(v) for v in out]
 
     def fetch_bounds(self, l: int):
+        """(min, max, scale) rows; for a batch arrays of shape (n, stride)."""
         la = self.mesh.lists[l]
-        n = max(1, la.stride)
-        mn, mx, sc = (np.zeros(n, dtype=np.uint8) for _ in range(3))
+        n, ns = max(1, la.stride), len(self.meshes)
+        mn, mx, sc = (np.zeros((ns, n), dtype=np.uint8) for _ in range(3))
         self.ctx._check(self.ctx.lib.hb_dmesh_fetch_bounds(self.h, l, mn.ctypes.data, mx.ctypes.data, sc.ctypes.data),
                         "hb_dmesh_fetch_bounds")
-        return mn[: la.stride], mx[: la.stride], sc[: la.stride]
+        if ns == 1:
+            return mn[0, : la.stride], mx[0, : la.stride], sc[0, : la.stride]
+        return mn[:, : la.stride], mx[:, : la.stride], sc[:, : la.stride]

@@ -74,9 +74,7 @@ extern "C" int hb_ctx_create(int device, hb_ctx **out)
 	CREATE_TRY(cudaSetDevice(device));
 	CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-	CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
-	CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_up[0], cudaEventDisableTiming));
-	CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_up[1], cudaEventDisableTiming));
+	CREATE_TRY(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 6; ++i) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
 	CREATE_TRY(cudaMalloc((void **)&ctx->d_err, sizeof(int)));
 	CREATE_TRY(cudaMemset(ctx->d_err, 0, sizeof(int)));
@@ -102,9 +100,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-	if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
-	for (int i = 0; i < 2; ++i)
-		if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
+	if (ctx->out_stream) { cudaStreamSynchronize(ctx->out_stream); cudaStreamDestroy(ctx->out_stream); }
 	for (int i = 0; i < 6; ++i)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -194,7 +190,10 @@ int hb_dalloc(hb_dmesh *m, void **p, size_t bytes)
 {
 	if (*p) return 0; // already allocated by an earlier run over the same mesh (sizes are per-mesh constants)
 	if (bytes == 0) bytes = 16;
-	cudaError_t e = cudaMallocAsync(p, bytes, m->ctx->stream);
+	// upload buffers of the host-buffer entry points come from the copy stream (the upload does not have to wait for
+	// the kernels of the previous mesh / group that are still queued on the compute stream)
+	cudaStream_t st = m->alloc_on_copy_stream ? m->ctx->copy_stream : m->ctx->stream;
+	cudaError_t e = cudaMallocAsync(p, bytes, st);
 	if (e != cudaSuccess) {
 		*p = nullptr;
 		return hb_fail(m->ctx, e == cudaErrorMemoryAllocation ? HB_ERR_NOMEM : HB_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
@@ -255,36 +254,72 @@ static int validate_list(hb_ctx *ctx, const hb_list_desc &L, bool for_coder)
 	return 0;
 }
 
+// host -> device copy of one uploaded array (on the copy stream for the host-buffer entry points)
+static int copy_in(hb_dmesh *m, void *dst, const void *src, size_t bytes)
+{
+	if (!(bytes && src)) return 0;
+	hb_ctx *ctx = m->ctx;
+	HB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m->async_copy ? ctx->copy_stream : ctx->stream));
+	return 0;
+}
 static int upload(hb_dmesh *m, void **dst, const void *src, size_t bytes)
 {
 	HB_TRY(hb_dalloc(m, dst, bytes));
-	if (!(bytes && src)) return 0;
-	hb_ctx *ctx = m->ctx;
-	if (m->async_copy) {
-		// the buffer comes from the stream-ordered pool of ctx->stream: the copy stream may touch it
-		// once it has waited for an event recorded behind the allocation
-		HB_CUDA(ctx, cudaEventRecord(ctx->ev_alloc, ctx->stream));
-		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_alloc, 0));
-		HB_CUDA(ctx, cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-	} else {
-		HB_CUDA(ctx, cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-	}
-	return 0;
+	return copy_in(m, *dst, src, bytes);
 }
 
-static int add_list(hb_dmesh *m, const hb_list_desc &L, bool for_coder)
+static bool same_format(const hb_list_desc &a, const hb_list_desc &b)
 {
-	HB_TRY(validate_list(m->ctx, L, for_coder));
+	if (a.ncomp != b.ncomp || a.stride != b.stride || a.target != b.target) return false;
+	for (int j = 0; j < a.ncomp; ++j)
+		if (a.type[j] != b.type[j] || a.quant[j] != b.quant[j] || a.offset[j] != b.offset[j]) return false;
+	return true;
+}
+
+// list l of all segments: rows concatenated (segment bases padded to multiples of 16 rows), one bounds triple per segment
+static int add_list(hb_dmesh *m, const hb_mesh_desc *descs, const hb_list_desc *single, uint32_t nseg, int l, bool for_coder)
+{
+	hb_ctx *ctx = m->ctx;
+	const hb_list_desc &L0 = single ? *single : descs[0].lists[l];
 	DevList dl;
 	memset(&dl.p, 0, sizeof dl.p);
-	hb_fill_list_params(dl.p, L);
+	dl.h_rowbase.assign((size_t)nseg + 1, 0);
+	dl.h_rownum.assign((size_t)nseg, 0);
+	uint64_t acc = 0;
+	for (uint32_t s = 0; s < nseg; ++s) {
+		const hb_list_desc &L = single ? *single : descs[s].lists[l];
+		HB_TRY(validate_list(ctx, L, for_coder));
+		if (s && !same_format(L0, L)) return hb_fail(ctx, HB_ERR_INVALID, "batch: list %d of mesh %u has another format than in mesh 0", l, s);
+		dl.h_rowbase[s] = (uint32_t)acc;
+		dl.h_rownum[s] = L.nrows;
+		acc += L.nrows;
+		if (s + 1 < nseg) acc = (acc + 15) & ~(uint64_t)15;
+		if (acc >= 0xfffffff0ull) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "batch: more than 2^32 rows in list %d", l);
+	}
+	dl.h_rowbase[nseg] = (uint32_t)acc;
+	hb_list_desc Lc = L0;
+	Lc.nrows = (uint32_t)acc;
+	hb_fill_list_params(dl.p, Lc);
 	void *rows = nullptr;
-	HB_TRY(upload(m, &rows, L.ncomp ? L.rows : nullptr, (size_t)L.nrows * L.stride));
+	HB_TRY(hb_dalloc(m, &rows, (size_t)acc * L0.stride));
 	dl.p.rows = (uint8_t *)rows;
+	if (L0.ncomp)
+		for (uint32_t s = 0; s < nseg; ++s) {
+			const hb_list_desc &L = single ? *single : descs[s].lists[l];
+			HB_TRY(copy_in(m, dl.p.rows + (size_t)dl.h_rowbase[s] * L0.stride, L.rows, (size_t)L.nrows * L0.stride));
+		}
+	// segment tables of the list: bases (nseg + 1) and row counts (nseg), back to back
+	std::vector<uint32_t> tab(dl.h_rowbase);
+	tab.insert(tab.end(), dl.h_rownum.begin(), dl.h_rownum.end());
+	void *dtab = nullptr;
+	HB_TRY(upload(m, &dtab, tab.data(), sizeof(uint32_t) * tab.size())); // (pageable source: staged before the call returns)
+	dl.d_rowbase = (uint32_t *)dtab;
+	dl.d_rownum = dl.d_rowbase + nseg + 1;
+	dl.bounds_pitch = (3 * (size_t)L0.stride + 16 + 15) & ~(size_t)15;
 	void *b = nullptr;
-	HB_TRY(hb_dalloc(m, &b, 3 * (size_t)L.stride + 16));
+	HB_TRY(hb_dalloc(m, &b, dl.bounds_pitch * nseg));
 	dl.d_bounds = (uint8_t *)b;
-	HB_CUDA(m->ctx, cudaMemsetAsync(b, 0, 3 * (size_t)L.stride + 16, m->ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(b, 0, dl.bounds_pitch * nseg, m->alloc_on_copy_stream ? ctx->copy_stream : ctx->stream));
 	m->lists.push_back(dl);
 	return 0;
 }
@@ -296,7 +331,18 @@ extern "C" void hb_dmesh_free(hb_dmesh *m)
 	if (m->async_copy) cudaStreamSynchronize(m->ctx->copy_stream); // nothing may still be landing in these buffers
 	for (void *p : m->allocs) cudaFreeAsync(p, m->ctx->stream);
 	cudaStreamSynchronize(m->ctx->stream);
+	if (m->ev_up[0]) cudaEventDestroy(m->ev_up[0]);
+	if (m->ev_up[1]) cudaEventDestroy(m->ev_up[1]);
+	if (m->ev_done) cudaEventDestroy(m->ev_done);
 	delete m;
+}
+
+// device memory of a group goes back to the pool behind the work queued on `st` (pipelined batches); the host object
+// stays (its segment tables are still needed for the stream views)
+static void dmesh_release_device(hb_dmesh *m, cudaStream_t st)
+{
+	for (void *p : m->allocs) cudaFreeAsync(p, st);
+	m->allocs.clear();
 }
 
 static int build_slot_table(hb_ctx *ctx, const int32_t *off, const uint16_t *lists, int nregs, int nlists, std::vector<int16_t> &slot, std::vector<int> *counts)
@@ -317,23 +363,65 @@ static int build_slot_table(hb_ctx *ctx, const int32_t *off, const uint16_t *lis
 	return 0;
 }
 
+static bool same_region_table(const int32_t *off_a, const uint16_t *la, const int32_t *off_b, const uint16_t *lb, int nregs)
+{
+	for (int r = 0; r <= nregs; ++r)
+		if (off_a[r] != off_b[r]) return false;
+	for (int k = 0; k < off_a[nregs]; ++k)
+		if (la[k] != lb[k]) return false;
+	return true;
+}
+
+// Upload of `nseg` meshes of one schema as one device mesh (hb_internal.cuh, "segments").
 // vertex_only: the caller will only reconstruct vertex lists (hb_attr_decode of a mesh whose face and
 // corner lists carry no components): the face-side arrays (order_f, face regions, face / corner bindings --
 // 280 MB on the 10M-vertex mesh) are then neither uploaded nor ranked
-static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh *m, bool vertex_only = false)
+static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t nseg, hb_dmesh *m, bool vertex_only = false)
 {
+	if (nseg == 0) return hb_fail(ctx, HB_ERR_INVALID, "batch: no mesh");
+	const hb_mesh_desc *d = &descs[0];
 	m->ctx = ctx;
-	m->nv = d->nv; m->nf = d->nf; m->ne = d->ne;
-	m->norder = d->norder;
+	m->nseg = nseg;
+	m->alloc_on_copy_stream = m->async_copy;
 	m->has_order_f = d->order_f != nullptr && !vertex_only;
-	m->norder_f = vertex_only ? 0 : (d->order_f ? d->norder_f : d->nf);
 	m->nb_face = d->nb_face; m->nb_vtx = d->nb_vtx; m->nb_corner = d->nb_corner;
 	m->nregs_face = d->nregs_face; m->nregs_vtx = d->nregs_vtx; m->nlists = d->nlists;
-	if (d->ne && (!d->edges || !d->face_off)) return hb_fail(ctx, HB_ERR_INVALID, "mesh: edges / face_off == NULL");
-	if (d->nf && d->face_off[d->nf] != d->ne) return hb_fail(ctx, HB_ERR_INVALID, "mesh: face_off[nf] != ne");
-	if (d->norder && !d->order) return hb_fail(ctx, HB_ERR_INVALID, "mesh: order == NULL");
-	if ((d->nv && !d->vtx_regs) || (d->nf && !d->face_regs)) return hb_fail(ctx, HB_ERR_INVALID, "mesh: region arrays == NULL");
 	if (d->nlists && !d->lists) return hb_fail(ctx, HB_ERR_INVALID, "mesh: lists == NULL");
+	// ---- segment bases -----------------------------------------------------------------------------
+	m->h_vbase.assign((size_t)nseg + 1, 0); m->h_fbase.assign((size_t)nseg + 1, 0); m->h_ebase.assign((size_t)nseg + 1, 0);
+	m->h_obase.assign((size_t)nseg + 1, 0); m->h_ofbase.assign((size_t)nseg + 1, 0);
+	uint64_t av = 0, af = 0, ae = 0, ao = 0, aof = 0;
+	for (uint32_t s = 0; s < nseg; ++s) {
+		const hb_mesh_desc &ds = descs[s];
+		if (ds.ne && (!ds.edges || !ds.face_off)) return hb_fail(ctx, HB_ERR_INVALID, "mesh: edges / face_off == NULL");
+		if (ds.nf && ds.face_off[ds.nf] != ds.ne) return hb_fail(ctx, HB_ERR_INVALID, "mesh: face_off[nf] != ne");
+		if (ds.nf && ds.face_off[0] != 0) return hb_fail(ctx, HB_ERR_INVALID, "mesh: face_off[0] != 0");
+		if (ds.norder && !ds.order) return hb_fail(ctx, HB_ERR_INVALID, "mesh: order == NULL");
+		if ((ds.nv && !ds.vtx_regs) || (ds.nf && !ds.face_regs)) return hb_fail(ctx, HB_ERR_INVALID, "mesh: region arrays == NULL");
+		if (s) {
+			if (ds.nlists != d->nlists || ds.nb_face != d->nb_face || ds.nb_vtx != d->nb_vtx || ds.nb_corner != d->nb_corner || ds.nregs_face != d->nregs_face ||
+			    ds.nregs_vtx != d->nregs_vtx || (ds.order_f != nullptr) != (d->order_f != nullptr) || (ds.emit_type != nullptr) != (d->emit_type != nullptr) ||
+			    !same_region_table(d->off_reg_vtx, d->reg_vtxlist, ds.off_reg_vtx, ds.reg_vtxlist, d->nregs_vtx) ||
+			    !same_region_table(d->off_reg_face, d->reg_facelist, ds.off_reg_face, ds.reg_facelist, d->nregs_face) ||
+			    !same_region_table(d->off_reg_corner, d->reg_cornerlist, ds.off_reg_corner, ds.reg_cornerlist, d->nregs_face))
+				return hb_fail(ctx, HB_ERR_INVALID, "batch: mesh %u has another schema (lists, regions, bindings) than mesh 0", s);
+		}
+		m->h_vbase[s] = (uint32_t)av; m->h_fbase[s] = (uint32_t)af; m->h_ebase[s] = (uint32_t)ae; m->h_obase[s] = (uint32_t)ao; m->h_ofbase[s] = (uint32_t)aof;
+		av += ds.nv; af += ds.nf; ae += ds.ne; ao += ds.norder;
+		aof += vertex_only ? 0 : (ds.order_f ? ds.norder_f : ds.nf);
+		if (av >= 0x7fffffffull || af + nseg >= 0x7fffffffull || ae >= 0x7fffffffull || ao >= 0x7fffffffull)
+			return hb_fail(ctx, HB_ERR_UNSUPPORTED, "batch: more than 2^31 vertices / faces / half-edges (split the batch)");
+	}
+	m->h_vbase[nseg] = (uint32_t)av; m->h_fbase[nseg] = (uint32_t)af; m->h_ebase[nseg] = (uint32_t)ae; m->h_obase[nseg] = (uint32_t)ao; m->h_ofbase[nseg] = (uint32_t)aof;
+	m->nv = (uint32_t)av; m->nf = (uint32_t)af; m->ne = (uint32_t)ae; m->norder = (uint32_t)ao; m->norder_f = (uint32_t)aof;
+	{
+		std::vector<uint32_t> tab;
+		tab.reserve(5 * ((size_t)nseg + 1));
+		for (const std::vector<uint32_t> *v : { &m->h_vbase, &m->h_fbase, &m->h_ebase, &m->h_obase, &m->h_ofbase }) tab.insert(tab.end(), v->begin(), v->end());
+		HB_TRY(upload(m, (void **)&m->d_segtab, tab.data(), sizeof(uint32_t) * tab.size()));
+		const size_t w = (size_t)nseg + 1;
+		m->d_vbase = m->d_segtab; m->d_fbase = m->d_segtab + w; m->d_ebase = m->d_segtab + 2 * w; m->d_obase = m->d_segtab + 3 * w; m->d_ofbase = m->d_segtab + 4 * w;
+	}
 	HB_TRY(build_slot_table(ctx, d->off_reg_vtx, d->reg_vtxlist, d->nregs_vtx, d->nlists, m->h_slot_vtx, nullptr));
 	HB_TRY(build_slot_table(ctx, d->off_reg_face, d->reg_facelist, d->nregs_face, d->nlists, m->h_slot_face, nullptr));
 	HB_TRY(build_slot_table(ctx, d->off_reg_corner, d->reg_cornerlist, d->nregs_face, d->nlists, m->h_slot_corner, &m->reg_ncorner));
@@ -349,57 +437,98 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh *m, bo
 			if (m->h_slot_corner[(size_t)r * d->nlists + l] >= 0 && cls != HB_CORNER) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "list %d bound to corners but declared with target %d", l, cls);
 		}
 	}
-	HB_TRY(upload(m, (void **)&m->d_edges_raw, d->edges, 12 * (size_t)d->ne));
-	HB_TRY(upload(m, (void **)&m->d_face_off, d->face_off, sizeof(uint32_t) * ((size_t)d->nf + 1)));
-	HB_TRY(upload(m, (void **)&m->d_order, d->order, 8 * (size_t)d->norder));
-	if (d->order_f && !vertex_only) HB_TRY(upload(m, (void **)&m->d_order_f, d->order_f, 8 * (size_t)d->norder_f));
-	HB_TRY(upload(m, (void **)&m->d_vtx_regs, d->vtx_regs, sizeof(uint16_t) * (size_t)d->nv));
-	// everything K0 / K3 / K4 read is on its way: first milestone of the copy stream
-	if (m->async_copy) HB_CUDA(ctx, cudaEventRecord(ctx->ev_up[0], ctx->copy_stream));
-	if (!vertex_only) {
-		HB_TRY(upload(m, (void **)&m->d_face_regs, d->face_regs, sizeof(uint16_t) * (size_t)d->nf));
-		HB_TRY(upload(m, (void **)&m->d_bind_face, d->bind_face_attr, sizeof(uint32_t) * (size_t)d->nf * d->nb_face));
+	// ---- allocate, then copy segment by segment ----------------------------------------------------------
+	const bool up_faces = !vertex_only;
+	HB_TRY(hb_dalloc(m, (void **)&m->d_edges_raw, 12 * (size_t)m->ne));
+	if (nseg == 1) HB_TRY(hb_dalloc(m, (void **)&m->d_face_off, sizeof(uint32_t) * ((size_t)m->nf + 1)));
+	else HB_TRY(hb_dalloc(m, (void **)&m->d_face_off_raw, sizeof(uint32_t) * ((size_t)m->nf + nseg)));
+	HB_TRY(hb_dalloc(m, (void **)&m->d_order, 8 * (size_t)m->norder));
+	if (m->has_order_f) HB_TRY(hb_dalloc(m, (void **)&m->d_order_f, 8 * (size_t)m->norder_f));
+	HB_TRY(hb_dalloc(m, (void **)&m->d_vtx_regs, sizeof(uint16_t) * (size_t)m->nv));
+	uint32_t *face_off_dst = nseg == 1 ? m->d_face_off : m->d_face_off_raw;
+	for (uint32_t s = 0; s < nseg; ++s) {
+		const hb_mesh_desc &ds = descs[s];
+		HB_TRY(copy_in(m, m->d_edges_raw + 12 * (size_t)m->h_ebase[s], ds.edges, 12 * (size_t)ds.ne));
+		HB_TRY(copy_in(m, face_off_dst + m->h_fbase[s] + s, ds.face_off, sizeof(uint32_t) * ((size_t)ds.nf + 1)));
+		HB_TRY(copy_in(m, m->d_order + 8 * (size_t)m->h_obase[s], ds.order, 8 * (size_t)ds.norder));
+		if (m->has_order_f) HB_TRY(copy_in(m, m->d_order_f + 8 * (size_t)m->h_ofbase[s], ds.order_f, 8 * (size_t)ds.norder_f));
+		HB_TRY(copy_in(m, m->d_vtx_regs + m->h_vbase[s], ds.vtx_regs, sizeof(uint16_t) * (size_t)ds.nv));
 	}
-	HB_TRY(upload(m, (void **)&m->d_bind_vtx, d->bind_vtx_attr, sizeof(uint32_t) * (size_t)d->nv * d->nb_vtx));
-	if (!vertex_only) HB_TRY(upload(m, (void **)&m->d_bind_corner, d->bind_corner_attr, sizeof(uint32_t) * (size_t)d->ne * d->nb_corner));
+	// everything K0 / K3 / K4 read is on its way: first milestone of the copy stream
+	if (m->async_copy) {
+		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_up[0], cudaEventDisableTiming));
+		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_up[1], cudaEventDisableTiming));
+		HB_CUDA(ctx, cudaEventRecord(m->ev_up[0], ctx->copy_stream));
+	}
+	if (up_faces) {
+		HB_TRY(hb_dalloc(m, (void **)&m->d_face_regs, sizeof(uint16_t) * (size_t)m->nf));
+		HB_TRY(hb_dalloc(m, (void **)&m->d_bind_face, sizeof(uint32_t) * (size_t)m->nf * d->nb_face));
+		HB_TRY(hb_dalloc(m, (void **)&m->d_bind_corner, sizeof(uint32_t) * (size_t)m->ne * d->nb_corner));
+	}
+	HB_TRY(hb_dalloc(m, (void **)&m->d_bind_vtx, sizeof(uint32_t) * (size_t)m->nv * d->nb_vtx));
+	for (uint32_t s = 0; s < nseg; ++s) {
+		const hb_mesh_desc &ds = descs[s];
+		if (up_faces) {
+			HB_TRY(copy_in(m, m->d_face_regs + m->h_fbase[s], ds.face_regs, sizeof(uint16_t) * (size_t)ds.nf));
+			HB_TRY(copy_in(m, m->d_bind_face + (size_t)m->h_fbase[s] * d->nb_face, ds.bind_face_attr, sizeof(uint32_t) * (size_t)ds.nf * d->nb_face));
+			HB_TRY(copy_in(m, m->d_bind_corner + (size_t)m->h_ebase[s] * d->nb_corner, ds.bind_corner_attr, sizeof(uint32_t) * (size_t)ds.ne * d->nb_corner));
+		}
+		HB_TRY(copy_in(m, m->d_bind_vtx + (size_t)m->h_vbase[s] * d->nb_vtx, ds.bind_vtx_attr, sizeof(uint32_t) * (size_t)ds.nv * d->nb_vtx));
+	}
 	if (vertex_only) m->any_corner = false;
 	HB_TRY(upload(m, (void **)&m->d_slot_vtx, m->h_slot_vtx.data(), sizeof(int16_t) * m->h_slot_vtx.size()));
 	HB_TRY(upload(m, (void **)&m->d_slot_face, m->h_slot_face.data(), sizeof(int16_t) * m->h_slot_face.size()));
 	HB_TRY(upload(m, (void **)&m->d_slot_corner, m->h_slot_corner.data(), sizeof(int16_t) * m->h_slot_corner.size()));
 	for (int l = 0; l < d->nlists; ++l) {
-		HB_TRY(add_list(m, d->lists[l], true));
-		if (d->emit_type && d->emit_type[l]) {
-			if (!d->emit_count) return hb_fail(ctx, HB_ERR_INVALID, "mesh: emit_type without emit_count");
+		HB_TRY(add_list(m, descs, nullptr, nseg, l, true));
+		if (d->emit_type) {
+			// drained type symbols: all segments or none, concatenated in segment order
 			DevList &dl = m->lists.back();
-			dl.emit_count = d->emit_count[l];
-			HB_TRY(upload(m, (void **)&dl.d_emit_type, d->emit_type[l], dl.emit_count));
+			bool any = false, all = true;
+			uint64_t total = 0;
+			dl.h_emitbase.assign((size_t)nseg + 1, 0);
+			for (uint32_t s = 0; s < nseg; ++s) {
+				const bool has = descs[s].emit_type && descs[s].emit_type[l];
+				any = any || has; all = all && has;
+				if (has && !descs[s].emit_count) return hb_fail(ctx, HB_ERR_INVALID, "mesh: emit_type without emit_count");
+				dl.h_emitbase[s] = (uint32_t)total;
+				if (has) total += descs[s].emit_count[l];
+			}
+			dl.h_emitbase[nseg] = (uint32_t)total;
+			if (any && !all) return hb_fail(ctx, HB_ERR_INVALID, "batch: emit_type[%d] given for some meshes only", l);
+			if (all) {
+				dl.emit_count = (uint32_t)total;
+				HB_TRY(hb_dalloc(m, (void **)&dl.d_emit_type, total));
+				for (uint32_t s = 0; s < nseg; ++s) HB_TRY(copy_in(m, dl.d_emit_type + dl.h_emitbase[s], descs[s].emit_type[l], descs[s].emit_count[l]));
+			}
 		}
 	}
-	if (m->async_copy) HB_CUDA(ctx, cudaEventRecord(ctx->ev_up[1], ctx->copy_stream));
+	if (m->async_copy) HB_CUDA(ctx, cudaEventRecord(m->ev_up[1], ctx->copy_stream));
+	m->alloc_on_copy_stream = false;
 	return 0;
 }
 
 // host-buffer entry points: connectivity stages under the tail of the upload, everything else behind it
-static int upload_overlapped(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_dmesh *m, bool vertex_only)
+static int upload_overlapped(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t nseg, hb_dmesh *m, bool vertex_only)
 {
 	m->async_copy = true;
-	HB_TRY(dmesh_upload_impl(ctx, mesh, m, vertex_only));
-	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
+	HB_TRY(dmesh_upload_impl(ctx, meshes, nseg, m, vertex_only));
+	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_up[0], 0));
 	HB_TRY(hb_build_conn(m));
 	bool need_v = false;
 	for (int l = 0; l < m->nlists; ++l)
 		if (m->lists[l].p.target == HB_VTX && m->lists[l].p.ncomp) need_v = true;
 	if (need_v) HB_TRY(hb_build_vertex_candidates(m));
-	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[1], 0));
+	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_up[1], 0));
 	return 0;
 }
 
-extern "C" int hb_dmesh_upload(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh **out)
+extern "C" int hb_dmesh_upload_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t n, hb_dmesh **out)
 {
 	*out = nullptr;
 	HB_CUDA(ctx, cudaSetDevice(ctx->device));
 	hb_dmesh *m = new hb_dmesh();
-	int rc = dmesh_upload_impl(ctx, d, m);
+	int rc = dmesh_upload_impl(ctx, meshes, n, m);
 	if (rc == 0) {
 		cudaError_t e = cudaStreamSynchronize(ctx->stream); // the host buffers may be reused after return
 		if (e != cudaSuccess) rc = hb_fail(ctx, HB_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -408,13 +537,14 @@ extern "C" int hb_dmesh_upload(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh **ou
 	*out = m;
 	return 0;
 }
+extern "C" int hb_dmesh_upload(hb_ctx *ctx, const hb_mesh_desc *d, hb_dmesh **out) { return hb_dmesh_upload_batch(ctx, d, 1, out); }
+extern "C" uint32_t hb_dmesh_segments(hb_dmesh *m) { return m->nseg; }
 
 extern "C" int hb_dmesh_quantize(hb_dmesh *m, uint32_t l, const uint8_t *new_quant, const uint8_t *groups)
 {
 	if (l >= m->lists.size()) return hb_fail(m->ctx, HB_ERR_INVALID, "list %u out of range", l);
 	HB_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
-	HB_TRY(hb_list_bounds(m, l));
-	HB_TRY(hb_list_scale(m, l, groups));
+	HB_TRY(hb_list_bounds(m, l, groups)); // min, max and (tail of the same kernel) scale rows of every segment
 	return hb_list_requant(m, l, new_quant);
 }
 
@@ -427,17 +557,18 @@ extern "C" int hb_dmesh_dequantize(hb_dmesh *m, uint32_t l)
 }
 
 // bounds rows for list l supplied by the host (decode side: min / max come from the .hry header,
-// the scale from set_scale)
+// the scale from set_scale); a batch passes the rows of its meshes back to back (nseg * stride bytes each)
 extern "C" int hb_dmesh_set_bounds(hb_dmesh *m, uint32_t l, const void *min_row, const void *max_row, const void *scale_row)
 {
 	if (l >= m->lists.size()) return hb_fail(m->ctx, HB_ERR_INVALID, "list %u out of range", l);
 	DevList &dl = m->lists[l];
 	const size_t s = dl.p.stride;
-	HB_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
-	if (min_row) HB_CUDA(m->ctx, cudaMemcpyAsync(dl.d_bounds, min_row, s, cudaMemcpyHostToDevice, m->ctx->stream));
-	if (max_row) HB_CUDA(m->ctx, cudaMemcpyAsync(dl.d_bounds + s, max_row, s, cudaMemcpyHostToDevice, m->ctx->stream));
-	if (scale_row) HB_CUDA(m->ctx, cudaMemcpyAsync(dl.d_bounds + 2 * s, scale_row, s, cudaMemcpyHostToDevice, m->ctx->stream));
-	HB_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
+	hb_ctx *ctx = m->ctx;
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	const void *src[3] = { min_row, max_row, scale_row };
+	for (int w = 0; w < 3; ++w)
+		if (src[w] && s) HB_CUDA(ctx, cudaMemcpy2DAsync(dl.d_bounds + w * s, dl.bounds_pitch, src[w], s, s, m->nseg, cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return 0;
 }
 
@@ -446,24 +577,27 @@ extern "C" int hb_dmesh_fetch_bounds(hb_dmesh *m, uint32_t l, void *min_row, voi
 	if (l >= m->lists.size()) return hb_fail(m->ctx, HB_ERR_INVALID, "list %u out of range", l);
 	DevList &dl = m->lists[l];
 	const size_t s = dl.p.stride;
-	HB_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
-	if (min_row) HB_CUDA(m->ctx, cudaMemcpyAsync(min_row, dl.d_bounds, s, cudaMemcpyDeviceToHost, m->ctx->stream));
-	if (max_row) HB_CUDA(m->ctx, cudaMemcpyAsync(max_row, dl.d_bounds + s, s, cudaMemcpyDeviceToHost, m->ctx->stream));
-	if (scale_row) HB_CUDA(m->ctx, cudaMemcpyAsync(scale_row, dl.d_bounds + 2 * s, s, cudaMemcpyDeviceToHost, m->ctx->stream));
-	HB_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
-	return hb_check_device_error(m->ctx, "bounds");
+	hb_ctx *ctx = m->ctx;
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	void *dst[3] = { min_row, max_row, scale_row };
+	for (int w = 0; w < 3; ++w)
+		if (dst[w] && s) HB_CUDA(ctx, cudaMemcpy2DAsync(dst[w], s, dl.d_bounds + w * s, dl.bounds_pitch, s, m->nseg, cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return hb_check_device_error(ctx, "bounds");
 }
 
-extern "C" int hb_dmesh_fetch_rows(hb_dmesh *m, uint32_t l, void *rows_out)
+// rows of list l of segment `seg` (nrows_seg * stride bytes)
+extern "C" int hb_dmesh_fetch_rows_seg(hb_dmesh *m, uint32_t seg, uint32_t l, void *rows_out)
 {
-	if (l >= m->lists.size()) return hb_fail(m->ctx, HB_ERR_INVALID, "list %u out of range", l);
+	if (l >= m->lists.size() || seg >= m->nseg) return hb_fail(m->ctx, HB_ERR_INVALID, "list %u / mesh %u out of range", l, seg);
 	DevList &dl = m->lists[l];
 	HB_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
-	const size_t bytes = (size_t)dl.p.nrows * dl.p.stride;
-	if (bytes) HB_CUDA(m->ctx, cudaMemcpyAsync(rows_out, dl.p.rows, bytes, cudaMemcpyDeviceToHost, m->ctx->stream));
+	const size_t bytes = (size_t)dl.h_rownum[seg] * dl.p.stride;
+	if (bytes) HB_CUDA(m->ctx, cudaMemcpyAsync(rows_out, dl.p.rows + (size_t)dl.h_rowbase[seg] * dl.p.stride, bytes, cudaMemcpyDeviceToHost, m->ctx->stream));
 	HB_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
 	return hb_check_device_error(m->ctx, "fetch rows");
 }
+extern "C" int hb_dmesh_fetch_rows(hb_dmesh *m, uint32_t l, void *rows_out) { return hb_dmesh_fetch_rows_seg(m, 0, l, rows_out); }
 
 // keep / restore a device copy of all rows and quantization states (bench loops re-run stages
 // that work in place)
@@ -601,87 +735,216 @@ __global__ void k_region_stream(const uint32_t *__restrict__ ent, const uint4 *_
 	out[i] = regs[e];
 }
 
-extern "C" int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out)
+// per segment: emission and DATA-row offsets of its first element (entries nseg: the totals)
+__global__ void k_segment_offsets(const uint32_t *__restrict__ elem_base, uint32_t nseg, const uint32_t *__restrict__ ek, const uint32_t *__restrict__ dord, uint32_t *__restrict__ out)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s > nseg) return;
+	const uint32_t e = elem_base[s];
+	out[s] = ek ? ek[e] : e;
+	out[nseg + 1 + s] = dord[e];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streams of a device mesh -> page-locked host memory.  One block per (list, stream) for ALL segments; the
+// hb_streams of segment s are views into those blocks (hb_batch_streams owns them).  Two phases so that a
+// pipelined batch can queue the copies of group g and collect them after it has queued the work of group g + 1:
+//   begin   small read-back of the per-segment offsets (one synchronisation of `st`), then the sized copies
+//   finish  (after `st` was synchronised) fills the per-mesh views
+// ------------------------------------------------------------------------------------------------
+struct hb_batch_streams_priv {
+	std::vector<void *> blocks;   // page-locked blocks (g_pinned)
+	std::vector<hb_list_streams *> list_arrays;
+};
+struct FetchState {
+	hb_dmesh *m = nullptr;
+	uint32_t seg0 = 0;             // index of the group's first mesh in the caller's batch
+	std::vector<uint32_t *> offs;  // per list: page-locked [2 * (nseg + 1)] emission / DATA offsets
+	std::vector<uint8_t *> type;
+	std::vector<uint32_t *> aux;
+	std::vector<uint8_t *> sym;
+	std::vector<uint64_t *> hist;
+	uint16_t *reg_vtx = nullptr, *reg_face = nullptr;
+	uint16_t *d_reg = nullptr;
+};
+
+static void *priv_alloc(hb_batch_streams_priv *pv, size_t bytes)
+{
+	void *p = g_pinned.alloc(bytes);
+	if (p) pv->blocks.push_back(p);
+	return p;
+}
+
+extern "C" void hb_batch_streams_free(hb_batch_streams *b)
+{
+	if (!b) return;
+	hb_batch_streams_priv *pv = (hb_batch_streams_priv *)b->priv;
+	if (pv) {
+		for (void *p : pv->blocks) g_pinned.release(p);
+		for (hb_list_streams *l : pv->list_arrays) free(l);
+		delete pv;
+	}
+	free(b->mesh);
+	free(b);
+}
+
+#define FETCH_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return hb_fail(ctx, HB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); } while (0)
+static int fetch_begin(hb_dmesh *m, cudaStream_t st, hb_batch_streams_priv *pv, FetchState &fs)
 {
 	hb_ctx *ctx = m->ctx;
-	*out = nullptr;
 	if (!m->encoded) return hb_fail(ctx, HB_ERR_INVALID, "fetch_streams before encode");
-	HB_CUDA(ctx, cudaSetDevice(ctx->device));
-	hb_streams *s = (hb_streams *)calloc(1, sizeof(hb_streams));
-	if (!s) return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
-	s->n_vtx = m->norder;
-	s->n_face = m->norder_f;
-	s->nlists = m->nlists;
-	// a mesh with a single vertex (face) region has an all-zero region stream: NULL stands for it
+	const uint32_t nseg = m->nseg;
+	fs.m = m;
 	const bool reg_v = m->nregs_vtx > 1, reg_f = m->nregs_face > 1;
-	s->reg_vtx = reg_v ? (uint16_t *)g_pinned.alloc(sizeof(uint16_t) * ((size_t)m->norder + 1)) : nullptr;
-	s->reg_face = reg_f ? (uint16_t *)g_pinned.alloc(sizeof(uint16_t) * ((size_t)m->norder_f + 1)) : nullptr;
+	// region symbol streams (io.h:109-116): region of every traversed vertex / face; a mesh with a single vertex (face)
+	// region has an all-zero stream: NULL stands for it
+	if (reg_v || reg_f) {
+		const uint32_t nmax = m->norder > m->norder_f ? m->norder : m->norder_f;
+		FETCH_CUDA(cudaMallocAsync((void **)&fs.d_reg, sizeof(uint16_t) * (2 * (size_t)nmax + 2), st));
+		if (m->norder && reg_v) {
+			fs.reg_vtx = (uint16_t *)priv_alloc(pv, sizeof(uint16_t) * ((size_t)m->norder + 1));
+			if (!fs.reg_vtx) return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
+			k_region_stream<<<hb_div_up(m->norder, 256), 256, 0, st>>>(m->d_ord_v, m->d_he, m->d_vtx_regs, m->norder, 0, fs.d_reg);
+			ctx->launches++;
+			FETCH_CUDA(cudaMemcpyAsync(fs.reg_vtx, fs.d_reg, sizeof(uint16_t) * m->norder, cudaMemcpyDeviceToHost, st));
+		}
+		if (m->norder_f && reg_f) {
+			fs.reg_face = (uint16_t *)priv_alloc(pv, sizeof(uint16_t) * ((size_t)m->norder_f + 1));
+			if (!fs.reg_face) return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
+			k_region_stream<<<hb_div_up(m->norder_f, 256), 256, 0, st>>>(m->d_ford_h, m->d_he, m->d_face_regs, m->norder_f, 1, fs.d_reg + nmax + 1);
+			ctx->launches++;
+			FETCH_CUDA(cudaMemcpyAsync(fs.reg_face, fs.d_reg + nmax + 1, sizeof(uint16_t) * m->norder_f, cudaMemcpyDeviceToHost, st));
+		}
+		FETCH_CUDA(cudaFreeAsync(fs.d_reg, st));
+	}
+	const int nl = m->nlists;
+	fs.offs.assign(nl, nullptr); fs.type.assign(nl, nullptr); fs.aux.assign(nl, nullptr); fs.sym.assign(nl, nullptr); fs.hist.assign(nl, nullptr);
+	// per-segment offsets and histograms (with the type counters) first: they size the other copies
+	std::vector<uint32_t *> d_offs(nl, nullptr);
+	for (int l = 0; l < nl; ++l) {
+		DevList &dl = m->lists[l];
+		if (!dl.n_elems && !dl.d_hist) continue; // list not coded (no class / no corner bindings)
+		const size_t hist_pitch = (size_t)dl.p.sym_stride * 256 + 4;
+		fs.offs[l] = (uint32_t *)priv_alloc(pv, sizeof(uint32_t) * 2 * ((size_t)nseg + 1));
+		fs.hist[l] = (uint64_t *)priv_alloc(pv, sizeof(uint64_t) * hist_pitch * nseg);
+		if (!fs.offs[l] || !fs.hist[l]) return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
+		const int cls = dl.p.target;
+		const uint32_t *elem_base = cls == HB_VTX ? m->d_obase : cls == HB_FACE ? m->d_ofbase : m->d_cebase;
+		FETCH_CUDA(cudaMallocAsync((void **)&d_offs[l], sizeof(uint32_t) * 2 * ((size_t)nseg + 1), st));
+		if (dl.n_elems) {
+			k_segment_offsets<<<hb_div_up(nseg + 1, 128), 128, 0, st>>>(elem_base, nseg, dl.d_ek, dl.d_dord, d_offs[l]);
+			ctx->launches++;
+		} else {
+			FETCH_CUDA(cudaMemsetAsync(d_offs[l], 0, sizeof(uint32_t) * 2 * ((size_t)nseg + 1), st));
+		}
+		FETCH_CUDA(cudaMemcpyAsync(fs.offs[l], d_offs[l], sizeof(uint32_t) * 2 * ((size_t)nseg + 1), cudaMemcpyDeviceToHost, st));
+		FETCH_CUDA(cudaMemcpyAsync(fs.hist[l], dl.d_hist, sizeof(uint64_t) * hist_pitch * nseg, cudaMemcpyDeviceToHost, st));
+		FETCH_CUDA(cudaFreeAsync(d_offs[l], st));
+	}
+	FETCH_CUDA(cudaStreamSynchronize(st));
+	for (int l = 0; l < nl; ++l) {
+		DevList &dl = m->lists[l];
+		if (!fs.offs[l]) continue;
+		const size_t hist_pitch = (size_t)dl.p.sym_stride * 256 + 4;
+		const uint32_t n_emit = fs.offs[l][nseg], n_data = fs.offs[l][2 * nseg + 1];
+		// every emission of every segment is a DATA row (no shared attribute rows): the type and history-offset
+		// streams are all zero -- NULL stands for them, nothing is copied
+		bool all_data = true;
+		for (uint32_t sg = 0; sg < nseg; ++sg) {
+			const uint64_t *th = fs.hist[l] + hist_pitch * sg + (size_t)dl.p.sym_stride * 256;
+			all_data = all_data && th[HB_HIST] + th[HB_LHIST] == 0;
+		}
+		if (!all_data && n_emit) {
+			fs.type[l] = (uint8_t *)priv_alloc(pv, (size_t)n_emit + 1);
+			fs.aux[l] = (uint32_t *)priv_alloc(pv, sizeof(uint32_t) * ((size_t)n_emit + 1));
+			if (!fs.type[l] || !fs.aux[l]) return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
+			FETCH_CUDA(cudaMemcpyAsync(fs.type[l], dl.d_type, n_emit, cudaMemcpyDeviceToHost, st));
+			FETCH_CUDA(cudaMemcpyAsync(fs.aux[l], dl.d_aux, sizeof(uint32_t) * n_emit, cudaMemcpyDeviceToHost, st));
+		}
+		const size_t sym_bytes = (size_t)n_data * dl.p.sym_stride;
+		fs.sym[l] = (uint8_t *)priv_alloc(pv, sym_bytes + 1);
+		if (!fs.sym[l]) return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
+		if (sym_bytes) FETCH_CUDA(cudaMemcpyAsync(fs.sym[l], dl.d_sym, sym_bytes, cudaMemcpyDeviceToHost, st));
+	}
+	return 0;
+}
+
+// views of segment sg (after `st` has been synchronised)
+static void fetch_view(const FetchState &fs, hb_batch_streams_priv *pv, uint32_t sg, hb_streams *s)
+{
+	hb_dmesh *m = fs.m;
+	const uint32_t nseg = m->nseg;
+	memset(s, 0, sizeof *s);
+	s->n_vtx = m->h_obase[sg + 1] - m->h_obase[sg];
+	s->n_face = m->h_ofbase[sg + 1] - m->h_ofbase[sg];
+	s->nlists = m->nlists;
+	s->reg_vtx = fs.reg_vtx ? fs.reg_vtx + m->h_obase[sg] : nullptr;
+	s->reg_face = fs.reg_face ? fs.reg_face + m->h_ofbase[sg] : nullptr;
 	s->lists = (hb_list_streams *)calloc((size_t)m->nlists + 1, sizeof(hb_list_streams));
-	int rc = 0;
-	uint16_t *d_reg = nullptr;
-	const uint32_t nmax = m->norder > m->norder_f ? m->norder : m->norder_f;
-#define FETCH_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = hb_fail(ctx, HB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); goto fail; } } while (0)
-	if ((reg_v && !s->reg_vtx) || (reg_f && !s->reg_face) || !s->lists) { rc = hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); goto fail; }
-	// region symbol streams (io.h:109-116): region of every traversed vertex / face
-	FETCH_CUDA(cudaMallocAsync((void **)&d_reg, sizeof(uint16_t) * ((size_t)nmax + 1), ctx->stream));
-	if (m->norder && reg_v) {
-		k_region_stream<<<hb_div_up(m->norder, 256), 256, 0, ctx->stream>>>(m->d_ord_v, m->d_he, m->d_vtx_regs, m->norder, 0, d_reg);
-		ctx->launches++;
-		FETCH_CUDA(cudaMemcpyAsync(s->reg_vtx, d_reg, sizeof(uint16_t) * m->norder, cudaMemcpyDeviceToHost, ctx->stream));
-	}
-	if (m->norder_f && reg_f) {
-		k_region_stream<<<hb_div_up(m->norder_f, 256), 256, 0, ctx->stream>>>(m->d_ford_h, m->d_he, m->d_face_regs, m->norder_f, 1, d_reg);
-		ctx->launches++;
-		FETCH_CUDA(cudaMemcpyAsync(s->reg_face, d_reg, sizeof(uint16_t) * m->norder_f, cudaMemcpyDeviceToHost, ctx->stream));
-	}
-	FETCH_CUDA(cudaFreeAsync(d_reg, ctx->stream));
-	// counts first (sizes of the compacted streams)
+	pv->list_arrays.push_back(s->lists);
 	for (int l = 0; l < m->nlists; ++l) {
 		DevList &dl = m->lists[l];
 		hb_list_streams &ls = s->lists[l];
 		ls.sym_stride = dl.p.sym_stride;
-		ls.n_emit = 0;
-		ls.n_data = 0;
-		if (!dl.n_elems) continue;
-		if (dl.d_ek) FETCH_CUDA(cudaMemcpyAsync(&ls.n_emit, dl.d_ek + dl.n_elems, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		else ls.n_emit = dl.n_elems;
-		FETCH_CUDA(cudaMemcpyAsync(&ls.n_data, dl.d_dord + dl.n_elems, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		FETCH_CUDA(cudaMemcpyAsync(ls.type_hist, dl.d_type_hist, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	}
-	FETCH_CUDA(cudaStreamSynchronize(ctx->stream));
-	for (int l = 0; l < m->nlists; ++l) {
-		DevList &dl = m->lists[l];
-		hb_list_streams &ls = s->lists[l];
-		// every emission is a DATA row (no shared attribute rows): the type and history-offset streams are
-		// all zero -- NULL stands for them, nothing is copied
-		const bool all_data = ls.type_hist[HB_HIST] + ls.type_hist[HB_LHIST] == 0;
-		ls.type = all_data ? nullptr : (uint8_t *)g_pinned.alloc((size_t)ls.n_emit + 1);
-		ls.aux = all_data ? nullptr : (uint32_t *)g_pinned.alloc(sizeof(uint32_t) * ((size_t)ls.n_emit + 1));
-		ls.symbols = (uint8_t *)g_pinned.alloc((size_t)ls.n_data * ls.sym_stride + 1);
-		ls.hist = (uint64_t *)g_pinned.alloc(sizeof(uint64_t) * ((size_t)ls.sym_stride * 256 + 4));
-		if ((!all_data && (!ls.type || !ls.aux)) || !ls.symbols || !ls.hist) { rc = hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); goto fail; }
-		memset(ls.hist, 0, sizeof(uint64_t) * ((size_t)ls.sym_stride * 256 + 4));
-		if (!dl.n_elems) continue;
-		if (ls.n_emit && !all_data) {
-			FETCH_CUDA(cudaMemcpyAsync(ls.type, dl.d_type, ls.n_emit, cudaMemcpyDeviceToHost, ctx->stream));
-			FETCH_CUDA(cudaMemcpyAsync(ls.aux, dl.d_aux, sizeof(uint32_t) * ls.n_emit, cudaMemcpyDeviceToHost, ctx->stream));
-		}
-		if ((size_t)ls.n_data * ls.sym_stride) FETCH_CUDA(cudaMemcpyAsync(ls.symbols, dl.d_sym, (size_t)ls.n_data * ls.sym_stride, cudaMemcpyDeviceToHost, ctx->stream));
-		FETCH_CUDA(cudaMemcpyAsync(ls.hist, dl.d_hist, sizeof(uint64_t) * ((size_t)ls.sym_stride * 256 + 4), cudaMemcpyDeviceToHost, ctx->stream));
-	}
-	FETCH_CUDA(cudaStreamSynchronize(ctx->stream));
-	for (int l = 0; l < m->nlists; ++l) {
-		hb_list_streams &ls = s->lists[l];
+		if (!fs.offs[l]) continue;
+		const size_t hist_pitch = (size_t)dl.p.sym_stride * 256 + 4;
+		const uint32_t e0 = fs.offs[l][sg], e1 = fs.offs[l][sg + 1], d0 = fs.offs[l][nseg + 1 + sg], d1 = fs.offs[l][nseg + 1 + sg + 1];
+		ls.n_emit = e1 - e0;
+		ls.n_data = d1 - d0;
+		ls.hist = fs.hist[l] + hist_pitch * sg;
 		for (int k = 0; k < 4; ++k) ls.type_hist[k] = ls.hist[(size_t)ls.sym_stride * 256 + k];
+		const bool all_data = ls.type_hist[HB_HIST] + ls.type_hist[HB_LHIST] == 0;
+		ls.type = (all_data || !fs.type[l]) ? nullptr : fs.type[l] + e0;
+		ls.aux = (all_data || !fs.aux[l]) ? nullptr : fs.aux[l] + e0;
+		ls.symbols = fs.sym[l] + (size_t)d0 * ls.sym_stride;
 	}
-	rc = hb_check_device_error(ctx, "attribute encode");
-	if (rc) goto fail;
+}
+#undef FETCH_CUDA
+
+extern "C" int hb_dmesh_fetch_streams_batch(hb_dmesh *m, hb_batch_streams **out)
+{
+	hb_ctx *ctx = m->ctx;
+	*out = nullptr;
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	hb_batch_streams *b = (hb_batch_streams *)calloc(1, sizeof(hb_batch_streams));
+	hb_batch_streams_priv *pv = new hb_batch_streams_priv();
+	if (!b) { delete pv; return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); }
+	b->priv = pv;
+	b->n = m->nseg;
+	b->mesh = (hb_streams *)calloc(m->nseg, sizeof(hb_streams));
+	FetchState fs;
+	int rc = b->mesh ? fetch_begin(m, ctx->stream, pv, fs) : hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
+	if (rc == 0 && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = hb_fail(ctx, HB_ERR_CUDA, "stream download failed: %s", cudaGetErrorString(cudaGetLastError()));
+	if (rc == 0) rc = hb_check_device_error(ctx, "attribute encode");
+	if (rc) { hb_batch_streams_free(b); return rc; }
+	for (uint32_t sg = 0; sg < m->nseg; ++sg) fetch_view(fs, pv, sg, &b->mesh[sg]);
+	*out = b;
+	return 0;
+}
+
+// single mesh: the same download, handed out as a standalone hb_streams (every array its own page-locked block,
+// released one by one by hb_streams_free)
+extern "C" int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out)
+{
+	*out = nullptr;
+	if (m->nseg != 1) return hb_fail(m->ctx, HB_ERR_INVALID, "fetch_streams on a batch: use hb_dmesh_fetch_streams_batch");
+	hb_batch_streams *b = nullptr;
+	HB_TRY(hb_dmesh_fetch_streams_batch(m, &b));
+	hb_batch_streams_priv *pv = (hb_batch_streams_priv *)b->priv;
+	hb_streams *s = (hb_streams *)calloc(1, sizeof(hb_streams));
+	*s = b->mesh[0];
+	// blocks that are not handed out (the offset tables) go back to the cache now; the others are released by
+	// hb_streams_free through the pointers of the hb_streams (all views start at offset 0 for a single segment)
+	for (void *p : pv->blocks) {
+		bool used = p == s->reg_vtx || p == s->reg_face;
+		for (int l = 0; l < s->nlists; ++l) used = used || p == s->lists[l].type || p == s->lists[l].aux || p == s->lists[l].symbols || p == s->lists[l].hist;
+		if (!used) g_pinned.release(p);
+	}
+	delete pv;
+	free(b->mesh);
+	free(b);
 	*out = s;
 	return 0;
-fail:
-	hb_streams_free(s);
-	return rc;
-#undef FETCH_CUDA
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -708,7 +971,8 @@ static int single_list_mesh(hb_ctx *ctx, const hb_list_desc *list, hb_dmesh *m)
 {
 	m->ctx = ctx;
 	m->nlists = 1;
-	return add_list(m, *list, false);
+	m->nseg = 1;
+	return add_list(m, nullptr, list, 1, 0, false);
 }
 
 extern "C" int hb_bounds(hb_ctx *ctx, const hb_list_desc *list, void *min_row, void *max_row)
@@ -719,7 +983,7 @@ extern "C" int hb_bounds(hb_ctx *ctx, const hb_list_desc *list, void *min_row, v
 	t.mark(0);
 	int rc = single_list_mesh(ctx, list, m);
 	t.mark(1);
-	if (rc == 0) rc = hb_list_bounds(m, 0);
+	if (rc == 0) rc = hb_list_bounds(m, 0, nullptr);
 	t.mark(2);
 	if (rc == 0 && list->ncomp) rc = hb_dmesh_fetch_bounds(m, 0, min_row, max_row, nullptr);
 	t.mark(3);
@@ -755,6 +1019,12 @@ extern "C" int hb_twin_match(hb_ctx *ctx, uint32_t nv, uint32_t nf, const uint32
 	if (org_stride != 4 && org_stride != 12) return hb_fail(ctx, HB_ERR_INVALID, "twin_match: org_stride must be 4 (packed) or 12 (edge records)");
 	const uint32_t ne = nf ? face_off[nf] : 0;
 	if (nf && face_off[0] != 0) return hb_fail(ctx, HB_ERR_INVALID, "twin_match: face_off[0] != 0");
+	// the fill pass hands out one slot per corner: the offsets must be a monotone CSR with degrees the 16-bit local
+	// edge index can hold, or the sum of the degrees would exceed ne (one pass over nf + 1 words)
+	for (uint32_t f = 0; f < nf; ++f) {
+		if (face_off[f + 1] < face_off[f]) return hb_fail(ctx, HB_ERR_INVALID, "twin_match: face_off is not monotone at face %u", f);
+		if (face_off[f + 1] - face_off[f] > 0xffffu) return hb_fail(ctx, HB_ERR_INVALID, "twin_match: face %u has more than 65535 corners", f);
+	}
 	HB_CUDA(ctx, cudaSetDevice(ctx->device));
 	hb_dmesh *m = new hb_dmesh();
 	m->ctx = ctx;
@@ -775,15 +1045,19 @@ extern "C" int hb_twin_match(hb_ctx *ctx, uint32_t nv, uint32_t nf, const uint32
 	t.mark(1);
 	if (rc == 0) rc = hb_twin_build(m, nv, nf, ne, d_face_off, org_stride == 4 ? d_org : d_out, org_stride / 4, d_out);
 	t.mark(2);
+	// the caller's records (possibly the origins themselves, in place) are only overwritten by a table that is valid
+	if (rc == 0) rc = hb_check_device_error(ctx, "twin matching");
 	if (rc == 0 && ne && cudaMemcpyAsync(edges_out, d_out, 12 * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
 		rc = hb_fail(ctx, HB_ERR_CUDA, "twin_match: download failed: %s", cudaGetErrorString(cudaGetLastError()));
 	t.mark(3);
 	t.finish(4);
-	if (rc == 0) rc = hb_check_device_error(ctx, "twin matching");
 	hb_dmesh_free(m);
 	return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// attribute coder on host buffers: single mesh = batch of one
+// ------------------------------------------------------------------------------------------------
 extern "C" int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams **out)
 {
 	*out = nullptr;
@@ -791,7 +1065,7 @@ extern "C" int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams 
 	hb_dmesh *m = new hb_dmesh();
 	PhaseTimer t(ctx);
 	t.mark(0);
-	int rc = upload_overlapped(ctx, mesh, m, false);
+	int rc = upload_overlapped(ctx, mesh, 1, m, false);
 	t.mark(1);
 	if (rc == 0) rc = hb_encode_lists(m);
 	t.mark(2);
@@ -802,16 +1076,20 @@ extern "C" int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams 
 	return rc;
 }
 
+static bool decode_is_vertex_only(const hb_mesh_desc *mesh)
+{
+	for (int l = 0; l < mesh->nlists; ++l)
+		if (mesh->lists[l].target != HB_VTX && mesh->lists[l].ncomp && mesh->lists[l].nrows) return false;
+	return true;
+}
+
 extern "C" int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh)
 {
 	HB_CUDA(ctx, cudaSetDevice(ctx->device));
 	hb_dmesh *m = new hb_dmesh();
 	PhaseTimer t(ctx);
 	t.mark(0);
-	bool vertex_only = true;
-	for (int l = 0; l < mesh->nlists; ++l)
-		if (mesh->lists[l].target != HB_VTX && mesh->lists[l].ncomp && mesh->lists[l].nrows) vertex_only = false;
-	int rc = upload_overlapped(ctx, mesh, m, vertex_only);
+	int rc = upload_overlapped(ctx, mesh, 1, m, decode_is_vertex_only(mesh));
 	t.mark(1);
 	if (rc == 0) rc = hb_decode_lists(m);
 	t.mark(2);
@@ -821,5 +1099,160 @@ extern "C" int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh)
 	t.finish(4);
 	if (rc == 0) rc = hb_check_device_error(ctx, "attribute decode");
 	hb_dmesh_free(m);
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batches of independent meshes on host buffers (BASELINE configs[4]; the reference runs one process per mesh,
+// main.cc:93-122).  The batch is cut into groups of meshes (about HB_GROUP_HALF_EDGES half-edges each); every group
+// is one device mesh (one launch per stage over all its meshes).  Software pipeline over the groups:
+//   copy stream     upload of group g + 1
+//   compute stream  kernels of group g (wait for its upload only)
+//   out stream      download of group g - 1
+// The host waits exactly once per group (for the per-mesh stream sizes of the group before) and once at the end.
+// ------------------------------------------------------------------------------------------------
+static uint64_t group_half_edges()
+{
+	const char *env = getenv("HARRY_B200_GROUP_HALF_EDGES"); // read per call: tests force many small groups
+	const uint64_t v = env ? strtoull(env, nullptr, 10) : 0;
+	return v ? v : (uint64_t)48 << 20;
+}
+static void make_groups(const hb_mesh_desc *meshes, uint32_t n, std::vector<uint32_t> &starts)
+{
+	const uint64_t budget = group_half_edges();
+	starts.clear();
+	uint64_t acc = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (i == 0 || acc + meshes[i].ne > budget) { starts.push_back(i); acc = 0; }
+		acc += meshes[i].ne;
+	}
+	starts.push_back(n);
+}
+
+extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t n, const hb_quant_req *q, uint32_t nq, void *const *bounds_out, hb_batch_streams **out)
+{
+	*out = nullptr;
+	if (n == 0) return hb_fail(ctx, HB_ERR_INVALID, "batch: no mesh");
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	hb_batch_streams *b = (hb_batch_streams *)calloc(1, sizeof(hb_batch_streams));
+	hb_batch_streams_priv *pv = new hb_batch_streams_priv();
+	if (!b) { delete pv; return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory"); }
+	b->priv = pv;
+	b->n = n;
+	b->mesh = (hb_streams *)calloc(n, sizeof(hb_streams));
+	std::vector<uint32_t> starts;
+	make_groups(meshes, n, starts);
+	const size_t G = starts.size() - 1;
+	std::vector<hb_dmesh *> dm(G, nullptr);
+	std::vector<FetchState> fs(G);
+	int rc = b->mesh ? 0 : hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
+	auto upload_group = [&](size_t g) -> int {
+		dm[g] = new hb_dmesh();
+		dm[g]->async_copy = true;
+		return dmesh_upload_impl(ctx, meshes + starts[g], starts[g + 1] - starts[g], dm[g], false);
+	};
+	auto run_group = [&](size_t g) -> int {
+		hb_dmesh *m = dm[g];
+		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_up[1], 0));
+		for (uint32_t k = 0; k < nq; ++k) {
+			if (q[k].list >= (uint32_t)m->nlists) return hb_fail(ctx, HB_ERR_INVALID, "batch: quantization request for list %u", q[k].list);
+			HB_TRY(hb_list_bounds(m, q[k].list, q[k].groups));
+			HB_TRY(hb_list_requant(m, q[k].list, q[k].new_quant));
+		}
+		HB_TRY(hb_encode_lists(m));
+		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+		HB_CUDA(ctx, cudaEventRecord(m->ev_done, ctx->stream));
+		return 0;
+	};
+	auto download_group = [&](size_t g) -> int {
+		hb_dmesh *m = dm[g];
+		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, m->ev_done, 0));
+		fs[g].seg0 = starts[g];
+		for (uint32_t k = 0; k < nq; ++k) { // bounds rows of the group's meshes: min, max, scale per mesh
+			if (!bounds_out || !bounds_out[k]) continue;
+			DevList &dl = m->lists[q[k].list];
+			const size_t s3 = 3 * (size_t)dl.p.stride;
+			if (s3) HB_CUDA(ctx, cudaMemcpy2DAsync((uint8_t *)bounds_out[k] + s3 * starts[g], s3, dl.d_bounds, dl.bounds_pitch, s3, m->nseg, cudaMemcpyDeviceToHost, ctx->out_stream));
+		}
+		HB_TRY(fetch_begin(m, ctx->out_stream, pv, fs[g]));
+		dmesh_release_device(m, ctx->out_stream);
+		return 0;
+	};
+	if (rc == 0) rc = upload_group(0);
+	for (size_t g = 0; rc == 0 && g < G; ++g) {
+		if (g + 1 < G) rc = upload_group(g + 1);
+		if (rc == 0) rc = run_group(g);
+		if (rc == 0 && g >= 1) rc = download_group(g - 1);
+	}
+	if (rc == 0) rc = download_group(G - 1);
+	if (rc == 0 && cudaStreamSynchronize(ctx->out_stream) != cudaSuccess) rc = hb_fail(ctx, HB_ERR_CUDA, "batch download failed: %s", cudaGetErrorString(cudaGetLastError()));
+	if (rc == 0) rc = hb_check_device_error(ctx, "batch encode");
+	if (rc == 0)
+		for (size_t g = 0; g < G; ++g)
+			for (uint32_t sg = 0; sg < dm[g]->nseg; ++sg) fetch_view(fs[g], pv, sg, &b->mesh[starts[g] + sg]);
+	cudaStreamSynchronize(ctx->out_stream);
+	for (hb_dmesh *m : dm) hb_dmesh_free(m);
+	if (rc) { hb_batch_streams_free(b); return rc; }
+	*out = b;
+	return 0;
+}
+
+extern "C" int hb_decode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t n, const hb_dequant_req *q, uint32_t nq)
+{
+	if (n == 0) return hb_fail(ctx, HB_ERR_INVALID, "batch: no mesh");
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	std::vector<uint32_t> starts;
+	make_groups(meshes, n, starts);
+	const size_t G = starts.size() - 1;
+	std::vector<hb_dmesh *> dm(G, nullptr);
+	bool vertex_only = true;
+	for (uint32_t i = 0; i < n; ++i) vertex_only = vertex_only && decode_is_vertex_only(&meshes[i]);
+	int rc = 0;
+	auto upload_group = [&](size_t g) -> int {
+		dm[g] = new hb_dmesh();
+		dm[g]->async_copy = true;
+		hb_dmesh *m = dm[g];
+		HB_TRY(dmesh_upload_impl(ctx, meshes + starts[g], starts[g + 1] - starts[g], m, vertex_only));
+		for (uint32_t k = 0; k < nq; ++k) { // bounds rows of the lists to dequantize (min, max, scale per mesh)
+			if (q[k].list >= (uint32_t)m->nlists || !q[k].bounds) return hb_fail(ctx, HB_ERR_INVALID, "batch: dequantization request for list %u", q[k].list);
+			DevList &dl = m->lists[q[k].list];
+			const size_t s3 = 3 * (size_t)dl.p.stride;
+			if (s3) HB_CUDA(ctx, cudaMemcpy2DAsync(dl.d_bounds, dl.bounds_pitch, (const uint8_t *)q[k].bounds + s3 * starts[g], s3, s3, m->nseg, cudaMemcpyHostToDevice, ctx->copy_stream));
+		}
+		HB_CUDA(ctx, cudaEventRecord(m->ev_up[1], ctx->copy_stream));
+		return 0;
+	};
+	auto run_group = [&](size_t g) -> int {
+		hb_dmesh *m = dm[g];
+		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_up[1], 0));
+		HB_TRY(hb_decode_lists(m));
+		uint8_t zero[HB_MAX_COMP] = { 0 };
+		for (uint32_t k = 0; k < nq; ++k) HB_TRY(hb_list_requant(m, q[k].list, zero));
+		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+		HB_CUDA(ctx, cudaEventRecord(m->ev_done, ctx->stream));
+		// rows back to the caller's lists
+		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, m->ev_done, 0));
+		for (int l = 0; l < m->nlists; ++l) {
+			DevList &dl = m->lists[l];
+			if (!dl.p.ncomp) continue;
+			for (uint32_t sg = 0; sg < m->nseg; ++sg) {
+				const hb_list_desc &L = meshes[starts[g] + sg].lists[l];
+				const size_t bytes = (size_t)L.nrows * L.stride;
+				if (bytes) HB_CUDA(ctx, cudaMemcpyAsync(L.rows, dl.p.rows + (size_t)dl.h_rowbase[sg] * L.stride, bytes, cudaMemcpyDeviceToHost, ctx->out_stream));
+			}
+		}
+		dmesh_release_device(m, ctx->out_stream);
+		return 0;
+	};
+	rc = upload_group(0);
+	for (size_t g = 0; rc == 0 && g < G; ++g) {
+		if (g + 1 < G) rc = upload_group(g + 1);
+		if (rc == 0) rc = run_group(g);
+		// at most three groups resident: wait for the downloads of the group before the last one
+		if (rc == 0 && g >= 2) { cudaEventSynchronize(dm[g - 2]->ev_done); }
+	}
+	if (cudaStreamSynchronize(ctx->out_stream) != cudaSuccess && rc == 0) rc = hb_fail(ctx, HB_ERR_CUDA, "batch download failed: %s", cudaGetErrorString(cudaGetLastError()));
+	if (rc == 0) rc = hb_check_device_error(ctx, "batch decode");
+	for (hb_dmesh *m : dm) hb_dmesh_free(m);
 	return rc;
 }

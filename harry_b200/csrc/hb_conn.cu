@@ -153,36 +153,71 @@ int hb_scan_exclusive_u32(hb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, ui
 
 // ------------------------------------------------------------------------------------------------
 // K0: raw 12-byte {org, twin_face, twin_edge:16} records -> uint4 {org, twin, le | deg << 16, face}
+// The raw records of a segment (mesh of a batch) carry indices local to it; the segment of a face is found by
+// binary search over the face bases (nseg == 1: no search).  A record that is flagged as invalid is stored in a
+// SAFE form (origin 0, its own twin; faces of impossible degree as isolated one-edge faces), so the kernels
+// behind K0 -- which run before the host looks at the error flag -- never leave their arrays.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_flatten_halfedges(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ face_off, uint4 *__restrict__ he, uint32_t nf, uint32_t nv, int *err)
+struct SegView {
+	uint32_t nseg;
+	const uint32_t *vbase, *fbase, *ebase, *obase, *ofbase;
+};
+
+// global CSR offsets of the concatenated faces from the per-segment ones (segment s uploaded nf_s + 1 offsets
+// starting at 0, stored at fbase[s] + s)
+__global__ void __launch_bounds__(256) k_global_face_off(const uint32_t *__restrict__ raw, SegView sv, uint32_t nf, uint32_t *__restrict__ face_off)
+{
+	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f > nf) return;
+	if (f == nf) { face_off[f] = sv.ebase[sv.nseg]; return; }
+	const uint32_t s = hb_seg_find(sv.fbase, sv.nseg, f);
+	face_off[f] = raw[f + s] + sv.ebase[s];
+}
+
+__global__ void __launch_bounds__(256) k_flatten_halfedges(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ face_off, uint4 *__restrict__ he, uint32_t nf, uint32_t ne,
+                                                           SegView sv, int *err)
 {
 	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= nf) return;
+	const uint32_t s = hb_seg_find(sv.fbase, sv.nseg, f);
+	const uint32_t vb = sv.vbase[s], fb = sv.fbase[s];
+	const uint32_t nv_s = sv.vbase[s + 1] - vb, nf_s = sv.fbase[s + 1] - fb;
 	const uint32_t b = face_off[f], e = face_off[f + 1];
 	const uint32_t deg = e - b;
-	if (deg > 0xffffu || e < b) { atomicExch(err, 1); return; }
+	if (e < b || e > ne) { atomicExch(err, 1); return; }
+	if (deg > 0xffffu) {
+		atomicExch(err, 1);
+		for (uint32_t h = b; h < e; ++h) he[h] = make_uint4(vb, h, 0u | (1u << 16), f);
+		return;
+	}
 	for (uint32_t h = b; h < e; ++h) {
-		const uint32_t org = raw[3 * (size_t)h], tf = raw[3 * (size_t)h + 1], te = raw[3 * (size_t)h + 2] & 0xffffu;
+		uint32_t org = raw[3 * (size_t)h];
+		const uint32_t tf = raw[3 * (size_t)h + 1], te = raw[3 * (size_t)h + 2] & 0xffffu;
 		uint32_t tw = h;
-		if (org >= nv || tf >= nf) {
+		if (org >= nv_s || tf >= nf_s) {
 			atomicExch(err, 2);
+			if (org >= nv_s) org = 0;
 		} else {
-			const uint32_t tb = face_off[tf];
-			if (tb + te >= face_off[tf + 1]) atomicExch(err, 2);
+			const uint32_t tb = face_off[tf + fb];
+			if (tb + te >= face_off[tf + fb + 1]) atomicExch(err, 2);
 			else tw = tb + te;
 		}
-		he[h] = make_uint4(org, tw, (h - b) | (deg << 16), f);
+		he[h] = make_uint4(org + vb, tw, (h - b) | (deg << 16), f);
 	}
 }
 
 // order[i] = fepair {u32 face; u16 edge} -> half-edge, vertex, and the vertex rank (first visit)
-__global__ void k_vertex_order(const uint32_t *__restrict__ order, const uint32_t *__restrict__ face_off, const uint4 *__restrict__ he, uint32_t n, uint32_t nf,
-                               uint32_t *__restrict__ ord_h, uint32_t *__restrict__ ord_v, uint32_t *__restrict__ vrank, int *err)
+__global__ void __launch_bounds__(256) k_vertex_order(const uint32_t *__restrict__ order, const uint32_t *__restrict__ face_off, const uint4 *__restrict__ he, uint32_t n, SegView sv,
+                                                      uint32_t *__restrict__ ord_h, uint32_t *__restrict__ ord_v, uint32_t *__restrict__ vrank, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const uint32_t f = order[2 * (size_t)i], e = order[2 * (size_t)i + 1] & 0xffffu;
-	if (f >= nf || face_off[f] + e >= face_off[f + 1]) { atomicExch(err, 3); ord_h[i] = 0; ord_v[i] = 0; return; }
+	const uint32_t s = hb_seg_find(sv.obase, sv.nseg, i);
+	const uint32_t fb = sv.fbase[s], nf_s = sv.fbase[s + 1] - fb;
+	const uint32_t fl = order[2 * (size_t)i], e = order[2 * (size_t)i + 1] & 0xffffu;
+	const uint32_t f = fl + fb;
+	// an invalid entry takes the first half-edge of its segment (any valid one keeps the later kernels in bounds)
+	if (fl >= nf_s || face_off[f] + e >= face_off[f + 1]) { atomicExch(err, 3); ord_h[i] = sv.ebase[s]; ord_v[i] = sv.vbase[s]; return; }
 	const uint32_t h = face_off[f] + e;
 	const uint32_t v = he[h].x;
 	ord_h[i] = h;
@@ -191,39 +226,52 @@ __global__ void k_vertex_order(const uint32_t *__restrict__ order, const uint32_
 }
 
 // face order -> frank[f], gate half-edge per rank, degree per rank (for the corner-element scan)
-__global__ void k_face_order(const uint32_t *__restrict__ order_f, const uint32_t *__restrict__ face_off, uint32_t n, uint32_t nf,
-                             uint32_t *__restrict__ frank, uint32_t *__restrict__ ford_h, uint32_t *__restrict__ fdeg, int *err)
+__global__ void __launch_bounds__(256) k_face_order(const uint32_t *__restrict__ order_f, const uint32_t *__restrict__ face_off, uint32_t n, SegView sv,
+                                                    uint32_t *__restrict__ frank, uint32_t *__restrict__ ford_h, uint32_t *__restrict__ fdeg, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	uint32_t f = i, e = 0;
+	const uint32_t s = hb_seg_find(sv.ofbase, sv.nseg, i);
+	const uint32_t fb = sv.fbase[s], nf_s = sv.fbase[s + 1] - fb;
+	uint32_t fl = i - sv.ofbase[s], e = 0; // no face order: faces in index order, gate corner 0 (the decoder, attrcode.h:543-548)
 	if (order_f) {
-		f = order_f[2 * (size_t)i];
+		fl = order_f[2 * (size_t)i];
 		e = order_f[2 * (size_t)i + 1] & 0xffffu;
 	}
-	if (f >= nf || face_off[f] + e >= face_off[f + 1]) { atomicExch(err, 4); ford_h[i] = 0; fdeg[i] = 0; return; }
+	const uint32_t f = fl + fb;
+	if (fl >= nf_s || face_off[f] + e >= face_off[f + 1]) { atomicExch(err, 4); ford_h[i] = sv.ebase[s]; fdeg[i] = 0; return; }
 	atomicMin(&frank[f], i);
 	ford_h[i] = face_off[f] + e;
 	fdeg[i] = face_off[f + 1] - face_off[f];
 }
 
 // corner elements in emission order: face rank fr, corners starting at the gate corner
-// (attrcode.h:405-414); celem_h[ce] = half-edge, he_celem[h] = corner element
-__global__ void k_corner_elems(const uint32_t *__restrict__ ford_h, const uint32_t *__restrict__ cbase, const uint4 *__restrict__ he, uint32_t n,
-                               uint32_t *__restrict__ celem_h, uint32_t *__restrict__ he_celem)
+// (attrcode.h:405-414); celem_h[ce] = half-edge, he_celem[h] = corner element.  Every face is traversed exactly
+// once, so there are exactly ne corner elements; anything else is an invalid face order (flagged, never out of bounds:
+// the arrays were cleared to element / half-edge 0).
+__global__ void __launch_bounds__(256) k_corner_elems(const uint32_t *__restrict__ ford_h, const uint32_t *__restrict__ cbase, const uint4 *__restrict__ he, uint32_t n, uint32_t ne,
+                                                      uint32_t *__restrict__ celem_h, uint32_t *__restrict__ he_celem, int *err)
 {
 	const uint32_t fr = blockIdx.x * blockDim.x + threadIdx.x;
 	if (fr >= n) return;
+	if (fr == 0 && cbase[n] != ne) atomicExch(err, 4);
 	const uint32_t hg = ford_h[fr];
 	const uint32_t ld = he[hg].z;
 	const uint32_t deg = ld >> 16, base = cbase[fr];
 	const uint32_t gate = ld & 0xffffu, f0 = hg - gate;
+	if (cbase[fr + 1] - base != deg || base + deg > ne) { atomicExch(err, 4); return; } // a face listed twice / a gate outside its face
 	for (uint32_t j = 0; j < deg; ++j) {
 		uint32_t le = gate + j;
 		if (le >= deg) le -= deg;
 		celem_h[base + j] = f0 + le;
 		he_celem[f0 + le] = base + j;
 	}
+}
+// corner-element base of every segment
+__global__ void k_seg_corner_base(const uint32_t *__restrict__ cbase, SegView sv, uint32_t *__restrict__ cebase)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s <= sv.nseg) cebase[s] = cbase[sv.ofbase[s]];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,14 +411,16 @@ __device__ __forceinline__ void paral_visit_t(const uint4 *__restrict__ he, uint
 #define VC_WALK_CAP 64
 #define VC_MAXWIDE 64
 #define VC_WIDE_MARK 0xffffffffu
+#define VC_WIDE_ARENA (1u << 20)  // fan nodes of all wide vertices of one launch (split evenly between them)
 struct WideCtl {
 	uint32_t n;                    // wide vertices registered (may exceed VC_MAXWIDE)
+	uint32_t per;                  // arena nodes per wide vertex
 	uint32_t vtx[VC_MAXWIDE], rank[VC_MAXWIDE], deg[VC_MAXWIDE], base[VC_MAXWIDE + 1], fill[VC_MAXWIDE], ncand[VC_MAXWIDE];
 };
 
 __global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ ord_v,
                                                                   const uint32_t *__restrict__ vrank, const uint16_t *__restrict__ vtx_regs, uint32_t n, uint32_t ne,
-                                                                  uint32_t *__restrict__ cnt, uint32_t *__restrict__ stage, WideCtl *__restrict__ wide, int *err)
+                                                                  uint32_t *__restrict__ cnt, uint32_t *__restrict__ stage, WideCtl *__restrict__ wide, uint32_t walk_cap, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -385,7 +435,7 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__
 	sink.count = 0;
 	uint32_t st[3 * VC_STAGE];
 	sink.stage = st;
-	bool ok = fan_walk(he, ord_h[i], VC_WALK_CAP, [&](uint32_t e, const uint4 &rec) { paral_visit_t(he, e, rec, sink); });
+	bool ok = fan_walk(he, ord_h[i], walk_cap, [&](uint32_t e, const uint4 &rec) { paral_visit_t(he, e, rec, sink); });
 	if (!ok) {
 		const uint32_t slot = atomicAdd(&wide->n, 1u);
 		if (slot < VC_MAXWIDE) {
@@ -411,12 +461,14 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__
 // Pass 2: staged triples -> CSR (streaming); vertices that overflowed the staging slot walk again
 __global__ void __launch_bounds__(256) k_vertex_candidates_compact(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ ord_v,
                                                                     const uint32_t *__restrict__ vrank, const uint16_t *__restrict__ vtx_regs, uint32_t n, uint32_t ne,
-                                                                    const uint32_t *__restrict__ off, const uint32_t *__restrict__ stage, uint32_t *__restrict__ tri, int *err)
+                                                                    const uint32_t *__restrict__ off, const uint32_t *__restrict__ stage, uint32_t *__restrict__ tri, uint32_t cap, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint32_t o0 = off[i], K = off[i + 1] - o0;
 	if (K == 0) return;
+	// every fan half-edge yields at most two candidates and belongs to one vertex: 2 ne triples hold any valid input
+	if ((unsigned long long)o0 + K > cap) { atomicExch(err, 3); return; }
 	if (stage[(size_t)i * 3 * VC_STAGE] == VC_WIDE_MARK) return; // written by k_wide_copy
 	if (K <= VC_STAGE) {
 		const uint32_t *st = stage + (size_t)i * 3 * VC_STAGE;
@@ -438,11 +490,12 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_compact(const uint4 *
 // half-edges whose origin is a wide vertex: count per vertex (SCATTER = false), then scatter into
 // contiguous node lists and note every node's index (SCATTER = true)
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ he, uint32_t ne, WideCtl *__restrict__ wide, uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos,
-                                                      uint32_t cap_per_slot)
+__global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ he, uint32_t ne, WideCtl *__restrict__ wide, uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos)
 {
 	__shared__ uint32_t s_v[VC_MAXWIDE];
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
+	if (nw == 0) return; // the usual mesh: no wide fan, nothing to stream
+	const uint32_t cap_per_slot = wide->per;
 	if (threadIdx.x < nw) s_v[threadIdx.x] = wide->vtx[threadIdx.x];
 	__syncthreads();
 	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
@@ -452,7 +505,7 @@ __global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ 
 			if (!SCATTER) atomicAdd(&wide->deg[w], 1u);
 			else {
 				const uint32_t k = atomicAdd(&wide->fill[w], 1u);
-				if (k >= cap_per_slot) continue; // evenly split arena too small: the host falls back to exact slots
+				if (k >= cap_per_slot) continue; // fan larger than its share of the arena: k_wide_rank walks it sequentially
 				const uint32_t idx = wide->base[w] + k;
 				nodes[idx] = e;
 				pos[e] = idx;
@@ -460,30 +513,19 @@ __global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ 
 		}
 	}
 }
-// evenly split arena: slot w owns [w * per, (w + 1) * per); base[VC_MAXWIDE] doubles as the overflow flag
-__global__ void k_wide_even_bases(WideCtl *wide, uint32_t per)
+// evenly split arena: slot w owns [w * per, (w + 1) * per)
+__global__ void k_wide_even_bases(WideCtl *wide)
 {
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
+	const uint32_t per = VC_WIDE_ARENA / (nw ? nw : 1u);
+	wide->per = per;
 	for (uint32_t w = 0; w <= nw; ++w) wide->base[w] = w * per;
 	for (uint32_t w = 0; w < nw; ++w) wide->fill[w] = 0;
-	wide->base[VC_MAXWIDE] = 0;
 }
-__global__ void k_wide_fill_to_deg(WideCtl *wide, uint32_t per)
+__global__ void k_wide_fill_to_deg(WideCtl *wide)
 {
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
-	uint32_t overflow = 0;
-	for (uint32_t w = 0; w < nw; ++w) {
-		wide->deg[w] = wide->fill[w];
-		if (wide->fill[w] > per) overflow = 1;
-	}
-	wide->base[VC_MAXWIDE] = overflow;
-}
-__global__ void k_wide_bases(WideCtl *wide)
-{
-	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
-	uint32_t acc = 0;
-	for (uint32_t w = 0; w < nw; ++w) { wide->base[w] = acc; acc += wide->deg[w]; wide->fill[w] = 0; }
-	wide->base[nw] = acc;
+	for (uint32_t w = 0; w < nw; ++w) wide->deg[w] = wide->fill[w];
 }
 
 // One CTA per wide vertex: rank its fan by pointer doubling (distance to the tail of the
@@ -495,14 +537,30 @@ __global__ void k_wide_bases(WideCtl *wide)
 __global__ void __launch_bounds__(WIDE_T) k_wide_rank(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ vrank,
                                                       const uint16_t *__restrict__ vtx_regs, WideCtl *__restrict__ wide, const uint32_t *__restrict__ nodes,
                                                       const uint32_t *__restrict__ pos, uint32_t *nxtA, uint32_t *nxtB, uint32_t *dA, uint32_t *dB, uint32_t *lastA, uint32_t *lastB,
-                                                      uint32_t *__restrict__ order, uint32_t *__restrict__ arena, uint32_t *__restrict__ cnt, int *err)
+                                                      uint32_t *__restrict__ order, uint32_t *__restrict__ arena, uint32_t *__restrict__ cnt, uint32_t *__restrict__ stage, uint32_t ne, int *err)
 {
 	const uint32_t NIL = 0xffffffffu;
 	const uint32_t slot = blockIdx.x, t = threadIdx.x;
+	if (slot >= min(wide->n, (uint32_t)VC_MAXWIDE)) return;
 	const uint32_t b = wide->base[slot], d = wide->deg[slot], self = wide->rank[slot];
 	const uint32_t ein = ord_h[self];
 	const uint16_t reg = vtx_regs[wide->vtx[slot]];
 	__shared__ uint32_t s_warp[32], s_carry, s_total;
+	if (d > wide->per) {
+		// the fan does not fit its share of the arena (more than VC_WIDE_ARENA / #wide vertices half-edges around one
+		// vertex): one thread walks it in order, like the stage kernel does for the vertices beyond VC_MAXWIDE
+		if (t == 0) {
+			ParalStageSink sink;
+			sink.vrank = vrank; sink.vtx_regs = vtx_regs; sink.self = self; sink.reg = reg; sink.count = 0;
+			uint32_t st[3 * VC_STAGE];
+			sink.stage = st;
+			if (!fan_walk(he, ein, ne + 2, [&](uint32_t e, const uint4 &rec) { paral_visit_t(he, e, rec, sink); })) atomicExch(err, 5);
+			cnt[self] = sink.count;
+			for (uint32_t w = 0; w < 3 * VC_STAGE; ++w) stage[(size_t)self * 3 * VC_STAGE + w] = w < 3 * min(sink.count, (uint32_t)VC_STAGE) ? st[w] : 0u; // clears the wide mark
+			wide->ncand[slot] = 0;
+		}
+		return;
+	}
 	for (uint32_t k = t; k < d; k += WIDE_T) {
 		const uint32_t e = nodes[b + k];
 		const uint4 rec = he[e];
@@ -594,10 +652,12 @@ __global__ void __launch_bounds__(WIDE_T) k_wide_rank(const uint4 *__restrict__ 
 	}
 	if (t == 0) { wide->ncand[slot] = s_carry; cnt[self] = s_carry; }
 }
-__global__ void __launch_bounds__(256) k_wide_copy(const WideCtl *__restrict__ wide, const uint32_t *__restrict__ off, const uint32_t *__restrict__ arena, uint32_t *__restrict__ tri)
+__global__ void __launch_bounds__(256) k_wide_copy(const WideCtl *__restrict__ wide, const uint32_t *__restrict__ off, const uint32_t *__restrict__ arena, uint32_t *__restrict__ tri, uint32_t cap)
 {
 	const uint32_t slot = blockIdx.x;
+	if (slot >= min(wide->n, (uint32_t)VC_MAXWIDE)) return;
 	const uint32_t nc = wide->ncand[slot], b = wide->base[slot], o0 = off[wide->rank[slot]];
+	if ((unsigned long long)o0 + nc > cap) return; // flagged by k_vertex_candidates_compact
 	for (uint32_t w = threadIdx.x; w < 3 * nc; w += blockDim.x) tri[3 * (size_t)o0 + w] = arena[3 * (size_t)(2 * b) + w];
 }
 
@@ -631,10 +691,19 @@ __global__ void __launch_bounds__(256) k_corner_candidates(const uint4 *__restri
 // ------------------------------------------------------------------------------------------------
 // host drivers
 // ------------------------------------------------------------------------------------------------
+static SegView seg_view(const hb_dmesh *m)
+{
+	SegView sv;
+	sv.nseg = m->nseg;
+	sv.vbase = m->d_vbase; sv.fbase = m->d_fbase; sv.ebase = m->d_ebase; sv.obase = m->d_obase; sv.ofbase = m->d_ofbase;
+	return sv;
+}
+
 int hb_build_conn(hb_dmesh *m)
 {
 	hb_ctx *ctx = m->ctx;
 	if (m->conn_ready) return 0;
+	const SegView sv = seg_view(m);
 	HB_TRY(hb_dalloc_t(m, &m->d_he, (size_t)m->ne + 1));
 	HB_TRY(hb_dalloc_t(m, &m->d_vrank, (size_t)m->nv + 1));
 	HB_TRY(hb_dalloc_t(m, &m->d_ord_h, (size_t)m->norder + 1));
@@ -644,24 +713,27 @@ int hb_build_conn(hb_dmesh *m)
 	HB_TRY(hb_dalloc_t(m, &m->d_cbase, (size_t)m->norder_f + 2));
 	HB_CUDA(ctx, cudaMemsetAsync(m->d_vrank, 0xff, sizeof(uint32_t) * ((size_t)m->nv + 1), ctx->stream));
 	HB_CUDA(ctx, cudaMemsetAsync(m->d_frank, 0xff, sizeof(uint32_t) * ((size_t)m->nf + 1), ctx->stream));
-	if (m->nf) HB_LAUNCH(ctx, k_flatten_halfedges, hb_div_up(m->nf, 256), 256, 0, (const uint32_t *)m->d_edges_raw, m->d_face_off, m->d_he, m->nf, m->nv, ctx->d_err);
+	if (m->nseg > 1) {
+		HB_TRY(hb_dalloc_t(m, &m->d_face_off, (size_t)m->nf + 1));
+		HB_LAUNCH(ctx, k_global_face_off, hb_div_up((uint64_t)m->nf + 1, 256), 256, 0, m->d_face_off_raw, sv, m->nf, m->d_face_off);
+	}
+	if (m->nf) HB_LAUNCH(ctx, k_flatten_halfedges, hb_div_up(m->nf, 256), 256, 0, (const uint32_t *)m->d_edges_raw, m->d_face_off, m->d_he, m->nf, m->ne, sv, ctx->d_err);
 	if (m->norder)
-		HB_LAUNCH(ctx, k_vertex_order, hb_div_up(m->norder, 256), 256, 0, (const uint32_t *)m->d_order, m->d_face_off, m->d_he, m->norder, m->nf, m->d_ord_h, m->d_ord_v, m->d_vrank, ctx->d_err);
+		HB_LAUNCH(ctx, k_vertex_order, hb_div_up(m->norder, 256), 256, 0, (const uint32_t *)m->d_order, m->d_face_off, m->d_he, m->norder, sv, m->d_ord_h, m->d_ord_v, m->d_vrank, ctx->d_err);
 	if (m->norder_f)
-		HB_LAUNCH(ctx, k_face_order, hb_div_up(m->norder_f, 256), 256, 0, m->has_order_f ? (const uint32_t *)m->d_order_f : (const uint32_t *)nullptr, m->d_face_off, m->norder_f, m->nf, m->d_frank, m->d_ford_h, m->d_cbase, ctx->d_err);
+		HB_LAUNCH(ctx, k_face_order, hb_div_up(m->norder_f, 256), 256, 0, m->has_order_f ? (const uint32_t *)m->d_order_f : (const uint32_t *)nullptr, m->d_face_off, m->norder_f, sv, m->d_frank, m->d_ford_h, m->d_cbase, ctx->d_err);
 	// corner elements are only materialized when some region binds corner lists
 	m->n_corner_elems = 0;
 	if (m->any_corner && m->norder_f) {
 		HB_TRY(hb_scan_exclusive_u32(ctx, m->d_cbase, m->d_cbase, m->norder_f, nullptr));
-		uint32_t total = 0;
-		HB_CUDA(ctx, cudaMemcpyAsync(&total, m->d_cbase + m->norder_f, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		HB_TRY(hb_check_device_error(ctx, "connectivity"));
-		m->n_corner_elems = total;
-		HB_TRY(hb_dalloc_t(m, &m->d_celem_h, (size_t)total + 1));
+		m->n_corner_elems = m->ne; // every face is traversed once (k_corner_elems flags anything else): no read-back
+		HB_TRY(hb_dalloc_t(m, &m->d_celem_h, (size_t)m->ne + 1));
 		HB_TRY(hb_dalloc_t(m, &m->d_he_celem, (size_t)m->ne + 1));
-		HB_CUDA(ctx, cudaMemsetAsync(m->d_he_celem, 0xff, sizeof(uint32_t) * ((size_t)m->ne + 1), ctx->stream));
-		HB_LAUNCH(ctx, k_corner_elems, hb_div_up(m->norder_f, 256), 256, 0, m->d_ford_h, m->d_cbase, m->d_he, m->norder_f, m->d_celem_h, m->d_he_celem);
+		HB_TRY(hb_dalloc_t(m, &m->d_cebase, (size_t)m->nseg + 1));
+		HB_CUDA(ctx, cudaMemsetAsync(m->d_celem_h, 0, sizeof(uint32_t) * ((size_t)m->ne + 1), ctx->stream));
+		HB_CUDA(ctx, cudaMemsetAsync(m->d_he_celem, 0, sizeof(uint32_t) * ((size_t)m->ne + 1), ctx->stream));
+		HB_LAUNCH(ctx, k_corner_elems, hb_div_up(m->norder_f, 256), 256, 0, m->d_ford_h, m->d_cbase, m->d_he, m->norder_f, m->ne, m->d_celem_h, m->d_he_celem, ctx->d_err);
+		HB_LAUNCH(ctx, k_seg_corner_base, hb_div_up(m->nseg + 1, 128), 128, 0, m->d_cbase, sv, m->d_cebase);
 		HB_TRY(hb_dalloc_t(m, &m->d_reg_ncorner, m->reg_ncorner.size() + 1));
 		HB_CUDA(ctx, cudaMemcpyAsync(m->d_reg_ncorner, m->reg_ncorner.data(), sizeof(int) * m->reg_ncorner.size(), cudaMemcpyHostToDevice, ctx->stream));
 	}
@@ -669,6 +741,9 @@ int hb_build_conn(hb_dmesh *m)
 	return 0;
 }
 
+// No host synchronisation: the wide-fan kernels are launched unconditionally and return at once when the stage
+// pass registered no wide vertex; the CSR of triples is allocated at its upper bound (two candidates per fan
+// half-edge, every half-edge in the fan of one vertex).
 int hb_build_vertex_candidates(hb_dmesh *m)
 {
 	hb_ctx *ctx = m->ctx;
@@ -680,66 +755,33 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 	if (n) {
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_stage, (size_t)n * 3 * VC_STAGE + 4));
 		uint32_t *stage = m->d_vc_stage;
-		WideCtl *wide = nullptr;
 		HB_TRY(hb_dalloc(m, &m->d_vc_wide, sizeof(WideCtl)));
-		wide = (WideCtl *)m->d_vc_wide;
+		WideCtl *wide = (WideCtl *)m->d_vc_wide;
 		HB_CUDA(ctx, cudaMemsetAsync(wide, 0, sizeof(WideCtl), ctx->stream));
-		HB_LAUNCH(ctx, k_vertex_candidates_stage, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, wide, ctx->d_err);
-		uint32_t nwide = 0;
-		HB_CUDA(ctx, cudaMemcpyAsync(&nwide, &wide->n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		if (nwide > VC_MAXWIDE) nwide = VC_MAXWIDE;
-		uint32_t *arena = nullptr;
-		if (nwide) {
-			const uint32_t grid = (uint32_t)ctx->sm_count * 8;
-			// One streaming pass when the fans fit an evenly split arena (WIDE_ARENA nodes in all: a
-			// sphere pole has a few thousand); otherwise count first, then scatter into exact slots.
-			const uint32_t WIDE_ARENA = 1u << 20;
-			const uint32_t per = WIDE_ARENA / nwide;
-			uint32_t total = per * nwide;
-			HB_TRY(hb_dalloc_t(m, &m->d_vc_wpos, (size_t)m->ne + 1));
-			bool exact = m->vc_wide_cap > WIDE_ARENA; // a previous run over this mesh already needed exact slots
-			if (!exact) {
-				if (m->vc_wide_cap < total) { m->d_vc_wnodes = m->d_vc_wwork = m->d_vc_worder = m->d_vc_warena = nullptr; m->vc_wide_cap = total; }
-				HB_TRY(hb_dalloc_t(m, &m->d_vc_wnodes, (size_t)m->vc_wide_cap + 1));
-				HB_LAUNCH(ctx, k_wide_even_bases, 1, 1, 0, wide, per);
-				HB_LAUNCH(ctx, k_wide_collect<true>, grid, 256, 0, m->d_he, m->ne, wide, m->d_vc_wnodes, m->d_vc_wpos, per);
-				HB_LAUNCH(ctx, k_wide_fill_to_deg, 1, 1, 0, wide, per);
-				uint32_t overflow = 0;
-				HB_CUDA(ctx, cudaMemcpyAsync(&overflow, &wide->base[VC_MAXWIDE], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-				HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-				exact = overflow != 0;
-			}
-			if (exact) {
-				HB_CUDA(ctx, cudaMemsetAsync(wide->deg, 0, sizeof(wide->deg), ctx->stream));
-				HB_LAUNCH(ctx, k_wide_collect<false>, grid, 256, 0, m->d_he, m->ne, wide, (uint32_t *)nullptr, (uint32_t *)nullptr, 0u);
-				HB_LAUNCH(ctx, k_wide_bases, 1, 1, 0, wide);
-				HB_CUDA(ctx, cudaMemcpyAsync(&total, &wide->base[nwide], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-				HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-				if (total > m->vc_wide_cap || m->vc_wide_cap <= WIDE_ARENA) {
-					m->d_vc_wnodes = m->d_vc_wwork = m->d_vc_worder = m->d_vc_warena = nullptr; // the old ones stay in m->allocs until the mesh is freed
-					m->vc_wide_cap = total > WIDE_ARENA ? total : WIDE_ARENA + 1;
-				}
-				HB_TRY(hb_dalloc_t(m, &m->d_vc_wnodes, (size_t)m->vc_wide_cap + 1));
-				HB_LAUNCH(ctx, k_wide_collect<true>, grid, 256, 0, m->d_he, m->ne, wide, m->d_vc_wnodes, m->d_vc_wpos, 0xffffffffu);
-			}
-			// scratch of the ranking: sized like the node arena, released with the mesh
-			const size_t cap = m->vc_wide_cap;
-			HB_TRY(hb_dalloc_t(m, &m->d_vc_wwork, 6 * cap + 6));
-			HB_TRY(hb_dalloc_t(m, &m->d_vc_worder, cap + 1));
-			HB_TRY(hb_dalloc_t(m, &m->d_vc_warena, 6 * cap + 6));
-			uint32_t *nodes = m->d_vc_wnodes, *pos = m->d_vc_wpos, *work = m->d_vc_wwork, *order = m->d_vc_worder;
-			arena = m->d_vc_warena;
-			HB_LAUNCH(ctx, k_wide_rank, nwide, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + cap, work + 2 * cap, work + 3 * cap,
-			          work + 4 * cap, work + 5 * cap, order, arena, m->d_vc_off, ctx->d_err);
-		}
+		// a batch has many moderately wide fans (two poles per sphere): they are walked by their own thread; the
+		// pointer-doubling path is for the few huge fans of one big mesh
+		const uint32_t walk_cap = m->nseg > 1 ? 1024u : (uint32_t)VC_WALK_CAP;
+		HB_LAUNCH(ctx, k_vertex_candidates_stage, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, wide, walk_cap, ctx->d_err);
+		const size_t cap = VC_WIDE_ARENA;
+		m->vc_wide_cap = (uint32_t)cap;
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_wpos, (size_t)m->ne + 1));
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_wnodes, cap + 1));
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_wwork, 6 * cap + 6));
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_worder, cap + 1));
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_warena, 6 * cap + 6));
+		uint32_t *nodes = m->d_vc_wnodes, *pos = m->d_vc_wpos, *work = m->d_vc_wwork, *order = m->d_vc_worder, *arena = m->d_vc_warena;
+		HB_LAUNCH(ctx, k_wide_even_bases, 1, 1, 0, wide);
+		HB_LAUNCH(ctx, k_wide_collect<true>, (uint32_t)ctx->sm_count * 8, 256, 0, m->d_he, m->ne, wide, nodes, pos);
+		HB_LAUNCH(ctx, k_wide_fill_to_deg, 1, 1, 0, wide);
+		HB_LAUNCH(ctx, k_wide_rank, VC_MAXWIDE, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + cap, work + 2 * cap, work + 3 * cap,
+		          work + 4 * cap, work + 5 * cap, order, arena, m->d_vc_off, stage, m->ne, ctx->d_err);
 		HB_TRY(hb_scan_exclusive_u32(ctx, m->d_vc_off, m->d_vc_off, n, nullptr));
-		HB_CUDA(ctx, cudaMemcpyAsync(&m->vc_total, m->d_vc_off + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		HB_TRY(hb_check_device_error(ctx, "vertex fan walk"));
-		HB_TRY(hb_dalloc_t(m, &m->d_vc_tri, 3 * (size_t)m->vc_total + 3));
-		HB_LAUNCH(ctx, k_vertex_candidates_compact, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, m->d_vc_tri, ctx->d_err);
-		if (nwide) HB_LAUNCH(ctx, k_wide_copy, nwide, 256, 0, wide, m->d_vc_off, arena, m->d_vc_tri);
+		const uint64_t tri_cap = 2 * (uint64_t)m->ne + 8;
+		if (tri_cap > 0xffffffffull) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "mesh (or batch) with more than 2^31 half-edges");
+		m->vc_total = (uint32_t)tri_cap;
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_tri, 3 * (size_t)tri_cap + 3));
+		HB_LAUNCH(ctx, k_vertex_candidates_compact, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, m->d_vc_tri, (uint32_t)tri_cap, ctx->d_err);
+		HB_LAUNCH(ctx, k_wide_copy, VC_MAXWIDE, 256, 0, wide, m->d_vc_off, arena, m->d_vc_tri, (uint32_t)tri_cap);
 	} else {
 		HB_CUDA(ctx, cudaMemsetAsync(m->d_vc_off, 0, sizeof(uint32_t) * 2, ctx->stream));
 	}

@@ -13,7 +13,6 @@
 //     comes from components, lists and -- for batches -- meshes.
 #include "hb_lists.cuh"
 #include "hb_decode_spec.cuh"
-#include "hb_decode_spec3.cuh"
 #include "hb_decode_scan.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -26,7 +25,7 @@ struct WalkArgs {
 	uint8_t stype[HB_MAX_COMP], quant[HB_MAX_COMP];
 	const uint32_t *erow, *first, *cand_off, *cand;
 	unsigned long long *rp;
-	uint32_t n;
+	uint32_t base, n; // ranks [base, n) of one segment
 };
 
 __global__ void __launch_bounds__(32) k_decode_vertex_chain(const WalkArgs *__restrict__ args)
@@ -38,8 +37,8 @@ __global__ void __launch_bounds__(32) k_decode_vertex_chain(const WalkArgs *__re
 	const uint32_t n = a.n;
 	const uint32_t *__restrict__ erow = a.erow, *__restrict__ first = a.first, *__restrict__ coff = a.cand_off, *__restrict__ cand = a.cand;
 	unsigned long long *rp = a.rp;
-	uint32_t c0 = n ? coff[0] : 0;
-	for (uint32_t i = 0; i < n; ++i) {
+	uint32_t c0 = a.base < n ? coff[a.base] : 0;
+	for (uint32_t i = a.base; i < n; ++i) {
 		const uint32_t c1 = coff[i + 1];
 		const uint32_t row = erow[i];
 		if (row != HB_NONE) {
@@ -101,68 +100,31 @@ __global__ void __launch_bounds__(256) k_scatter_compact(ListParams p, const uin
 }
 
 template <typename T, int NC, bool FP>
-static int launch_spec_nc(hb_ctx *ctx, const SpecArgs *d_args)
+static int launch_spec_nc(hb_ctx *ctx, const SpecArgs *d_args, uint32_t nseg)
 {
 	const int threads = spec_threads<T, NC>();
 	const size_t smem = (size_t)threads * 4 * SPEC_HB * sizeof(SpecRec<T, NC>);
 	HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_spec<T, NC, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	HB_LAUNCH(ctx, (k_decode_vertex_spec<T, NC, FP>), 1, threads, smem, d_args);
+	HB_LAUNCH(ctx, (k_decode_vertex_spec<T, NC, FP>), nseg, threads, smem, d_args);
 	return 0;
 }
 template <typename T, bool FP>
-static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args)
+static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, uint32_t nseg)
 {
 	switch (ncomp) {
-	case 1: return launch_spec_nc<T, 1, FP>(ctx, d_args);
-	case 2: return launch_spec_nc<T, 2, FP>(ctx, d_args);
-	case 3: return launch_spec_nc<T, 3, FP>(ctx, d_args);
-	default: return launch_spec_nc<T, 4, FP>(ctx, d_args);
-	}
-}
-
-// cluster launch of the lane-mapped hypothesis kernel (integer lists)
-template <typename T, int NC>
-static int launch_spec3_nc(hb_ctx *ctx, const SpecArgs *d_args, Spec3Scratch *scratch, uint32_t *g_excl, uint8_t *g_inner)
-{
-	const int threads = 4 * spec3_cpc<T, NC>();
-	const size_t smem = spec3_smem<T, NC>();
-	HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_spec3<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(SPEC3_CLUSTER);
-	cfg.blockDim = dim3(threads);
-	cfg.dynamicSmemBytes = smem;
-	cfg.stream = ctx->stream;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeClusterDimension;
-	attr[0].val.clusterDim.x = SPEC3_CLUSTER;
-	attr[0].val.clusterDim.y = 1;
-	attr[0].val.clusterDim.z = 1;
-	cfg.attrs = attr;
-	cfg.numAttrs = 1;
-	cudaEvent_t pa = nullptr, pb = nullptr;
-	if (ctx->profiling) { pa = hb_prof_event(ctx); pb = hb_prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
-	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_decode_vertex_spec3<T, NC>, d_args, scratch, g_excl, g_inner));
-	ctx->launches++;
-	if (pa) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back(hb_ctx::ProfRec{ "k_decode_vertex_spec3", pa, pb }); }
-	return 0;
-}
-template <typename T>
-static int launch_spec3(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, Spec3Scratch *scratch, uint32_t *g_excl, uint8_t *g_inner)
-{
-	switch (ncomp) {
-	case 1: return launch_spec3_nc<T, 1>(ctx, d_args, scratch, g_excl, g_inner);
-	case 2: return launch_spec3_nc<T, 2>(ctx, d_args, scratch, g_excl, g_inner);
-	case 3: return launch_spec3_nc<T, 3>(ctx, d_args, scratch, g_excl, g_inner);
-	default: return launch_spec3_nc<T, 4>(ctx, d_args, scratch, g_excl, g_inner);
+	case 1: return launch_spec_nc<T, 1, FP>(ctx, d_args, nseg);
+	case 2: return launch_spec_nc<T, 2, FP>(ctx, d_args, nseg);
+	case 3: return launch_spec_nc<T, 3, FP>(ctx, d_args, nseg);
+	default: return launch_spec_nc<T, 4, FP>(ctx, d_args, nseg);
 	}
 }
 
 // cluster launch of the verified-scan kernel (integer lists): one cluster per component
 template <typename T>
-static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster)
+static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster, uint32_t nseg)
 {
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(cluster * ncomp);
+	cfg.gridDim = dim3((uint32_t)cluster * (uint32_t)ncomp * nseg); // one cluster per (segment, component)
 	cfg.blockDim = dim3(SCAN_NTB);
 	cfg.dynamicSmemBytes = 0;
 	cfg.stream = ctx->stream;
@@ -183,12 +145,12 @@ static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int clust
 }
 // CTAs per cluster: the window is about one cut-border length (~ sqrt(2 n) on a regular mesh);
 // two ranks per thread
-static int scan_cluster_size(uint32_t n, int ncomp)
+static int scan_cluster_size(uint32_t n, uint32_t nseg)
 {
 	static const char *env = getenv("HARRY_B200_SCAN_CLUSTER");
 	if (env && atoi(env) > 0) return atoi(env) > SCAN_MAXC ? SCAN_MAXC : atoi(env);
-	(void)ncomp;
-	const double need = 1.2 * sqrt(2.0 * (double)n) / (double)SCAN_NTB;
+	// a batch fills the machine with chains: one CTA per chain whenever a window nearly fits (no cluster hand-offs)
+	const double need = (nseg > 1 ? 0.9 : 1.2) * sqrt(2.0 * (double)n) / (double)SCAN_NTB;
 	int c = 1;
 	while (c < SCAN_MAXC && (double)c < need) c <<= 1;
 	return c;
@@ -215,7 +177,6 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 	HB_TRY(hb_dalloc_t(m, &dl.d_src, (size_t)n + 1));
 	HB_TRY(hb_dalloc_t(m, &dl.d_cres, (size_t)(n + 1) * ncp * esize));
 	HB_TRY(hb_dalloc_t(m, &dl.d_cx, (size_t)(n + 1) * ncp * esize));
-	HB_TRY(hb_dalloc_t(m, &dl.d_spec_args, 1));
 	HB_TRY(hb_dalloc_t(m, &dl.d_spec_stats, 8));
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_spec_stats, 0, 64, ctx->stream));
 	const uint32_t g = hb_div_up(n, 256);
@@ -228,32 +189,33 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 		srec = (ScanRec *)dl.d_srec;
 		HB_LAUNCH(ctx, k_scan_prep, g, 256, 0, dl.d_kind, dl.d_src, m->d_vc_off, m->d_vc_tri, n, srec);
 	}
-	SpecArgs a;
-	a.srec = srec;
-	a.kind = dl.d_kind; a.src = dl.d_src; a.cand_off = m->d_vc_off; a.cand = m->d_vc_tri;
-	a.resid = dl.d_cres; a.x = dl.d_cx; a.n = n; a.stats = dl.d_spec_stats;
-	for (int j = 0; j < 4; ++j) a.bits[j] = j < p.ncomp ? (p.quant[j] ? p.quant[j] : 8 * esize) : 8 * esize;
-	HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_args, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream));
-	HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `a` is a stack object
+	// one argument block per segment (mesh of a batch): the kernels run one CTA / cluster set per block
+	const uint32_t nseg = m->nseg;
+	uint32_t max_n = 0;
+	m->h_spec_args.resize(nseg);
+	for (uint32_t sg = 0; sg < nseg; ++sg) {
+		SpecArgs &a = m->h_spec_args[sg];
+		a.srec = srec;
+		a.kind = dl.d_kind; a.src = dl.d_src; a.cand_off = m->d_vc_off; a.cand = m->d_vc_tri;
+		a.resid = dl.d_cres; a.x = dl.d_cx;
+		a.base = m->h_obase[sg]; a.n = m->h_obase[sg + 1];
+		a.stats = sg == 0 ? dl.d_spec_stats : nullptr;
+		for (int j = 0; j < 4; ++j) a.bits[j] = j < p.ncomp ? (p.quant[j] ? p.quant[j] : 8 * esize) : 8 * esize;
+		if (a.n - a.base > max_n) max_n = a.n - a.base;
+	}
+	HB_TRY(hb_dalloc_t(m, &dl.d_spec_args, nseg));
+	// pageable source: the runtime stages it before cudaMemcpyAsync returns, no synchronisation needed
+	HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_args, m->h_spec_args.data(), sizeof(SpecArgs) * nseg, cudaMemcpyHostToDevice, ctx->stream));
 	static const bool single_cta = getenv("HARRY_B200_SPEC1") != nullptr; // A/B switch: single-CTA kernel
-	static const bool use_spec3 = getenv("HARRY_B200_SPEC3") != nullptr;  // A/B switch: hypothesis kernel
-	if (st != HB_FLOAT && !single_cta && !use_spec3) {
-		const int cl = scan_cluster_size(n, p.ncomp);
-		if (st == HB_UCHAR) HB_TRY(launch_scan<uint8_t>(ctx, p.ncomp, dl.d_spec_args, cl));
-		else if (st == HB_USHORT) HB_TRY(launch_scan<uint16_t>(ctx, p.ncomp, dl.d_spec_args, cl));
-		else HB_TRY(launch_scan<uint32_t>(ctx, p.ncomp, dl.d_spec_args, cl));
-	} else if (st != HB_FLOAT && !single_cta) {
-		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_scratch, 1));
-		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_excl, (size_t)SPEC3_CLUSTER * SPEC3_MAXCPC));
-		HB_TRY(hb_dalloc_t(m, &dl.d_spec3_inner, (size_t)SPEC3_CLUSTER * SPEC3_MAXCPC));
-		HB_CUDA(ctx, cudaMemsetAsync(dl.d_spec3_scratch, 0xff, 128, ctx->stream));
-		if (st == HB_UCHAR) HB_TRY(launch_spec3<uint8_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec3_scratch, dl.d_spec3_excl, dl.d_spec3_inner));
-		else if (st == HB_USHORT) HB_TRY(launch_spec3<uint16_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec3_scratch, dl.d_spec3_excl, dl.d_spec3_inner));
-		else HB_TRY(launch_spec3<uint32_t>(ctx, p.ncomp, dl.d_spec_args, dl.d_spec3_scratch, dl.d_spec3_excl, dl.d_spec3_inner));
-	} else if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args)));
-	else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, p.ncomp, dl.d_spec_args)));
-	else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, p.ncomp, dl.d_spec_args)));
-	else HB_TRY((launch_spec<uint32_t, true>(ctx, p.ncomp, dl.d_spec_args)));
+	if (st != HB_FLOAT && !single_cta) {
+		const int cl = scan_cluster_size(max_n, nseg);
+		if (st == HB_UCHAR) HB_TRY(launch_scan<uint8_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg));
+		else if (st == HB_USHORT) HB_TRY(launch_scan<uint16_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg));
+		else HB_TRY(launch_scan<uint32_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg));
+	} else if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
+	else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
+	else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
+	else HB_TRY((launch_spec<uint32_t, true>(ctx, p.ncomp, dl.d_spec_args, nseg)));
 	HB_LAUNCH(ctx, k_scatter_compact, g, 256, 0, p, dl.d_erow, dl.d_kind, n, dl.d_cx, esize, ncp);
 	return 0;
 }
@@ -356,14 +318,17 @@ int hb_decode_lists(hb_dmesh *m)
 			WalkArgs w;
 			w.ncomp = p.ncomp;
 			for (int j = 0; j < p.ncomp; ++j) { w.stype[j] = p.stype[j]; w.quant[j] = p.quant[j]; }
-			w.erow = dl.d_erow; w.first = dl.d_first; w.cand_off = m->d_vc_off; w.cand = m->d_vc_tri; w.rp = dl.d_rp; w.n = n;
-			walks.push_back(w);
+			w.erow = dl.d_erow; w.first = dl.d_first; w.cand_off = m->d_vc_off; w.cand = m->d_vc_tri; w.rp = dl.d_rp;
+			for (uint32_t sg = 0; sg < m->nseg; ++sg) { // one chain per segment (mesh of a batch)
+				w.base = m->h_obase[sg]; w.n = m->h_obase[sg + 1];
+				walks.push_back(w);
+			}
 			walk_lists.push_back(l);
 		} else {
-			uint8_t *done = nullptr;
-			uint32_t *remaining = nullptr;
-			HB_TRY(hb_dalloc_t(m, &done, (size_t)n + 1));
-			HB_TRY(hb_dalloc_t(m, &remaining, 1));
+			HB_TRY(hb_dalloc_t(m, &dl.d_done, (size_t)n + 1));   // kept with the list: reused by the next decode of this mesh
+			HB_TRY(hb_dalloc_t(m, &dl.d_remaining, 1));
+			uint8_t *done = dl.d_done;
+			uint32_t *remaining = dl.d_remaining;
 			HB_CUDA(ctx, cudaMemsetAsync(done, 0, (size_t)n + 1, ctx->stream));
 			uint32_t prev = 0xffffffffu;
 			for (uint32_t sweep = 0;; ++sweep) {
@@ -380,13 +345,11 @@ int hb_decode_lists(hb_dmesh *m)
 		}
 	}
 	if (!walks.empty()) {
-		WalkArgs *d_walks = nullptr;
-		HB_TRY(hb_dalloc_t(m, &d_walks, walks.size()));
+		HB_TRY(hb_dalloc(m, &m->d_walks, sizeof(WalkArgs) * walks.size()));
+		WalkArgs *d_walks = (WalkArgs *)m->d_walks;
 		HB_CUDA(ctx, cudaMemcpyAsync(d_walks, walks.data(), sizeof(WalkArgs) * walks.size(), cudaMemcpyHostToDevice, ctx->stream));
-		HB_LAUNCH(ctx, k_decode_vertex_chain, (uint32_t)walks.size(), 32, 0, d_walks);
-		// the pageable source buffer must outlive the async copy
-		HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		for (size_t k = 0; k < walks.size(); ++k) {
+		HB_LAUNCH(ctx, k_decode_vertex_chain, (uint32_t)walks.size(), 32, 0, d_walks); // (the pageable source was staged by the copy call)
+		for (size_t k = 0; k < walk_lists.size(); ++k) {
 			DevList &dl = m->lists[walk_lists[k]];
 			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(dl.n_elems, 256), 256, 0, dl.p, dl.d_erow, dl.d_first, dl.n_elems, dl.d_rp);
 		}

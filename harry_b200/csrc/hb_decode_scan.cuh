@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	const SpecArgs a = args[list];
 	const uint32_t RS = ncomp == 3 ? 4 : ncomp;        // elements per value record
 	const ScanRec *__restrict__ srec = (const ScanRec *)a.srec;
-	const uint32_t n = a.n;
+	const uint32_t n = a.n, base = a.base;              // this chain: ranks [base, n) of the concatenated order
 	const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	const uint32_t grp = lane;
 	constexpr bool live = true;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	const int cbw = cb;
 	const int lgC = 31 - __clz((int)C);
 
-	uint32_t done = 0, gend = 0, est = NSEGT;
+	uint32_t done = base, gend = base, est = NSEGT;
 	bool widehead = false, seqmode = false, lastseq = false;
 	uint32_t seqlen = SCAN_SEQ_MIN, smallrun = 0;
 	uint32_t lastadv = 0, pref_i = 0xffffffffu; // advance of the last sweep; rank whose record sits in s_pref[t]
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		const uint32_t i = active ? (uint32_t)i64 : n;
 		const unsigned long long wend64 = (unsigned long long)done + nact;
 		const uint32_t wend = wend64 < n ? (uint32_t)wend64 : n;
-		const uint32_t x0 = done ? scan_ld(xc + (size_t)(done - 1) * RS) : 0u;
+		const uint32_t x0 = done > base ? scan_ld(xc + (size_t)(done - 1) * RS) : 0u;
 		if (active && (unsigned long long)i + est < n) {
 			// the record and residual this slot will most likely need in the next sweep: pull them into L2 now
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(srec + i + est));
@@ -1030,7 +1030,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	if (crank == 0 && t == 0) printf("comp %u: sweeps %llu fails %llu capped %llu fallback %llu nseq %llu cycles %lld\n", c, sweeps, fails, capped, nfallback, nseq, cyA + cyB + cyC + cyD);
 #endif
 	if (crank == 0 && t == 0 && a.stats && c == 0) {
-		a.stats[0] = sweeps; a.stats[1] = fails | (capped << 32); a.stats[2] = nfallback | (wides << 32) | (nseq << 40); a.stats[3] = n;
+		a.stats[0] = sweeps; a.stats[1] = fails | (capped << 32); a.stats[2] = nfallback | (wides << 32) | (nseq << 40); a.stats[3] = n - base;
 		a.stats[4] = (unsigned long long)cyA; a.stats[5] = (unsigned long long)cyB; a.stats[6] = (unsigned long long)cyC; a.stats[7] = (unsigned long long)cyD;
 	}
 }

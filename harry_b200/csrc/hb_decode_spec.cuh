@@ -42,19 +42,6 @@ template <typename T> struct alignas(sizeof(T) * 2) SpecRec<T, 2> { T c[2]; };
 template <typename T> struct alignas(sizeof(T) * 4) SpecRec<T, 3> { T c[4]; };
 template <typename T> struct alignas(sizeof(T) * 4) SpecRec<T, 4> { T c[4]; };
 
-struct SpecArgs {
-	const uint8_t *kind;      // per rank: 0 skip, 1 DATA, 2 copy from src[i] (HIST)
-	const uint32_t *src;      // kind 2: owning rank
-	const uint32_t *cand_off; // n + 1
-	const uint32_t *cand;     // rank triples
-	const void *resid;        // compact records: residuals (read only)
-	void *x;                  // compact records: values (in/out)
-	uint32_t n;
-	int bits[4];              // quantization bits per component (prediction.h:22-25)
-	unsigned long long *stats; // [0] sweeps, [1] hypothesis sweeps, [2] plain sweeps
-	const void *srec;         // hb_decode_scan.cuh: one ScanRec per rank
-};
-
 // one reconstruction step for all components of a rank.  `get(r)` returns the record of rank r.
 // FP = lossless float list (T == uint32_t holding the IEEE bits).
 template <typename T, int NC, bool FP, typename Get>
@@ -220,7 +207,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_vertex_spec(const SpecArgs *
 	traj.base = (Rec *)s_dyn;
 	traj.nthreads = NT;
 	traj.t = t;
-	uint32_t done = 0, B = FP ? SPEC_HB : 4 * SPEC_HB;
+	uint32_t done = a.base, B = FP ? SPEC_HB : 4 * SPEC_HB; // this chain: ranks [base, n) of the concatenated order
 	bool hyp = !FP;            // hypothesis mode
 	int poor = 0;              // consecutive hypothesis sweeps that advanced by <= 2 chunks
 	unsigned long long sweeps = 0, hsweeps = 0, hadv = 0, unk = 0;
@@ -243,7 +230,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_vertex_spec(const SpecArgs *
 			uint32_t minread = 0xffffffffu; // lowest window rank read besides the predecessor rank
 			uint32_t map = SPEC_MAP_IDENTITY;
 			if (active) {
-				Rec pst = resid[0];
+				Rec pst = resid[a.base];
 				const bool pred_in_window = start > done; // chunk 0: the predecessor is final
 				if (pred_in_window) pst = x[start - 1];
 				for (uint32_t k = 0; k < len; ++k) traj.at(3, k) = x[start + k];

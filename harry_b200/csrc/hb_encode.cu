@@ -12,15 +12,26 @@
 #include "hb_decode_spec.cuh" // SpecRec: packed rank-space records
 
 // ------------------------------------------------------------------------------------------------
+// The binding tables hold row indices local to the segment (mesh of a batch) of the element; the segment is found
+// from the entity (vertex / face / half-edge) by binary search over `ent_base`.
+struct RowSeg {
+	uint32_t nseg;
+	const uint32_t *ent_base;         // vbase / fbase / ebase of the class
+	const uint32_t *rowbase, *rownum; // of the list
+};
 template <int CLS>
-__global__ void __launch_bounds__(256) k_elem_rows(ElemCtx c, int l, uint32_t nrows, uint32_t *__restrict__ erow, uint32_t *__restrict__ bound_flag, int *err)
+__global__ void __launch_bounds__(256) k_elem_rows(ElemCtx c, int l, RowSeg rs, uint32_t *__restrict__ erow, uint32_t *__restrict__ bound_flag, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= c.n) return;
 	uint32_t row, entity;
 	int a;
 	bool ok = elem_lookup<CLS>(c, i, l, row, a, entity);
-	if (ok && row >= nrows) { atomicExch(err, 7); ok = false; }
+	if (ok) {
+		const uint32_t s = hb_seg_find(rs.ent_base, rs.nseg, entity);
+		if (row >= rs.rownum[s]) { atomicExch(err, 7); ok = false; }
+		row += rs.rowbase[s];
+	}
 	erow[i] = ok ? row : HB_NONE;
 	if (bound_flag) bound_flag[i] = ok ? 1u : 0u;
 }
@@ -190,7 +201,23 @@ struct EncodeArgs {
 	int l;
 	uint32_t *wide;       // [0] = count, [1..] = element indices whose candidate count exceeds ENC_WIDE_K
 	uint32_t wide_cap;
+	// histograms are kept per segment (mesh of a batch): hist + s * hist_pitch, type counters behind the contexts
+	uint32_t nseg;
+	const uint32_t *elem_base; // first element of every segment (nseg + 1)
+	size_t hist_pitch;         // in u64 words
 };
+// segment of the elements of this block: the common one, or HB_NONE when the block straddles a boundary
+// (then every thread adds to the histograms of its own segment with global atomics)
+__device__ __forceinline__ uint32_t block_segment(const EncodeArgs &a, uint32_t first, uint32_t &mine, uint32_t i)
+{
+	mine = 0;
+	if (a.nseg <= 1) return 0;
+	const uint32_t last = min(first + ENC_THREADS, a.n) - 1;
+	const uint32_t s0 = hb_seg_find(a.elem_base, a.nseg, first), s1 = hb_seg_find(a.elem_base, a.nseg, last);
+	if (s0 == s1) { mine = s0; return s0; }
+	mine = hb_seg_find(a.elem_base, a.nseg, i < a.n ? i : last);
+	return HB_NONE;
+}
 
 template <int CLS>
 __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, EncodeArgs a)
@@ -202,6 +229,10 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 	uint32_t *s_type = s_hist + nctx_s * 256;
 
 	const uint32_t i = blockIdx.x * ENC_THREADS + threadIdx.x;
+	uint32_t myseg;
+	const uint32_t bseg = block_segment(a, blockIdx.x * ENC_THREADS, myseg, i);
+	const bool agg = bseg != HB_NONE; // one segment in this block: shared-memory histograms
+	unsigned long long *ghist = a.hist + (size_t)myseg * a.hist_pitch, *gtype = a.type_hist + (size_t)myseg * a.hist_pitch;
 	const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
 	int t = -1;                 // emission type of this element, -1 = no emission
 	unsigned long long res[HB_MAX_COMP > 8 ? 8 : HB_MAX_COMP]; // residuals of the first 8 components (register resident)
@@ -258,8 +289,8 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 				} else { // rare wide rows: no aggregation
 					for (int b = 0; b < p.size[j]; ++b) {
 						const uint32_t ctx = p.sym_off[j] + b, s = (uint32_t)(r >> (8 * b)) & 0xffu;
-						if ((int)ctx < nctx_s) atomicAdd(&s_hist[ctx * 256 + s], 1u);
-						else atomicAdd(&a.hist[(size_t)ctx * 256 + s], 1ull);
+						if (agg && (int)ctx < nctx_s) atomicAdd(&s_hist[ctx * 256 + s], 1u);
+						else atomicAdd(&ghist[(size_t)ctx * 256 + s], 1ull);
 					}
 				}
 			}
@@ -274,25 +305,36 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 		for (int j = 0; j < ncj; ++j) {
 			for (int b = 0; b < p.size[j]; ++b) {
 				const uint32_t ctx = p.sym_off[j] + b;
+				if (!agg) { // block across a segment boundary (rare): plain global atomics on the thread's own segment
+					if (is_data) atomicAdd(&ghist[(size_t)ctx * 256 + ((uint32_t)(res[j] >> (8 * b)) & 0xffu)], 1ull);
+					continue;
+				}
 				const uint32_t s = is_data ? (uint32_t)(res[j] >> (8 * b)) & 0xffu : 0x100u + (threadIdx.x & 31u);
 				const unsigned grp = __match_any_sync(0xffffffffu, s);
 				if (is_data && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31u)) {
 					const uint32_t cnt = __popc(grp);
 					if ((int)ctx < nctx_s) atomicAdd(&s_hist[ctx * 256 + s], cnt);
-					else atomicAdd(&a.hist[(size_t)ctx * 256 + s], (unsigned long long)cnt);
+					else atomicAdd(&ghist[(size_t)ctx * 256 + s], (unsigned long long)cnt);
 				}
 			}
 		}
 		// emission-type counts: one shared-memory atomic per warp and type
-		for (int ty = 0; ty < 3; ++ty) {
-			const unsigned m = __ballot_sync(0xffffffffu, t == ty || (ty == HB_DATA && t == -2));
-			if (m && (threadIdx.x & 31u) == 0) atomicAdd(&s_type[ty], (uint32_t)__popc(m));
+		if (agg) {
+			for (int ty = 0; ty < 3; ++ty) {
+				const unsigned m = __ballot_sync(0xffffffffu, t == ty || (ty == HB_DATA && t == -2));
+				if (m && (threadIdx.x & 31u) == 0) atomicAdd(&s_type[ty], (uint32_t)__popc(m));
+			}
+		} else if (t >= 0 || t == -2) {
+			atomicAdd(&gtype[t == -2 ? HB_DATA : t], 1ull);
 		}
 	}
 	__syncthreads();
-	for (int k = threadIdx.x; k < nctx_s * 256; k += ENC_THREADS)
-		if (s_hist[k]) atomicAdd(&a.hist[k], (unsigned long long)s_hist[k]);
-	if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&a.type_hist[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+	if (agg) {
+		unsigned long long *bh = a.hist + (size_t)bseg * a.hist_pitch, *bt = a.type_hist + (size_t)bseg * a.hist_pitch;
+		for (int k = threadIdx.x; k < nctx_s * 256; k += ENC_THREADS)
+			if (s_hist[k]) atomicAdd(&bh[k], (unsigned long long)s_hist[k]);
+		if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&bt[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+	}
 }
 
 // One warp per wide vertex element: the candidate predictions are summed with a warp-strided loop
@@ -306,6 +348,7 @@ __global__ void __launch_bounds__(128) k_encode_wide(ListParams p, EncodeArgs a)
 	const uint32_t i = a.wide[1 + w];
 	const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
 	uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+	unsigned long long *ghist = a.hist + (size_t)hb_seg_find(a.elem_base, a.nseg, i) * a.hist_pitch;
 	for (int j = 0; j < p.ncomp; ++j) {
 		const int st = p.stype[j], q = p.quant[j];
 		unsigned long long pred;
@@ -337,7 +380,7 @@ __global__ void __launch_bounds__(128) k_encode_wide(ListParams p, EncodeArgs a)
 			const unsigned long long r = hb_enc(st, a.rp[(size_t)i * p.ncomp + j], pred, q);
 			hb_st_bits(out + p.sym_off[j], p.size[j], r);
 			for (int b = 0; b < p.size[j]; ++b)
-				atomicAdd(&a.hist[(size_t)(p.sym_off[j] + b) * 256 + ((uint32_t)(r >> (8 * b)) & 0xffu)], 1ull);
+				atomicAdd(&ghist[(size_t)(p.sym_off[j] + b) * 256 + ((uint32_t)(r >> (8 * b)) & 0xffu)], 1ull);
 		}
 	}
 }
@@ -378,6 +421,9 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p,
 	uint32_t *s_type = s_hist + NCTX * 256;
 
 	const uint32_t i = blockIdx.x * ENC_THREADS + threadIdx.x;
+	uint32_t myseg;
+	const uint32_t bseg = block_segment(a, blockIdx.x * ENC_THREADS, myseg, i);
+	const bool agg = bseg != HB_NONE; // one segment in this block: shared-memory histograms
 	const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
 	int t = -1;
 	T res[NC];
@@ -427,20 +473,31 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p,
 #pragma unroll
 			for (int b = 0; b < (int)sizeof(T); ++b) {
 				const uint32_t ctx = p.sym_off[j] + b;
+				if (!agg) { // block across a segment boundary (rare): plain global atomics on the thread's own segment
+					if (is_data) atomicAdd(&a.hist[(size_t)myseg * a.hist_pitch + (size_t)ctx * 256 + (((uint32_t)res[j] >> (8 * b)) & 0xffu)], 1ull);
+					continue;
+				}
 				const uint32_t s = is_data ? ((uint32_t)res[j] >> (8 * b)) & 0xffu : 0x100u + (threadIdx.x & 31u);
 				const unsigned grp = __match_any_sync(0xffffffffu, s);
 				if (is_data && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31u)) atomicAdd(&s_hist[ctx * 256 + s], (uint32_t)__popc(grp));
 			}
 		}
-		for (int ty = 0; ty < 3; ++ty) {
-			const unsigned m = __ballot_sync(0xffffffffu, t == ty || (ty == HB_DATA && t == -2));
-			if (m && (threadIdx.x & 31u) == 0) atomicAdd(&s_type[ty], (uint32_t)__popc(m));
+		if (agg) {
+			for (int ty = 0; ty < 3; ++ty) {
+				const unsigned m = __ballot_sync(0xffffffffu, t == ty || (ty == HB_DATA && t == -2));
+				if (m && (threadIdx.x & 31u) == 0) atomicAdd(&s_type[ty], (uint32_t)__popc(m));
+			}
+		} else if (t >= 0 || t == -2) {
+			atomicAdd(&a.type_hist[(size_t)myseg * a.hist_pitch + (t == -2 ? HB_DATA : t)], 1ull);
 		}
 	}
 	__syncthreads();
-	for (int k = threadIdx.x; k < NCTX * 256; k += ENC_THREADS)
-		if (s_hist[k]) atomicAdd(&a.hist[k], (unsigned long long)s_hist[k]);
-	if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&a.type_hist[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+	if (agg) {
+		unsigned long long *bh = a.hist + (size_t)bseg * a.hist_pitch, *bt = a.type_hist + (size_t)bseg * a.hist_pitch;
+		for (int k = threadIdx.x; k < NCTX * 256; k += ENC_THREADS)
+			if (s_hist[k]) atomicAdd(&bh[k], (unsigned long long)s_hist[k]);
+		if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&bt[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
+	}
 }
 
 // one CTA per wide vertex (integer sums are order independent)
@@ -475,13 +532,14 @@ __global__ void __launch_bounds__(ENC_WIDE_T) k_encode_wide_packed(ListParams p,
 		if (threadIdx.x == 0) {
 			const Rec raw = rec[i];
 			uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+			unsigned long long *ghist = a.hist + (size_t)hb_seg_find(a.elem_base, a.nseg, i) * a.hist_pitch;
 #pragma unroll
 			for (int j = 0; j < NC; ++j) {
 				const T pred = (T)hb_divround_i64((long long)s_sum[j], (int)K);
 				const T r = IntOps<T>::enc(raw.c[j], pred, hb_stype_bits(p.stype[j], p.quant[j]));
 				hb_st_bits(out + p.sym_off[j], (int)sizeof(T), r);
 				for (int b = 0; b < (int)sizeof(T); ++b)
-					atomicAdd(&a.hist[(size_t)(p.sym_off[j] + b) * 256 + (((uint32_t)r >> (8 * b)) & 0xffu)], 1ull);
+					atomicAdd(&ghist[(size_t)(p.sym_off[j] + b) * 256 + (((uint32_t)r >> (8 * b)) & 0xffu)], 1ull);
 			}
 		}
 		__syncthreads();
@@ -498,7 +556,7 @@ static int encode_vtx_packed_nc(hb_dmesh *m, DevList &dl, const EncodeArgs &a)
 	HB_LAUNCH(ctx, (k_gather_packed<T, NC>), hb_div_up(n, 256), 256, 0, dl.p, dl.d_erow, n, rec);
 	const size_t smem = sizeof(uint32_t) * ((size_t)NC * sizeof(T) * 256 + 4);
 	HB_LAUNCH(ctx, (k_encode_vtx_packed<T, NC>), hb_div_up(n, ENC_THREADS), ENC_THREADS, smem, dl.p, a, rec);
-	if (a.wide) HB_LAUNCH(ctx, (k_encode_wide_packed<T, NC>), 64, ENC_WIDE_T, 0, dl.p, a, rec);
+	if (a.wide) HB_LAUNCH(ctx, (k_encode_wide_packed<T, NC>), 2 * ctx->sm_count, ENC_WIDE_T, 0, dl.p, a, rec);
 	return 0;
 }
 template <typename T>
@@ -568,9 +626,13 @@ int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp, bool decode)
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_dord, 0, sizeof(uint32_t) * ((size_t)n + 2), ctx->stream));
 	if (n) {
 		const uint32_t g = hb_div_up(n, 256);
-		if (cls == CLS_VTX) HB_LAUNCH(ctx, k_elem_rows<CLS_VTX>, g, 256, 0, c, l, dl.p.nrows, dl.d_erow, dl.d_ek, ctx->d_err);
-		else if (cls == CLS_FACE) HB_LAUNCH(ctx, k_elem_rows<CLS_FACE>, g, 256, 0, c, l, dl.p.nrows, dl.d_erow, dl.d_ek, ctx->d_err);
-		else HB_LAUNCH(ctx, k_elem_rows<CLS_CORNER>, g, 256, 0, c, l, dl.p.nrows, dl.d_erow, dl.d_ek, ctx->d_err);
+		RowSeg rs;
+		rs.nseg = m->nseg;
+		rs.ent_base = cls == CLS_VTX ? m->d_vbase : cls == CLS_FACE ? m->d_fbase : m->d_ebase;
+		rs.rowbase = dl.d_rowbase; rs.rownum = dl.d_rownum;
+		if (cls == CLS_VTX) HB_LAUNCH(ctx, k_elem_rows<CLS_VTX>, g, 256, 0, c, l, rs, dl.d_erow, dl.d_ek, ctx->d_err);
+		else if (cls == CLS_FACE) HB_LAUNCH(ctx, k_elem_rows<CLS_FACE>, g, 256, 0, c, l, rs, dl.d_erow, dl.d_ek, ctx->d_err);
+		else HB_LAUNCH(ctx, k_elem_rows<CLS_CORNER>, g, 256, 0, c, l, rs, dl.d_erow, dl.d_ek, ctx->d_err);
 		if (dl.d_ek) HB_TRY(hb_scan_exclusive_u32(ctx, dl.d_ek, dl.d_ek, n, nullptr));
 		if (decode && dl.d_emit_type)
 			HB_LAUNCH(ctx, k_owner_from_types, g, 256, 0, dl.d_erow, dl.d_ek, dl.d_emit_type, dl.emit_count, n, dl.d_first, ctx->d_err);
@@ -639,9 +701,10 @@ int hb_encode_lists(hb_dmesh *m)
 		HB_TRY(hb_dalloc_t(m, &dl.d_type, (size_t)n + 1));
 		HB_TRY(hb_dalloc_t(m, &dl.d_aux, (size_t)n + 1));
 		HB_TRY(hb_dalloc_t(m, &dl.d_sym, (size_t)n * p.sym_stride + 8));
-		HB_TRY(hb_dalloc_t(m, &dl.d_hist, (size_t)p.sym_stride * 256 + 4));
+		const size_t hist_pitch = (size_t)p.sym_stride * 256 + 4; // per segment: the contexts, then the four type counters
+		HB_TRY(hb_dalloc_t(m, &dl.d_hist, hist_pitch * m->nseg));
 		dl.d_type_hist = dl.d_hist + (size_t)p.sym_stride * 256;
-		HB_CUDA(ctx, cudaMemsetAsync(dl.d_hist, 0, sizeof(unsigned long long) * ((size_t)p.sym_stride * 256 + 4), ctx->stream));
+		HB_CUDA(ctx, cudaMemsetAsync(dl.d_hist, 0, sizeof(unsigned long long) * hist_pitch * m->nseg, ctx->stream));
 		if (!n) continue;
 		EncodeArgs a;
 		a.erow = dl.d_erow; a.ek = dl.d_ek; a.first = dl.d_first; a.dord = dl.d_dord;
@@ -653,9 +716,12 @@ int hb_encode_lists(hb_dmesh *m)
 		a.celem_h = m->d_celem_h; a.he = m->d_he;
 		a.type = dl.d_type; a.aux = dl.d_aux; a.sym = dl.d_sym; a.hist = dl.d_hist; a.type_hist = dl.d_type_hist;
 		a.n = n; a.l = l;
+		a.nseg = m->nseg;
+		a.elem_base = cls == CLS_VTX ? m->d_obase : cls == CLS_FACE ? m->d_ofbase : m->d_cebase;
+		a.hist_pitch = hist_pitch;
 		a.wide = nullptr; a.wide_cap = 0;
 		if (cls == CLS_VTX && p.ncomp) {
-			a.wide_cap = 4096;
+			a.wide_cap = 4096 + 4 * m->nseg;
 			HB_TRY(hb_dalloc_t(m, &dl.d_wide, (size_t)a.wide_cap + 1));
 			HB_CUDA(ctx, cudaMemsetAsync(dl.d_wide, 0, sizeof(uint32_t), ctx->stream));
 			a.wide = dl.d_wide;

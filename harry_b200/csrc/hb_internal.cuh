@@ -27,7 +27,7 @@ struct hb_ctx {
 	// host-buffer entry points upload on a second stream: the connectivity stages (K0, K3, K4) start as soon as
 	// their arrays have landed and run under the rest of the upload
 	cudaStream_t copy_stream = nullptr;
-	cudaEvent_t ev_alloc = nullptr, ev_up[2] = { nullptr, nullptr };
+	cudaStream_t out_stream = nullptr;  // device -> host copies of pipelined batches
 	cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	std::string err;
 	uint64_t launches = 0;
@@ -43,8 +43,21 @@ struct hb_ctx {
 };
 cudaEvent_t hb_prof_event(hb_ctx *ctx);
 
-struct SpecArgs;
-struct Spec3Scratch;
+// argument block of the vertex-reconstruction kernels (hb_decode_spec.cuh, hb_decode_scan.cuh): one per segment.
+// All indices are global (positions in the concatenated traversal order); a kernel works on [base, n).
+struct SpecArgs {
+	const uint8_t *kind;      // per rank: 0 skip, 1 DATA, 2 copy from src[i] (HIST)
+	const uint32_t *src;      // kind 2: owning rank
+	const uint32_t *cand_off; // n + 1
+	const uint32_t *cand;     // rank triples
+	const void *resid;        // compact records: residuals (read only)
+	void *x;                  // compact records: values (in/out)
+	uint32_t base;            // first rank of the segment
+	uint32_t n;               // end of the segment (exclusive)
+	int bits[4];              // quantization bits per component (prediction.h:22-25)
+	unsigned long long *stats; // [0] sweeps, [1] hypothesis sweeps, [2] plain sweeps (segment 0 only)
+	const void *srec;         // hb_decode_scan.cuh: one ScanRec per rank
+};
 struct ListParams {
 	uint8_t *rows;          // AoS rows in HBM (nrows * stride)
 	uint32_t nrows, stride;
@@ -58,8 +71,15 @@ struct ListParams {
 
 struct DevList {
 	ListParams p;
-	// bounds rows (dequantized layout, `stride` bytes each): min, max, scale
+	// bounds rows (dequantized layout, `stride` bytes each): min, max, scale -- one triple per segment (mesh of a
+	// batch), `bounds_pitch` bytes apart
 	uint8_t *d_bounds = nullptr;
+	size_t bounds_pitch = 0;
+	// segments: rows of mesh s are [rowbase[s], rowbase[s] + rownum[s]) of the concatenated list (bases padded to
+	// multiples of 16 rows, so that every segment starts on a 16-byte boundary whatever the stride)
+	std::vector<uint32_t> h_rowbase, h_rownum;
+	uint32_t *d_rowbase = nullptr, *d_rownum = nullptr;
+	std::vector<uint32_t> h_emitbase; // decode: offsets of the segments in the concatenated type-symbol stream
 	// encode outputs (device)
 	uint32_t n_elems = 0;       // elements of the list's target class (emission slots)
 	uint32_t n_emit = 0, n_data = 0;
@@ -78,25 +98,38 @@ struct DevList {
 	uint8_t *d_kind = nullptr;
 	uint32_t *d_src = nullptr;
 	uint8_t *d_cres = nullptr, *d_cx = nullptr; // compact residual / value records
-	struct SpecArgs *d_spec_args = nullptr;
+	SpecArgs *d_spec_args = nullptr;
 	unsigned long long *d_spec_stats = nullptr;
-	struct Spec3Scratch *d_spec3_scratch = nullptr;
-	uint32_t *d_spec3_excl = nullptr;
-	uint8_t *d_spec3_inner = nullptr;
 	void *d_srec = nullptr;             // hb_decode_scan.cuh records
 	uint32_t *d_wide = nullptr;         // encode: elements deferred to the warp-per-element kernel
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
+	uint8_t *d_done = nullptr;          // decode: corner wavefront flags
+	uint32_t *d_remaining = nullptr;
 	uint8_t *d_rows_backup = nullptr;   // hb_dmesh_snapshot
 	uint8_t backup_quant[HB_MAX_COMP];
 };
 
 struct hb_dmesh {
 	hb_ctx *ctx = nullptr;
+	// A device mesh is the concatenation of `nseg` independent meshes (a batch; nseg == 1 for a single mesh): vertices,
+	// faces, half-edges, traversal orders and attribute rows of segment s occupy [base[s], base[s + 1]) of the global
+	// index spaces.  Prediction never crosses a segment (a candidate needs vertices of the same connected component
+	// that were coded earlier), so every kernel behind the ingest kernels runs on the concatenation unchanged.
+	uint32_t nseg = 1;
+	std::vector<uint32_t> h_vbase, h_fbase, h_ebase, h_obase, h_ofbase; // nseg + 1 each
+	uint32_t *d_segtab = nullptr;                                        // the five tables, back to back
+	const uint32_t *d_vbase = nullptr, *d_fbase = nullptr, *d_ebase = nullptr, *d_obase = nullptr, *d_ofbase = nullptr;
+	uint32_t *d_cebase = nullptr;          // corner-element base per segment (computed on the device)
+	uint32_t *d_face_off_raw = nullptr;    // per-segment CSR offsets as uploaded (nseg > 1); d_face_off is the global CSR
+	std::vector<SpecArgs> h_spec_args; // kernel argument blocks staged for upload (kept until the mesh is freed)
 	uint32_t nv = 0, nf = 0, ne = 0, norder = 0, norder_f = 0;
 	uint16_t nb_face = 0, nb_vtx = 0, nb_corner = 0, nregs_face = 0, nregs_vtx = 0, nlists = 0;
 	bool has_order_f = false;
 	bool async_copy = false;     // uploads go to ctx->copy_stream (hb_attr_encode / hb_attr_decode)
+	bool alloc_on_copy_stream = false; // while the upload buffers are being allocated
+	cudaEvent_t ev_up[2] = { nullptr, nullptr }; // copy-stream milestones: connectivity landed / everything landed
+	cudaEvent_t ev_done = nullptr;               // kernels of this mesh / group finished (pipelined batches)
 	std::vector<void *> allocs;
 	// uploaded
 	uint8_t *d_edges_raw = nullptr;
@@ -126,8 +159,23 @@ struct hb_dmesh {
 	uint32_t *d_celem_h = nullptr;  // half-edge of corner element
 	bool conn_ready = false, vcand_ready = false, ccand_ready = false;
 	std::vector<DevList> lists;
+	void *d_walks = nullptr;            // decode: argument blocks of the generic chain walker
 	bool encoded = false;
 };
+
+// segment lookup: the s < nseg with base[s] <= x < base[s + 1] (empty segments are skipped)
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t hb_seg_find(const uint32_t *__restrict__ base, uint32_t nseg, uint32_t x)
+{
+	uint32_t lo = 0, hi = nseg;
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (__ldg(base + mid) <= x) lo = mid;
+		else hi = mid;
+	}
+	return lo;
+}
+#endif
 
 // error plumbing ---------------------------------------------------------------------------------
 int hb_fail(hb_ctx *ctx, int code, const char *fmt, ...);
@@ -175,7 +223,7 @@ int hb_build_corner_candidates(hb_dmesh *m); // cc_off / cc_idx
 int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp, bool decode);
 int hb_encode_lists(hb_dmesh *m);
 int hb_decode_lists(hb_dmesh *m);
-int hb_list_bounds(hb_dmesh *m, uint32_t l);
+int hb_list_bounds(hb_dmesh *m, uint32_t l, const uint8_t *groups /* or nullptr: min and max rows only */);
 int hb_list_scale(hb_dmesh *m, uint32_t l, const uint8_t *groups);
 int hb_list_requant(hb_dmesh *m, uint32_t l, const uint8_t *new_quant);
 void hb_fill_list_params(ListParams &p, const hb_list_desc &L);

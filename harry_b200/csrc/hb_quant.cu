@@ -7,6 +7,10 @@
 // for the usual all-float rows consecutive lanes touch consecutive 4-byte words (fully coalesced
 // 128-byte requests) even though the layout is AoS.  The thread count is a multiple of ncomp, so
 // each thread keeps one component for the whole grid-stride loop.
+//
+// Every kernel is segmented: blockIdx.y = segment (mesh of a batch, hb_internal.cuh), the rows of a
+// segment are [rowbase, rowbase + rownum) of the concatenated list, its bounds rows live at
+// bounds + segment * pitch.  A single mesh is one segment.
 #include "hb_internal.cuh"
 
 #include <float.h>
@@ -52,88 +56,25 @@ __device__ __forceinline__ unsigned long long seed_bits(int type, bool for_min)
 	}
 }
 
-// scratch per component: [0] min key, [1] max key, [2] first row holding -0.0, [3] first row holding +0.0
-__global__ void k_bounds_init(ListParams p, unsigned long long *__restrict__ scratch)
-{
-	const int j = threadIdx.x;
-	if (j >= p.ncomp) return;
-	scratch[4 * j + 0] = key_of(seed_bits(p.type[j], true), p.type[j]);
-	scratch[4 * j + 1] = key_of(seed_bits(p.type[j], false), p.type[j]);
-	scratch[4 * j + 2] = ~0ull;
-	scratch[4 * j + 3] = ~0ull;
-}
 
-__global__ void __launch_bounds__(256) k_bounds_reduce(ListParams p, unsigned long long *__restrict__ scratch, uint32_t rows_per_step)
-{
-	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t total_threads = rows_per_step * (uint32_t)p.ncomp;
-	const int j = (int)(tid % (uint32_t)p.ncomp);
-	const int type = p.type[j];
-	const int size = hb_type_size(type);
-	const bool is_fp = type == HB_FLOAT || type == HB_DOUBLE;
-	unsigned long long kmin = key_of(seed_bits(type, true), type), kmax = key_of(seed_bits(type, false), type);
-	unsigned long long zneg = ~0ull, zpos = ~0ull;
-	const uint8_t *base = p.rows + p.offset[j];
-	for (uint32_t row = tid < total_threads ? tid / (uint32_t)p.ncomp : p.nrows; row < p.nrows; row += rows_per_step) {
-		const unsigned long long bits = hb_ld_bits(base + (size_t)row * p.stride, size);
-		if (is_fp) {
-			// NaN never replaces a bound (both comparisons are false)
-			const bool nan = type == HB_FLOAT ? ((bits & 0x7fffffffu) > 0x7f800000u) : ((bits & 0x7fffffffffffffffull) > 0x7ff0000000000000ull);
-			if (nan) continue;
-			// -0.0 == +0.0 for the reference's `<`: remember which zero came first in row order
-			const unsigned long long mag = type == HB_FLOAT ? (bits & 0x7fffffffu) : (bits & 0x7fffffffffffffffull);
-			if (mag == 0) {
-				const bool neg = type == HB_FLOAT ? (bits >> 31) != 0 : (bits >> 63) != 0;
-				if (neg) zneg = zneg < row ? zneg : row;
-				else zpos = zpos < row ? zpos : row;
-			}
-		}
-		const unsigned long long k = key_of(bits, type);
-		kmin = k < kmin ? k : kmin;
-		kmax = k > kmax ? k : kmax;
-	}
-	// block-level combine in shared memory (one slot per component), then one global atomic per
-	// block and component instead of one per thread
-	__shared__ unsigned long long s_red[4 * HB_MAX_COMP];
-	for (int k = threadIdx.x; k < 4 * p.ncomp; k += blockDim.x) s_red[k] = (k & 3) == 1 ? 0ull : ~0ull;
-	__syncthreads();
-	atomicMin(&s_red[4 * j + 0], kmin);
-	atomicMax(&s_red[4 * j + 1], kmax);
-	if (zneg != ~0ull) atomicMin(&s_red[4 * j + 2], zneg);
-	if (zpos != ~0ull) atomicMin(&s_red[4 * j + 3], zpos);
-	__syncthreads();
-	for (int k = threadIdx.x; k < 4 * p.ncomp; k += blockDim.x) {
-		if ((k & 3) == 1) atomicMax(&scratch[k], s_red[k]);
-		else if (s_red[k] != ~0ull) atomicMin(&scratch[k], s_red[k]);
-	}
-}
+// Reduction scratch per (segment, component): four u64 words, ALL combined with atomicMax so that a zero-filled
+// buffer is the identity: [0] ~(smallest key), [1] largest key, [2] ~(first row holding -0.0), [3] ~(first row
+// holding +0.0).  Behind the words of a segment: one u32 ticket counter -- the last block of a segment to finish
+// writes the bounds rows (and the scale row when the interpretation groups are known): no init / finish kernels.
+struct BoundsSeg {
+	const uint32_t *rowbase, *rownum;
+	unsigned long long *scratch;   // [nseg][4 * ncomp]
+	uint32_t *ticket;              // [nseg]
+	uint8_t *bounds;               // [nseg] triples of rows, `pitch` bytes apart
+	size_t pitch;
+	uint8_t groups[HB_MAX_COMP];   // interpretation-group leader per component (quant.h:54-91)
+	int have_groups;
+	int *err;
+};
 
-// bounds rows: [0] min, [1] max, [2] scale -- `stride` bytes each, components at their row offsets
-__global__ void k_bounds_finish(ListParams p, const unsigned long long *__restrict__ scratch, uint8_t *__restrict__ bounds)
+// quant.h:46-96 for one segment (groups whose members share one type)
+__device__ void scale_segment(const ListParams &p, uint8_t *__restrict__ bounds, const uint8_t *groups, int *err)
 {
-	const int j = threadIdx.x;
-	if (j >= p.ncomp) return;
-	const int type = p.type[j];
-	const int size = hb_type_size(type);
-	unsigned long long mn = value_of(scratch[4 * j + 0], type);
-	const unsigned long long mx = value_of(scratch[4 * j + 1], type);
-	if (type == HB_FLOAT || type == HB_DOUBLE) {
-		// minimum is a zero: its sign is that of the first zero in row order (`e < cur` is false
-		// between -0.0 and +0.0, so a later zero never replaces an earlier one)
-		const unsigned long long mag = type == HB_FLOAT ? (mn & 0x7fffffffu) : (mn & 0x7fffffffffffffffull);
-		if (mag == 0) {
-			const bool neg_first = scratch[4 * j + 2] < scratch[4 * j + 3];
-			mn = neg_first ? (type == HB_FLOAT ? 0x80000000ull : 0x8000000000000000ull) : 0ull;
-		}
-	}
-	hb_st_bits(bounds + p.offset[j], size, mn);
-	hb_st_bits(bounds + p.stride + p.offset[j], size, mx);
-}
-
-// quant.h:46-96 for groups whose members share one type
-__global__ void k_scale(ListParams p, uint8_t *__restrict__ bounds, const uint8_t *__restrict__ groups, int *err)
-{
-	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	const uint8_t *mnr = bounds, *mxr = bounds + p.stride;
 	uint8_t *scr = bounds + 2 * (size_t)p.stride;
 	for (int k = 0; k < p.ncomp; ++k) {
@@ -183,6 +124,91 @@ __global__ void k_scale(ListParams p, uint8_t *__restrict__ bounds, const uint8_
 	}
 }
 
+// the block's partial results are in the scratch words: the last block of the segment turns them into rows
+// [0] min, [1] max (, [2] scale) -- `stride` bytes each, components at their row offsets
+__device__ void bounds_tail(const ListParams &p, const BoundsSeg &b, uint32_t seg, uint32_t blocks_per_seg)
+{
+	__shared__ uint32_t s_last;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		s_last = atomicAdd(&b.ticket[seg], 1u) == blocks_per_seg - 1 ? 1u : 0u;
+	}
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	volatile unsigned long long *sc = b.scratch + (size_t)seg * 4 * p.ncomp;
+	uint8_t *bounds = b.bounds + (size_t)seg * b.pitch;
+	if ((int)threadIdx.x < p.ncomp) {
+		const int j = threadIdx.x;
+		const int type = p.type[j];
+		const int size = hb_type_size(type);
+		unsigned long long mn = value_of(~sc[4 * j + 0], type);
+		const unsigned long long mx = value_of(sc[4 * j + 1], type);
+		if (type == HB_FLOAT || type == HB_DOUBLE) {
+			// minimum is a zero: its sign is that of the first zero in row order (`e < cur` is false
+			// between -0.0 and +0.0, so a later zero never replaces an earlier one)
+			const unsigned long long mag = type == HB_FLOAT ? (mn & 0x7fffffffu) : (mn & 0x7fffffffffffffffull);
+			if (mag == 0) {
+				const bool neg_first = ~sc[4 * j + 2] < ~sc[4 * j + 3];
+				mn = neg_first ? (type == HB_FLOAT ? 0x80000000ull : 0x8000000000000000ull) : 0ull;
+			}
+		}
+		hb_st_bits(bounds + p.offset[j], size, mn);
+		hb_st_bits(bounds + p.stride + p.offset[j], size, mx);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0 && b.have_groups) scale_segment(p, bounds, b.groups, b.err);
+}
+
+// generic runtime-typed reduction: one (row, component) scalar per thread and step
+__global__ void __launch_bounds__(256) k_bounds_reduce(ListParams p, BoundsSeg b, uint32_t rows_per_step)
+{
+	const uint32_t seg = blockIdx.y;
+	const uint32_t r0 = b.rowbase[seg], nrows = b.rownum[seg];
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t total_threads = rows_per_step * (uint32_t)p.ncomp;
+	const int j = (int)(tid % (uint32_t)p.ncomp);
+	const int type = p.type[j];
+	const int size = hb_type_size(type);
+	const bool is_fp = type == HB_FLOAT || type == HB_DOUBLE;
+	unsigned long long kmin = key_of(seed_bits(type, true), type), kmax = key_of(seed_bits(type, false), type);
+	unsigned long long zneg = ~0ull, zpos = ~0ull;
+	const uint8_t *base = p.rows + (size_t)r0 * p.stride + p.offset[j];
+	for (uint32_t row = tid < total_threads ? tid / (uint32_t)p.ncomp : nrows; row < nrows; row += rows_per_step) {
+		const unsigned long long bits = hb_ld_bits(base + (size_t)row * p.stride, size);
+		if (is_fp) {
+			// NaN never replaces a bound (both comparisons are false)
+			const bool nan = type == HB_FLOAT ? ((bits & 0x7fffffffu) > 0x7f800000u) : ((bits & 0x7fffffffffffffffull) > 0x7ff0000000000000ull);
+			if (nan) continue;
+			// -0.0 == +0.0 for the reference's `<`: remember which zero came first in row order
+			const unsigned long long mag = type == HB_FLOAT ? (bits & 0x7fffffffu) : (bits & 0x7fffffffffffffffull);
+			if (mag == 0) {
+				const bool neg = type == HB_FLOAT ? (bits >> 31) != 0 : (bits >> 63) != 0;
+				if (neg) zneg = zneg < row ? zneg : row;
+				else zpos = zpos < row ? zpos : row;
+			}
+		}
+		const unsigned long long k = key_of(bits, type);
+		kmin = k < kmin ? k : kmin;
+		kmax = k > kmax ? k : kmax;
+	}
+	// block-level combine in shared memory (one slot per component), then one global atomic per
+	// block and component instead of one per thread
+	__shared__ unsigned long long s_red[4 * HB_MAX_COMP];
+	for (int k = threadIdx.x; k < 4 * p.ncomp; k += blockDim.x) s_red[k] = 0ull;
+	__syncthreads();
+	atomicMax(&s_red[4 * j + 0], ~kmin);
+	atomicMax(&s_red[4 * j + 1], kmax);
+	if (zneg != ~0ull) atomicMax(&s_red[4 * j + 2], ~zneg);
+	if (zpos != ~0ull) atomicMax(&s_red[4 * j + 3], ~zpos);
+	__syncthreads();
+	unsigned long long *sc = b.scratch + (size_t)seg * 4 * p.ncomp;
+	for (int k = threadIdx.x; k < 4 * p.ncomp; k += blockDim.x)
+		if (s_red[k]) atomicMax(&sc[k], s_red[k]);
+	bounds_tail(p, b, seg, gridDim.x);
+}
+
 // quant.h:98-112, integer flavour, evaluated in T (narrow types compute in int and truncate)
 __device__ __forceinline__ unsigned long long rescale_int(int t, unsigned long long val, unsigned long long from, unsigned long long to)
 {
@@ -201,11 +227,19 @@ __device__ __forceinline__ unsigned long long rescale_int(int t, unsigned long l
 struct RequantParams {
 	uint8_t dq[HB_MAX_COMP]; // destination quantization bits per component
 };
+struct RequantSeg {
+	const uint32_t *rowbase, *rownum;
+	const uint8_t *bounds;
+	size_t pitch;
+};
 
 // quant.h:114-214 for every (row, component); four separately rounded float operations
 // (no FMA contraction), truncating float -> integer conversion.
-__global__ void __launch_bounds__(256) k_requant(ListParams p, RequantParams rq, const uint8_t *__restrict__ bounds, uint32_t rows_per_step)
+__global__ void __launch_bounds__(256) k_requant(ListParams p, RequantParams rq, RequantSeg sg_, uint32_t rows_per_step)
 {
+	const uint32_t seg = blockIdx.y;
+	const uint32_t r0 = sg_.rowbase[seg], nrows = sg_.rownum[seg];
+	const uint8_t *bounds = sg_.bounds + (size_t)seg * sg_.pitch;
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t total_threads = rows_per_step * (uint32_t)p.ncomp;
 	if (tid >= total_threads) return;
@@ -224,8 +258,8 @@ __global__ void __launch_bounds__(256) k_requant(ListParams p, RequantParams rq,
 	const float mn_f = __uint_as_float((uint32_t)mn_b), sc_f = __uint_as_float((uint32_t)sc_b);
 	const float m_dst_f = (float)(int32_t)m_dst, m_src_f = (float)(int32_t)m_src;
 	const bool sg = t == HB_LONG || t == HB_INT || t == HB_SHORT || t == HB_CHAR;
-	uint8_t *base = p.rows + p.offset[j];
-	for (uint32_t row = tid / (uint32_t)p.ncomp; row < p.nrows; row += rows_per_step) {
+	uint8_t *base = p.rows + (size_t)r0 * p.stride + p.offset[j];
+	for (uint32_t row = tid / (uint32_t)p.ncomp; row < nrows; row += rows_per_step) {
 		uint8_t *ptr = base + (size_t)row * p.stride;
 		unsigned long long q;
 		if (sq) {
@@ -253,10 +287,12 @@ __global__ void __launch_bounds__(256) k_requant(ListParams p, RequantParams rq,
 
 // ------------------------------------------------------------------------------------------------
 // Fast paths for the usual list: every component float32, rows tightly packed (stride == 4 * ncomp),
-// unquantized or at most 16 / 32 bits.  The AoS buffer is then one flat float array: 128-bit loads
-// and stores, four scalars per thread per step; the grid is a multiple of ncomp threads, so the
-// component of each of a thread's four lanes never changes.  Same arithmetic as the generic kernels.
+// unquantized or at most 31 bits.  The rows of a segment are then one flat float array that starts on a
+// 16-byte boundary: 128-bit loads and stores, FOUR independent vectors in flight per thread and step;
+// the threads of a segment are a multiple of ncomp, so the component of each of a thread's four lanes
+// never changes.  Same arithmetic as the generic kernels.
 // ------------------------------------------------------------------------------------------------
+#define FLAT_UNROLL 4
 static bool flat_f32(const ListParams &p)
 {
 	if (p.ncomp < 1 || p.ncomp > 4 || p.stride != 4u * (uint32_t)p.ncomp || (((size_t)p.rows) & 15u)) return false;
@@ -266,20 +302,22 @@ static bool flat_f32(const ListParams &p)
 }
 
 template <int NC>
-__global__ void __launch_bounds__(256) k_bounds_reduce_f32(const uint4 *__restrict__ rows4, const uint32_t *__restrict__ rows1, uint32_t nscal,
-                                                           unsigned long long *__restrict__ scratch)
+__global__ void __launch_bounds__(256) k_bounds_reduce_f32(ListParams p, BoundsSeg b)
 {
 	constexpr uint32_t ncomp = NC;
+	const uint32_t seg = blockIdx.y;
+	const uint32_t nscal = b.rownum[seg] * ncomp;
+	const uint4 *__restrict__ rows4 = (const uint4 *)(p.rows + (size_t)b.rowbase[seg] * p.stride);
+	const uint32_t *__restrict__ rows1 = (const uint32_t *)rows4;
 	const uint32_t G = gridDim.x * blockDim.x; // a multiple of ncomp
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t nvec = nscal >> 2;
-	uint32_t kmin[4], kmax[4], zneg[4], zpos[4], comp[4];
+	uint32_t kmin[4], kmax[4], zneg[4], zpos[4];
 #pragma unroll
 	for (int m = 0; m < 4; ++m) {
 		kmin[m] = 0x7f7fffffu ^ 0x80000000u;   // key of numeric_limits<float>::max()
 		kmax[m] = 0x00800000u ^ 0x80000000u;   // key of numeric_limits<float>::min() (quant.h:33)
 		zneg[m] = zpos[m] = 0xffffffffu;
-		comp[m] = (4u * tid + (uint32_t)m) % ncomp;
 	}
 	auto take = [&](int m, uint32_t bits, uint32_t e) {
 		if ((bits & 0x7fffffffu) > 0x7f800000u) return; // NaN never replaces a bound
@@ -292,71 +330,79 @@ __global__ void __launch_bounds__(256) k_bounds_reduce_f32(const uint4 *__restri
 		kmin[m] = min(kmin[m], k);
 		kmax[m] = max(kmax[m], k);
 	};
-	// two vectors in flight per thread and step
-	uint32_t v = tid;
-	for (; v + G < nvec; v += 2 * G) {
-		const uint4 q = rows4[v], q2 = rows4[v + G];
-		take(0, q.x, 4u * v); take(1, q.y, 4u * v + 1u); take(2, q.z, 4u * v + 2u); take(3, q.w, 4u * v + 3u);
-		const uint32_t e2 = 4u * (v + G);
-		take(0, q2.x, e2); take(1, q2.y, e2 + 1u); take(2, q2.z, e2 + 2u); take(3, q2.w, e2 + 3u);
+	for (uint32_t v = tid; v < nvec; v += FLAT_UNROLL * G) {
+		uint4 q[FLAT_UNROLL];
+#pragma unroll
+		for (int u = 0; u < FLAT_UNROLL; ++u) {
+			const uint32_t vv = v + (uint32_t)u * G;
+			q[u] = vv < nvec ? __ldcs(rows4 + vv) : make_uint4(0x7fc00000u, 0x7fc00000u, 0x7fc00000u, 0x7fc00000u); // NaN: ignored
+		}
+#pragma unroll
+		for (int u = 0; u < FLAT_UNROLL; ++u) {
+			const uint32_t e = 4u * (v + (uint32_t)u * G);
+			take(0, q[u].x, e); take(1, q[u].y, e + 1u); take(2, q[u].z, e + 2u); take(3, q[u].w, e + 3u);
+		}
 	}
-	if (v < nvec) {
-		const uint4 q = rows4[v];
-		take(0, q.x, 4u * v); take(1, q.y, 4u * v + 1u); take(2, q.z, 4u * v + 2u); take(3, q.w, 4u * v + 3u);
+	// per-component accumulators of this thread, then a shuffle reduction over the warp, one shared-memory
+	// slot per warp, and one set of global atomics per block
+	uint32_t amin[NC], amax[NC], azn[NC], azp[NC];
+#pragma unroll
+	for (int c = 0; c < NC; ++c) { amin[c] = 0xffffffffu; amax[c] = 0u; azn[c] = azp[c] = 0xffffffffu; }
+#pragma unroll
+	for (int m = 0; m < 4; ++m) {
+		const uint32_t j = (4u * tid + (uint32_t)m) % ncomp;
+#pragma unroll
+		for (int c = 0; c < NC; ++c)
+			if (j == (uint32_t)c) { amin[c] = min(amin[c], kmin[m]); amax[c] = max(amax[c], kmax[m]); azn[c] = min(azn[c], zneg[m]); azp[c] = min(azp[c], zpos[m]); }
 	}
-	__shared__ unsigned long long s_red[4 * 4];
-	if (threadIdx.x < 16) s_red[threadIdx.x] = (threadIdx.x & 3) == 1 ? 0ull : ~0ull;
-	__syncthreads();
-	// the up to three scalars behind the last full vector: one thread, component = index % ncomp
+	// the up to three scalars behind the last full vector
 	if (tid == 0) {
 		for (uint32_t e = nvec << 2; e < nscal; ++e) {
 			const uint32_t bits = rows1[e], j = e % ncomp, row = e / ncomp;
 			if ((bits & 0x7fffffffu) > 0x7f800000u) continue;
-			if ((bits & 0x7fffffffu) == 0u) atomicMin(&s_red[4 * j + ((bits >> 31) ? 2 : 3)], (unsigned long long)row);
 			const uint32_t k = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
-			atomicMin(&s_red[4 * j + 0], (unsigned long long)k);
-			atomicMax(&s_red[4 * j + 1], (unsigned long long)k);
+#pragma unroll
+			for (int c = 0; c < NC; ++c)
+				if (j == (uint32_t)c) {
+					if ((bits & 0x7fffffffu) == 0u) { if (bits >> 31) azn[c] = min(azn[c], row); else azp[c] = min(azp[c], row); }
+					amin[c] = min(amin[c], k); amax[c] = max(amax[c], k);
+				}
 		}
 	}
-	// warp-level combine first: lanes l and l + ncomp * x hold the same components only if 4 * 32 is a
-	// multiple of ncomp; keep it simple -- shared-memory atomics, 16 per thread at most, once per kernel
 #pragma unroll
-	for (int m = 0; m < 4; ++m) {
-		const uint32_t j = comp[m];
-		atomicMin(&s_red[4 * j + 0], (unsigned long long)kmin[m]);
-		atomicMax(&s_red[4 * j + 1], (unsigned long long)kmax[m]);
-		if (zneg[m] != 0xffffffffu) atomicMin(&s_red[4 * j + 2], (unsigned long long)zneg[m]);
-		if (zpos[m] != 0xffffffffu) atomicMin(&s_red[4 * j + 3], (unsigned long long)zpos[m]);
+	for (int c = 0; c < NC; ++c) {
+		amin[c] = __reduce_min_sync(0xffffffffu, amin[c]);
+		amax[c] = __reduce_max_sync(0xffffffffu, amax[c]);
+		azn[c] = __reduce_min_sync(0xffffffffu, azn[c]);
+		azp[c] = __reduce_min_sync(0xffffffffu, azp[c]);
+	}
+	__shared__ uint32_t s_w[8][4 * NC];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0) {
+#pragma unroll
+		for (int c = 0; c < NC; ++c) { s_w[warp][4 * c] = amin[c]; s_w[warp][4 * c + 1] = amax[c]; s_w[warp][4 * c + 2] = azn[c]; s_w[warp][4 * c + 3] = azp[c]; }
 	}
 	__syncthreads();
-	if (threadIdx.x < 4 * ncomp) {
+	if (threadIdx.x < 4 * NC) {
 		const uint32_t k = threadIdx.x;
-		if ((k & 3) == 1) atomicMax(&scratch[k], s_red[k]);
-		else if (s_red[k] != ~0ull) atomicMin(&scratch[k], s_red[k]);
+		uint32_t v = s_w[0][k];
+		for (int w = 1; w < 8; ++w) v = (k & 3) == 1 ? max(v, s_w[w][k]) : min(v, s_w[w][k]);
+		unsigned long long *sc = b.scratch + (size_t)seg * 4 * NC;
+		if ((k & 3) == 1) atomicMax(&sc[k], (unsigned long long)v);
+		else if ((k & 3) == 0) atomicMax(&sc[k], ~(unsigned long long)v);          // keys: 32-bit, stored as ~(u64)key
+		else if (v != 0xffffffffu) atomicMax(&sc[k], ~(unsigned long long)v);
 	}
+	bounds_tail(p, b, seg, gridDim.x);
 }
 
 struct FlatRequant {
-	float mn[4], sc[4], m_src[4], m_dst[4];
+	float m_src[4], m_dst[4];
 	uint32_t smask[4], dmask[4]; // low-byte masks of the source / destination storage type (0: the float itself)
 	uint8_t sq[4], dq[4];
 };
+struct FlatLane { float mn, sc, m_src, m_dst; uint32_t smask, dmask, sq, dq; };
 // one scalar: quant.h:135 (float -> fixed), :167-169 (fixed -> fixed), :182 (fixed -> float); the bytes of the
 // slot above the destination storage type keep their old contents
-__device__ __forceinline__ uint32_t requant_f32_one(uint32_t bits, const FlatRequant &r, int j)
-{
-	if (r.sq[j] == 0 && r.dq[j] == 0) return bits;
-	unsigned long long q;
-	if (r.sq[j]) q = bits & r.smask[j];
-	else q = (unsigned long long)__fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__uint_as_float(bits), r.mn[j]), r.sc[j]), r.m_dst[j]), 0.5f);
-	if (r.sq[j] && r.dq[j]) {
-		const unsigned long long ms = (unsigned long long)(long long)(int32_t)((1u << r.sq[j]) - 1u), md = (unsigned long long)(long long)(int32_t)((1u << r.dq[j]) - 1u);
-		q = q / ms * md + q % ms * md / ms;
-	}
-	if (r.dq[j]) return (bits & ~r.dmask[j]) | ((uint32_t)q & r.dmask[j]);
-	return __float_as_uint(__fadd_rn(__fmul_rn(__fdiv_rn((float)q, r.m_src[j]), r.sc[j]), r.mn[j]));
-}
-struct FlatLane { float mn, sc, m_src, m_dst; uint32_t smask, dmask, sq, dq; };
 __device__ __forceinline__ uint32_t requant_f32_lane(uint32_t bits, const FlatLane &r)
 {
 	if (r.sq == 0 && r.dq == 0) return bits;
@@ -370,10 +416,18 @@ __device__ __forceinline__ uint32_t requant_f32_lane(uint32_t bits, const FlatLa
 	if (r.dq) return (bits & ~r.dmask) | ((uint32_t)q & r.dmask);
 	return __float_as_uint(__fadd_rn(__fmul_rn(__fdiv_rn((float)q, r.m_src), r.sc), r.mn));
 }
-__global__ void __launch_bounds__(256) k_requant_f32(uint4 *__restrict__ rows4, uint32_t *__restrict__ rows1, uint32_t nscal, uint32_t ncomp, FlatRequant r, const float *__restrict__ bounds)
+// MODE 0: every component has its own source / destination quantization; 1: all components float -> the same number
+// of bits (the quantizer of `-q`); 2: all components the same number of bits -> float (requant(clear))
+template <int MODE>
+__global__ void __launch_bounds__(256) k_requant_f32(ListParams p, FlatRequant r, RequantSeg sg)
 {
-	// bounds rows (k_bounds_finish / k_scale): min at row 0, scale at row 2, `ncomp` floats each
-	for (uint32_t j = 0; j < ncomp; ++j) { r.mn[j] = bounds[j]; r.sc[j] = bounds[2 * ncomp + j]; }
+	const uint32_t seg = blockIdx.y;
+	const uint32_t ncomp = (uint32_t)p.ncomp;
+	const uint32_t nscal = sg.rownum[seg] * ncomp;
+	uint4 *__restrict__ rows4 = (uint4 *)(p.rows + (size_t)sg.rowbase[seg] * p.stride);
+	uint32_t *__restrict__ rows1 = (uint32_t *)rows4;
+	// bounds rows: min at row 0, scale at row 2, `ncomp` floats each
+	const float *__restrict__ bounds = (const float *)(sg.bounds + (size_t)seg * sg.pitch);
 	const uint32_t G = gridDim.x * blockDim.x; // a multiple of ncomp
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t nvec = nscal >> 2;
@@ -381,46 +435,77 @@ __global__ void __launch_bounds__(256) k_requant_f32(uint4 *__restrict__ rows4, 
 #pragma unroll
 	for (int m = 0; m < 4; ++m) {
 		const int j = (int)((4u * tid + (uint32_t)m) % ncomp);
-		L[m].mn = r.mn[j]; L[m].sc = r.sc[j]; L[m].m_src = r.m_src[j]; L[m].m_dst = r.m_dst[j];
-		L[m].smask = r.smask[j]; L[m].dmask = r.dmask[j]; L[m].sq = r.sq[j]; L[m].dq = r.dq[j];
+		L[m].mn = bounds[j]; L[m].sc = bounds[2 * ncomp + j];
+		const int ju = MODE == 0 ? j : 0;
+		L[m].m_src = r.m_src[ju]; L[m].m_dst = r.m_dst[ju];
+		L[m].smask = r.smask[ju]; L[m].dmask = r.dmask[ju]; L[m].sq = r.sq[ju]; L[m].dq = r.dq[ju];
 	}
-	uint32_t v = tid;
-	for (; v + G < nvec; v += 2 * G) {
-		uint4 q = rows4[v], q2 = rows4[v + G];
-		q.x = requant_f32_lane(q.x, L[0]); q.y = requant_f32_lane(q.y, L[1]); q.z = requant_f32_lane(q.z, L[2]); q.w = requant_f32_lane(q.w, L[3]);
-		q2.x = requant_f32_lane(q2.x, L[0]); q2.y = requant_f32_lane(q2.y, L[1]); q2.z = requant_f32_lane(q2.z, L[2]); q2.w = requant_f32_lane(q2.w, L[3]);
-		rows4[v] = q;
-		rows4[v + G] = q2;
-	}
-	if (v < nvec) {
-		uint4 q = rows4[v];
-		q.x = requant_f32_lane(q.x, L[0]); q.y = requant_f32_lane(q.y, L[1]); q.z = requant_f32_lane(q.z, L[2]); q.w = requant_f32_lane(q.w, L[3]);
-		rows4[v] = q;
+	auto one = [&](uint32_t bits, const FlatLane &l) -> uint32_t {
+		if (MODE == 1) {
+			const unsigned long long q = (unsigned long long)__fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__uint_as_float(bits), l.mn), l.sc), L[0].m_dst), 0.5f);
+			return (bits & ~L[0].dmask) | ((uint32_t)q & L[0].dmask);
+		}
+		if (MODE == 2) return __float_as_uint(__fadd_rn(__fmul_rn(__fdiv_rn((float)(unsigned long long)(bits & L[0].smask), L[0].m_src), l.sc), l.mn));
+		return requant_f32_lane(bits, l);
+	};
+	for (uint32_t v = tid; v < nvec; v += FLAT_UNROLL * G) {
+		uint4 q[FLAT_UNROLL];
+#pragma unroll
+		for (int u = 0; u < FLAT_UNROLL; ++u) {
+			const uint32_t vv = v + (uint32_t)u * G;
+			if (vv < nvec) q[u] = rows4[vv];
+		}
+#pragma unroll
+		for (int u = 0; u < FLAT_UNROLL; ++u) {
+			const uint32_t vv = v + (uint32_t)u * G;
+			if (vv < nvec) {
+				q[u].x = one(q[u].x, L[0]); q[u].y = one(q[u].y, L[1]); q[u].z = one(q[u].z, L[2]); q[u].w = one(q[u].w, L[3]);
+				rows4[vv] = q[u];
+			}
+		}
 	}
 	if (tid == 0)
-		for (uint32_t e = nvec << 2; e < nscal; ++e) rows1[e] = requant_f32_one(rows1[e], r, (int)(e % ncomp));
+		for (uint32_t e = nvec << 2; e < nscal; ++e) {
+			const int j = (int)(e % ncomp);
+			FlatLane l;
+			l.mn = bounds[j]; l.sc = bounds[2 * ncomp + j]; l.m_src = r.m_src[j]; l.m_dst = r.m_dst[j];
+			l.smask = r.smask[j]; l.dmask = r.dmask[j]; l.sq = r.sq[j]; l.dq = r.dq[j];
+			rows1[e] = requant_f32_lane(rows1[e], l);
+		}
 }
-// threads of a flat kernel: ~8 blocks of 256 per SM, a multiple of 256 * ncomp, not more than the work
-static uint32_t flat_blocks(hb_ctx *ctx, uint32_t nvec, uint32_t ncomp)
+
+// largest segment of the list (rows)
+static uint32_t max_seg_rows(const DevList &dl)
 {
-	uint32_t blocks = (uint32_t)ctx->sm_count * 8;
-	const uint32_t need = hb_div_up(nvec ? nvec : 1, 256);
+	uint32_t mx = 0;
+	for (uint32_t r : dl.h_rownum) mx = r > mx ? r : mx;
+	return mx;
+}
+
+// blocks per segment of a flat kernel: the whole grid (blocks * nseg) should be ~8 blocks of 256 per SM, a
+// multiple of ncomp per segment, not more than the work of the largest segment
+static uint32_t flat_blocks(hb_ctx *ctx, uint32_t nvec, uint32_t ncomp, uint32_t nseg)
+{
+	uint32_t blocks = hb_div_up((uint64_t)ctx->sm_count * 8, nseg);
+	const uint32_t need = hb_div_up(nvec ? nvec : 1, 256 * FLAT_UNROLL);
 	if (blocks > need) blocks = need;
+	if (blocks == 0) blocks = 1;
 	blocks = (blocks + ncomp - 1) / ncomp * ncomp;
 	return blocks;
 }
 
-static uint32_t pick_rows_per_step(hb_ctx *ctx, const ListParams &p)
+static uint32_t pick_rows_per_step(hb_ctx *ctx, const ListParams &p, uint32_t nrows, uint32_t nseg)
 {
-	// ~8 resident blocks of 256 threads per SM, rounded so that threads = rows_per_step * ncomp
-	const uint64_t want_threads = (uint64_t)ctx->sm_count * 8 * 256;
+	// ~8 resident blocks of 256 threads per SM over all segments, threads = rows_per_step * ncomp
+	const uint64_t want_threads = (uint64_t)ctx->sm_count * 8 * 256 / nseg + 256;
 	uint64_t rps = want_threads / (uint64_t)p.ncomp;
-	if (rps > p.nrows) rps = p.nrows;
+	if (rps > nrows) rps = nrows;
 	if (rps == 0) rps = 1;
 	return (uint32_t)rps;
 }
 
-int hb_list_bounds(hb_dmesh *m, uint32_t l)
+// set_bounds of every segment of list l; with `groups` the scale rows too (set_scale, quant.h:46-96)
+int hb_list_bounds(hb_dmesh *m, uint32_t l, const uint8_t *groups)
 {
 	hb_ctx *ctx = m->ctx;
 	DevList &dl = m->lists[l];
@@ -428,44 +513,56 @@ int hb_list_bounds(hb_dmesh *m, uint32_t l)
 	if (p.ncomp == 0) return 0;
 	for (int j = 0; j < p.ncomp; ++j)
 		if (p.quant[j]) return hb_fail(ctx, HB_ERR_INVALID, "set_bounds on a quantized list (the reference only calls it on unquantized data)");
+	const uint32_t nseg = m->nseg;
+	const size_t words = (size_t)nseg * 4 * p.ncomp;
 	unsigned long long *scratch = nullptr;
-	HB_CUDA(ctx, cudaMallocAsync((void **)&scratch, sizeof(unsigned long long) * 4 * HB_MAX_COMP, ctx->stream));
-	HB_LAUNCH(ctx, k_bounds_init, 1, HB_MAX_COMP, 0, p, scratch);
-	if (p.nrows && flat_f32(p) && (uint64_t)p.nrows * p.ncomp < 0xffffffffull) {
-		bool unq = true;
-		for (int j = 0; j < p.ncomp; ++j) unq = unq && p.quant[j] == 0;
-		if (unq) {
-			const uint32_t nscal = p.nrows * (uint32_t)p.ncomp;
-			const uint32_t fb = flat_blocks(ctx, nscal >> 2, (uint32_t)p.ncomp);
-			switch (p.ncomp) {
-			case 1: HB_LAUNCH(ctx, k_bounds_reduce_f32<1>, fb, 256, 0, (const uint4 *)p.rows, (const uint32_t *)p.rows, nscal, scratch); break;
-			case 2: HB_LAUNCH(ctx, k_bounds_reduce_f32<2>, fb, 256, 0, (const uint4 *)p.rows, (const uint32_t *)p.rows, nscal, scratch); break;
-			case 3: HB_LAUNCH(ctx, k_bounds_reduce_f32<3>, fb, 256, 0, (const uint4 *)p.rows, (const uint32_t *)p.rows, nscal, scratch); break;
-			default: HB_LAUNCH(ctx, k_bounds_reduce_f32<4>, fb, 256, 0, (const uint4 *)p.rows, (const uint32_t *)p.rows, nscal, scratch); break;
-			}
-		} else {
-			const uint32_t rps = pick_rows_per_step(ctx, p);
-			HB_LAUNCH(ctx, k_bounds_reduce, hb_div_up((uint64_t)rps * p.ncomp, 256), 256, 0, p, scratch, rps);
+	HB_CUDA(ctx, cudaMallocAsync((void **)&scratch, sizeof(unsigned long long) * words + sizeof(uint32_t) * nseg, ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * words + sizeof(uint32_t) * nseg, ctx->stream));
+	BoundsSeg b;
+	memset(&b, 0, sizeof b);
+	b.rowbase = dl.d_rowbase; b.rownum = dl.d_rownum;
+	b.scratch = scratch; b.ticket = (uint32_t *)(scratch + words);
+	b.bounds = dl.d_bounds; b.pitch = dl.bounds_pitch;
+	b.have_groups = groups != nullptr;
+	if (groups) memcpy(b.groups, groups, p.ncomp);
+	b.err = ctx->d_err;
+	const uint32_t mxrows = max_seg_rows(dl);
+	if (flat_f32(p) && (uint64_t)mxrows * p.ncomp < 0xffffffffull) {
+		const dim3 grid(flat_blocks(ctx, (mxrows * (uint32_t)p.ncomp) >> 2, (uint32_t)p.ncomp, nseg), nseg);
+		switch (p.ncomp) {
+		case 1: HB_LAUNCH(ctx, k_bounds_reduce_f32<1>, grid, 256, 0, p, b); break;
+		case 2: HB_LAUNCH(ctx, k_bounds_reduce_f32<2>, grid, 256, 0, p, b); break;
+		case 3: HB_LAUNCH(ctx, k_bounds_reduce_f32<3>, grid, 256, 0, p, b); break;
+		default: HB_LAUNCH(ctx, k_bounds_reduce_f32<4>, grid, 256, 0, p, b); break;
 		}
-	} else if (p.nrows) {
-		const uint32_t rps = pick_rows_per_step(ctx, p);
-		HB_LAUNCH(ctx, k_bounds_reduce, hb_div_up((uint64_t)rps * p.ncomp, 256), 256, 0, p, scratch, rps);
+	} else {
+		const uint32_t rps = pick_rows_per_step(ctx, p, mxrows, nseg);
+		const dim3 grid(hb_div_up((uint64_t)rps * p.ncomp, 256), nseg);
+		HB_LAUNCH(ctx, k_bounds_reduce, grid, 256, 0, p, b, rps);
 	}
-	HB_LAUNCH(ctx, k_bounds_finish, 1, HB_MAX_COMP, 0, p, scratch, dl.d_bounds);
 	HB_CUDA(ctx, cudaFreeAsync(scratch, ctx->stream));
 	return 0;
 }
 
+__global__ void k_scale(ListParams p, BoundsSeg b)
+{
+	if (threadIdx.x != 0) return;
+	scale_segment(p, b.bounds + (size_t)blockIdx.x * b.pitch, b.groups, b.err);
+}
+
+// set_scale alone (the bounds rows were supplied by the caller)
 int hb_list_scale(hb_dmesh *m, uint32_t l, const uint8_t *groups)
 {
 	hb_ctx *ctx = m->ctx;
 	DevList &dl = m->lists[l];
 	if (dl.p.ncomp == 0) return 0;
-	uint8_t *d_groups = nullptr;
-	HB_CUDA(ctx, cudaMallocAsync((void **)&d_groups, HB_MAX_COMP, ctx->stream));
-	HB_CUDA(ctx, cudaMemcpyAsync(d_groups, groups, dl.p.ncomp, cudaMemcpyHostToDevice, ctx->stream));
-	HB_LAUNCH(ctx, k_scale, 1, 32, 0, dl.p, dl.d_bounds, d_groups, ctx->d_err);
-	HB_CUDA(ctx, cudaFreeAsync(d_groups, ctx->stream));
+	BoundsSeg b;
+	memset(&b, 0, sizeof b);
+	b.bounds = dl.d_bounds; b.pitch = dl.bounds_pitch;
+	b.have_groups = 1;
+	memcpy(b.groups, groups, dl.p.ncomp);
+	b.err = ctx->d_err;
+	HB_LAUNCH(ctx, k_scale, m->nseg, 32, 0, dl.p, b);
 	return 0;
 }
 
@@ -485,11 +582,16 @@ int hb_list_requant(hb_dmesh *m, uint32_t l, const uint8_t *new_quant)
 		if (p.type[j] == HB_DOUBLE) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "requant: double lists (the reference shifts an int by >= 32 bits, undefined)");
 		if (p.quant[j] > 31 || new_quant[j] > 31) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "requant: more than 31 bits (the reference computes 1 << q in int, undefined)");
 	}
-	bool flat = any && p.nrows && flat_f32(p) && (uint64_t)p.nrows * p.ncomp < 0xffffffffull;
+	const uint32_t nseg = m->nseg;
+	const uint32_t mxrows = max_seg_rows(dl);
+	RequantSeg sg;
+	sg.rowbase = dl.d_rowbase; sg.rownum = dl.d_rownum; sg.bounds = dl.d_bounds; sg.pitch = dl.bounds_pitch;
+	bool flat = any && mxrows && flat_f32(p) && (uint64_t)mxrows * p.ncomp < 0xffffffffull;
 	for (int j = 0; flat && j < p.ncomp; ++j) flat = p.quant[j] <= 31 && new_quant[j] <= 31;
 	if (flat) {
 		FlatRequant fr;
 		memset(&fr, 0, sizeof fr);
+		bool uni_q = true, uni_d = true; // float -> one width / one width -> float
 		for (int j = 0; j < p.ncomp; ++j) {
 			const int sq = p.quant[j], dq = new_quant[j];
 			fr.sq[j] = (uint8_t)sq; fr.dq[j] = (uint8_t)dq;
@@ -497,12 +599,17 @@ int hb_list_requant(hb_dmesh *m, uint32_t l, const uint8_t *new_quant)
 			fr.m_dst[j] = dq ? (float)(int32_t)((1u << dq) - 1u) : 0.f;
 			fr.smask[j] = sq ? (sq <= 8 ? 0xffu : sq <= 16 ? 0xffffu : 0xffffffffu) : 0u;
 			fr.dmask[j] = dq ? (dq <= 8 ? 0xffu : dq <= 16 ? 0xffffu : 0xffffffffu) : 0u;
+			uni_q = uni_q && sq == 0 && dq != 0 && dq == new_quant[0];
+			uni_d = uni_d && dq == 0 && sq != 0 && sq == p.quant[0];
 		}
-		const uint32_t nscal = p.nrows * (uint32_t)p.ncomp;
-		HB_LAUNCH(ctx, k_requant_f32, flat_blocks(ctx, nscal >> 2, (uint32_t)p.ncomp), 256, 0, (uint4 *)p.rows, (uint32_t *)p.rows, nscal, (uint32_t)p.ncomp, fr, (const float *)dl.d_bounds);
-	} else if (any && p.nrows) {
-		const uint32_t rps = pick_rows_per_step(ctx, p);
-		HB_LAUNCH(ctx, k_requant, hb_div_up((uint64_t)rps * p.ncomp, 256), 256, 0, p, rq, dl.d_bounds, rps);
+		const dim3 grid(flat_blocks(ctx, (mxrows * (uint32_t)p.ncomp) >> 2, (uint32_t)p.ncomp, nseg), nseg);
+		if (uni_q) HB_LAUNCH(ctx, k_requant_f32<1>, grid, 256, 0, p, fr, sg);
+		else if (uni_d) HB_LAUNCH(ctx, k_requant_f32<2>, grid, 256, 0, p, fr, sg);
+		else HB_LAUNCH(ctx, k_requant_f32<0>, grid, 256, 0, p, fr, sg);
+	} else if (any && mxrows) {
+		const uint32_t rps = pick_rows_per_step(ctx, p, mxrows, nseg);
+		const dim3 grid(hb_div_up((uint64_t)rps * p.ncomp, 256), nseg);
+		HB_LAUNCH(ctx, k_requant, grid, 256, 0, p, rq, sg, rps);
 	}
 	for (int j = 0; j < p.ncomp; ++j) p.quant[j] = new_quant[j];
 	hb_list_desc tmp;

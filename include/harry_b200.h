@@ -156,6 +156,28 @@ typedef struct hb_streams {
 	hb_list_streams *lists;
 } hb_streams;
 
+/* Streams of a batch of meshes: mesh[i] are the streams of the i-th mesh; their arrays are views into page-locked
+ * blocks owned by this object (release everything with hb_batch_streams_free, never hb_streams_free on an entry). */
+typedef struct hb_batch_streams {
+	uint32_t n;
+	hb_streams *mesh;
+	void *priv;
+} hb_batch_streams;
+
+/* Quantization of one list of every mesh of a batch: what the reference does per mesh with
+ * quant::set_bounds (formats/ply/reader.cc:428) + quant::requant (main.cc:108, structs/quant.h:222-242). */
+typedef struct hb_quant_req {
+	uint32_t list;
+	uint8_t new_quant[HB_MAX_COMP]; /* target bits per component, 0 = leave it unquantized */
+	uint8_t groups[HB_MAX_COMP];    /* interpretation-group leader of every component (quant.h:54-91) */
+} hb_quant_req;
+/* requant(clear) of one list of every mesh: bounds = n * 3 rows (min, max, scale of mesh 0, of mesh 1, ...),
+ * `stride` bytes each, as read from the .hry headers + set_scale. */
+typedef struct hb_dequant_req {
+	uint32_t list;
+	const void *bounds;
+} hb_dequant_req;
+
 typedef struct hb_ctx hb_ctx;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -197,6 +219,23 @@ void hb_streams_free(hb_streams *s);
  * filled from the HIST/LHIST symbols.  Out: rows hold the reconstructed attribute values. */
 int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh);
 
+/* ---- batches of independent meshes (host buffers) -------------------------------------------
+ * BASELINE configs[4]; the reference processes one mesh per process (main.cc:93-122).  All meshes of a batch must
+ * share one schema (number of lists, their formats, region and binding tables); they differ in size and content.
+ * The library cuts the batch into groups, runs every stage ONCE per group over all its meshes (one launch per
+ * stage, no host synchronisation inside a stage) and overlaps upload, kernels and download of consecutive groups.
+ *
+ * hb_encode_batch   per mesh: set_bounds + set_scale + requant of the lists named in q[0..nq), then
+ *                   AttrCoder::encode.  bounds_out[k] (may be NULL) receives for request k the rows min, max, scale
+ *                   of mesh 0, mesh 1, ... (3 * stride bytes per mesh): the .hry header needs min and max.  The host
+ *                   rows are not modified (the quantized rows only exist on the device, as input of the coder).
+ * hb_decode_batch   per mesh: AttrDecoder::decode (lists[l].rows in: residual rows; out: values), then
+ *                   requant(clear) of the lists named in q[0..nq) -- their rows come back unquantized. */
+int hb_encode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t n, const hb_quant_req *q, uint32_t nq,
+                    void *const *bounds_out, hb_batch_streams **out);
+int hb_decode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t n, const hb_dequant_req *q, uint32_t nq);
+void hb_batch_streams_free(hb_batch_streams *b);
+
 /* ---- ingest: twin matching (host buffers) ------------------------------------------------ */
 /* Half-edge (f, e) = global index face_off[f] + e runs from its origin to the origin of the next corner
  * of f.  Matches half-edges of opposite direction on the same vertex pair exactly like the reference's
@@ -216,6 +255,10 @@ int hb_twin_match(hb_ctx *ctx, uint32_t nv, uint32_t nf, const uint32_t *face_of
  *      bench.py's kernel-only timing) ---------------------------------------------------- */
 typedef struct hb_dmesh hb_dmesh;
 int hb_dmesh_upload(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_dmesh **out);
+/* n meshes of one schema as ONE device mesh: every stage below then runs once over all of them.  Bounds rows are
+ * passed / returned for all meshes back to back (n * stride bytes per row kind). */
+int hb_dmesh_upload_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t n, hb_dmesh **out);
+uint32_t hb_dmesh_segments(hb_dmesh *m); /* number of meshes in the device mesh */
 void hb_dmesh_free(hb_dmesh *m);
 /* bounds + scale (per `groups`: component j shares the scale of component groups[j], the
  * interpretation-group leader, quant.h:54-91) + requant of list `l`, all on the device. */
@@ -226,9 +269,11 @@ int hb_dmesh_dequantize(hb_dmesh *m, uint32_t l);
 int hb_dmesh_set_bounds(hb_dmesh *m, uint32_t l, const void *min_row, const void *max_row, const void *scale_row);
 int hb_dmesh_fetch_bounds(hb_dmesh *m, uint32_t l, void *min_row, void *max_row, void *scale_row);
 int hb_dmesh_encode(hb_dmesh *m);                    /* kernels only, streams stay on the device */
-int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out);
+int hb_dmesh_fetch_streams(hb_dmesh *m, hb_streams **out);              /* single mesh */
+int hb_dmesh_fetch_streams_batch(hb_dmesh *m, hb_batch_streams **out);  /* one hb_streams per mesh */
 int hb_dmesh_decode(hb_dmesh *m);                    /* kernels only, rows reconstructed in place */
-int hb_dmesh_fetch_rows(hb_dmesh *m, uint32_t l, void *rows_out); /* nrows * stride bytes */
+int hb_dmesh_fetch_rows(hb_dmesh *m, uint32_t l, void *rows_out); /* nrows * stride bytes (mesh 0) */
+int hb_dmesh_fetch_rows_seg(hb_dmesh *m, uint32_t mesh, uint32_t l, void *rows_out);
 /* diagnostics of the speculative vertex reconstruction of list l (8 counters, see hb_api.cu) */
 int hb_dmesh_decode_stats(hb_dmesh *m, uint32_t l, uint64_t *out8);
 /* keep / restore a device copy of all rows + quantization state (stages work in place) */
