@@ -4,10 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            (ours;  N > 1 under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path)
 
-Workload (config.workload): N = 1 runs BASELINE.json configs[1], one synthetic 10M-vertex UV
-sphere (9 999 394 vertices, 19 998 784 triangles), positions quantized `-l1 -q14`, encode + decode.
+Workload (config.workload): BASELINE.json configs[1], one synthetic 10M-vertex UV sphere
+(9 999 394 vertices, 19 998 784 triangles), positions quantized `-l1 -q14`, encode + decode.
 With N > 1 every rank owns one such mesh (meshes are independent units: sharding by mesh, no
-collective, weak scaling).  One step = the whole hot path over the mesh:
+collective, weak scaling).  EVERY run (N = 1, 2, 4, 8) also measures BASELINE configs[4], the mesh
+batch (`batch` object: 1250 independent 100K-vertex meshes per GPU through the batched entry points,
+`value`, `e2e` and -- on rank 0 at N = 1 -- the reference on all host cores).  One step = the whole
+hot path over the mesh:
 
     encode side   set_bounds + set_scale + requant(q14)  ->  flatten / ranks / fan gather
                   ->  prediction + residual + byte-plane symbols + histograms
@@ -20,7 +23,10 @@ collective, weak scaling).  One step = the whole hot path over the mesh:
           inside the timed region.
 `roofline` for the kernel with the largest share of the step, from per-launch CUDA events.
 `cpu_baseline` the unmodified reference (oracle/_ref, compiled from /root/reference) timed on
-          one host core on a bounded sample of the same workload.
+          one host core on the SAME mesh (one step of the full workload, taken while the inputs are prepared).
+`cli`     wall clock and the reference's own phase prints of `oracle/_ref/harry` and the drop-in
+          `harry_b200/host/bin/harry_b200` on configs[1] (encode, decode -c), N = 1 only.
+`configs` device-resident / e2e lines for configs[0], [2], [3] with their dominant kernel, N = 1 only.
 
 Inputs are prepared (untimed) by the reference's own host code -- PLY reader, Cut-Border-Machine
 traversal, .hry writer/reader -- because those sequential stages are outside the GPU path.
@@ -77,6 +83,7 @@ class Workload:
         self.raw = rm.arrays()
         self.loq = [(1, -1, QBITS)]
         self.cpu_times = None
+        self.ply = ply
         if keep_ref:
             # time the reference's own functions on this mesh (one core)
             self.cpu_times = rm.time_path(self.loq)
@@ -108,8 +115,18 @@ class Workload:
         self.dec.emit_types = [ls.type for ls in st.lists]
         self.n_attrs = self.raw.n_attrs()
         self.nv, self.nf, self.ne = self.raw.nv, self.raw.nf, self.raw.ne
-        os.remove(ply)
         log(f"[bench] workload {nr}x{ns}: {self.nv} vertices, {self.nf} faces, {self.n_attrs} attrs, prepared in {time.time() - t0:.1f}s")
+
+    def cpu_baseline(self):
+        """The reference's own functions on THIS mesh, one core, one step (timed during the preparation)."""
+        t = self.cpu_times
+        enc_s = t[0] + t[1] + t[3]
+        dec_s = t[4] + t[5]
+        return {"value": self.n_attrs / (enc_s + dec_s) / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"one step of the full workload: UV sphere {self.nr}x{self.ns} ({self.nv} vertices, {self.n_attrs} attrs), -l1 -q{QBITS}; set_bounds {t[0]*1e3:.0f} ms + "
+                          f"requant {t[1]*1e3:.0f} ms + AttrCoder<NullWriter>::encode {t[3]*1e3:.0f} ms (vertices only: {t[2]*1e3:.0f} ms) + AttrDecoder<Replay>::decode {t[4]*1e3:.0f} ms + "
+                          f"requant(clear) {t[5]*1e3:.0f} ms; single thread (the reference is single-threaded per mesh)",
+                "encode_s": enc_s, "decode_s": dec_s}
 
 
     def _fallback(self, nr: int, ns: int):
@@ -234,7 +251,9 @@ def algorithmic_bytes(w: Workload) -> dict:
         "k_bounds_reduce": A * s,
         "k_bounds_reduce_f32<3>": A * s,
         "k_requant": A * (s + wd),
-        "k_requant_f32": A * (s + s),          # in place: the 4-byte slot is read and written (the quantized value sits in its low bytes)
+        "k_requant_f32<1>": A * (s + wd),      # s + w per attribute (the in-place kernel moves s + s: read-modify-write of the 4-byte slot)
+        "k_requant_f32<2>": A * (s + wd),
+        "k_requant_f32<0>": A * (s + wd),
         "(k_encode_vtx_packed<T, NC>)": k5,
         "k_vertex_candidates_stage": conn + 4.0 * nv + 12.0 * P * nv,
         "k_vertex_candidates_compact": 2 * 12.0 * P * nv + 4.0 * nv,
@@ -312,10 +331,32 @@ def pin_mesh(m: capi.MeshArrays) -> capi.MeshArrays:
     return m
 
 
+def allreduce_max(dist, local_rank, vals):
+    if dist is None:
+        return list(vals)
+    import torch
+    t = torch.tensor(list(vals), dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def kernel_table(prof, alg, peak, steps, total_ms):
+    kernels = {}
+    for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        k = {"launches_per_step": n / steps, "ms_per_step": ms / steps, "share_of_step": ms / total_ms if total_ms else None}
+        if alg.get(name):
+            k["GBps"] = alg[name] / (ms / n * 1e-3) / 1e9
+            k["frac_of_peak"] = k["GBps"] / peak
+        kernels[name] = k
+    return kernels
+
+
 def run_ours(args, rank: int, world: int, local_rank: int, dist):
     workdir = tempfile.mkdtemp(prefix="harry_bench_")
     nr, ns = (args.nr, args.ns) if args.nr else FULL
-    w = Workload(nr, ns, workdir)
+    import oracle_lib as ol
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu and ol.have_ref()
+    w = Workload(nr, ns, workdir, keep_ref=want_cpu)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx = capi.Context(local_rank)
@@ -359,12 +400,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     ctx.profile(False)
     clocks = sampler.stop()
     launches = ctx.launches() - launches0
-    total_ms = enc_ms + dec_ms
+    total_ms, enc_ms, dec_ms = allreduce_max(dist, local_rank, [enc_ms + dec_ms, enc_ms, dec_ms])
     if dist is not None:
-        import torch
-        t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, enc_ms, dec_ms = (float(x) for x in t.tolist())
         dist.barrier()
     ms_per_step = total_ms / args.steps
     value = world * w.n_attrs / (ms_per_step * 1e-3) / 1e6
@@ -386,110 +423,126 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     else:
         roof["achieved"] = None
         roof["frac"] = None
-    kernels = {}
-    for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-        k = {"launches_per_step": n / args.steps, "ms_per_step": ms / args.steps}
-        if alg.get(name):
-            k["GBps"] = alg[name] / (ms / n * 1e-3) / 1e9
-            k["frac_of_peak"] = k["GBps"] / peak
-        kernels[name] = k
+    if tname == "k_decode_vertex_scan":
+        roof["note"] = ("latency-bound dependency chain of ONE mesh (SURVEY 8d: reported as such, not hidden); the same kernel over a batch of "
+                        "meshes is in batch.kernels")
+    kernels = kernel_table(prof, alg, peak, args.steps, total_ms)
 
     # ---- end to end through the host-buffer C ABI (rank-local, pinned host memory) ----------
     e2e = None
     if not args.no_e2e:
-        hraw = pin_mesh(w.raw)
-        hdec = pin_mesh(w.dec)
-        pristine_raw = [la.rows.copy() for la in w.raw.lists]
-        pristine_dec = [la.rows.copy() for la in w.dec.lists]
-        n_e2e = max(1, min(args.steps, args.e2e_steps))
-        h2d = d2h = 0
-        t_e2e = 0.0
-        for it in range(n_e2e + 1):
-            for la, src in zip(hraw.lists, pristine_raw):
-                la.rows[...] = src
-                la.quants = [0] * la.ncomp
-            for la, src, ref in zip(hdec.lists, pristine_dec, w.dec.lists):
-                la.rows[...] = src
-                la.quants = list(ref.quants)
-            t0 = time.perf_counter()
-            la = hraw.lists[vl]
-            mn, mx = ctx.bounds(la)
-            sc = float_scale_row(la, mn, mx)
-            ctx.requant(la, w.new_quant[vl], mn, sc)
-            streams, release = ctx.attr_encode_view(hraw)   # the library's page-locked output buffers, as a C++ caller sees them
-            ctx.attr_decode(hdec)
-            ld = hdec.lists[vl]
-            ctx.requant(ld, [0] * ld.ncomp, w.dec_bounds[vl][0], w.dec_bounds[vl][2])
-            dt = time.perf_counter() - t0
-            if it == 0:      # warm-up
-                del streams
-                release()
-                continue
-            t_e2e += dt
-            if it == 1:
-                rows_b = la.rows.nbytes
-                conn_b = sum(getattr(hraw, n).nbytes for n in ("edges", "face_off", "order", "order_f", "vtx_regs", "face_regs", "bind_face", "bind_vtx"))
-                # hb_attr_decode of a mesh whose face / corner lists carry no components uploads no face-side arrays (target 1 == HB_VTX)
-                vertex_only = all(l.ncomp == 0 or l.nrows == 0 or l.target == 1 for l in hdec.lists)
-                dnames = ("edges", "face_off", "order", "vtx_regs", "bind_vtx") if vertex_only else ("edges", "face_off", "order", "vtx_regs", "face_regs", "bind_face", "bind_vtx")
-                dconn_b = sum(getattr(hdec, n).nbytes for n in dnames) + \
-                    (hdec.order_f.nbytes if hdec.order_f is not None and not vertex_only else 0)
-                h2d = rows_b * 2 + conn_b + rows_b + dconn_b + ld.rows.nbytes * 2 + sum(len(t) for t in w.dec.emit_types)
-                d2h = rows_b + ld.rows.nbytes * 2 + streams.nbytes_copied   # all-zero streams come back as NULL, not copied
-            del streams
-            release()
-        t_step = t_e2e / n_e2e
-        if dist is not None:
-            import torch
-            t = torch.tensor([t_step], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_step = float(t.item())
-        e2e = {"value": world * w.n_attrs / t_step / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": t_step * 1e3, "steps": n_e2e, "timer": "host wall clock around the synchronous C-ABI calls"}
-
-    # ---- CPU baseline: the unmodified reference on a bounded sample, one core ---------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        import oracle_lib as ol
-        if ol.have_ref():
-            cpu = reference_measure(SAMPLE if not args.nr else (args.nr, args.ns), workdir, steps=1)
-        else:
-            cpu = port_measure(SAMPLE if not args.nr else (args.nr, args.ns))
+        e2e = run_e2e(args, ctx, w, vl, dist, local_rank, world)
 
     E.close()
     D.close()
+    cpu = w.cpu_baseline() if want_cpu else None
     twin = None
     if world == 1 and not args.no_twin:
         try:
             twin = run_twin(ctx, w, peak, args.no_cpu)
         except Exception as e:  # the headline line must survive a failure of the extra measurement
             twin = {"error": repr(e)}
-    ctx.close()
+    n_attrs, nv, nf = w.n_attrs, w.nv, w.nf
+    ply, hry = w.ply, w.hry
+    del w, E, D
+    pinned_like.keep.clear()
+
+    # ---- BASELINE configs[4]: the mesh batch, on every rank at every N ------------------------------
     batch = None
-    if args.batch_meshes > 0 and world == 1:
-        import oracle_lib as ol
-        if ol.have_ref():
-            try:
-                batch = run_batch(local_rank, args.batch_meshes, args.batch_threads, 2, workdir)
-            except Exception as e:  # the headline line must survive a failure of the extra measurement
-                batch = {"error": repr(e)}
+    if args.batch_meshes > 0 and ol.have_ref():
+        try:
+            batch = run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak)
+        except Exception as e:  # the headline line must survive a failure of the extra measurement
+            import traceback
+            log(traceback.format_exc())
+            batch = {"error": repr(e)}
+    pinned_like.keep.clear()
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and ol.have_ref():
+        try:
+            configs = run_other_configs(ctx, workdir, peak)
+        except Exception as e:
+            configs = {"error": repr(e)}
+    ctx.close()
+    cli = None
+    if rank == 0 and world == 1 and not args.no_cli:
+        try:
+            cli = run_cli(ply, workdir, n_attrs)
+        except Exception as e:
+            cli = {"error": repr(e)}
+    for f in (ply, hry):
+        try:
+            os.remove(f)
+        except OSError:
+            pass
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16", "data": "synthetic",
-            "config": {"workload": f"configs[1]: UV sphere {nr}x{ns}, {w.nv} vertices / {w.nf} triangles per GPU, float32 xyz, -l1 -q{QBITS}, encode+decode",
+            "config": {"workload": f"configs[1]: UV sphere {nr}x{ns}, {nv} vertices / {nf} triangles per GPU, float32 xyz, -l1 -q{QBITS}, encode+decode",
                        "inputs_prepared_by": Workload.source,
-                       "vertex_attributes_per_gpu": w.n_attrs, "meshes": world, "parallelism": f"mesh-sharded x{world}, no collective",
-                       "l2": "inputs (>= 1.3 GB of connectivity + rows per mesh) exceed the 126 MB L2; no explicit flush"},
+                       "vertex_attributes_per_gpu": n_attrs, "meshes": world, "parallelism": f"mesh-sharded x{world}, no collective",
+                       "l2": "inputs (>= 1.3 GB of connectivity + rows per mesh) exceed the 126 MB L2; no explicit flush",
+                       "batch_config": "configs[4] (the mesh batch north_star scales on) is measured in the same run at every N: see `batch`"},
             "encode_ms_per_step": enc_ms / args.steps, "decode_ms_per_step": dec_ms / args.steps,
-            "encode_M_attrs_per_s": world * w.n_attrs / (enc_ms / args.steps * 1e-3) / 1e6 if enc_ms else None,
-            "decode_M_attrs_per_s": world * w.n_attrs / (dec_ms / args.steps * 1e-3) / 1e6 if dec_ms else None,
+            "encode_M_attrs_per_s": world * n_attrs / (enc_ms / args.steps * 1e-3) / 1e6 if enc_ms else None,
+            "decode_M_attrs_per_s": world * n_attrs / (dec_ms / args.steps * 1e-3) / 1e6 if dec_ms else None,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "kernels": kernels,
-            "cpu_baseline": cpu, "batch100k": batch, "twin_match": twin,
+            "cpu_baseline": cpu, "batch": batch, "cli": cli, "configs": configs, "twin_match": twin,
         }
         print(json.dumps(out), flush=True)
+
+
+def run_e2e(args, ctx, w, vl, dist, local_rank, world):
+    """configs[1] through the calls the drop-in adapter makes (hb_bounds, hb_requant, hb_attr_encode, hb_attr_decode,
+    hb_requant(clear)) on page-locked HOST buffers: every upload and download inside the timer, all `--steps` steps."""
+    hraw = pin_mesh(w.raw)
+    hdec = pin_mesh(w.dec)
+    pristine_raw = [la.rows.copy() for la in w.raw.lists]
+    pristine_dec = [la.rows.copy() for la in w.dec.lists]
+    n_e2e = max(1, args.steps)
+    h2d = d2h = 0
+    t_e2e = 0.0
+    for it in range(n_e2e + 1):
+        for la, src in zip(hraw.lists, pristine_raw):
+            la.rows[...] = src
+            la.quants = [0] * la.ncomp
+        for la, src, ref in zip(hdec.lists, pristine_dec, w.dec.lists):
+            la.rows[...] = src
+            la.quants = list(ref.quants)
+        t0 = time.perf_counter()
+        la = hraw.lists[vl]
+        mn, mx = ctx.bounds(la)
+        sc = float_scale_row(la, mn, mx)
+        ctx.requant(la, w.new_quant[vl], mn, sc)
+        streams, release = ctx.attr_encode_view(hraw)   # the library's page-locked output buffers, as a C++ caller sees them
+        ctx.attr_decode(hdec)
+        ld = hdec.lists[vl]
+        ctx.requant(ld, [0] * ld.ncomp, w.dec_bounds[vl][0], w.dec_bounds[vl][2])
+        dt = time.perf_counter() - t0
+        if it == 0:      # warm-up
+            del streams
+            release()
+            continue
+        t_e2e += dt
+        if it == 1:
+            rows_b = la.rows.nbytes
+            conn_b = sum(getattr(hraw, n).nbytes for n in ("edges", "face_off", "order", "order_f", "vtx_regs", "face_regs", "bind_face", "bind_vtx"))
+            # hb_attr_decode of a mesh whose face / corner lists carry no components uploads no face-side arrays (target 1 == HB_VTX)
+            vertex_only = all(l.ncomp == 0 or l.nrows == 0 or l.target == 1 for l in hdec.lists)
+            dnames = ("edges", "face_off", "order", "vtx_regs", "bind_vtx") if vertex_only else ("edges", "face_off", "order", "vtx_regs", "face_regs", "bind_face", "bind_vtx")
+            dconn_b = sum(getattr(hdec, n).nbytes for n in dnames) + \
+                (hdec.order_f.nbytes if hdec.order_f is not None and not vertex_only else 0)
+            h2d = rows_b * 2 + conn_b + rows_b + dconn_b + ld.rows.nbytes * 2 + sum(len(t) for t in w.dec.emit_types)
+            d2h = rows_b + ld.rows.nbytes * 2 + streams.nbytes_copied   # all-zero streams come back as NULL, not copied
+        del streams
+        release()
+    t_step = allreduce_max(dist, local_rank, [t_e2e / n_e2e])[0]
+    return {"value": world * w.n_attrs / t_step / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": t_step * 1e3, "steps": n_e2e, "timer": "host wall clock around the synchronous C-ABI calls",
+            "calls": "hb_bounds, hb_requant, hb_attr_encode, hb_attr_decode, hb_requant(clear) -- what the drop-in CLI adapter calls"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -555,75 +608,29 @@ def run_twin(ctx, w, peak: float, no_cpu: bool, reps: int = 3):
 
 
 # ----------------------------------------------------------------------------------------------
-# BASELINE configs[4]: batch of independent 100K-vertex meshes on one GPU (device resident)
+# BASELINE configs[4]: batch of independent 100K-vertex meshes (sharded by mesh: every rank its own batch)
 # ----------------------------------------------------------------------------------------------
-def run_batch(local_rank: int, n_meshes: int, n_threads: int, reps: int, workdir: str):
-    """Many independent meshes keep the whole GPU busy even though one mesh's vertex chain only
-    occupies one 8-SM cluster: one hb_ctx (= one CUDA stream) per host thread, meshes dealt round
-    robin to the threads (harry_b200/shard.py), no exchange of any kind."""
-    import concurrent.futures as cf
-    from harry_b200 import shard
-    distinct = min(n_meshes, 8)
-    loads = []
-    for k in range(distinct):
-        loads.append(BatchMesh(225, 447, 100 + k, workdir))
-    plan = shard.shard_plan(n_meshes, n_threads)
-    n_attrs = sum(loads[i % distinct].n_attrs for i in range(n_meshes))
-
-    def worker(tid):
-        ctx = capi.Context(local_rank)
-        mine = []
-        for i in plan[tid]:
-            bm = loads[i % distinct]
-            E = capi.DeviceMesh(ctx, bm.raw)
-            E.snapshot()
-            D = capi.DeviceMesh(ctx, bm.dec)
-            D.set_bounds(1, *bm.dec_bounds)
-            D.snapshot()
-            mine.append((bm, E, D))
-        ctx.sync()
-        return ctx, mine
-
-    with cf.ThreadPoolExecutor(n_threads) as pool:
-        states = list(pool.map(worker, range(n_threads)))
-
-        def run(st):
-            ctx, mine = st
-            for bm, E, D in mine:
-                E.restore()
-                D.restore()
-                E.quantize(1, bm.new_quant, bm.groups)
-                E.encode()
-                D.decode()
-                D.dequantize(1)
-            ctx.sync()
-
-        list(pool.map(run, states))              # warm-up
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            list(pool.map(run, states))
-        dt = (time.perf_counter() - t0) / reps
-    launches = sum(st[0].launches() for st in states)
-    for ctx, mine in states:
-        for _, E, D in mine:
-            E.close()
-            D.close()
-        ctx.close()
-    return {"value": n_attrs / dt / 1e6, "unit": UNIT, "meshes": n_meshes, "vertices_per_mesh": loads[0].nv, "host_threads": n_threads,
-            "ms_per_batch": dt * 1e3, "ms_per_mesh_amortized": dt * 1e3 / n_meshes, "distinct_meshes": distinct, "gpu_launches_total": int(launches),
-            "workload": "configs[4] shape: UV spheres 225x447 (100 130 vertices) with per-mesh seeded radial noise, -l1 -q14, encode+decode, device resident, "
-                        "timer: host wall clock around all threads + stream syncs"}
+BATCH_SHAPE = (225, 447)   # 100 130 vertices, 200 256 triangles
 
 
 class BatchMesh:
-    def __init__(self, nr, ns, seed, workdir):
+    """One mesh of the batch, prepared (untimed) by the reference's host code like the N = 1 workload."""
+
+    def __init__(self, nr, ns, seed, workdir, keep_ref=False):
         import oracle_lib as ol
-        ply = os.path.join(workdir, f"b_{seed}.ply")
+        ply = os.path.join(workdir, f"b_{os.getpid()}_{seed}.ply")
         meshgen.write_ply(ply, meshgen.uv_sphere(nr, ns, noise_seed=seed))
         rm = ol.RefMesh(ply)
         self.raw = rm.arrays()
-        rm.requant([(1, -1, QBITS)])
-        rm.traverse()
+        self.cpu_times = None
+        if keep_ref:
+            rm.snapshot()
+            rm.time_encode_step([(1, -1, QBITS)])      # warm-up (also runs the traversal once)
+            rm.restore()
+            self.cpu_times = rm.time_encode_step([(1, -1, QBITS)])
+        else:
+            rm.requant([(1, -1, QBITS)])
+            rm.traverse()
         enc = rm.arrays()
         self.new_quant = enc.lists[1].quants
         self.groups = self.raw.lists[1].groups
@@ -631,11 +638,19 @@ class BatchMesh:
         hry = ply + ".hry"
         rm.write(hry)
         rm.close()
+        if keep_ref:
+            rdec = ol.RefDecoder(hry)
+            rdec.step()
+            td = rdec.step()
+            rdec.close()
+            self.cpu_times[4], self.cpu_times[5] = td[4], td[5]
         rd = ol.RefMesh(hry)
         dec = rd.arrays()
         st = rd.logged_streams()
         rd.set_scale(1)
         self.dec_bounds = tuple(rd.bounds_row(1, w, dec.lists[1].stride) for w in (0, 1, 2))
+        rd.requant([], clear=True)
+        self.deq_rows = rd.arrays().lists[1].rows.copy()    # what the reference's `-c` decode yields
         rd.close()
         self.dec = dec.copy()
         self.dec.lists = capi.residual_rows_from_streams(dec, st)
@@ -646,34 +661,311 @@ class BatchMesh:
         os.remove(hry)
 
 
+def _batch_cpu_worker(a):
+    seed, workdir = a
+    bm = BatchMesh(*BATCH_SHAPE, seed, workdir, keep_ref=True)
+    t = bm.cpu_times
+    return bm.n_attrs, t[0] + t[1] + t[3] + t[4] + t[5]
+
+
+def batch_cpu_baseline(workdir):
+    """The reference on ALL host cores: one process per mesh (main.cc:93-122 is one mesh per process), disjoint meshes."""
+    import multiprocessing as mp
+    nproc = max(1, os.cpu_count() or 1)
+    nproc = min(nproc, 64)
+    with mp.get_context("spawn").Pool(nproc) as pool:
+        res = pool.map(_batch_cpu_worker, [(9000 + k, workdir) for k in range(nproc)])
+    rate = sum(n / t for n, t in res) / 1e6
+    return {"value": rate, "unit": UNIT, "cores": nproc, "kind": "reference",
+            "sample": f"{nproc} processes in parallel, one 100 130-vertex mesh each (disjoint seeds), one timed step after a warm-up step: set_bounds + requant + "
+                      f"AttrCoder<NullWriter>::encode + AttrDecoder<Replay>::decode + requant(clear); mean {1e3 * float(np.mean([t for _, t in res])):.0f} ms per mesh and core"}
+
+
+def run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak):
+    """configs[4] on this rank: `--batch-meshes` independent meshes (cycled from `--batch-distinct` prepared ones).
+    value: device resident -- `--batch-resident` meshes live in HBM as device meshes of one group each (one launch per
+    stage over the group); a step runs quantize + encode + decode + dequantize over every group, `passes` times.
+    e2e: hb_encode_batch + hb_decode_batch on page-locked host buffers, all meshes, uploads and downloads inside."""
+    import ctypes as C
+    n_meshes, distinct = args.batch_meshes, min(args.batch_distinct, args.batch_meshes)
+    t0 = time.time()
+    loads = [BatchMesh(*BATCH_SHAPE, 1000 * rank + 100 + k, workdir) for k in range(distinct)]
+    log(f"[bench] batch: {distinct} distinct meshes prepared in {time.time() - t0:.1f}s")
+    attrs_per_mesh = loads[0].n_attrs
+    ne_mesh = loads[0].raw.ne
+    group = max(1, min(n_meshes, int(args.batch_group_half_edges // max(1, ne_mesh))))
+    resident = min(n_meshes, max(group, args.batch_resident // group * group))
+    n_groups = resident // group
+    passes = max(1, round(n_meshes / resident))
+    n_value = passes * n_groups * group           # meshes per device-resident step
+    # ---- device resident ---------------------------------------------------------------------
+    Es, Ds = [], []
+    for g in range(n_groups):
+        idx = [(g * group + k) % distinct for k in range(group)]
+        E = capi.DeviceMesh(ctx, [loads[i].raw for i in idx])
+        E.snapshot()
+        D = capi.DeviceMesh(ctx, [loads[i].dec for i in idx])
+        D.set_bounds(1, *(np.stack([loads[i].dec_bounds[wh] for i in idx]) for wh in (0, 1, 2)))
+        D.snapshot()
+        Es.append(E)
+        Ds.append(D)
+    ctx.sync()
+    bm0 = loads[0]
+
+    def step():
+        ctx.mark(2)
+        for _ in range(passes):
+            for E, D in zip(Es, Ds):
+                E.restore()
+                D.restore()
+                E.quantize(1, bm0.new_quant, bm0.groups)
+                E.encode()
+                D.decode()
+                D.dequantize(1)
+        ctx.mark(3)
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    # parity spot check inside the bench: first and last mesh of the last group against the reference's decode
+    idx_last = [((n_groups - 1) * group + k) % distinct for k in range(group)]
+    for seg in (0, group - 1):
+        if not np.array_equal(Ds[-1].fetch_rows(1, seg), loads[idx_last[seg]].deq_rows):
+            raise RuntimeError("batch decode differs from the reference")
+    if dist is not None:
+        dist.barrier()
+    launches0 = ctx.launches()
+    ctx.profile(True)
+    ms = 0.0
+    for _ in range(args.steps):
+        step()
+        ms += ctx.elapsed(2, 3)
+    ctx.sync()
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    launches = ctx.launches() - launches0
+    ms = allreduce_max(dist, local_rank, [ms])[0]
+    if dist is not None:
+        dist.barrier()
+    ms_step = ms / args.steps
+    value = world * n_value * attrs_per_mesh / (ms_step * 1e-3) / 1e6
+    A = n_value * attrs_per_mesh
+    nvv, nee = n_value * bm0.nv, n_value * ne_mesh
+    alg = {"k_bounds_reduce_f32<3>": A * 4, "k_requant_f32<1>": A * 6, "k_requant_f32<2>": A * 6, "(k_encode_vtx_packed<T, NC>)": A * 12.0,
+           "k_decode_vertex_scan": A * 12.0, "k_flatten_halfedges": 28.0 * nee * 2, "k_vertex_candidates_stage": (16.0 * nee + 8.0 * nvv + 24.0 * nvv) * 2,
+           "k_vertex_candidates_compact": (48.0 * nvv + 4.0 * nvv) * 2, "k_scan_prep": (24.0 + 9.0 + 64.0) * nvv}
+    # per-launch figures: a kernel is launched passes * n_groups (* 2 for stages shared by encode and decode) times per step
+    kernels = {}
+    for name, (n, kms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        k = {"launches_per_step": n / args.steps, "ms_per_step": kms / args.steps, "share_of_step": kms / ms if ms else None}
+        if alg.get(name):
+            k["GBps"] = alg[name] / (kms / args.steps * 1e-3) / 1e9
+            k["frac_of_peak"] = k["GBps"] / peak
+        kernels[name] = k
+    for E, D in zip(Es, Ds):
+        E.close()
+        D.close()
+    del Es, Ds
+    out = {"value": value, "unit": UNIT, "ms_per_step": ms_step, "meshes_per_gpu_per_step": n_value, "vertices_per_mesh": bm0.nv, "attrs_per_mesh": attrs_per_mesh,
+           "meshes_per_launch": group, "resident_meshes": resident, "passes_per_step": passes, "distinct_meshes": distinct, "n_gpus": world,
+           "gpu_launches_per_step": launches / args.steps, "launches_per_mesh": launches / args.steps / n_value,
+           "ms_per_mesh_amortized": ms_step / n_value, "kernels": kernels,
+           "workload": f"configs[4]: UV spheres {BATCH_SHAPE[0]}x{BATCH_SHAPE[1]} (100 130 vertices) with per-mesh seeded radial noise, -l1 -q{QBITS}, encode+decode; "
+                       f"{n_value} meshes per GPU and step, sharded by mesh over {world} GPU(s), no collective",
+           "timer": "CUDA events on the library stream around each step, max over ranks"}
+    # ---- end to end: host buffers, pipelined groups ----------------------------------------------
+    if not args.no_e2e:
+        lib = ctx.lib
+        hraw = [pin_mesh(bm.raw) for bm in loads]
+        hdec = [pin_mesh(bm.dec) for bm in loads]
+        pristine = [bm.dec.lists[1].rows for bm in loads]
+        n_e2e = n_meshes
+        # decode works in place on the rows of every mesh: each of the n meshes gets its own page-locked row buffer
+        dec_meshes = []
+        for i in range(n_e2e):
+            m = hdec[i % distinct].copy()            # shares the connectivity arrays, owns its rows
+            m.lists[1].rows = pinned_like(pristine[i % distinct])
+            dec_meshes.append(m)
+        enc_descs = capi._desc_array([hraw[i % distinct] for i in range(n_e2e)])
+        dec_descs = capi._desc_array(dec_meshes)
+        req = (capi.QuantReq * 1)()
+        req[0].list = 1
+        for j, v in enumerate(bm0.new_quant):
+            req[0].new_quant[j] = v
+        for j, v in enumerate(bm0.groups):
+            req[0].groups[j] = v
+        stride = bm0.raw.lists[1].stride
+        bounds_out = pinned_like(np.zeros((n_e2e, 3, stride), np.uint8))
+        bptr = (C.c_void_p * 1)(bounds_out.ctypes.data)
+        dq_bounds = pinned_like(np.stack([np.stack(loads[i % distinct].dec_bounds) for i in range(n_e2e)]))
+        dreq = (capi.DequantReq * 1)()
+        dreq[0].list = 1
+        dreq[0].bounds = dq_bounds.ctypes.data
+        t_sum, d2h_streams = 0.0, 0
+        n_steps = max(1, min(args.steps, 5))
+        for it in range(n_steps + 1):
+            for i, m in enumerate(dec_meshes):       # fresh residual rows (untimed)
+                m.lists[1].rows[...] = pristine[i % distinct]
+            t0 = time.perf_counter()
+            bp = C.POINTER(capi.BatchStreams)()
+            ctx._check(lib.hb_encode_batch(ctx.h, enc_descs, n_e2e, req, 1, bptr, C.byref(bp)), "hb_encode_batch")
+            ctx._check(lib.hb_decode_batch(ctx.h, dec_descs, n_e2e, dreq, 1), "hb_decode_batch")
+            dt = time.perf_counter() - t0
+            if it == 1:
+                st = capi.streams_struct_to_py(bp.contents.mesh[n_e2e - 1], copy=False)
+                d2h_streams = st.nbytes_copied
+                if not np.array_equal(dec_meshes[n_e2e - 1].lists[1].rows, loads[(n_e2e - 1) % distinct].deq_rows):
+                    raise RuntimeError("hb_decode_batch differs from the reference")
+                del st
+            lib.hb_batch_streams_free(bp)
+            if it:
+                t_sum += dt
+        t_step = allreduce_max(dist, local_rank, [t_sum / n_steps])[0]
+        m0 = hraw[0]
+        up_enc = sum(getattr(m0, n).nbytes for n in ("edges", "face_off", "order", "order_f", "vtx_regs", "face_regs", "bind_face", "bind_vtx")) + m0.lists[1].rows.nbytes
+        d0 = hdec[0]
+        up_dec = sum(getattr(d0, n).nbytes for n in ("edges", "face_off", "order", "vtx_regs", "bind_vtx")) + d0.lists[1].rows.nbytes + sum(len(t) for t in loads[0].dec.emit_types) + 3 * stride
+        out["e2e"] = {"value": world * n_e2e * attrs_per_mesh / t_step / 1e6, "unit": UNIT, "ms_per_step": t_step * 1e3, "meshes_per_gpu_per_step": n_e2e, "steps": n_steps,
+                      "h2d_bytes_per_step": int(n_e2e * (up_enc + up_dec)), "d2h_bytes_per_step": int(n_e2e * (d2h_streams + 3 * stride + d0.lists[1].rows.nbytes)),
+                      "calls": "hb_encode_batch (set_bounds + set_scale + requant + encode) + hb_decode_batch (decode + requant(clear)), page-locked host buffers, "
+                               "groups of meshes pipelined over copy / compute / download streams",
+                      "timer": "host wall clock around the two synchronous C-ABI calls, max over ranks"}
+        del dec_meshes, hraw, hdec, bounds_out, dq_bounds
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = batch_cpu_baseline(workdir)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# the other BASELINE configs, one line each (N = 1): lossless float vertex lists, OBJ corner lists, polygons
+# ----------------------------------------------------------------------------------------------
+def run_other_configs(ctx, workdir, peak, reps=5):
+    import cases
+
+    def obj(d):
+        pth = os.path.join(d, "cfg3.obj")
+        meshgen.write_obj_latlong(pth, 400, 600)
+        return pth
+
+    todo = [
+        ("configs[0]: UV sphere 133x264 (34 850 vertices), lossless float32", (lambda d: cases._ply(d, "cfg1.ply", meshgen.uv_sphere(133, 264))), []),
+        ("configs[2]: OBJ lat-long sphere 401x600 (240 600 vertices, 480 000 triangles) with vt + vn corner lists, -l0 -q14 -l2 -q10", obj, [(0, -1, 14), (2, -1, 10)]),
+        ("configs[3]: polygon grid n=600 (tri / quad / 5- / 6-gons + non-manifold fin), per-vertex and per-face floats, lossless", (lambda d: cases._ply(d, "cfg4.ply", meshgen.poly_grid(600))), []),
+    ]
+    out = []
+    for title, gen, loq in todo:
+        c = cases.Case(workdir, "cfg_" + str(len(out)), gen, loq)
+        n_attrs = c.raw.n_attrs()
+        raw = c.raw.copy()
+        raw.order, raw.order_f, raw.edges = c.enc.order, c.enc.order_f, c.enc.edges
+        E = capi.DeviceMesh(ctx, raw)
+        E.snapshot()
+        din = c.decode_input()
+        D = capi.DeviceMesh(ctx, din)
+        for l, (mn, mx) in enumerate(c.dec_bounds):
+            if din.lists[l].ncomp:
+                D.set_bounds(l, mn, mx, c.deq_scale[l] if c.deq is not None else None)
+        D.snapshot()
+        qreq = [(l, c.enc.lists[l].quants, la.groups) for l, la in enumerate(raw.lists) if la.ncomp and c.enc.lists[l].quants != la.quants]
+
+        def step():
+            E.restore()
+            D.restore()
+            ctx.mark(2)
+            for l, nq, gr in qreq:
+                E.quantize(l, nq, gr)
+            E.encode()
+            ctx.mark(3)
+            D.decode()
+            for l, _, _ in qreq:
+                D.dequantize(l)
+            ctx.mark(4)
+
+        for _ in range(3):
+            step()
+        ok, why = E.fetch_streams().equal(c.enc_streams)
+        want = c.deq if c.deq is not None else c.dec
+        for l, la in enumerate(want.lists):
+            ok = ok and (la.ncomp == 0 or np.array_equal(D.fetch_rows(l), la.rows))
+        ctx.profile(True)
+        enc = dec = 0.0
+        for _ in range(reps):
+            step()
+            enc += ctx.elapsed(2, 3)
+            dec += ctx.elapsed(3, 4)
+        prof = ctx.profile_report()
+        ctx.profile(False)
+        top = max(prof.items(), key=lambda kv: kv[1][1])
+        E.close()
+        D.close()
+        # e2e: the adapter's calls on host buffers (pageable here: what the CLI passes)
+        t0 = time.perf_counter()
+        hr = raw.copy()
+        for l, nq, gr in qreq:
+            la = hr.lists[l]
+            mn, mx = ctx.bounds(la)
+            ctx.requant(la, nq, mn, c.raw_scale[l])
+        ctx.attr_encode(hr)
+        hd = c.decode_input()
+        ctx.attr_decode(hd)
+        for l, _, _ in qreq:
+            ctx.requant(hd.lists[l], [0] * hd.lists[l].ncomp, c.dec_bounds[l][0], c.deq_scale[l])
+        t_e2e = time.perf_counter() - t0
+        out.append({"workload": title, "vertex_attributes": n_attrs, "parity_vs_reference": bool(ok),
+                    "value": n_attrs / ((enc + dec) / reps * 1e-3) / 1e6, "unit": UNIT, "encode_ms": enc / reps, "decode_ms": dec / reps,
+                    "e2e_value": n_attrs / t_e2e / 1e6, "e2e_ms": t_e2e * 1e3,
+                    "dominant_kernel": {"name": top[0], "launches_per_step": top[1][0] / reps, "ms_per_step": top[1][1] / reps, "share_of_step": top[1][1] / (enc + dec)}})
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# SURVEY 8d(i): the CLIs side by side on configs[1] (main.cc:98-120 phase prints)
+# ----------------------------------------------------------------------------------------------
+def run_cli(ply, workdir, n_attrs):
+    import re
+    ref = os.path.join(ROOT, "oracle", "_ref", "harry")
+    ours = os.path.join(ROOT, "harry_b200", "host", "bin", "harry_b200")
+    if not (os.path.exists(ref) and os.path.exists(ours) and os.path.exists(ply)):
+        return {"unavailable": "CLI binaries (built from /root/reference in the build container) or the input are missing"}
+
+    def run(binary, a, b, flags):
+        t0 = time.perf_counter()
+        r = subprocess.run([binary, a, b] + flags, capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise RuntimeError(f"{binary} failed: {r.stderr[-300:]}")
+        phases = {}
+        for line in r.stdout.replace("\r", "\n").splitlines():
+            m = re.match(r"\s*(Reading input|Quantization|Writing output) took:?\s*([0-9.]+)", line)
+            if m:
+                phases[m.group(1)] = float(m.group(2))
+        return dt, phases
+
+    out = {"workload": "configs[1]: in.ply -> out.hry -l1 -q14, then out.hry -> back.ply -c", "unit": "s wall clock per process"}
+    files = {}
+    for name, binary in (("reference", ref), ("harry_b200", ours)):
+        hry = os.path.join(workdir, f"cli_{name}.hry")
+        back = os.path.join(workdir, f"cli_{name}.ply")
+        te, pe = run(binary, ply, hry, ["-l1", "-q14"])
+        td, pd = run(binary, hry, back, ["-c"])
+        out[name] = {"encode_s": te, "decode_s": td, "encode_phases": pe, "decode_phases": pd,
+                     "M_vertex_attributes_per_s": n_attrs / (te + td) / 1e6}
+        files[name] = (hry, back)
+    same = all(open(files["reference"][k], "rb").read() == open(files["harry_b200"][k], "rb").read() for k in (0, 1))
+    out["byte_identical_outputs"] = bool(same)
+    out["speedup_wall_clock"] = (out["reference"]["encode_s"] + out["reference"]["decode_s"]) / (out["harry_b200"]["encode_s"] + out["harry_b200"]["decode_s"])
+    for pair in files.values():
+        for f in pair:
+            os.remove(f)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle/_ref = the unmodified reference behind a C harness)
 # ----------------------------------------------------------------------------------------------
-def reference_measure(shape, workdir, steps=1):
-    import oracle_lib as ol
-    if not ol.have_ref():
-        raise RuntimeError("oracle/_ref/libharry_ref.so missing (built from /root/reference by __graft_entry__.build())")
-    nr, ns = shape
-    tot = np.zeros(6)
-    n_attrs = None
-    for _ in range(steps):
-        w = Workload(nr, ns, workdir, keep_ref=True)
-        tot += np.array(w.cpu_times)
-        n_attrs = w.n_attrs
-        nv = w.nv
-    t = tot / steps
-    enc_s = t[0] + t[1] + t[3]
-    dec_s = t[4] + t[5]
-    return {"value": n_attrs / (enc_s + dec_s) / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": f"UV sphere {nr}x{ns} ({nv} vertices, {n_attrs} attrs), -l1 -q{QBITS}; set_bounds {t[0]*1e3:.0f} ms + requant {t[1]*1e3:.0f} ms + "
-                      f"AttrCoder<NullWriter>::encode {t[3]*1e3:.0f} ms (vertices only: {t[2]*1e3:.0f} ms) + AttrDecoder<Replay>::decode {t[4]*1e3:.0f} ms + "
-                      f"requant(clear) {t[5]*1e3:.0f} ms; single thread (the reference is single-threaded per mesh)",
-            "encode_s": enc_s, "decode_s": dec_s}
-
-
 def port_measure(shape):
     """CPU baseline when the reference build is absent: the C restatement (oracle/harry_oracle.c),
-    one core, on the same bounded sample ("kind": "port")."""
+    one core, on a bounded sample ("kind": "port")."""
     import oracle_lib as ol
     from harry_b200 import flatten
     nr, ns = shape
@@ -698,51 +990,80 @@ def port_measure(shape):
 
 
 def _ref_worker(a):
-    shape, steps = a
+    """One process = one mesh of configs[1] (the reference is single-threaded per mesh): prepare ONCE, then time
+    `steps` steps of the path on that mesh (rows and formats restored between steps, untimed)."""
+    shape, steps, warmup, budget_s, seed = a
+    import oracle_lib as ol
     workdir = tempfile.mkdtemp(prefix="harry_ref_")
-    reference_measure(shape, workdir, 1)          # warm-up (page cache, allocator)
-    vals, res = [], None
-    t0 = time.time()
-    for k in range(steps):
-        res = reference_measure(shape, workdir, 1)
-        vals.append(res["value"])
-        if time.time() - t0 > 200:                 # keep the arm within a few minutes
+    nr, ns = shape
+    ply = os.path.join(workdir, f"ref_{os.getpid()}.ply")
+    meshgen.write_ply(ply, meshgen.uv_sphere(nr, ns))
+    rm = ol.RefMesh(ply)
+    os.remove(ply)
+    n_attrs, nv = rm.arrays().n_attrs(), 0
+    loq = [(1, -1, QBITS)]
+    rm.snapshot()
+    rm.time_encode_step(loq)                 # first pass: traversal (untimed part) + the quantized state the file needs
+    hry = os.path.join(workdir, "ref.hry")
+    rm.write(hry)
+    dec = ol.RefDecoder(hry)                 # (the file stays: every step reads its header again)
+    times, t_start = [], time.time()
+    for k in range(warmup + steps):
+        rm.restore()
+        t = rm.time_encode_step(loq)
+        td = dec.step()
+        t[4], t[5] = td[4], td[5]
+        if k >= warmup:
+            times.append(t)
+        if time.time() - t_start > budget_s and len(times) >= 1:
             break
-    return float(np.mean(vals)), len(vals), res
+    dec.close()
+    rm.close()
+    os.remove(hry)
+    tm = np.mean(np.array(times), axis=0)
+    return n_attrs, [float(x) for x in tm], len(times)
 
 
 def run_reference(args, rank: int, world: int):
-    """The reference's own CPU implementation of the path.  It is single-threaded per mesh; with
-    N > 1 (N independent meshes, one per GPU in our arm) it gets N host processes, one per mesh."""
+    """The reference's own CPU implementation of the path on the SAME config as our arm: configs[1], one mesh per GPU of
+    our arm = one host process per mesh here (the reference is single-threaded per mesh, main.cc:93-122)."""
     if rank != 0:
         return
-    shape = (args.nr, args.ns) if args.nr else SAMPLE
+    shape = (args.nr, args.ns) if args.nr else FULL
     import oracle_lib as ol
     if not ol.have_ref():
-        res = port_measure(shape)
+        res = port_measure(SAMPLE)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": 1,
                           "warmup": args.warmup, "ms_per_step": 1e3 * (res["encode_s"] + res["decode_s"]), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-                          "config": {"workload": "configs[1] shape, bounded sample: " + res["sample"], "parallelism": "1 host thread"},
+                          "config": {"workload": "configs[1] shape, bounded sample (oracle/_ref absent): " + res["sample"], "parallelism": "1 host thread"},
                           "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                           "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
     nproc = max(1, min(world, os.cpu_count() or 1))
+    warm = min(args.warmup, 1)
+    job = (shape, args.steps, warm, 150.0, 0)
     if nproc == 1:
-        results = [_ref_worker((shape, args.steps))]
+        results = [_ref_worker(job)]
     else:
         import multiprocessing as mp
         with mp.get_context("spawn").Pool(nproc) as pool:
-            results = pool.map(_ref_worker, [(shape, args.steps)] * nproc)
-    v = float(sum(r[0] for r in results)) * (world / nproc)
-    steps = min(r[1] for r in results)
-    res = results[0][2]
-    enc_dec_s = res["encode_s"] + res["decode_s"]
-    sample = res["sample"] + (f"; {nproc} processes, one mesh each" if nproc > 1 else "")
+            results = pool.map(_ref_worker, [job] * nproc)
+    n_attrs = results[0][0]
+    rates = [r[0] / (r[1][0] + r[1][1] + r[1][3] + r[1][4] + r[1][5]) / 1e6 for r in results]
+    v = float(sum(rates)) * (world / nproc)
+    steps = min(r[2] for r in results)
+    t = results[0][1]
+    step_s = t[0] + t[1] + t[3] + t[4] + t[5]
+    sample = (f"the full workload: UV sphere {shape[0]}x{shape[1]} ({n_attrs} attrs per mesh), -l1 -q{QBITS}, prepared once, {steps} timed step(s) per mesh; set_bounds {t[0]*1e3:.0f} ms + "
+              f"requant {t[1]*1e3:.0f} ms + AttrCoder<NullWriter>::encode {t[3]*1e3:.0f} ms + AttrDecoder<Replay>::decode {t[4]*1e3:.0f} ms + requant(clear) {t[5]*1e3:.0f} ms"
+              + (f"; {nproc} processes, one mesh each" if nproc > 1 else "; single thread (the reference is single-threaded per mesh)"))
     out = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": enc_dec_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": f"configs[1] shape, bounded sample: {sample}", "parallelism": f"{nproc} host process(es), one mesh each (the reference is single-threaded per mesh)"},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"configs[1]: UV sphere {shape[0]}x{shape[1]}, float32 xyz, -l1 -q{QBITS}, encode+decode (same mesh as the GPU arm)",
+                   "vertex_attributes_per_gpu": n_attrs, "meshes": world,
+                   "parallelism": f"{nproc} host process(es), one mesh each (the reference is single-threaded per mesh)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -761,9 +1082,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the extra measurement of hb_twin_match (SURVEY 8f row f2)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--batch-meshes", type=int, default=64, help="extra measurement: batch of independent 100K-vertex meshes (0 = skip)")
-    ap.add_argument("--batch-threads", type=int, default=8)
+    ap.add_argument("--no-cli", action="store_true", help="skip the side-by-side run of the two CLIs on configs[1]")
+    ap.add_argument("--no-configs", action="store_true", help="skip the lines for configs[0], [2], [3]")
+    ap.add_argument("--batch-meshes", type=int, default=1250, help="configs[4]: independent 100K-vertex meshes per GPU and step (0 = skip)")
+    ap.add_argument("--batch-distinct", type=int, default=16, help="distinct prepared meshes the batch cycles through")
+    ap.add_argument("--batch-resident", type=int, default=320, help="meshes kept resident in HBM for the device-resident batch value")
+    ap.add_argument("--batch-group-half-edges", type=int, default=48 << 20, help="half-edges per device mesh (group of meshes run by one launch per stage)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -203,6 +203,9 @@ struct ref_mesh {
 	std::vector<hb_list_desc> lists;
 	std::vector<int32_t> off_face, off_corner, off_vtx;
 	std::vector<std::vector<uint8_t>> groups;
+	/* ref_snapshot / ref_restore */
+	std::vector<std::vector<unsigned char>> snap_rows, snap_bounds;
+	std::vector<mixing::Fmt> snap_fmt;
 };
 
 extern "C" {
@@ -477,18 +480,90 @@ int ref_time_path(ref_mesh *rm, int n, const int *loq, double *times)
 	return 0;
 }
 
-/* decode side: read `hry_path` with the real decoder once (logging), then time (a) the real
+/* ---- several timed steps on ONE prepared mesh (bench.py --impl reference: prepare once, time K steps) ---- */
+/* The timed functions work in place: keep / restore a copy of all attribute rows, bounds rows and formats. */
+int ref_snapshot(ref_mesh *rm)
+{
+	rm->snap_rows.clear(); rm->snap_bounds.clear(); rm->snap_fmt.clear();
+	for (size_t l = 0; l < rm->mesh.attrs.size(); ++l) {
+		mesh::attr::Attr &a = rm->mesh.attrs[l];
+		rm->snap_rows.emplace_back(a.data(), a.data() + a.bytes());
+		rm->snap_bounds.emplace_back(a.bounds().data(), a.bounds().data() + a.bounds().bytes());
+		rm->snap_fmt.push_back(a.fmt());
+	}
+	return 0;
+}
+int ref_restore(ref_mesh *rm)
+{
+	if (rm->snap_rows.size() != rm->mesh.attrs.size()) { g_err = "restore without snapshot"; return -1; }
+	for (size_t l = 0; l < rm->mesh.attrs.size(); ++l) {
+		mesh::attr::Attr &a = rm->mesh.attrs[l];
+		a.tmp() = rm->snap_fmt[l];
+		a.restore_fmt();
+		if (a.bytes() != rm->snap_rows[l].size()) { g_err = "restore: list size changed"; return -1; }
+		if (a.bytes()) std::memcpy(a.data(), rm->snap_rows[l].data(), a.bytes());
+		if (a.bounds().bytes()) std::memcpy(a.bounds().data(), rm->snap_bounds[l].data(), a.bounds().bytes());
+	}
+	return 0;
+}
+/* encode side of one step: times[0] set_bounds, [1] requant(quantize), [3] AttrCoder<NullWriter>::encode (full);
+ * the Cut-Border-Machine traversal (outside the path) runs once, untimed, the first time */
+int ref_time_encode_step(ref_mesh *rm, int n, const int *loq, double *times)
+{
+	try {
+		double t0 = now_s();
+		quant::set_bounds(rm->mesh.attrs);
+		double t1 = now_s();
+		times[0] = t1 - t0;
+		if (ref_requant(rm, n, loq, 0)) return -1;
+		times[1] = now_s() - t1;
+		if (!rm->traversed && ref_traverse(rm)) return -1;
+		progress::voidhandle prog;
+		NullWriter nw;
+		hry::attrcode::AttrCoder<NullWriter> ac(rm->mesh, nw);
+		ac.order = rm->order;
+		ac.order_f = rm->order_f;
+		double a = now_s();
+		ac.encode(prog);
+		times[3] = now_s() - a;
+		times[2] = 0;
+	} catch (const std::exception &e) {
+		g_err = e.what();
+		return -1;
+	}
+	return 0;
+}
+
+/* decode side: `hry_path` is read with the real decoder once (logging); every step then times (a) the real
  * AttrDecoder fed from the logged streams on a fresh mesh with the same connectivity and (b)
  * quant::requant(clear).  times[4], times[5] as above. */
-int ref_time_decode(const char *hry_path, double *times)
+struct ref_decode_ctx {
+	ref_mesh *src;
+	std::string path;
+};
+ref_decode_ctx *ref_decode_open(const char *hry_path)
 {
 	ref_mesh *src = ref_read(hry_path);
-	if (!src) return -1;
+	if (!src) return nullptr;
+	ref_decode_ctx *c = new ref_decode_ctx();
+	c->src = src;
+	c->path = hry_path;
+	return c;
+}
+void ref_decode_close(ref_decode_ctx *c)
+{
+	if (!c) return;
+	ref_free(c->src);
+	delete c;
+}
+int ref_decode_step(ref_decode_ctx *c, double *times)
+{
+	ref_mesh *src = c->src;
 	int rc = 0;
 	try {
 		/* fresh mesh: header again, connectivity copied, attribute decode replayed */
 		ref_mesh dst;
-		std::ifstream is(hry_path, std::ifstream::binary);
+		std::ifstream is(c->path, std::ifstream::binary);
 		mesh::Builder builder(dst.mesh);
 		hry::reader::HeaderReader hr(is);
 		hr.read_syntax(builder);
@@ -516,7 +591,14 @@ int ref_time_decode(const char *hry_path, double *times)
 		g_err = e.what();
 		rc = -1;
 	}
-	ref_free(src);
+	return rc;
+}
+int ref_time_decode(const char *hry_path, double *times)
+{
+	ref_decode_ctx *c = ref_decode_open(hry_path);
+	if (!c) return -1;
+	const int rc = ref_decode_step(c, times);
+	ref_decode_close(c);
 	return rc;
 }
 

@@ -166,6 +166,15 @@ def ref():
         lib.ref_streams_free.restype = None
         lib.ref_time_path.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         lib.ref_time_decode.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
+        if hasattr(lib, "ref_snapshot"):     # several timed steps on one prepared mesh
+            lib.ref_snapshot.argtypes = [vp]
+            lib.ref_restore.argtypes = [vp]
+            lib.ref_time_encode_step.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+            lib.ref_decode_open.argtypes = [C.c_char_p]
+            lib.ref_decode_open.restype = vp
+            lib.ref_decode_close.argtypes = [vp]
+            lib.ref_decode_close.restype = None
+            lib.ref_decode_step.argtypes = [vp, C.POINTER(C.c_double)]
         if hasattr(lib, "ref_twin_match"):   # harness builds older than the twin matching row lack it
             lib.ref_twin_match.argtypes = [C.c_uint32, vp, vp, vp, C.POINTER(C.c_double)]
         _ref = lib
@@ -260,6 +269,47 @@ class RefMesh:
             rc = self.lib.ref_time_path(self.h, len(loq), arr, t)
         self._check(rc, "time_path")
         return list(t)
+
+
+    def snapshot(self):
+        self._check(self.lib.ref_snapshot(self.h), "snapshot")
+
+    def restore(self):
+        self._check(self.lib.ref_restore(self.h), "restore")
+
+    def time_encode_step(self, loq):
+        """[set_bounds, requant, 0, AttrCoder<NullWriter>::encode, 0, 0] seconds; works in place (restore() first)."""
+        flat = [int(x) for t in loq for x in t]
+        arr = (C.c_int * max(1, len(flat)))(*flat)
+        t = (C.c_double * 6)()
+        with quiet_stdout():
+            rc = self.lib.ref_time_encode_step(self.h, len(loq), arr, t)
+        self._check(rc, "time_encode_step")
+        return list(t)
+
+
+class RefDecoder:
+    """A .hry read once by the reference's decoder; step() times AttrDecoder<Replay>::decode + requant(clear)."""
+
+    def __init__(self, hry_path: str):
+        self.lib = ref()
+        with quiet_stdout():
+            self.h = self.lib.ref_decode_open(hry_path.encode())
+        if not self.h:
+            raise RuntimeError(f"ref_decode_open({hry_path}): {self.lib.ref_last_error().decode()}")
+
+    def step(self):
+        t = (C.c_double * 6)()
+        with quiet_stdout():
+            rc = self.lib.ref_decode_step(self.h, t)
+        if rc != 0:
+            raise RuntimeError(f"reference decode_step: {self.lib.ref_last_error().decode()}")
+        return list(t)
+
+    def close(self):
+        if self.h:
+            self.lib.ref_decode_close(self.h)
+            self.h = None
 
 
 def have_ref_twin() -> bool:
