@@ -407,11 +407,13 @@ __device__ __forceinline__ void paral_visit_t(const uint4 *__restrict__ he, uint
 // VC_WALK_CAP steps hands the vertex over to the wide path, which collects the vertex's half-edges
 // with one streaming pass, ranks the list by pointer doubling and evaluates the parallelograms of
 // all fan positions in parallel -- a 4472-face sphere pole costs one thread ~5 ms, the wide path
-// well under a millisecond.  More than VC_MAXWIDE such vertices: the rest walk sequentially.
+// well under a millisecond.  A batch of meshes has many such vertices (two poles per sphere): each registers a
+// slot, a per-vertex slot table routes the half-edges to their fan in the collecting pass.  More than VC_MAXWIDE
+// such vertices: the rest walk sequentially.
 #define VC_WALK_CAP 64
-#define VC_MAXWIDE 64
+#define VC_MAXWIDE 4096
 #define VC_WIDE_MARK 0xffffffffu
-#define VC_WIDE_ARENA (1u << 20)  // fan nodes of all wide vertices of one launch (split evenly between them)
+#define VC_WIDE_ARENA (1u << 21)  // fan nodes of all wide vertices of one launch (split evenly between them)
 struct WideCtl {
 	uint32_t n;                    // wide vertices registered (may exceed VC_MAXWIDE)
 	uint32_t per;                  // arena nodes per wide vertex
@@ -420,7 +422,8 @@ struct WideCtl {
 
 __global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ ord_v,
                                                                   const uint32_t *__restrict__ vrank, const uint16_t *__restrict__ vtx_regs, uint32_t n, uint32_t ne,
-                                                                  uint32_t *__restrict__ cnt, uint32_t *__restrict__ stage, WideCtl *__restrict__ wide, uint32_t walk_cap, int *err)
+                                                                  uint32_t *__restrict__ cnt, uint32_t *__restrict__ stage, WideCtl *__restrict__ wide, uint32_t *__restrict__ vslot,
+                                                                  uint32_t walk_cap, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -441,6 +444,7 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__
 		if (slot < VC_MAXWIDE) {
 			wide->vtx[slot] = ord_v[i];
 			wide->rank[slot] = i;
+			vslot[ord_v[i]] = slot;
 			cnt[i] = 0; // set by k_wide_rank
 			stage[(size_t)i * 3 * VC_STAGE] = VC_WIDE_MARK;
 			return;
@@ -490,26 +494,22 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_compact(const uint4 *
 // half-edges whose origin is a wide vertex: count per vertex (SCATTER = false), then scatter into
 // contiguous node lists and note every node's index (SCATTER = true)
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ he, uint32_t ne, WideCtl *__restrict__ wide, uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos)
+__global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ he, uint32_t ne, WideCtl *__restrict__ wide, const uint32_t *__restrict__ vslot,
+                                                      uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos)
 {
-	__shared__ uint32_t s_v[VC_MAXWIDE];
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
 	if (nw == 0) return; // the usual mesh: no wide fan, nothing to stream
 	const uint32_t cap_per_slot = wide->per;
-	if (threadIdx.x < nw) s_v[threadIdx.x] = wide->vtx[threadIdx.x];
-	__syncthreads();
 	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
-		const uint32_t org = he[e].x;
-		for (uint32_t w = 0; w < nw; ++w) {
-			if (org != s_v[w]) continue;
-			if (!SCATTER) atomicAdd(&wide->deg[w], 1u);
-			else {
-				const uint32_t k = atomicAdd(&wide->fill[w], 1u);
-				if (k >= cap_per_slot) continue; // fan larger than its share of the arena: k_wide_rank walks it sequentially
-				const uint32_t idx = wide->base[w] + k;
-				nodes[idx] = e;
-				pos[e] = idx;
-			}
+		const uint32_t w = vslot[he[e].x];
+		if (w == HB_NONE) continue;
+		if (!SCATTER) atomicAdd(&wide->deg[w], 1u);
+		else {
+			const uint32_t k = atomicAdd(&wide->fill[w], 1u);
+			if (k >= cap_per_slot) continue; // fan larger than its share of the arena: k_wide_rank walks it sequentially
+			const uint32_t idx = wide->base[w] + k;
+			nodes[idx] = e;
+			pos[e] = idx;
 		}
 	}
 }
@@ -518,14 +518,14 @@ __global__ void k_wide_even_bases(WideCtl *wide)
 {
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
 	const uint32_t per = VC_WIDE_ARENA / (nw ? nw : 1u);
-	wide->per = per;
-	for (uint32_t w = 0; w <= nw; ++w) wide->base[w] = w * per;
-	for (uint32_t w = 0; w < nw; ++w) wide->fill[w] = 0;
+	if (threadIdx.x == 0) wide->per = per;
+	for (uint32_t w = threadIdx.x; w <= nw; w += blockDim.x) wide->base[w] = w * per;
+	for (uint32_t w = threadIdx.x; w < nw; w += blockDim.x) wide->fill[w] = 0;
 }
 __global__ void k_wide_fill_to_deg(WideCtl *wide)
 {
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
-	for (uint32_t w = 0; w < nw; ++w) wide->deg[w] = wide->fill[w];
+	for (uint32_t w = threadIdx.x; w < nw; w += blockDim.x) wide->deg[w] = wide->fill[w];
 }
 
 // One CTA per wide vertex: rank its fan by pointer doubling (distance to the tail of the
@@ -758,10 +758,10 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 		HB_TRY(hb_dalloc(m, &m->d_vc_wide, sizeof(WideCtl)));
 		WideCtl *wide = (WideCtl *)m->d_vc_wide;
 		HB_CUDA(ctx, cudaMemsetAsync(wide, 0, sizeof(WideCtl), ctx->stream));
-		// a batch has many moderately wide fans (two poles per sphere): they are walked by their own thread; the
-		// pointer-doubling path is for the few huge fans of one big mesh
-		const uint32_t walk_cap = m->nseg > 1 ? 1024u : (uint32_t)VC_WALK_CAP;
-		HB_LAUNCH(ctx, k_vertex_candidates_stage, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, wide, walk_cap, ctx->d_err);
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_wslot, (size_t)m->nv + 1));
+		HB_CUDA(ctx, cudaMemsetAsync(m->d_vc_wslot, 0xff, sizeof(uint32_t) * ((size_t)m->nv + 1), ctx->stream));
+		HB_LAUNCH(ctx, k_vertex_candidates_stage, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, wide,
+		          m->d_vc_wslot, (uint32_t)VC_WALK_CAP, ctx->d_err);
 		const size_t cap = VC_WIDE_ARENA;
 		m->vc_wide_cap = (uint32_t)cap;
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_wpos, (size_t)m->ne + 1));
@@ -770,9 +770,9 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_worder, cap + 1));
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_warena, 6 * cap + 6));
 		uint32_t *nodes = m->d_vc_wnodes, *pos = m->d_vc_wpos, *work = m->d_vc_wwork, *order = m->d_vc_worder, *arena = m->d_vc_warena;
-		HB_LAUNCH(ctx, k_wide_even_bases, 1, 1, 0, wide);
-		HB_LAUNCH(ctx, k_wide_collect<true>, (uint32_t)ctx->sm_count * 8, 256, 0, m->d_he, m->ne, wide, nodes, pos);
-		HB_LAUNCH(ctx, k_wide_fill_to_deg, 1, 1, 0, wide);
+		HB_LAUNCH(ctx, k_wide_even_bases, 1, 256, 0, wide);
+		HB_LAUNCH(ctx, k_wide_collect<true>, (uint32_t)ctx->sm_count * 8, 256, 0, m->d_he, m->ne, wide, m->d_vc_wslot, nodes, pos);
+		HB_LAUNCH(ctx, k_wide_fill_to_deg, 1, 256, 0, wide);
 		HB_LAUNCH(ctx, k_wide_rank, VC_MAXWIDE, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + cap, work + 2 * cap, work + 3 * cap,
 		          work + 4 * cap, work + 5 * cap, order, arena, m->d_vc_off, stage, m->ne, ctx->d_err);
 		HB_TRY(hb_scan_exclusive_u32(ctx, m->d_vc_off, m->d_vc_off, n, nullptr));

@@ -18,43 +18,158 @@
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
-// VTX: chain walker
+// VTX: sequential walker for the lists the scan kernel does not take -- lossless float lists (the prediction picks
+// ONE candidate, `closest to the mean` in float arithmetic: no map algebra to compose) and lists with mixed or wide
+// storage types.  The chain x[i] = f(x[i - 1], older values) is walked in order by ONE thread per (segment, component)
+// -- components are independent chains -- but that thread only does the dependent arithmetic.  Its warp works as a
+// two-stage pipeline, 32 ranks per batch:
+//   PREPARE (all lanes, one rank each, one batch ahead): element kind, candidate triples, residual, and every operand
+//           value that is already final (from a shared-memory ring of the last WALK_RING values, else from L2), parked
+//           as a 128-byte work item in shared memory.  Its loads are in flight while lane 0 executes.
+//   EXECUTE (lane 0): the items of the current batch in order; only operands produced inside the last two batches are
+//           read at that point (from the ring).  get_prediction / decodeDelta exactly as in hb_lists.cuh.
 // ------------------------------------------------------------------------------------------------
 struct WalkArgs {
-	int ncomp;
-	uint8_t stype[HB_MAX_COMP], quant[HB_MAX_COMP];
+	int ncomp, comp;             // this chain reconstructs component `comp`
+	int stype, quant;
 	const uint32_t *erow, *first, *cand_off, *cand;
-	unsigned long long *rp;
+	unsigned long long *rp;      // rank-space containers, ncomp per element: residual in, value out
 	uint32_t base, n; // ranks [base, n) of one segment
 };
+#define WALK_RING 2048
+#define WALK_KIN 4
 
-__global__ void __launch_bounds__(32) k_decode_vertex_chain(const WalkArgs *__restrict__ args)
+// mean of the candidates and the prediction from it (attrcode.h:182-208), candidates given by `get(k)`; the division by
+// 1, 2 or 4 candidates is an exact scaling (same bits as the IEEE division, without its latency)
+template <typename Get>
+__device__ __forceinline__ unsigned long long walk_combine(int st, uint32_t K, Get &&get)
 {
-	const WalkArgs &a = args[blockIdx.x];
-	const int j = threadIdx.x;
-	if (j >= a.ncomp) return;
-	const int st = a.stype[j], q = a.quant[j], nc = a.ncomp;
-	const uint32_t n = a.n;
+	if (K == 0) return 0;
+	if (st == HB_FLOAT && (K == 1 || K == 2 || K == 4)) {
+		double sum = 0.0;
+		float p[4];
+#pragma unroll
+		for (uint32_t k = 0; k < 4; ++k)
+			if (k < K) { p[k] = __uint_as_float((uint32_t)get(k)); sum = __dadd_rn(sum, (double)p[k]); }
+		const float avg = __double2float_rn(__dmul_rn(sum, K == 1 ? 1.0 : (K == 2 ? 0.5 : 0.25)));
+		float res = FLT_MAX;
+#pragma unroll
+		for (uint32_t k = 0; k < 4; ++k)
+			if (k < K) res = hb_closest_step(res, p[k], avg);
+		return __float_as_uint(res);
+	}
+	return combine_candidates(st, K, get);
+}
+
+__global__ void __launch_bounds__(32) k_decode_vertex_walk(const WalkArgs *__restrict__ args)
+{
+	const WalkArgs a = args[blockIdx.x];
+	const uint32_t lane = threadIdx.x;
+	const int st = a.stype, q = a.quant, nc = a.ncomp, j = a.comp;
+	const uint32_t base = a.base, n = a.n;
 	const uint32_t *__restrict__ erow = a.erow, *__restrict__ first = a.first, *__restrict__ coff = a.cand_off, *__restrict__ cand = a.cand;
 	unsigned long long *rp = a.rp;
-	uint32_t c0 = a.base < n ? coff[a.base] : 0;
-	for (uint32_t i = a.base; i < n; ++i) {
-		const uint32_t c1 = coff[i + 1];
-		const uint32_t row = erow[i];
-		if (row != HB_NONE) {
-			const uint32_t fi = first[row];
-			if (fi != i) {
-				rp[(size_t)i * nc + j] = rp[(size_t)fi * nc + j]; // HIST reference: value already decoded
-			} else {
-				const uint32_t K = c1 - c0;
-				const unsigned long long pred = combine_candidates(st, K, [&](uint32_t kk) {
-					const uint32_t *tr = cand + 3 * (size_t)(c0 + kk);
-					return hb_predict(st, rp[(size_t)tr[0] * nc + j], rp[(size_t)tr[1] * nc + j], rp[(size_t)tr[2] * nc + j], q);
-				});
-				rp[(size_t)i * nc + j] = hb_dec(st, rp[(size_t)i * nc + j], pred, q);
+	__shared__ unsigned long long s_ring[WALK_RING];
+	__shared__ __align__(16) unsigned long long s_item[2][32][16];
+	if (base >= n) return;
+	auto ring = [&](uint32_t r) -> unsigned long long & { return s_ring[(r - base) & (WALK_RING - 1)]; };
+	// a final value: from the ring if it is still there (nothing at or behind `front` has been produced yet), else from L2
+	auto final_value = [&](uint32_t r, uint32_t front) -> unsigned long long {
+		if (r + WALK_RING >= front + 64) return ring(r);
+		return __ldcg(rp + (size_t)r * nc + j);
+	};
+	// registers of PREPARE between issue() and finish()
+	uint32_t p_kind = 0, p_K = 0, p_c0 = 0, p_late = 0, p_src = 0;
+	unsigned long long p_res = 0, p_op[3 * WALK_KIN];
+	// issue(b0): ranks [b0, b0 + 32); everything below `front` (the start of the batch that executes meanwhile) is final
+	auto issue = [&](uint32_t b0, uint32_t front) {
+		const uint32_t i = b0 + lane;
+		p_kind = 0; p_K = 0; p_late = 0; p_res = 0; p_src = 0; p_c0 = 0;
+		if (i >= n) return;
+		const uint32_t row = __ldg(erow + i);
+		if (row == HB_NONE) return;
+		const uint32_t fi = __ldg(first + row);
+		p_res = __ldcg(rp + (size_t)i * nc + j);
+		if (fi != i) { // HIST reference: the value of the owning element (attrcode.h:463-466)
+			p_kind = 2;
+			p_src = fi;
+			if (fi < front) { p_res = final_value(fi, front); p_kind = 0; }
+			else if (fi > i) p_kind = 0; // not emitted yet: rows start zeroed -- keeps what is there
+			return;
+		}
+		p_kind = 1;
+		p_c0 = __ldg(coff + i);
+		p_K = __ldg(coff + i + 1) - p_c0;
+		if (p_K > WALK_KIN) { p_kind = 3; return; }
+#pragma unroll
+		for (int w = 0; w < 3 * WALK_KIN; ++w) {
+			p_op[w] = 0;
+			if ((uint32_t)(w / 3) < p_K) {
+				const uint32_t r = __ldg(cand + 3 * (size_t)p_c0 + w);
+				if (r < front) p_op[w] = final_value(r, front);
+				else { p_late |= 1u << w; p_op[w] = r; }
 			}
 		}
-		c0 = c1;
+	};
+	auto finish = [&](uint32_t buf) {
+		unsigned long long *it = &s_item[buf][lane][0];
+		it[0] = (unsigned long long)(p_kind | (p_K << 2) | (p_late << 8)) | ((unsigned long long)(p_kind == 2 ? p_src : p_c0) << 32);
+		it[1] = p_res;
+		if (p_kind == 1) {
+#pragma unroll
+			for (int w = 0; w < 3 * WALK_KIN; ++w) it[2 + w] = p_op[w];
+		}
+	};
+	issue(base, base);
+	finish(0);
+	__syncwarp();
+	for (uint32_t b0 = base; b0 < n; b0 += 32) {
+		const uint32_t buf = ((b0 - base) >> 5) & 1u;
+		const bool more = b0 + 32 < n;
+		if (more) issue(b0 + 32, b0);
+		if (lane == 0) {
+			const uint32_t nl = min(32u, n - b0);
+#pragma unroll 1
+			for (uint32_t t = 0; t < nl; ++t) {
+				const unsigned long long *it = &s_item[buf][t][0];
+				const unsigned long long h = it[0];
+				const uint32_t kind = (uint32_t)h & 3u, K = ((uint32_t)h >> 2) & 0x3fu, late = ((uint32_t)h >> 8) & 0xfffu, aux = (uint32_t)(h >> 32);
+				const uint32_t i = b0 + t;
+				unsigned long long val = it[1];
+				if (kind == 1) {
+					const unsigned long long pred = walk_combine(st, K, [&](uint32_t k) -> unsigned long long {
+						unsigned long long v[3];
+#pragma unroll
+						for (int o = 0; o < 3; ++o) {
+							const unsigned long long x = it[2 + 3 * k + o];
+							v[o] = ((late >> (3 * k + o)) & 1u) ? ring((uint32_t)x) : x;
+						}
+						return hb_predict(st, v[0], v[1], v[2], q);
+					});
+					val = hb_dec(st, val, pred, q);
+				} else if (kind == 2) {
+					val = ring(aux); // owner inside the last two batches
+				} else if (kind == 3) {
+					// more candidates than an item holds (poles, closing vertices): straight from the CSR
+					const uint32_t Kf = __ldg(coff + i + 1) - aux;
+					const unsigned long long pred = combine_candidates(st, Kf, [&](uint32_t k) -> unsigned long long {
+						unsigned long long v[3];
+#pragma unroll
+						for (int o = 0; o < 3; ++o) {
+							const uint32_t r = __ldg(cand + 3 * (size_t)(aux + k) + o);
+							v[o] = r + WALK_RING > i ? ring(r) : __ldcg(rp + (size_t)r * nc + j);
+						}
+						return hb_predict(st, v[0], v[1], v[2], q);
+					});
+					val = hb_dec(st, val, pred, q);
+				}
+				ring(i) = val;
+				rp[(size_t)i * nc + j] = val;
+			}
+		}
+		__syncwarp();
+		if (more) finish(buf ^ 1u);
+		__syncwarp();
 	}
 }
 
@@ -160,7 +275,8 @@ static bool spec_eligible(const ListParams &p)
 {
 	if (p.ncomp < 1 || p.ncomp > 4) return false;
 	const int st = p.uniform_stype;
-	return st == HB_UCHAR || st == HB_USHORT || st == HB_UINT || st == HB_FLOAT;
+	static const bool float_spec = getenv("HARRY_B200_FLOAT_SPEC") != nullptr; // A/B switch: the chunk-parallel Jacobi kernel for float lists
+	return st == HB_UCHAR || st == HB_USHORT || st == HB_UINT || (st == HB_FLOAT && float_spec);
 }
 
 // reconstruct one vertex list with the speculative chunk-parallel kernel
@@ -317,11 +433,13 @@ int hb_decode_lists(hb_dmesh *m)
 		} else if (cls == CLS_VTX) {
 			WalkArgs w;
 			w.ncomp = p.ncomp;
-			for (int j = 0; j < p.ncomp; ++j) { w.stype[j] = p.stype[j]; w.quant[j] = p.quant[j]; }
 			w.erow = dl.d_erow; w.first = dl.d_first; w.cand_off = m->d_vc_off; w.cand = m->d_vc_tri; w.rp = dl.d_rp;
-			for (uint32_t sg = 0; sg < m->nseg; ++sg) { // one chain per segment (mesh of a batch)
+			for (uint32_t sg = 0; sg < m->nseg; ++sg) { // one chain per segment (mesh of a batch) and component
 				w.base = m->h_obase[sg]; w.n = m->h_obase[sg + 1];
-				walks.push_back(w);
+				for (int j = 0; j < p.ncomp; ++j) {
+					w.comp = j; w.stype = p.stype[j]; w.quant = p.quant[j];
+					walks.push_back(w);
+				}
 			}
 			walk_lists.push_back(l);
 		} else {
@@ -348,7 +466,7 @@ int hb_decode_lists(hb_dmesh *m)
 		HB_TRY(hb_dalloc(m, &m->d_walks, sizeof(WalkArgs) * walks.size()));
 		WalkArgs *d_walks = (WalkArgs *)m->d_walks;
 		HB_CUDA(ctx, cudaMemcpyAsync(d_walks, walks.data(), sizeof(WalkArgs) * walks.size(), cudaMemcpyHostToDevice, ctx->stream));
-		HB_LAUNCH(ctx, k_decode_vertex_chain, (uint32_t)walks.size(), 32, 0, d_walks); // (the pageable source was staged by the copy call)
+		HB_LAUNCH(ctx, k_decode_vertex_walk, (uint32_t)walks.size(), 32, 0, d_walks); // (the pageable source was staged by the copy call)
 		for (size_t k = 0; k < walk_lists.size(); ++k) {
 			DevList &dl = m->lists[walk_lists[k]];
 			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(dl.n_elems, 256), 256, 0, dl.p, dl.d_erow, dl.d_first, dl.n_elems, dl.d_rp);

@@ -153,6 +153,7 @@ struct hb_dmesh {
 	uint32_t n_corner_elems = 0;
 	uint32_t *d_vc_off = nullptr, *d_vc_tri = nullptr, *d_vc_stage = nullptr; uint32_t vc_total = 0;
 	void *d_vc_wide = nullptr;          // wide-fan control block and scratch (hb_conn.cu)
+	uint32_t *d_vc_wslot = nullptr;     // vertex -> wide slot
 	uint32_t *d_vc_wnodes = nullptr, *d_vc_wpos = nullptr, *d_vc_wwork = nullptr, *d_vc_worder = nullptr, *d_vc_warena = nullptr;
 	uint32_t vc_wide_cap = 0;
 	uint32_t *d_cc_off = nullptr, *d_cc_idx = nullptr; uint32_t cc_total = 0;

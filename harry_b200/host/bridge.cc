@@ -3,18 +3,37 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <future>
 
 namespace b200 {
 
 static hb_ctx *g_ctx = nullptr;
 
+// Creating the CUDA context takes 1-2 s in a fresh process -- as long as the whole attribute path of a 10M-vertex
+// mesh.  It starts on a helper thread when the program starts and runs under the file parsing (main.cc reads the
+// input first); the first GPU call joins it.  A failure (no device) surfaces at that first call, as before.
+struct Warmup {
+	std::future<int> done;
+	std::string error;
+	Warmup()
+	{
+		done = std::async(std::launch::async, [this]() -> int {
+			const char *dev = std::getenv("HARRY_B200_DEVICE");
+			const int rc = hb_ctx_create(dev ? std::atoi(dev) : 0, &g_ctx);
+			if (rc != 0) error = hb_last_error(nullptr);
+			return rc;
+		});
+	}
+};
+static Warmup g_warmup;
+
 hb_ctx *context()
 {
-	if (!g_ctx) {
-		const char *dev = std::getenv("HARRY_B200_DEVICE");
-		if (hb_ctx_create(dev ? std::atoi(dev) : 0, &g_ctx) != 0)
-			throw std::runtime_error(std::string("harry_b200: ") + hb_last_error(nullptr));
+	if (g_warmup.done.valid() && g_warmup.done.get() != 0) {
+		g_ctx = nullptr;
+		throw std::runtime_error(std::string("harry_b200: ") + g_warmup.error);
 	}
+	if (!g_ctx) throw std::runtime_error(std::string("harry_b200: ") + (g_warmup.error.empty() ? "no context" : g_warmup.error));
 	return g_ctx;
 }
 
