@@ -1104,7 +1104,7 @@ extern "C" int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh)
 
 // ------------------------------------------------------------------------------------------------
 // Batches of independent meshes on host buffers (BASELINE configs[4]; the reference runs one process per mesh,
-// main.cc:93-122).  The batch is cut into groups of meshes (about HB_GROUP_HALF_EDGES half-edges each); every group
+// main.cc:93-122).  The batch is cut into groups of meshes (about 120M half-edges each, HARRY_B200_GROUP_HALF_EDGES); every group
 // is one device mesh (one launch per stage over all its meshes).  Software pipeline over the groups:
 //   copy stream     upload of group g + 1
 //   compute stream  kernels of group g (wait for its upload only)
@@ -1115,7 +1115,7 @@ static uint64_t group_half_edges()
 {
 	const char *env = getenv("HARRY_B200_GROUP_HALF_EDGES"); // read per call: tests force many small groups
 	const uint64_t v = env ? strtoull(env, nullptr, 10) : 0;
-	return v ? v : (uint64_t)48 << 20;
+	return v ? v : (uint64_t)120 << 20; // ~200 meshes of 100K vertices: 600 (mesh, component) chains = four per SM in the scan decoder
 }
 static void make_groups(const hb_mesh_desc *meshes, uint32_t n, std::vector<uint32_t> &starts)
 {

@@ -235,12 +235,12 @@ static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, uint32_t 
 }
 
 // cluster launch of the verified-scan kernel (integer lists): one cluster per component
-template <typename T>
-static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster, uint32_t nseg)
+template <typename T, int NTB>
+static int launch_scan_ntb(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster, uint32_t nseg)
 {
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((uint32_t)cluster * (uint32_t)ncomp * nseg); // one cluster per (segment, component)
-	cfg.blockDim = dim3(SCAN_NTB);
+	cfg.blockDim = dim3(NTB);
 	cfg.dynamicSmemBytes = 0;
 	cfg.stream = ctx->stream;
 	cudaLaunchAttribute attr[1];
@@ -250,22 +250,40 @@ static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int clust
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	if (cluster > 8) HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_scan<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	if (cluster > 8) HB_CUDA(ctx, cudaFuncSetAttribute((k_decode_vertex_scan<T, NTB>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 	cudaEvent_t pa = nullptr, pb = nullptr;
 	if (ctx->profiling) { pa = hb_prof_event(ctx); pb = hb_prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
-	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_decode_vertex_scan<T>, d_args, (uint32_t)ncomp));
+	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, (k_decode_vertex_scan<T, NTB>), d_args, (uint32_t)ncomp));
 	ctx->launches++;
 	if (pa) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back(hb_ctx::ProfRec{ "k_decode_vertex_scan", pa, pb }); }
 	return 0;
 }
+static int scan_ntb(uint32_t chains, int sm_count)
+{
+	static const char *env = getenv("HARRY_B200_SCAN_NTB");
+	if (env && (atoi(env) == 128 || atoi(env) == 256 || atoi(env) == 512)) return atoi(env);
+	// the fixed cost of a sweep (two dependent memory round trips, four barriers, ~1000 dependent instructions) barely
+	// depends on the window length: the more chains an SM holds, the better it hides it (measured, 197 spheres of 100K
+	// vertices: 512 threads 8.3 ms per 196 meshes, 256: 6.3 ms, 128: 5.1 ms)
+	if (chains >= 4u * (uint32_t)sm_count - 4u) return 128;
+	return chains >= 2u * (uint32_t)sm_count - 2u ? 256 : 512;
+}
+template <typename T>
+static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster, uint32_t nseg, int ntb)
+{
+	if (ntb == 128) return launch_scan_ntb<T, 128>(ctx, ncomp, d_args, cluster, nseg);
+	if (ntb == 256) return launch_scan_ntb<T, 256>(ctx, ncomp, d_args, cluster, nseg);
+	return launch_scan_ntb<T, 512>(ctx, ncomp, d_args, cluster, nseg);
+}
 // CTAs per cluster: the window is about one cut-border length (~ sqrt(2 n) on a regular mesh);
 // two ranks per thread
-static int scan_cluster_size(uint32_t n, uint32_t nseg)
+static int scan_cluster_size(uint32_t n, uint32_t nseg, int ntb)
 {
 	static const char *env = getenv("HARRY_B200_SCAN_CLUSTER");
 	if (env && atoi(env) > 0) return atoi(env) > SCAN_MAXC ? SCAN_MAXC : atoi(env);
-	// a batch fills the machine with chains: one CTA per chain whenever a window nearly fits (no cluster hand-offs)
-	const double need = (nseg > 1 ? 0.9 : 1.2) * sqrt(2.0 * (double)n) / (double)SCAN_NTB;
+	// a batch fills the machine with chains: one CTA per chain (no cluster hand-offs)
+	if (nseg > 1 && ntb < 512) return 1;
+	const double need = (nseg > 1 ? 0.9 : 1.2) * sqrt(2.0 * (double)n) / (double)ntb;
 	int c = 1;
 	while (c < SCAN_MAXC && (double)c < need) c <<= 1;
 	return c;
@@ -324,10 +342,11 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 	HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_args, m->h_spec_args.data(), sizeof(SpecArgs) * nseg, cudaMemcpyHostToDevice, ctx->stream));
 	static const bool single_cta = getenv("HARRY_B200_SPEC1") != nullptr; // A/B switch: single-CTA kernel
 	if (st != HB_FLOAT && !single_cta) {
-		const int cl = scan_cluster_size(max_n, nseg);
-		if (st == HB_UCHAR) HB_TRY(launch_scan<uint8_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg));
-		else if (st == HB_USHORT) HB_TRY(launch_scan<uint16_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg));
-		else HB_TRY(launch_scan<uint32_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg));
+		const int ntb = scan_ntb(nseg * (uint32_t)p.ncomp, ctx->sm_count);
+		const int cl = scan_cluster_size(max_n, nseg, ntb);
+		if (st == HB_UCHAR) HB_TRY(launch_scan<uint8_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg, ntb));
+		else if (st == HB_USHORT) HB_TRY(launch_scan<uint16_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg, ntb));
+		else HB_TRY(launch_scan<uint32_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg, ntb));
 	} else if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
 	else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
 	else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));

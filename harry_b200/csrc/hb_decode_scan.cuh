@@ -439,15 +439,18 @@ __device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ 
 #define SCAN_PROBE(i, ta, tb)
 #endif
 
-template <typename T>
-__global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecArgs *__restrict__ args, uint32_t ncomp)
+// NTB threads per CTA: 512 (one CTA per SM; a single mesh wants the widest window), or 256 / 128 with two / four CTAs
+// per SM -- a batch has more chains than SMs, and resident chains hide each other's latencies and barriers
+template <typename T, int NTB>
+__global__ void __launch_bounds__(NTB, 512 / NTB) k_decode_vertex_scan(const SpecArgs *__restrict__ args, uint32_t ncomp)
 {
+	constexpr uint32_t NWARP = NTB / 32;
 	typedef FMap<T> Map;
 	typedef typename Map::W W;
 	typedef typename Map::SW SW;
 	constexpr int NC = 1;                              // components per thread group (one cluster per component)
 	constexpr uint32_t G = 32;                         // ranks per warp
-	constexpr uint32_t NSEG = SCAN_NWARP * G;          // ranks per CTA and sweep
+	constexpr uint32_t NSEG = NWARP * G;          // ranks per CTA and sweep
 	cgs::cluster_group cluster = cgs::this_cluster();
 	const uint32_t C = cluster.num_blocks();
 	const uint32_t crank = cluster.block_rank();
@@ -466,10 +469,10 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	T *xc = (T *)a.x + c;
 	const uint32_t NSEGT = C * NSEG;                    // ranks per window
 
-	__shared__ Map s_all[SCAN_MAXC * SCAN_NWARP]; // warp totals of the whole cluster (pushed by their owners), active warps only
+	__shared__ Map s_all[SCAN_MAXC * NWARP]; // warp totals of the whole cluster (pushed by their owners), active warps only
 	__shared__ __align__(8) unsigned long long s_bar; // transaction barrier of the incoming totals
-	__shared__ uint32_t s_eva[SCAN_MAXC * SCAN_NWARP];  // per element: its output if the predecessor says B
-	__shared__ uint32_t s_eam[SCAN_MAXC * SCAN_NWARP / 32], s_ebm[SCAN_MAXC * SCAN_NWARP / 32]; // anchor / broken-shortcut bit masks
+	__shared__ uint32_t s_eva[SCAN_MAXC * NWARP];  // per element: its output if the predecessor says B
+	__shared__ uint32_t s_eam[SCAN_MAXC * NWARP / 32], s_ebm[SCAN_MAXC * NWARP / 32]; // anchor / broken-shortcut bit masks
 	__shared__ uint32_t s_ndE[SCAN_MAXC];       // per CTA: first rank that reads a non-final window value
 	__shared__ uint32_t s_ndF[SCAN_MAXC];       // per CTA: first rank behind a failed boundary check
 	__shared__ uint32_t s_start[NSEG + 1][NC];  // presumed start value of every slot (+ of the next CTA's first slot)
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 	__shared__ unsigned long long s_sum[4];
 	__shared__ T s_seq[SCAN_SEQ_MAX];           // values of a sequential stretch
 	__shared__ __align__(16) uint32_t s_item[2][32][16]; // work items of the sequential stretch (two batches)
-	__shared__ __align__(16) uint4 s_pref[SCAN_NTB][3];  // record of the rank this thread will most likely own in the next sweep
+	__shared__ __align__(16) uint4 s_pref[NTB][3];  // record of the rank this thread will most likely own in the next sweep
 
 	const uint32_t hi = (uint32_t)IntOps<T>::mask(a.bits[c]);
 	const int cb = a.bits[c];
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 		// the window is dealt evenly to the CTAs of the cluster, whole warps each (instruction issue
 		// per SM is what bounds a sweep); warps beyond `wpc` sit the sweep out
 		uint32_t wpc = (((est + est / 8 + 8 + G * C - 1) >> lgC)) / G; // active warps per CTA
-		if (wpc > SCAN_NWARP) wpc = SCAN_NWARP;
+		if (wpc > NWARP) wpc = NWARP;
 		const uint32_t per = wpc * G;                       // slots per CTA
 		// warp totals travel to the CTA that owns them and to every CTA behind it; thread 0 announces
 		// how many bytes this CTA is going to receive in this sweep
@@ -894,7 +897,7 @@ __global__ void __launch_bounds__(SCAN_NTB, 1) k_decode_vertex_scan(const SpecAr
 				}
 				s_eva[t] = va;
 			}
-			if (t < SCAN_MAXC * SCAN_NWARP) {
+			if (t < SCAN_MAXC * NWARP) {
 				const uint32_t am = __ballot_sync(0xffffffffu, anch), bm = __ballot_sync(0xffffffffu, bad);
 				if (lane == 0) { s_eam[warp] = am; s_ebm[warp] = bm; }
 			}

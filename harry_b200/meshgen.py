@@ -222,37 +222,75 @@ def soup(nv: int = 30, nf: int = 400, seed: int = 1, min_deg: int = 1, max_deg: 
 # ----------------------------------------------------------------------------------------------
 # PLY writer (binary little endian)
 # ----------------------------------------------------------------------------------------------
-def write_ply(path: str, m: PolyMesh) -> None:
+PLY_TYPE = {"float32": "float", "float64": "double", "uint8": "uchar", "int8": "char", "uint16": "ushort", "int16": "short",
+            "uint32": "uint", "int32": "int"}
+
+
+def with_typed_props(m: PolyMesh, seed: int = 1, vtx: tuple = (), face: tuple = ()) -> PolyMesh:
+    """Adds typed per-vertex / per-face properties (PLY scalar types other than float: SURVEY Appendix C.13, the
+    `uchar` colours next to float coordinates of scanned meshes).  ``vtx`` / ``face``: (name, numpy dtype) pairs.
+    Values are smooth functions of the position plus seeded noise, spread over most of the type's range, with
+    negative values for the signed types."""
+    rng = np.random.default_rng(seed)
     nv, nf = m.nv, m.nf
-    vnames = ["x", "y", "z"] + list(m.vtx_props.keys())
-    hdr = ["ply", "format binary_little_endian 1.0", f"element vertex {nv}"]
-    hdr += [f"property float {nm}" for nm in vnames]
-    hdr += [f"element face {nf}", "property list uchar int vertex_indices"]
-    hdr += [f"property float {nm}" for nm in m.face_props.keys()]
-    hdr += ["end_header"]
-    vt = np.empty((nv, len(vnames)), dtype="<f4")
-    vt[:, :3] = m.pos
-    for k, nm in enumerate(m.vtx_props.keys()):
-        vt[:, 3 + k] = m.vtx_props[nm]
     deg = np.diff(m.face_off.astype(np.int64))
-    nfp = len(m.face_props)
+    centre = np.add.reduceat(m.pos[m.face_idx.astype(np.int64)], m.face_off[:-1].astype(np.int64), axis=0) / deg[:, None]
+
+    def make(points, k, dt):
+        dt = np.dtype(dt)
+        base = 0.5 + 0.45 * np.sin(3.0 * points[:, k % 3] + 0.7 * k) * np.cos(2.0 * points[:, (k + 1) % 3])
+        base = base + 0.02 * rng.standard_normal(points.shape[0])
+        if dt.kind == "f":
+            return base.astype(dt)
+        info = np.iinfo(dt)
+        lo, hi = info.min, info.max
+        if dt.itemsize >= 4:
+            # int32 arithmetic of the reference is not promoted: a difference of two values must not overflow (signed
+            # overflow is undefined there, prediction.h:82-99), so signed 32-bit values stay within +-2^28
+            lo, hi = (-(1 << 28), 1 << 28) if dt.kind == "i" else (0, info.max // 2)
+        return np.clip(np.rint(lo + np.clip(base, 0.0, 1.0) * (float(hi) - float(lo))), info.min, info.max).astype(dt)
+
+    out = PolyMesh(pos=m.pos, face_off=m.face_off, face_idx=m.face_idx, vtx_props=dict(m.vtx_props), face_props=dict(m.face_props))
+    for k, (name, dt) in enumerate(vtx):
+        out.vtx_props[name] = make(m.pos, k, dt)
+    for k, (name, dt) in enumerate(face):
+        out.face_props[name] = make(centre, k + 5, dt)
+    return out
+
+
+def write_ply(path: str, m: PolyMesh) -> None:
+    """Binary little-endian PLY; every property keeps the numpy dtype of its array (float32 unless made otherwise)."""
+    nv, nf = m.nv, m.nf
+    vprops = [("x", m.pos[:, 0]), ("y", m.pos[:, 1]), ("z", m.pos[:, 2])] + [(nm, np.asarray(a)) for nm, a in m.vtx_props.items()]
+    vprops = [(nm, a if a.dtype.name in PLY_TYPE else a.astype(np.float32)) for nm, a in vprops]
+    fprops = [(nm, np.asarray(a)) for nm, a in m.face_props.items()]
+    fprops = [(nm, a if a.dtype.name in PLY_TYPE else a.astype(np.float32)) for nm, a in fprops]
+    hdr = ["ply", "format binary_little_endian 1.0", f"element vertex {nv}"]
+    hdr += [f"property {PLY_TYPE[a.dtype.name]} {nm}" for nm, a in vprops]
+    hdr += [f"element face {nf}", "property list uchar int vertex_indices"]
+    hdr += [f"property {PLY_TYPE[a.dtype.name]} {nm}" for nm, a in fprops]
+    hdr += ["end_header"]
+    vt = np.empty(nv, dtype=[(nm, a.dtype.newbyteorder("<")) for nm, a in vprops])
+    for nm, a in vprops:
+        vt[nm] = a
     with open(path, "wb") as f:
         f.write(("\n".join(hdr) + "\n").encode("ascii"))
         f.write(vt.tobytes())
-        if m.is_tri and nfp == 0:
-            rec = np.empty(nf, dtype=[("n", "u1"), ("i", "<i4", 3)])
+        if m.is_tri:
+            rec = np.empty(nf, dtype=[("n", "u1"), ("i", "<i4", 3)] + [(nm, a.dtype.newbyteorder("<")) for nm, a in fprops])
             rec["n"] = 3
             rec["i"] = m.face_idx.reshape(-1, 3).astype("<i4")
+            for nm, a in fprops:
+                rec[nm] = a
             f.write(rec.tobytes())
         else:
-            fprops = [np.asarray(v, dtype="<f4") for v in m.face_props.values()]
             out = bytearray()
             for fi in range(nf):
                 s, e = int(m.face_off[fi]), int(m.face_off[fi + 1])
                 out += bytes([e - s])
                 out += m.face_idx[s:e].astype("<i4").tobytes()
-                for fp in fprops:
-                    out += fp[fi:fi + 1].tobytes()
+                for _, fp in fprops:
+                    out += fp[fi:fi + 1].astype(fp.dtype.newbyteorder("<")).tobytes()
             f.write(bytes(out))
 
 

@@ -35,8 +35,36 @@ CASES = {
     "cones_open_lossless": (lambda d: _ply(d, "coneso.ply", meshgen.cones(40, 100, seed=4, open_every=2)), []),
     "irr_big_q12": (lambda d: _ply(d, "irrb.ply", meshgen.tri_irregular(160, 5)), [(1, -1, 12)]),
     "obj_multi_all": (lambda d: _obj(d, "om.obj", True), [(0, -1, 12), (1, -1, 9), (2, -1, 10), (3, -1, 11)]),
+    # native integer / mixed source types (structs/mixing.h:18-19, quant.h:99-112,168, prediction.h:47-63,82-99; SURVEY
+    # Appendix C.13): uchar colours next to float coordinates -- quantization selected per component (`-a`), the colours
+    # lossless (mixed storage types in one list) or requantized from their integer type (rescale_int)
+    "rgb_xyz_q12": (lambda d: _ply(d, "rgb.ply", _rgb_sphere()), [(1, 0, 12), (1, 1, 12), (1, 2, 12)]),
+    "rgb_q5_xyz_q14": (lambda d: _ply(d, "rgb.ply", _rgb_sphere()), [(1, 0, 14), (1, 1, 14), (1, 2, 14), (1, 3, 5), (1, 4, 5), (1, 5, 5)]),
+    "rgb_lossless": (lambda d: _ply(d, "rgb.ply", _rgb_sphere()), []),
+    # signed and wide integer properties, lossless and quantized from the integer type; per-face integer properties
+    "ints_lossless": (lambda d: _ply(d, "ints.ply", _int_sphere()), []),
+    "ints_q": (lambda d: _ply(d, "ints.ply", _int_sphere()), [(1, 0, 11), (1, 1, 11), (1, 2, 11), (1, 3, 9), (1, 4, 6), (1, 5, 12), (1, 6, 20), (0, 0, 7)]),
+    # (component order after the reader's sorting: x y z red(uchar) material(int, byte offset 13) temp(short, offset 17): misaligned slots)
+    "ints_irr_q": (lambda d: _ply(d, "intsi.ply", _int_irregular()), [(1, 0, 10), (1, 1, 10), (1, 2, 10), (1, 3, 5), (1, 4, 13), (1, 5, 7), (0, 0, 9)]),
+    "ints_irr_lossless": (lambda d: _ply(d, "intsi.ply", _int_irregular()), []),
 }
 CONFIG1 = ("sphere35k_lossless", lambda d: _ply(d, "s35k.ply", meshgen.uv_sphere(133, 264)), [])
+
+
+def _rgb_sphere():
+    return meshgen.with_typed_props(meshgen.uv_sphere(31, 49, noise_seed=8), seed=3,
+                                    vtx=(("red", np.uint8), ("green", np.uint8), ("blue", np.uint8)))
+
+
+def _int_sphere():
+    return meshgen.with_typed_props(meshgen.uv_sphere(27, 41, noise_seed=12), seed=5,
+                                    vtx=(("material", np.int32), ("temp", np.int16), ("flags", np.uint16), ("ident", np.uint32), ("sgn", np.int8)),
+                                    face=(("group", np.uint8), ("fid", np.int32)))
+
+
+def _int_irregular():
+    return meshgen.with_typed_props(meshgen.tri_irregular(40, 9), seed=6,
+                                    vtx=(("material", np.int32), ("temp", np.int16), ("red", np.uint8)), face=(("group", np.int16),))
 
 
 def _ply(d, name, mesh):

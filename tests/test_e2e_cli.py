@@ -35,6 +35,14 @@ def gen(workdir, kind):
     elif kind == "poly":
         p = os.path.join(workdir, "e2e_p.ply")
         meshgen.write_ply(p, meshgen.poly_grid(60))                 # config 4: 3 723 vertices
+    elif kind == "rgb":
+        import cases
+        p = os.path.join(workdir, "e2e_rgb.ply")
+        meshgen.write_ply(p, cases._rgb_sphere())                   # float xyz + uchar colours (Appendix C.13)
+    elif kind == "ints":
+        import cases
+        p = os.path.join(workdir, "e2e_ints.ply")
+        meshgen.write_ply(p, cases._int_irregular())                # int / short / uchar vertex properties, short face property
     elif kind == "obj":
         p = os.path.join(workdir, "e2e_o.obj")
         meshgen.write_obj_latlong(p, 40, 60)                        # config 3: 2 460 vertices
@@ -53,6 +61,11 @@ CASES = [
     ("obj", ["-l0", "-q14", "-l2", "-q10"], "obj"),          # config 3
     ("obj", [], "obj"),
     ("obj_multi", ["-l0", "-q14"], "obj"),                   # multi-region variant
+    # integer source types: per-component quantization (-a), colours lossless next to quantized coordinates / requantized
+    ("rgb", ["-l1", "-a0", "-q12", "-a1", "-q12", "-a2", "-q12"], "ply"),
+    ("rgb", ["-l1", "-a0", "-q14", "-a1", "-q14", "-a2", "-q14", "-a3", "-q5", "-a4", "-q5", "-a5", "-q5"], "ply"),
+    ("ints", [], "ply"),
+    ("ints", ["-l1", "-a0", "-q10", "-a1", "-q10", "-a2", "-q10", "-a3", "-q5", "-a4", "-q13", "-a5", "-q7", "-l0", "-q9"], "ply"),
 ]
 
 

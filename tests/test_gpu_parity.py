@@ -168,3 +168,58 @@ def test_config2_full_size(ctx, workdir):
         if w.dec.lists[l].ncomp:
             assert np.array_equal(D.fetch_rows(l), exp), f"list {l}"
     D.close()
+
+
+# ---- BASELINE configs[2] and [3] at scale (corner lists with thousands of LHIST hits per region, deep polygon meshes) ----
+def _full_case_check(impl, workdir, name, gen, loq):
+    from cases import Case
+    case = Case(workdir, name, gen, loq)
+    checks.check_quant(impl, case)
+    checks.check_encode(impl, case)
+    checks.check_decode(impl, case)
+    return case
+
+
+@needs_ref
+def test_config3_at_scale(impl, workdir):
+    """OBJ lat-long sphere, 240 600 vertices / 480 000 triangles / 1.44 M corners, vt + vn corner lists, -l0 -q14 -l2 -q10"""
+    from harry_b200 import meshgen
+
+    def gen(d):
+        p = os.path.join(d, "cfg3_scale.obj")
+        meshgen.write_obj_latlong(p, 400, 600)
+        return p
+
+    case = _full_case_check(impl, workdir, "cfg3_scale", gen, [(0, -1, 14), (2, -1, 10)])
+    assert case.enc.nv == 240600 and int((case.enc_streams.lists[1].type == capi.LHIST).sum()) > 1000000
+
+
+@needs_ref
+def test_config3_multi_region_at_scale(impl, workdir):
+    from harry_b200 import meshgen
+
+    def gen(d):
+        p = os.path.join(d, "cfg3m_scale.obj")
+        meshgen.write_obj_latlong(p, 150, 220, multi_region=True)
+        return p
+
+    _full_case_check(impl, workdir, "cfg3m_scale", gen, [(0, -1, 12), (1, -1, 9), (2, -1, 10), (3, -1, 11)])
+
+
+@needs_ref
+@pytest.mark.parametrize("loq", [[], [(1, -1, 12), (0, -1, 9)]], ids=["lossless", "q12_q9"])
+def test_config4_at_scale(impl, workdir, loq):
+    """polygon grid n = 400 (161 607 vertices; tri / quad / 5- / 6-gons + the non-manifold fin), per-vertex and per-face floats"""
+    from cases import _ply
+    from harry_b200 import meshgen
+    _full_case_check(impl, workdir, "cfg4_scale" + ("q" if loq else ""), lambda d: _ply(d, "cfg4_scale.ply", meshgen.poly_grid(400)), loq)
+
+
+@needs_ref
+@pytest.mark.parametrize("loq", [[(1, -1, 12)], []], ids=["q12", "lossless"])
+def test_many_wide_fans(impl, workdir, loq):
+    """4 300 fans of 70 faces: more wide vertices than the wide-fan path takes at once (4096 slots) and than the encode
+    kernels defer to their cooperative path (wide_cap): the rest is walked / summed by single threads -- same streams"""
+    from cases import _ply
+    from harry_b200 import meshgen
+    _full_case_check(impl, workdir, "many_cones" + ("q" if loq else ""), lambda d: _ply(d, "many_cones.ply", meshgen.cones(4300, 70, seed=3)), loq)
