@@ -1087,7 +1087,7 @@ def main():
     ap.add_argument("--batch-meshes", type=int, default=1250, help="configs[4]: independent 100K-vertex meshes per GPU and step (0 = skip)")
     ap.add_argument("--batch-distinct", type=int, default=16, help="distinct prepared meshes the batch cycles through")
     ap.add_argument("--batch-resident", type=int, default=420, help="meshes kept resident in HBM for the device-resident batch value")
-    ap.add_argument("--batch-group-half-edges", type=int, default=120 << 20, help="half-edges per device mesh (group of meshes run by one launch per stage)")
+    ap.add_argument("--batch-group-half-edges", type=int, default=112 << 20, help="half-edges per device mesh (group of meshes run by one launch per stage)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -452,8 +452,11 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 		HB_TRY(copy_in(m, face_off_dst + m->h_fbase[s] + s, ds.face_off, sizeof(uint32_t) * ((size_t)ds.nf + 1)));
 		HB_TRY(copy_in(m, m->d_order + 8 * (size_t)m->h_obase[s], ds.order, 8 * (size_t)ds.norder));
 		if (m->has_order_f) HB_TRY(copy_in(m, m->d_order_f + 8 * (size_t)m->h_ofbase[s], ds.order_f, 8 * (size_t)ds.norder_f));
-		HB_TRY(copy_in(m, m->d_vtx_regs + m->h_vbase[s], ds.vtx_regs, sizeof(uint16_t) * (size_t)ds.nv));
+		if (d->nregs_vtx > 1) HB_TRY(copy_in(m, m->d_vtx_regs + m->h_vbase[s], ds.vtx_regs, sizeof(uint16_t) * (size_t)ds.nv));
 	}
+	// a single region: every entry is 0 by definition -- cleared on the device instead of uploaded
+	cudaStream_t up_stream = m->async_copy ? ctx->copy_stream : ctx->stream;
+	if (d->nregs_vtx <= 1 && m->nv) HB_CUDA(ctx, cudaMemsetAsync(m->d_vtx_regs, 0, sizeof(uint16_t) * (size_t)m->nv, up_stream));
 	// everything K0 / K3 / K4 read is on its way: first milestone of the copy stream
 	if (m->async_copy) {
 		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_up[0], cudaEventDisableTiming));
@@ -469,12 +472,13 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 	for (uint32_t s = 0; s < nseg; ++s) {
 		const hb_mesh_desc &ds = descs[s];
 		if (up_faces) {
-			HB_TRY(copy_in(m, m->d_face_regs + m->h_fbase[s], ds.face_regs, sizeof(uint16_t) * (size_t)ds.nf));
+			if (d->nregs_face > 1) HB_TRY(copy_in(m, m->d_face_regs + m->h_fbase[s], ds.face_regs, sizeof(uint16_t) * (size_t)ds.nf));
 			HB_TRY(copy_in(m, m->d_bind_face + (size_t)m->h_fbase[s] * d->nb_face, ds.bind_face_attr, sizeof(uint32_t) * (size_t)ds.nf * d->nb_face));
 			HB_TRY(copy_in(m, m->d_bind_corner + (size_t)m->h_ebase[s] * d->nb_corner, ds.bind_corner_attr, sizeof(uint32_t) * (size_t)ds.ne * d->nb_corner));
 		}
 		HB_TRY(copy_in(m, m->d_bind_vtx + (size_t)m->h_vbase[s] * d->nb_vtx, ds.bind_vtx_attr, sizeof(uint32_t) * (size_t)ds.nv * d->nb_vtx));
 	}
+	if (up_faces && d->nregs_face <= 1 && m->nf) HB_CUDA(ctx, cudaMemsetAsync(m->d_face_regs, 0, sizeof(uint16_t) * (size_t)m->nf, up_stream));
 	if (vertex_only) m->any_corner = false;
 	HB_TRY(upload(m, (void **)&m->d_slot_vtx, m->h_slot_vtx.data(), sizeof(int16_t) * m->h_slot_vtx.size()));
 	HB_TRY(upload(m, (void **)&m->d_slot_face, m->h_slot_face.data(), sizeof(int16_t) * m->h_slot_face.size()));
@@ -830,6 +834,10 @@ static int fetch_begin(hb_dmesh *m, cudaStream_t st, hb_batch_streams_priv *pv, 
 		if (!fs.offs[l] || !fs.hist[l]) return hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
 		const int cls = dl.p.target;
 		const uint32_t *elem_base = cls == HB_VTX ? m->d_obase : cls == HB_FACE ? m->d_ofbase : m->d_cebase;
+		if (dl.nocomp_fast) { // offsets follow from the segment tables and the type counters (filled in below)
+			FETCH_CUDA(cudaMemcpyAsync(fs.hist[l], dl.d_hist, sizeof(uint64_t) * hist_pitch * nseg, cudaMemcpyDeviceToHost, st));
+			continue;
+		}
 		FETCH_CUDA(cudaMallocAsync((void **)&d_offs[l], sizeof(uint32_t) * 2 * ((size_t)nseg + 1), st));
 		if (dl.n_elems) {
 			k_segment_offsets<<<hb_div_up(nseg + 1, 128), 128, 0, st>>>(elem_base, nseg, dl.d_ek, dl.d_dord, d_offs[l]);
@@ -846,6 +854,20 @@ static int fetch_begin(hb_dmesh *m, cudaStream_t st, hb_batch_streams_priv *pv, 
 		DevList &dl = m->lists[l];
 		if (!fs.offs[l]) continue;
 		const size_t hist_pitch = (size_t)dl.p.sym_stride * 256 + 4;
+		if (dl.nocomp_fast) {
+			const std::vector<uint32_t> &eb = dl.p.target == HB_VTX ? m->h_obase : m->h_ofbase;
+			uint32_t nd = 0;
+			bool any_hist = false;
+			for (uint32_t sg = 0; sg <= nseg; ++sg) {
+				fs.offs[l][sg] = eb[sg];
+				fs.offs[l][nseg + 1 + sg] = nd;
+				if (sg < nseg) {
+					nd += (uint32_t)fs.hist[l][hist_pitch * sg + HB_DATA];
+					any_hist = any_hist || fs.hist[l][hist_pitch * sg + HB_HIST] != 0;
+				}
+			}
+			if (any_hist) HB_TRY(hb_nocomp_finish(m, l, st)); // shared rows in a list without components: history offsets after all
+		}
 		const uint32_t n_emit = fs.offs[l][nseg], n_data = fs.offs[l][2 * nseg + 1];
 		// every emission of every segment is a DATA row (no shared attribute rows): the type and history-offset
 		// streams are all zero -- NULL stands for them, nothing is copied
@@ -1104,7 +1126,7 @@ extern "C" int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh)
 
 // ------------------------------------------------------------------------------------------------
 // Batches of independent meshes on host buffers (BASELINE configs[4]; the reference runs one process per mesh,
-// main.cc:93-122).  The batch is cut into groups of meshes (about 120M half-edges each, HARRY_B200_GROUP_HALF_EDGES); every group
+// main.cc:93-122).  The batch is cut into groups of meshes (about 117M half-edges each, HARRY_B200_GROUP_HALF_EDGES); every group
 // is one device mesh (one launch per stage over all its meshes).  Software pipeline over the groups:
 //   copy stream     upload of group g + 1
 //   compute stream  kernels of group g (wait for its upload only)
@@ -1115,7 +1137,7 @@ static uint64_t group_half_edges()
 {
 	const char *env = getenv("HARRY_B200_GROUP_HALF_EDGES"); // read per call: tests force many small groups
 	const uint64_t v = env ? strtoull(env, nullptr, 10) : 0;
-	return v ? v : (uint64_t)120 << 20; // ~200 meshes of 100K vertices: 600 (mesh, component) chains = four per SM in the scan decoder
+	return v ? v : (uint64_t)112 << 20; // ~195 meshes of 100K vertices: 585 (mesh, component) chains = four per SM in the scan decoder
 }
 static void make_groups(const hb_mesh_desc *meshes, uint32_t n, std::vector<uint32_t> &starts)
 {

@@ -720,7 +720,17 @@ int hb_build_conn(hb_dmesh *m)
 	if (m->nf) HB_LAUNCH(ctx, k_flatten_halfedges, hb_div_up(m->nf, 256), 256, 0, (const uint32_t *)m->d_edges_raw, m->d_face_off, m->d_he, m->nf, m->ne, sv, ctx->d_err);
 	if (m->norder)
 		HB_LAUNCH(ctx, k_vertex_order, hb_div_up(m->norder, 256), 256, 0, (const uint32_t *)m->d_order, m->d_face_off, m->d_he, m->norder, sv, m->d_ord_h, m->d_ord_v, m->d_vrank, ctx->d_err);
-	if (m->norder_f)
+	// face ranks and gate half-edges are only needed by face lists with components (or partly bound ones), corner lists
+	// and the face-region stream: the zero-component face list of a plain PLY is coded straight from order_f
+	bool need_face_order = m->any_corner || m->nregs_face > 1;
+	for (int l = 0; l < m->nlists; ++l) {
+		const ListParams &p = m->lists[l].p;
+		if (p.target != HB_FACE) continue;
+		bool everywhere = true;
+		for (int r = 0; r < m->nregs_face; ++r) everywhere = everywhere && m->h_slot_face[(size_t)r * m->nlists + l] >= 0;
+		if (p.ncomp > 0 || !everywhere) need_face_order = true;
+	}
+	if (m->norder_f && need_face_order)
 		HB_LAUNCH(ctx, k_face_order, hb_div_up(m->norder_f, 256), 256, 0, m->has_order_f ? (const uint32_t *)m->d_order_f : (const uint32_t *)nullptr, m->d_face_off, m->norder_f, sv, m->d_frank, m->d_ford_h, m->d_cbase, ctx->d_err);
 	// corner elements are only materialized when some region binds corner lists
 	m->n_corner_elems = 0;

@@ -176,6 +176,93 @@ __global__ void __launch_bounds__(128) k_lhist(const uint4 *__restrict__ he, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lists without components (the face list of a PLY without face properties: 20M elements at configs[1]).  The
+// reference still emits one type symbol per element (io.h:90-94): DATA for the first reference of a row, HIST after.
+// Two passes instead of the six of the general path (element rows, first reference, DATA flags, scan, K5): pass 1
+// finds the first reference of every row, pass 2 writes the type symbols and counts them per segment.  History
+// offsets need the scan of the DATA flags: only when pass 2 counted a HIST emission (checked when the streams are
+// fetched, hb_nocomp_finish) -- for identity bindings it never runs.
+// ------------------------------------------------------------------------------------------------
+struct NoCompArgs {
+	const uint32_t *order_f;   // FACE: traversal order (fepair records) or nullptr = index order
+	const uint32_t *ord_v;     // VTX: vertex of every traversal position
+	const uint16_t *regs;
+	const int16_t *slot;       // [region * nlists + list]
+	const uint32_t *bind;
+	uint32_t nb, nlists, n;
+	int l;
+	RowSeg rs;                 // ent_base = fbase / vbase
+	const uint32_t *elem_base; // ofbase / obase
+	uint32_t *erow, *first;
+	uint8_t *type;
+	unsigned long long *type_hist; // per segment, hist_pitch words apart
+	size_t hist_pitch;
+};
+template <int CLS>
+__device__ __forceinline__ uint32_t nocomp_row(const NoCompArgs &a, uint32_t i, int *err)
+{
+	uint32_t ent, s;
+	if (CLS == CLS_FACE) {
+		s = hb_seg_find(a.elem_base, a.rs.nseg, i);
+		const uint32_t fb = a.rs.ent_base[s];
+		const uint32_t fl = a.order_f ? a.order_f[2 * (size_t)i] : i - a.elem_base[s];
+		if (fl >= a.rs.ent_base[s + 1] - fb) { atomicExch(err, 4); return HB_NONE; }
+		ent = fl + fb;
+	} else {
+		ent = a.ord_v[i];
+		s = hb_seg_find(a.rs.ent_base, a.rs.nseg, ent);
+	}
+	const int sl = a.slot[(uint32_t)a.regs[ent] * a.nlists + (uint32_t)a.l];
+	if (sl < 0) return HB_NONE;
+	const uint32_t row = a.bind[(size_t)ent * a.nb + (uint32_t)sl];
+	if (row >= a.rs.rownum[s]) { atomicExch(err, 7); return HB_NONE; }
+	return row + a.rs.rowbase[s];
+}
+template <int CLS>
+__global__ void __launch_bounds__(256) k_nocomp_first(NoCompArgs a, int *err)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n) return;
+	const uint32_t row = nocomp_row<CLS>(a, i, err);
+	a.erow[i] = row;
+	if (row != HB_NONE) atomicMin(&a.first[row], i);
+}
+__global__ void __launch_bounds__(256) k_nocomp_types(NoCompArgs a)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	int t = -1;
+	if (i < a.n) {
+		const uint32_t row = a.erow[i];
+		if (row != HB_NONE) {
+			t = a.first[row] == i ? HB_DATA : HB_HIST;
+			a.type[i] = (uint8_t)t;
+		}
+	}
+	// per-segment counts: one atomic per warp, type and segment (a warp rarely straddles a boundary)
+	const uint32_t seg = a.rs.nseg > 1 && i < a.n ? hb_seg_find(a.elem_base, a.rs.nseg, i) : 0u;
+	const uint32_t seg0 = __shfl_sync(0xffffffffu, seg, 0);
+	const bool uniform = __all_sync(0xffffffffu, seg == seg0 || t < 0);
+	for (int ty = 0; ty < 2; ++ty) {
+		if (uniform) {
+			const unsigned mk = __ballot_sync(0xffffffffu, t == ty);
+			if (mk && (threadIdx.x & 31u) == 0) atomicAdd(&a.type_hist[(size_t)seg0 * a.hist_pitch + ty], (unsigned long long)__popc(mk));
+		} else if (t == ty) {
+			atomicAdd(&a.type_hist[(size_t)seg * a.hist_pitch + ty], 1ull);
+		}
+	}
+}
+// history offsets of the HIST emissions (attrcode.h:43-52): tidx - 1 - g
+__global__ void __launch_bounds__(256) k_nocomp_aux(const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, const uint32_t *__restrict__ dord, uint32_t n, uint32_t *__restrict__ aux)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t row = erow[i];
+	uint32_t v = 0;
+	if (row != HB_NONE && first[row] != i) v = dord[i] - 1u - dord[first[row]];
+	aux[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5: prediction + residual + byte-plane symbols + histograms
 // ------------------------------------------------------------------------------------------------
 #define ENC_THREADS 256
@@ -674,6 +761,68 @@ static int build_lhist(hb_dmesh *m)
 	return 0;
 }
 
+// a list without components that every region binds: type symbols in two passes (see k_nocomp_first)
+static int encode_nocomp(hb_dmesh *m, int l)
+{
+	hb_ctx *ctx = m->ctx;
+	DevList &dl = m->lists[l];
+	const int cls = dl.p.target;
+	const uint32_t n = cls == CLS_VTX ? m->norder : m->norder_f;
+	dl.n_elems = n;
+	dl.nocomp_fast = true;
+	dl.d_ek = nullptr;
+	const size_t hist_pitch = 4;
+	HB_TRY(hb_dalloc_t(m, &dl.d_erow, (size_t)n + 1));
+	HB_TRY(hb_dalloc_t(m, &dl.d_first, (size_t)dl.p.nrows + 1));
+	HB_TRY(hb_dalloc_t(m, &dl.d_type, (size_t)n + 1));
+	HB_TRY(hb_dalloc_t(m, &dl.d_hist, hist_pitch * m->nseg));
+	dl.d_type_hist = dl.d_hist;
+	HB_CUDA(ctx, cudaMemsetAsync(dl.d_first, 0xff, sizeof(uint32_t) * ((size_t)dl.p.nrows + 1), ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(dl.d_hist, 0, sizeof(unsigned long long) * hist_pitch * m->nseg, ctx->stream));
+	if (!n) return 0;
+	NoCompArgs a;
+	a.order_f = m->has_order_f ? (const uint32_t *)m->d_order_f : nullptr;
+	a.ord_v = m->d_ord_v;
+	a.regs = cls == CLS_VTX ? m->d_vtx_regs : m->d_face_regs;
+	a.slot = cls == CLS_VTX ? m->d_slot_vtx : m->d_slot_face;
+	a.bind = cls == CLS_VTX ? m->d_bind_vtx : m->d_bind_face;
+	a.nb = cls == CLS_VTX ? m->nb_vtx : m->nb_face;
+	a.nlists = m->nlists; a.n = n; a.l = l;
+	a.rs.nseg = m->nseg;
+	a.rs.ent_base = cls == CLS_VTX ? m->d_vbase : m->d_fbase;
+	a.rs.rowbase = dl.d_rowbase; a.rs.rownum = dl.d_rownum;
+	a.elem_base = cls == CLS_VTX ? m->d_obase : m->d_ofbase;
+	a.erow = dl.d_erow; a.first = dl.d_first; a.type = dl.d_type; a.type_hist = dl.d_type_hist; a.hist_pitch = hist_pitch;
+	const uint32_t g = hb_div_up(n, 256);
+	if (cls == CLS_VTX) HB_LAUNCH(ctx, k_nocomp_first<CLS_VTX>, g, 256, 0, a, ctx->d_err);
+	else HB_LAUNCH(ctx, k_nocomp_first<CLS_FACE>, g, 256, 0, a, ctx->d_err);
+	HB_LAUNCH(ctx, k_nocomp_types, g, 256, 0, a);
+	return 0;
+}
+
+// the streams of a zero-component list are being fetched and it has HIST emissions: their history offsets
+int hb_nocomp_finish(hb_dmesh *m, int l, cudaStream_t st)
+{
+	hb_ctx *ctx = m->ctx;
+	DevList &dl = m->lists[l];
+	const uint32_t n = dl.n_elems;
+	HB_TRY(hb_dalloc_t(m, &dl.d_dord, (size_t)n + 2));
+	HB_TRY(hb_dalloc_t(m, &dl.d_aux, (size_t)n + 1));
+	cudaStream_t keep = ctx->stream;
+	ctx->stream = st; // the helpers launch on the context stream
+	int rc = 0;
+	do {
+		const uint32_t g = hb_div_up(n, 256);
+		k_data_flags<<<g, 256, 0, st>>>(dl.d_erow, dl.d_first, n, dl.d_dord);
+		ctx->launches++;
+		if ((rc = hb_scan_exclusive_u32(ctx, dl.d_dord, dl.d_dord, n, nullptr)) != 0) break;
+		k_nocomp_aux<<<g, 256, 0, st>>>(dl.d_erow, dl.d_first, dl.d_dord, n, dl.d_aux);
+		ctx->launches++;
+	} while (0);
+	ctx->stream = keep;
+	return rc;
+}
+
 int hb_encode_lists(hb_dmesh *m)
 {
 	hb_ctx *ctx = m->ctx;
@@ -695,6 +844,11 @@ int hb_encode_lists(hb_dmesh *m)
 		const int cls = p.target;
 		if (cls != CLS_VTX && cls != CLS_FACE && cls != CLS_CORNER) { dl.n_elems = 0; continue; }
 		if (cls == CLS_CORNER && !m->any_corner) { dl.n_elems = 0; continue; }
+		dl.nocomp_fast = false;
+		if (p.ncomp == 0 && (cls == CLS_FACE || cls == CLS_VTX) && bound_everywhere(m, cls, l)) {
+			HB_TRY(encode_nocomp(m, l));
+			continue;
+		}
 		const bool packed = cls == CLS_VTX && packed_eligible(p);
 		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE && !packed, false));
 		const uint32_t n = dl.n_elems;

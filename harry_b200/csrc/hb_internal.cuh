@@ -104,6 +104,7 @@ struct DevList {
 	uint32_t *d_wide = nullptr;         // encode: elements deferred to the warp-per-element kernel
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
+	bool nocomp_fast = false;           // encode: zero-component list coded by the two-pass path (hb_encode.cu)
 	uint8_t *d_done = nullptr;          // decode: corner wavefront flags
 	uint32_t *d_remaining = nullptr;
 	uint8_t *d_rows_backup = nullptr;   // hb_dmesh_snapshot
@@ -223,6 +224,7 @@ int hb_build_vertex_candidates(hb_dmesh *m); // vc_off / vc_tri
 int hb_build_corner_candidates(hb_dmesh *m); // cc_off / cc_idx
 int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp, bool decode);
 int hb_encode_lists(hb_dmesh *m);
+int hb_nocomp_finish(hb_dmesh *m, int l, cudaStream_t st);
 int hb_decode_lists(hb_dmesh *m);
 int hb_list_bounds(hb_dmesh *m, uint32_t l, const uint8_t *groups /* or nullptr: min and max rows only */);
 int hb_list_scale(hb_dmesh *m, uint32_t l, const uint8_t *groups);

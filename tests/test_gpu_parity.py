@@ -223,3 +223,30 @@ def test_many_wide_fans(impl, workdir, loq):
     from cases import _ply
     from harry_b200 import meshgen
     _full_case_check(impl, workdir, "many_cones" + ("q" if loq else ""), lambda d: _ply(d, "many_cones.ply", meshgen.cones(4300, 70, seed=3)), loq)
+
+
+def test_zero_component_list_with_shared_rows(ctx):
+    """A list without components still emits DATA / HIST type symbols and history offsets (io.h:90-94,
+    attrcode.h:43-52).  No reader of the reference builds shared rows for such a list, so the two-pass path is
+    checked against the oracle on hand-made bindings: pairs of faces share a row, in a batch of two meshes."""
+    from harry_b200 import flatten, meshgen
+    meshes = []
+    for seed, (nr, ns) in ((3, (9, 14)), (5, (12, 11))):
+        mesh = flatten.mesh_arrays(meshgen.uv_sphere(nr, ns, noise_seed=seed))
+        fl = mesh.lists[0]
+        assert fl.ncomp == 0 and fl.target == capi.T_FACE
+        perm = np.random.default_rng(seed).permutation(mesh.nf)
+        mesh.bind_face = (perm // 2).astype(np.uint32)                      # two faces per row, scattered over the traversal
+        mesh.lists[0] = capi.empty_list((mesh.nf + 1) // 2, capi.T_FACE)
+        meshes.append(mesh)
+        got = ctx.attr_encode(mesh)
+        want = ol.o_attr_encode(mesh)
+        ok, why = got.equal(want)
+        assert ok, why
+        assert int((got.lists[0].type == capi.HIST).sum()) == mesh.nf // 2
+    dm = capi.DeviceMesh(ctx, meshes)
+    dm.encode()
+    for mesh, got in zip(meshes, dm.fetch_streams_batch()):
+        ok, why = got.equal(ol.o_attr_encode(mesh))
+        assert ok, why
+    dm.close()
