@@ -896,6 +896,7 @@ def run_other_configs(ctx, workdir, peak, reps=5):
         prof = ctx.profile_report()
         ctx.profile(False)
         top = max(prof.items(), key=lambda kv: kv[1][1])
+        dstats = [D.decode_stats(l) for l, la in enumerate(din.lists) if la.ncomp and la.target == 1]
         E.close()
         D.close()
         # e2e: the adapter's calls on host buffers (pageable here: what the CLI passes)
@@ -914,6 +915,7 @@ def run_other_configs(ctx, workdir, peak, reps=5):
         out.append({"workload": title, "vertex_attributes": n_attrs, "parity_vs_reference": bool(ok),
                     "value": n_attrs / ((enc + dec) / reps * 1e-3) / 1e6, "unit": UNIT, "encode_ms": enc / reps, "decode_ms": dec / reps,
                     "e2e_value": n_attrs / t_e2e / 1e6, "e2e_ms": t_e2e * 1e3,
+                    "vertex_decode_stats": dstats,
                     "dominant_kernel": {"name": top[0], "launches_per_step": top[1][0] / reps, "ms_per_step": top[1][1] / reps, "share_of_step": top[1][1] / (enc + dec)}})
     return out
 

@@ -173,6 +173,208 @@ __global__ void __launch_bounds__(32) k_decode_vertex_walk(const WalkArgs *__res
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lossless float vertex lists: which reconstruction per segment?
+//   chain-like traversal (triangle meshes: almost every vertex is predicted across a gate that ends in the vertex
+//   coded just before it, the DAG is a chain of depth ~N)          -> k_decode_vertex_walkf, a pipelined sequential walk
+//   shallow DAG (polygon meshes: candidates come from the own face) -> k_decode_vertex_spec, chunk-parallel Jacobi sweeps
+// k_chain_stat counts, per segment, the DATA ranks that read rank i - 1; both kernels are launched and the one that is
+// not chosen for a segment returns at once (no host synchronisation).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chain_stat(const uint8_t *__restrict__ kind, const uint32_t *__restrict__ cand_off, const uint32_t *__restrict__ cand, uint32_t n,
+                                                    const uint32_t *__restrict__ elem_base, uint32_t nseg, uint32_t *__restrict__ chain /* [nseg][2]: predecessor readers, DATA ranks */)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || kind[i] != 1) return;
+	const uint32_t c0 = cand_off[i], K = min(cand_off[i + 1] - c0, 8u);
+	bool pred = false;
+	for (uint32_t w = 0; w < 3 * K; ++w) pred = pred || cand[3 * (size_t)c0 + w] + 1 == i;
+	const uint32_t s = hb_seg_find(elem_base, nseg, i);
+	atomicAdd(&chain[2 * s + 1], 1u);
+	if (pred) atomicAdd(&chain[2 * s], 1u);
+}
+// measured: sphere 99.99 % predecessor readers (walk 14 ms, Jacobi 80 ms for 35K vertices), polygon grid 58.6 % (walk 150 ms,
+// Jacobi 39 ms for 361K vertices) -- three quarters is the line
+__device__ __forceinline__ bool chain_like(const uint32_t *chain, uint32_t seg) { return 4ull * chain[2 * seg] >= 3ull * chain[2 * seg + 1]; }
+
+#define WALKF_RING 1024
+// L2-coherent load of a whole compact record (4, 8 or 16 bytes)
+template <int NC> __device__ __forceinline__ SpecRec<uint32_t, NC> walkf_ldcg(const SpecRec<uint32_t, NC> *p)
+{
+	SpecRec<uint32_t, NC> r;
+	constexpr int RS = (int)(sizeof(r) / 4);
+	if (RS == 4) { const uint4 v = __ldcg((const uint4 *)p); r.c[0] = v.x; r.c[1] = v.y; r.c[RS > 2 ? 2 : 0] = v.z; r.c[RS > 3 ? 3 : 0] = v.w; }
+	else if (RS == 2) { const uint2 v = __ldcg((const uint2 *)p); r.c[0] = v.x; r.c[RS > 1 ? 1 : 0] = v.y; }
+	else r.c[0] = __ldcg((const unsigned int *)p);
+	return r;
+}
+// One warp per segment.  PREPARE: 32 lanes = the 32 ranks of the next batch (records of all components at once);
+// EXECUTE: lanes 0..NC-1 = the components of the list, which share kinds, candidates and late operands and so walk the
+// chain in lockstep.  Arithmetic of spec_step<.., FP = true> (attrcode.h:182-208, prediction.h:64-72).
+__device__ __forceinline__ uint32_t walkf_lds(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint4 walkf_lds4(uint32_t addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void walkf_sts(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+template <int NC>
+__global__ void __launch_bounds__(32) k_decode_vertex_walkf(const SpecArgs *__restrict__ args, const uint32_t *__restrict__ chain)
+{
+	typedef SpecRec<uint32_t, NC> Rec;
+	constexpr int RS = (int)(sizeof(Rec) / 4);
+	// work item of one rank (words): 0 kind | K << 2, 1 aux (CSR offset / owning rank), 2 K in full, 3 pad, 4.. residual record,
+	// then per candidate four words: the shared-memory ADDRESSES of its three operand records (a value parked in the item
+	// itself, or the ring slot a rank of the last two batches will have filled by then), then the parked operand records.
+	// EXECUTE reads every operand with the same two loads, no selects.
+	constexpr int OFF_ADDR = 4 + RS, OFF_VAL = OFF_ADDR + 16, ITEM = OFF_VAL + 12 * RS;
+	if (!chain_like(chain, blockIdx.x)) return;
+	const SpecArgs a = args[blockIdx.x];
+	const uint32_t lane = threadIdx.x;
+	const uint32_t base = a.base, n = a.n;
+	const Rec *__restrict__ resid = (const Rec *)a.resid;
+	Rec *x = (Rec *)a.x;
+	__shared__ Rec s_ring[WALKF_RING];
+	__shared__ __align__(16) uint32_t s_item[2][32][ITEM];
+	if (base >= n) return;
+	uint32_t ringb, itemb; // shared-window addresses, pinned in registers
+	asm volatile("mov.u32 %0, %1;" : "=r"(ringb) : "r"((uint32_t)__cvta_generic_to_shared(s_ring)));
+	asm volatile("mov.u32 %0, %1;" : "=r"(itemb) : "r"((uint32_t)__cvta_generic_to_shared(s_item)));
+	auto ring = [&](uint32_t r) -> Rec & { return s_ring[(r - base) & (WALKF_RING - 1)]; };
+	auto ring_addr = [&](uint32_t r) -> uint32_t { return ringb + 4u * RS * ((r - base) & (WALKF_RING - 1)); };
+	auto final_value = [&](uint32_t r, uint32_t front) -> Rec {
+		if (r + WALKF_RING >= front) return ring(r);
+		return walkf_ldcg<NC>(x + r);
+	};
+	uint32_t p_kind = 0, p_K = 0, p_late = 0, p_aux = 0;
+	Rec p_res, p_op[12];
+	auto issue = [&](uint32_t b0, uint32_t front) {
+		const uint32_t i = b0 + lane;
+		p_kind = 0; p_K = 0; p_late = 0; p_aux = 0;
+		if (i >= n) return;
+		const uint32_t kd = a.kind[i];
+		if (kd == 0) { p_res = walkf_ldcg<NC>(x + i); return; } // not bound: keeps what is there
+		if (kd == 2) {
+			const uint32_t fi = a.src[i];
+			if (fi < front) p_res = final_value(fi, front);
+			else { p_kind = 2; p_aux = fi; }
+			return;
+		}
+		p_res = resid[i];
+		p_aux = a.cand_off[i];
+		p_K = a.cand_off[i + 1] - p_aux;
+		if (p_K > 4) { p_kind = 3; return; }
+		p_kind = 1;
+#pragma unroll
+		for (int w = 0; w < 12; ++w) {
+			if ((uint32_t)(w / 3) < p_K) {
+				const uint32_t r = a.cand[3 * (size_t)p_aux + w];
+				if (r < front) p_op[w] = final_value(r, front);
+				else { p_late |= 1u << w; p_op[w].c[0] = r; }
+			}
+		}
+	};
+	auto finish = [&](uint32_t buf) {
+		uint32_t *it = &s_item[buf][lane][0];
+		const uint32_t ib = itemb + 4u * ITEM * (buf * 32u + lane);
+		it[0] = p_kind | (min(p_K, 63u) << 2);
+		it[1] = p_kind == 2 ? ring_addr(p_aux) : p_aux;
+		it[2] = p_K; // in full (a pole has hundreds of candidates)
+#pragma unroll
+		for (int e = 0; e < RS; ++e) it[4 + e] = p_res.c[e];
+		if (p_kind == 1) {
+#pragma unroll
+			for (int w = 0; w < 12; ++w)
+				if ((uint32_t)(w / 3) < p_K) {
+					const bool late = (p_late >> w) & 1u;
+					it[OFF_ADDR + 4 * (w / 3) + (w % 3)] = late ? ring_addr(p_op[w].c[0]) : ib + 4u * (OFF_VAL + w * RS);
+					if (!late) {
+#pragma unroll
+						for (int e = 0; e < RS; ++e) it[OFF_VAL + w * RS + e] = p_op[w].c[e];
+					}
+				}
+		}
+	};
+	const uint32_t j = lane < (uint32_t)NC ? lane : 0u; // my component in EXECUTE
+	issue(base, base);
+	finish(0);
+	__syncwarp();
+	for (uint32_t b0 = base; b0 < n; b0 += 32) {
+		const uint32_t buf = ((b0 - base) >> 5) & 1u;
+		const bool more = b0 + 32 < n;
+		if (more) issue(b0 + 32, b0);
+		if (lane < (uint32_t)NC) {
+			const uint32_t nl = min(32u, n - b0);
+			uint32_t ib = itemb + 4u * ITEM * (buf * 32u);
+			uint32_t ra = ring_addr(b0) + 4u * j;
+			const uint32_t ring_end = ringb + 4u * RS * WALKF_RING;
+			// one candidate prediction: v0 + (v1 - v2), operands through the parked addresses
+			auto cand_pred = [&](uint32_t k) -> float {
+				const uint4 ad = walkf_lds4(ib + 4u * (OFF_ADDR + 4 * k));
+				const float v0 = __uint_as_float(walkf_lds(ad.x + 4u * j)), v1 = __uint_as_float(walkf_lds(ad.y + 4u * j)), v2 = __uint_as_float(walkf_lds(ad.z + 4u * j));
+				return __fadd_rn(v0, __fsub_rn(v1, v2));
+			};
+#pragma unroll 1
+			for (uint32_t t = 0; t < nl; ++t, ib += 4u * ITEM) {
+				const uint4 h4 = walkf_lds4(ib);
+				const uint32_t kind = h4.x & 3u, K = (h4.x >> 2) & 0x3fu, aux = h4.y;
+				const uint32_t i = b0 + t;
+				uint32_t val = walkf_lds(ib + 4u * (4 + j));
+				if (kind == 1) {
+					uint32_t pred = 0;
+					if (K == 2) { // the usual vertex: two parallelograms
+						const float p0 = cand_pred(0), p1 = cand_pred(1);
+						const float avg = __double2float_rn(__dmul_rn(__dadd_rn((double)p0, (double)p1), 0.5)); // exact scaling == IEEE division by 2
+						pred = __float_as_uint(hb_closest_step(hb_closest_step(FLT_MAX, p0, avg), p1, avg));
+					} else if (K == 1) {
+						pred = __float_as_uint(cand_pred(0)); // mean of one candidate: itself
+					} else if (K) {
+						double sum = 0.0;
+						for (uint32_t k = 0; k < K; ++k) sum = __dadd_rn(sum, (double)cand_pred(k));
+						const float avg = __double2float_rn(__ddiv_rn(sum, (double)(int)K));
+						float best = FLT_MAX;
+						for (uint32_t k = 0; k < K; ++k) best = hb_closest_step(best, cand_pred(k), avg);
+						pred = __float_as_uint(best);
+					}
+					val = hb_flip_f32(IntOps<uint32_t>::dec(val, hb_flip_f32(pred), 32));
+				} else if (kind == 2) {
+					val = walkf_lds(aux + 4u * j);
+				} else if (kind == 3) {
+					// more candidates than an item holds (poles, closing vertices): straight from the CSR, two passes
+					const uint32_t *tri = a.cand + 3 * (size_t)aux;
+					const uint32_t Kf = h4.z;
+					auto getv = [&](uint32_t r) -> float { return __uint_as_float(r + WALKF_RING > i ? ring(r).c[j] : __ldcg(&x[r].c[j])); };
+					double sum = 0.0;
+					for (uint32_t k = 0; k < Kf; ++k) sum = __dadd_rn(sum, (double)__fadd_rn(getv(tri[3 * k]), __fsub_rn(getv(tri[3 * k + 1]), getv(tri[3 * k + 2]))));
+					const float avg = __double2float_rn(__ddiv_rn(sum, (double)(int)Kf));
+					float best = FLT_MAX;
+					for (uint32_t k = 0; k < Kf; ++k) best = hb_closest_step(best, __fadd_rn(getv(tri[3 * k]), __fsub_rn(getv(tri[3 * k + 1]), getv(tri[3 * k + 2]))), avg);
+					val = hb_flip_f32(IntOps<uint32_t>::dec(val, hb_flip_f32(__float_as_uint(best)), 32));
+				}
+				walkf_sts(ra, val);
+				ra += 4u * RS;
+				if (ra >= ring_end) ra -= 4u * RS * WALKF_RING;
+				x[i].c[j] = val;
+			}
+		}
+		__syncwarp();
+		if (more) finish(buf ^ 1u);
+		__syncwarp();
+	}
+}
+static int launch_walkf(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, uint32_t nseg, const uint32_t *chain)
+{
+	switch (ncomp) {
+	case 1: HB_LAUNCH(ctx, k_decode_vertex_walkf<1>, nseg, 32, 0, d_args, chain); break;
+	case 2: HB_LAUNCH(ctx, k_decode_vertex_walkf<2>, nseg, 32, 0, d_args, chain); break;
+	case 3: HB_LAUNCH(ctx, k_decode_vertex_walkf<3>, nseg, 32, 0, d_args, chain); break;
+	default: HB_LAUNCH(ctx, k_decode_vertex_walkf<4>, nseg, 32, 0, d_args, chain); break;
+	}
+	return 0;
+}
+
 // ---- speculative path helpers ---------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_spec_prep(const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, uint8_t *__restrict__ kind, uint32_t *__restrict__ src)
 {
@@ -215,22 +417,22 @@ __global__ void __launch_bounds__(256) k_scatter_compact(ListParams p, const uin
 }
 
 template <typename T, int NC, bool FP>
-static int launch_spec_nc(hb_ctx *ctx, const SpecArgs *d_args, uint32_t nseg)
+static int launch_spec_nc(hb_ctx *ctx, const SpecArgs *d_args, uint32_t nseg, const uint32_t *chain)
 {
 	const int threads = spec_threads<T, NC>();
 	const size_t smem = (size_t)threads * 4 * SPEC_HB * sizeof(SpecRec<T, NC>);
 	HB_CUDA(ctx, cudaFuncSetAttribute(k_decode_vertex_spec<T, NC, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	HB_LAUNCH(ctx, (k_decode_vertex_spec<T, NC, FP>), nseg, threads, smem, d_args);
+	HB_LAUNCH(ctx, (k_decode_vertex_spec<T, NC, FP>), nseg, threads, smem, d_args, chain);
 	return 0;
 }
 template <typename T, bool FP>
-static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, uint32_t nseg)
+static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, uint32_t nseg, const uint32_t *chain = nullptr)
 {
 	switch (ncomp) {
-	case 1: return launch_spec_nc<T, 1, FP>(ctx, d_args, nseg);
-	case 2: return launch_spec_nc<T, 2, FP>(ctx, d_args, nseg);
-	case 3: return launch_spec_nc<T, 3, FP>(ctx, d_args, nseg);
-	default: return launch_spec_nc<T, 4, FP>(ctx, d_args, nseg);
+	case 1: return launch_spec_nc<T, 1, FP>(ctx, d_args, nseg, chain);
+	case 2: return launch_spec_nc<T, 2, FP>(ctx, d_args, nseg, chain);
+	case 3: return launch_spec_nc<T, 3, FP>(ctx, d_args, nseg, chain);
+	default: return launch_spec_nc<T, 4, FP>(ctx, d_args, nseg, chain);
 	}
 }
 
@@ -293,8 +495,7 @@ static bool spec_eligible(const ListParams &p)
 {
 	if (p.ncomp < 1 || p.ncomp > 4) return false;
 	const int st = p.uniform_stype;
-	static const bool float_spec = getenv("HARRY_B200_FLOAT_SPEC") != nullptr; // A/B switch: the chunk-parallel Jacobi kernel for float lists
-	return st == HB_UCHAR || st == HB_USHORT || st == HB_UINT || (st == HB_FLOAT && float_spec);
+	return st == HB_UCHAR || st == HB_USHORT || st == HB_UINT || st == HB_FLOAT;
 }
 
 // reconstruct one vertex list with the speculative chunk-parallel kernel
@@ -350,7 +551,15 @@ static int decode_vertex_spec(hb_dmesh *m, int l)
 	} else if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
 	else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
 	else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
-	else HB_TRY((launch_spec<uint32_t, true>(ctx, p.ncomp, dl.d_spec_args, nseg)));
+	else {
+		// lossless float list: sequential walk for chain-like segments, Jacobi sweeps for shallow ones (decided on the device)
+		HB_TRY(hb_dalloc_t(m, &dl.d_chain, 2 * (size_t)nseg));
+		HB_CUDA(ctx, cudaMemsetAsync(dl.d_chain, 0, sizeof(uint32_t) * 2 * nseg, ctx->stream));
+		HB_LAUNCH(ctx, k_chain_stat, g, 256, 0, dl.d_kind, m->d_vc_off, m->d_vc_tri, n, m->d_obase, nseg, dl.d_chain);
+		HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_stats + 7, dl.d_chain, 8, cudaMemcpyDeviceToDevice, ctx->stream)); // diagnostics: segment 0
+		HB_TRY(launch_walkf(ctx, p.ncomp, dl.d_spec_args, nseg, dl.d_chain));
+		HB_TRY((launch_spec<uint32_t, true>(ctx, p.ncomp, dl.d_spec_args, nseg, dl.d_chain)));
+	}
 	HB_LAUNCH(ctx, k_scatter_compact, g, 256, 0, p, dl.d_erow, dl.d_kind, n, dl.d_cx, esize, ncp);
 	return 0;
 }

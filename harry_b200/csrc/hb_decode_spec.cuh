@@ -191,9 +191,11 @@ template <typename T, int NC> __host__ __device__ constexpr int spec_threads()
 }
 
 template <typename T, int NC, bool FP>
-__global__ void __launch_bounds__(1024, 1) k_decode_vertex_spec(const SpecArgs *__restrict__ args)
+__global__ void __launch_bounds__(1024, 1) k_decode_vertex_spec(const SpecArgs *__restrict__ args, const uint32_t *__restrict__ chain)
 {
 	extern __shared__ __align__(16) unsigned char s_dyn[];
+	// float lists: chain-like segments are reconstructed by k_decode_vertex_walkf (hb_decode.cu, k_chain_stat)
+	if (chain && 4ull * chain[2 * blockIdx.x] >= 3ull * chain[2 * blockIdx.x + 1]) return;
 	const SpecArgs a = args[blockIdx.x];
 	typedef SpecRec<T, NC> Rec;
 	const Rec *__restrict__ resid = (const Rec *)a.resid;

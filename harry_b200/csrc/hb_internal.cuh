@@ -100,6 +100,7 @@ struct DevList {
 	uint8_t *d_cres = nullptr, *d_cx = nullptr; // compact residual / value records
 	SpecArgs *d_spec_args = nullptr;
 	unsigned long long *d_spec_stats = nullptr;
+	uint32_t *d_chain = nullptr;        // float lists: per segment {ranks reading their predecessor, DATA ranks}
 	void *d_srec = nullptr;             // hb_decode_scan.cuh records
 	uint32_t *d_wide = nullptr;         // encode: elements deferred to the warp-per-element kernel
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
