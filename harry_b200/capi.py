@@ -498,6 +498,8 @@ def load_library():
     lib.hb_last_error.restype = C.c_char_p
     lib.hb_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.hb_last_timing.restype = None
+    lib.hb_ctx_set_row_cache.argtypes = [vp, C.c_int]
+    lib.hb_ctx_set_row_cache.restype = C.c_int
     lib.hb_kernel_launches.argtypes = [vp]
     lib.hb_kernel_launches.restype = C.c_uint64
     lib.hb_ctx_profile.argtypes = [vp, C.c_int]
@@ -574,7 +576,7 @@ EXPORTED_SYMBOLS = [
     "hb_dmesh_fetch_streams", "hb_dmesh_set_bounds", "hb_dmesh_snapshot", "hb_dmesh_restore", "hb_dmesh_decode", "hb_dmesh_fetch_rows",
     "hb_dmesh_fetch_bounds", "hb_dmesh_decode_stats", "hb_ctx_sync",
     "hb_dmesh_upload_batch", "hb_dmesh_segments", "hb_dmesh_fetch_streams_batch", "hb_dmesh_fetch_rows_seg",
-    "hb_encode_batch", "hb_decode_batch", "hb_batch_streams_free",
+    "hb_encode_batch", "hb_decode_batch", "hb_batch_streams_free", "hb_ctx_set_row_cache",
 ]
 
 
@@ -615,6 +617,10 @@ class Context:
         k, c = C.c_float(), C.c_float()
         self.lib.hb_last_timing(self.h, C.byref(k), C.byref(c))
         return k.value, c.value
+
+    def set_row_cache(self, enable: bool):
+        """Keep the device copy of a list's rows between the calls of one pipeline (harry_b200.h, hb_ctx_set_row_cache)."""
+        self._check(self.lib.hb_ctx_set_row_cache(self.h, 1 if enable else 0), "hb_ctx_set_row_cache")
 
     def launches(self) -> int:
         return int(self.lib.hb_kernel_launches(self.h))

@@ -98,6 +98,8 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	for (hb_ctx::RowEntry &e : ctx->rows_cached) cudaFreeAsync(e.dev, ctx->stream);
+	ctx->rows_cached.clear();
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	if (ctx->out_stream) { cudaStreamSynchronize(ctx->out_stream); cudaStreamDestroy(ctx->out_stream); }
@@ -268,6 +270,57 @@ static int upload(hb_dmesh *m, void **dst, const void *src, size_t bytes)
 	return copy_in(m, *dst, src, bytes);
 }
 
+// ---- row cache (hb_internal.cuh) ------------------------------------------------------------------
+static void row_cache_drop(hb_ctx *ctx, const void *host)
+{
+	for (size_t k = 0; k < ctx->rows_cached.size();)
+		if (ctx->rows_cached[k].host == host) {
+			cudaFreeAsync(ctx->rows_cached[k].dev, ctx->stream);
+			ctx->rows_cached.erase(ctx->rows_cached.begin() + (long)k);
+		} else ++k;
+}
+// device rows of `L` if the cache holds them in exactly this state (removed from the cache: the caller owns them now)
+static uint8_t *row_cache_take(hb_ctx *ctx, const hb_list_desc &L)
+{
+	if (!ctx->row_cache) return nullptr;
+	for (size_t k = 0; k < ctx->rows_cached.size(); ++k) {
+		hb_ctx::RowEntry &e = ctx->rows_cached[k];
+		if (e.host != L.rows || e.nrows != L.nrows || e.stride != L.stride || e.ncomp != L.ncomp) continue;
+		bool same = true;
+		for (int j = 0; j < L.ncomp; ++j) same = same && e.quant[j] == L.quant[j];
+		if (!same) continue;
+		uint8_t *dev = e.dev;
+		ctx->rows_cached.erase(ctx->rows_cached.begin() + (long)k);
+		return dev;
+	}
+	return nullptr;
+}
+// hands the rows buffer of list 0 of a single-segment device mesh over to the cache (it is taken off the mesh's free list)
+static void row_cache_put(hb_dmesh *m, int l, const void *host)
+{
+	hb_ctx *ctx = m->ctx;
+	if (!ctx->row_cache || m->nseg != 1 || !host) return;
+	DevList &dl = m->lists[l];
+	if (!dl.p.rows || !dl.p.ncomp || !dl.p.nrows) return;
+	for (size_t k = 0; k < m->allocs.size(); ++k)
+		if (m->allocs[k] == dl.p.rows) { m->allocs.erase(m->allocs.begin() + (long)k); break; }
+	row_cache_drop(ctx, host);
+	while (ctx->rows_cached.size() >= 8) row_cache_drop(ctx, ctx->rows_cached.front().host);
+	hb_ctx::RowEntry e;
+	e.host = host; e.nrows = dl.p.nrows; e.stride = dl.p.stride; e.dev = dl.p.rows; e.ncomp = dl.p.ncomp;
+	for (int j = 0; j < HB_MAX_COMP; ++j) e.quant[j] = j < dl.p.ncomp ? dl.p.quant[j] : 0;
+	ctx->rows_cached.push_back(e);
+	dl.p.rows = nullptr;
+}
+extern "C" int hb_ctx_set_row_cache(hb_ctx *ctx, int enable)
+{
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	ctx->row_cache = enable != 0;
+	if (!enable)
+		while (!ctx->rows_cached.empty()) row_cache_drop(ctx, ctx->rows_cached.front().host);
+	return 0;
+}
+
 static bool same_format(const hb_list_desc &a, const hb_list_desc &b)
 {
 	if (a.ncomp != b.ncomp || a.stride != b.stride || a.target != b.target) return false;
@@ -300,10 +353,20 @@ static int add_list(hb_dmesh *m, const hb_mesh_desc *descs, const hb_list_desc *
 	hb_list_desc Lc = L0;
 	Lc.nrows = (uint32_t)acc;
 	hb_fill_list_params(dl.p, Lc);
-	void *rows = nullptr;
-	HB_TRY(hb_dalloc(m, &rows, (size_t)acc * L0.stride));
+	// the rows may still be on the device: only for calls that CONTINUE a pipeline (requant, encode) -- set_bounds and
+	// decode start one, their host rows are new
+	void *rows = m->take_cached_rows && nseg == 1 && L0.ncomp && L0.nrows ? row_cache_take(ctx, L0) : nullptr;
+	const bool cached = rows != nullptr;
+	if (cached) {
+		m->allocs.push_back(rows);
+		// the buffer was last touched on the compute stream: an upload stream that fills sibling buffers need not wait,
+		// the kernels reading it run on the compute stream anyway
+	} else {
+		HB_TRY(hb_dalloc(m, &rows, (size_t)acc * L0.stride));
+	}
 	dl.p.rows = (uint8_t *)rows;
-	if (L0.ncomp)
+	dl.rows_from_cache = cached;
+	if (L0.ncomp && !cached)
 		for (uint32_t s = 0; s < nseg; ++s) {
 			const hb_list_desc &L = single ? *single : descs[s].lists[l];
 			HB_TRY(copy_in(m, dl.p.rows + (size_t)dl.h_rowbase[s] * L0.stride, L.rows, (size_t)L.nrows * L0.stride));
@@ -1010,6 +1073,7 @@ extern "C" int hb_bounds(hb_ctx *ctx, const hb_list_desc *list, void *min_row, v
 	if (rc == 0 && list->ncomp) rc = hb_dmesh_fetch_bounds(m, 0, min_row, max_row, nullptr);
 	t.mark(3);
 	t.finish(4);
+	if (rc == 0) row_cache_put(m, 0, list->rows); // requant of the same rows usually follows (quant.h:222-242)
 	hb_dmesh_free(m);
 	return rc;
 }
@@ -1020,6 +1084,7 @@ extern "C" int hb_requant(hb_ctx *ctx, hb_list_desc *list, const uint8_t *new_qu
 	hb_dmesh *m = new hb_dmesh();
 	PhaseTimer t(ctx);
 	t.mark(0);
+	m->take_cached_rows = true;
 	int rc = single_list_mesh(ctx, list, m);
 	if (rc == 0 && list->ncomp) rc = hb_dmesh_set_bounds(m, 0, min_row, nullptr, scale_row);
 	t.mark(1);
@@ -1030,6 +1095,7 @@ extern "C" int hb_requant(hb_ctx *ctx, hb_list_desc *list, const uint8_t *new_qu
 	t.finish(4);
 	if (rc == 0)
 		for (int j = 0; j < list->ncomp; ++j) list->quant[j] = new_quant[j];
+	if (rc == 0) row_cache_put(m, 0, list->rows); // the coder (or another requant) usually follows
 	hb_dmesh_free(m);
 	return rc;
 }
@@ -1085,6 +1151,7 @@ extern "C" int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams 
 	*out = nullptr;
 	HB_CUDA(ctx, cudaSetDevice(ctx->device));
 	hb_dmesh *m = new hb_dmesh();
+	m->take_cached_rows = true;
 	PhaseTimer t(ctx);
 	t.mark(0);
 	int rc = upload_overlapped(ctx, mesh, 1, m, false);
@@ -1120,6 +1187,7 @@ extern "C" int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh)
 	t.mark(3);
 	t.finish(4);
 	if (rc == 0) rc = hb_check_device_error(ctx, "attribute decode");
+	for (int l = 0; rc == 0 && l < mesh->nlists; ++l) row_cache_put(m, l, mesh->lists[l].rows); // requant(clear) may follow (main.cc:104-108)
 	hb_dmesh_free(m);
 	return rc;
 }

@@ -35,6 +35,12 @@ struct hb_ctx {
 	int *d_err = nullptr;   // device error flag (fan walk overflow, binding out of range)
 	int *h_err = nullptr;   // pinned mirror
 	int sm_count = 148;
+	// Optional row cache (hb_ctx_set_row_cache): the device copy of a list's rows survives from one host-buffer call to
+	// the next of the same pipeline (set_bounds -> requant -> encode; decode -> requant(clear)), keyed by the host
+	// pointer of the rows, so the rows travel once per direction instead of once per call.
+	struct RowEntry { const void *host; uint32_t nrows, stride; uint8_t *dev; uint8_t quant[HB_MAX_COMP]; int ncomp; };
+	bool row_cache = false;
+	std::vector<RowEntry> rows_cached;
 	// optional per-kernel timing (CUDA events around every launch on the context stream)
 	bool profiling = false;
 	struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -105,6 +111,7 @@ struct DevList {
 	uint32_t *d_wide = nullptr;         // encode: elements deferred to the warp-per-element kernel
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
+	bool rows_from_cache = false;       // the rows were already on the device (row cache): nothing was uploaded
 	bool nocomp_fast = false;           // encode: zero-component list coded by the two-pass path (hb_encode.cu)
 	uint8_t *d_done = nullptr;          // decode: corner wavefront flags
 	uint32_t *d_remaining = nullptr;
@@ -130,6 +137,7 @@ struct hb_dmesh {
 	bool has_order_f = false;
 	bool async_copy = false;     // uploads go to ctx->copy_stream (hb_attr_encode / hb_attr_decode)
 	bool alloc_on_copy_stream = false; // while the upload buffers are being allocated
+	bool take_cached_rows = false;     // rows may come from the context's row cache (requant / encode continue a pipeline)
 	cudaEvent_t ev_up[2] = { nullptr, nullptr }; // copy-stream milestones: connectivity landed / everything landed
 	cudaEvent_t ev_done = nullptr;               // kernels of this mesh / group finished (pipelined batches)
 	std::vector<void *> allocs;

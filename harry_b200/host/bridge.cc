@@ -21,6 +21,9 @@ struct Warmup {
 			const char *dev = std::getenv("HARRY_B200_DEVICE");
 			const int rc = hb_ctx_create(dev ? std::atoi(dev) : 0, &g_ctx);
 			if (rc != 0) error = hb_last_error(nullptr);
+			// main.cc never touches the rows between set_bounds -> requant -> write / read -> requant(clear): their device
+			// copy stays where it is between the calls (one upload per pipeline instead of one per call)
+			else hb_ctx_set_row_cache(g_ctx, 1);
 			return rc;
 		});
 	}

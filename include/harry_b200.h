@@ -187,6 +187,13 @@ const char *hb_last_error(hb_ctx *ctx); /* ctx may be NULL: last error of hb_ctx
 /* Times (ms, CUDA events on the context stream) of the last call: kernels only, and the
  * host<->device copies around them. */
 void hb_last_timing(hb_ctx *ctx, float *kernel_ms, float *copy_ms);
+/* Row cache (off by default).  While enabled, the device copy of a list's rows survives from one host-buffer call to
+ * the next call of the same pipeline -- set_bounds -> requant -> attr_encode, attr_decode -> requant(clear) -- keyed by
+ * the host address of the rows (plus row count, stride and quantization state), so the rows cross the link once per
+ * direction instead of once per call.  The host rows are still updated by every call.  Contract: between those calls the
+ * caller does not modify the rows behind the library's back (the reference's own pipeline, main.cc:98-117, never does).
+ * Disabling frees the cached copies. */
+int hb_ctx_set_row_cache(hb_ctx *ctx, int enable);
 /* Number of kernels this library launched on the context since creation. */
 uint64_t hb_kernel_launches(hb_ctx *ctx);
 

@@ -250,3 +250,46 @@ def test_zero_component_list_with_shared_rows(ctx):
         ok, why = got.equal(ol.o_attr_encode(mesh))
         assert ok, why
     dm.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["sphere_q14", "sphere_lossless", "obj_multi_all", "rgb_q5_xyz_q14", "poly_q10"])
+def test_row_cache_pipeline(workdir, name):
+    """hb_ctx_set_row_cache: the adapter's call order on the SAME host buffers (set_bounds -> requant -> encode, decode ->
+    requant(clear)), twice over refilled buffers -- same results as without the cache, no stale device rows"""
+    case = get_case(workdir, name)
+    c = capi.Context(0)
+    c.set_row_cache(True)
+    raw = case.raw.copy()
+    raw.order, raw.order_f, raw.edges = case.enc.order, case.enc.order_f, case.enc.edges
+    m = case.decode_input()
+    fresh_raw = [la.rows.copy() for la in raw.lists]
+    fresh_dec = [la.rows.copy() for la in m.lists]
+    dec_quants = [list(la.quants) for la in m.lists]
+    for rep in range(2):
+        for l, la in enumerate(raw.lists):
+            la.rows[...] = fresh_raw[l]
+            la.quants = [0] * la.ncomp
+            if not la.ncomp:
+                continue
+            mn, mx = c.bounds(la)
+            assert np.array_equal(mn, case.raw_bounds[l][0]) and np.array_equal(mx, case.raw_bounds[l][1])
+            nq = case.enc.lists[l].quants
+            if nq != la.quants:
+                c.requant(la, nq, mn, case.raw_scale[l])
+                assert np.array_equal(la.rows, case.enc.lists[l].rows), f"rep {rep}: quantized rows, list {l}"
+        ok, why = c.attr_encode(raw).equal(case.enc_streams)
+        assert ok, f"rep {rep}: {why}"
+        for l, la in enumerate(m.lists):
+            la.rows[...] = fresh_dec[l]
+            la.quants = list(dec_quants[l])
+        c.attr_decode(m)
+        for l, la in enumerate(case.dec.lists):
+            assert np.array_equal(m.lists[l].rows, la.rows), f"rep {rep}: decoded rows, list {l}"
+        if case.deq is not None:
+            for l, la in enumerate(case.dec.lists):
+                if any(la.quants):
+                    c.requant(m.lists[l], [0] * la.ncomp, case.dec_bounds[l][0], case.deq_scale[l])
+                    assert np.array_equal(m.lists[l].rows, case.deq.lists[l].rows), f"rep {rep}: dequantized rows, list {l}"
+    c.set_row_cache(False)
+    c.close()
