@@ -15,6 +15,7 @@
 
 #include <float.h>
 #include <string.h>
+#include <stdlib.h>
 
 // monotone u64 sort keys: unsigned order of the key == numeric order of the value
 __device__ __forceinline__ unsigned long long key_of(unsigned long long bits, int type)
@@ -65,6 +66,7 @@ struct BoundsSeg {
 	const uint32_t *rowbase, *rownum;
 	unsigned long long *scratch;   // [nseg][4 * ncomp]
 	uint32_t *ticket;              // [nseg]
+	uint32_t *partial;             // flat float kernel: [nseg][blocks][4 * ncomp] per-block results
 	uint8_t *bounds;               // [nseg] triples of rows, `pitch` bytes apart
 	size_t pitch;
 	uint8_t groups[HB_MAX_COMP];   // interpretation-group leader per component (quant.h:54-91)
@@ -126,7 +128,8 @@ __device__ void scale_segment(const ListParams &p, uint8_t *__restrict__ bounds,
 
 // the block's partial results are in the scratch words: the last block of the segment turns them into rows
 // [0] min, [1] max (, [2] scale) -- `stride` bytes each, components at their row offsets
-__device__ void bounds_tail(const ListParams &p, const BoundsSeg &b, uint32_t seg, uint32_t blocks_per_seg)
+// true in the block that finishes last in its segment (every block's results are visible to it)
+__device__ bool bounds_is_last(const BoundsSeg &b, uint32_t seg, uint32_t blocks_per_seg)
 {
 	__shared__ uint32_t s_last;
 	__syncthreads();
@@ -135,9 +138,12 @@ __device__ void bounds_tail(const ListParams &p, const BoundsSeg &b, uint32_t se
 		s_last = atomicAdd(&b.ticket[seg], 1u) == blocks_per_seg - 1 ? 1u : 0u;
 	}
 	__syncthreads();
-	if (!s_last) return;
-	__threadfence();
-	volatile unsigned long long *sc = b.scratch + (size_t)seg * 4 * p.ncomp;
+	if (s_last) __threadfence();
+	return s_last != 0;
+}
+// sc: the combined words of the segment (global scratch, or shared memory of the last block)
+__device__ void bounds_finish(const ListParams &p, const BoundsSeg &b, uint32_t seg, const volatile unsigned long long *sc)
+{
 	uint8_t *bounds = b.bounds + (size_t)seg * b.pitch;
 	if ((int)threadIdx.x < p.ncomp) {
 		const int j = threadIdx.x;
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(256) k_bounds_reduce(ListParams p, BoundsSeg b
 	unsigned long long *sc = b.scratch + (size_t)seg * 4 * p.ncomp;
 	for (int k = threadIdx.x; k < 4 * p.ncomp; k += blockDim.x)
 		if (s_red[k]) atomicMax(&sc[k], s_red[k]);
-	bounds_tail(p, b, seg, gridDim.x);
+	if (bounds_is_last(b, seg, gridDim.x)) bounds_finish(p, b, seg, b.scratch + (size_t)seg * 4 * p.ncomp);
 }
 
 // quant.h:98-112, integer flavour, evaluated in T (narrow types compute in int and truncate)
@@ -292,7 +298,9 @@ __global__ void __launch_bounds__(256) k_requant(ListParams p, RequantParams rq,
 // the threads of a segment are a multiple of ncomp, so the component of each of a thread's four lanes
 // never changes.  Same arithmetic as the generic kernels.
 // ------------------------------------------------------------------------------------------------
+#ifndef FLAT_UNROLL
 #define FLAT_UNROLL 4
+#endif
 static bool flat_f32(const ListParams &p)
 {
 	if (p.ncomp < 1 || p.ncomp > 4 || p.stride != 4u * (uint32_t)p.ncomp || (((size_t)p.rows) & 15u)) return false;
@@ -319,16 +327,24 @@ __global__ void __launch_bounds__(256) k_bounds_reduce_f32(ListParams p, BoundsS
 		kmax[m] = 0x00800000u ^ 0x80000000u;   // key of numeric_limits<float>::min() (quant.h:33)
 		zneg[m] = zpos[m] = 0xffffffffu;
 	}
-	auto take = [&](int m, uint32_t bits, uint32_t e) {
-		if ((bits & 0x7fffffffu) > 0x7f800000u) return; // NaN never replaces a bound
-		if ((bits & 0x7fffffffu) == 0u) { // remember which zero came first in row order
-			const uint32_t row = e / ncomp;
-			if (bits >> 31) zneg[m] = min(zneg[m], row);
-			else zpos[m] = min(zpos[m], row);
-		}
-		const uint32_t k = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
-		kmin[m] = min(kmin[m], k);
-		kmax[m] = max(kmax[m], k);
+	// Branch-free per scalar: the order-preserving key of a NaN lies outside [key(-inf), key(+inf)], so one unsigned
+	// range test keeps NaNs from replacing a bound.  Zeros (their first row decides the sign of a zero minimum) are
+	// rare: one test per vector, details on the slow path.
+	auto take = [&](int m, uint32_t bits) {
+		const uint32_t k = bits ^ ((uint32_t)((int32_t)bits >> 31) | 0x80000000u);
+		const bool valid = k - 0x007fffffu <= 0xff800000u - 0x007fffffu;
+		kmin[m] = min(kmin[m], valid ? k : 0xffffffffu);
+		kmax[m] = max(kmax[m], valid ? k : 0u);
+	};
+	auto zeros = [&](const uint4 &q, uint32_t e) {
+		const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+		for (int m = 0; m < 4; ++m)
+			if ((w[m] << 1) == 0u) {
+				const uint32_t row = (e + (uint32_t)m) / ncomp;
+				if (w[m] >> 31) zneg[m] = min(zneg[m], row);
+				else zpos[m] = min(zpos[m], row);
+			}
 	};
 	for (uint32_t v = tid; v < nvec; v += FLAT_UNROLL * G) {
 		uint4 q[FLAT_UNROLL];
@@ -339,8 +355,8 @@ __global__ void __launch_bounds__(256) k_bounds_reduce_f32(ListParams p, BoundsS
 		}
 #pragma unroll
 		for (int u = 0; u < FLAT_UNROLL; ++u) {
-			const uint32_t e = 4u * (v + (uint32_t)u * G);
-			take(0, q[u].x, e); take(1, q[u].y, e + 1u); take(2, q[u].z, e + 2u); take(3, q[u].w, e + 3u);
+			take(0, q[u].x); take(1, q[u].y); take(2, q[u].z); take(3, q[u].w);
+			if (min(min(q[u].x << 1, q[u].y << 1), min(q[u].z << 1, q[u].w << 1)) == 0u) zeros(q[u], 4u * (v + (uint32_t)u * G));
 		}
 	}
 	// per-component accumulators of this thread, then a shuffle reduction over the warp, one shared-memory
@@ -383,16 +399,41 @@ __global__ void __launch_bounds__(256) k_bounds_reduce_f32(ListParams p, BoundsS
 		for (int c = 0; c < NC; ++c) { s_w[warp][4 * c] = amin[c]; s_w[warp][4 * c + 1] = amax[c]; s_w[warp][4 * c + 2] = azn[c]; s_w[warp][4 * c + 3] = azp[c]; }
 	}
 	__syncthreads();
+	// one slot of partial results per block -- a thousand blocks hammering a dozen addresses with atomics cost more than
+	// the whole streaming loop of a 120 MB list; the block that finishes last folds the slots
+	uint32_t *part = b.partial + ((size_t)seg * gridDim.x + blockIdx.x) * 4 * NC;
 	if (threadIdx.x < 4 * NC) {
 		const uint32_t k = threadIdx.x;
 		uint32_t v = s_w[0][k];
 		for (int w = 1; w < 8; ++w) v = (k & 3) == 1 ? max(v, s_w[w][k]) : min(v, s_w[w][k]);
-		unsigned long long *sc = b.scratch + (size_t)seg * 4 * NC;
-		if ((k & 3) == 1) atomicMax(&sc[k], (unsigned long long)v);
-		else if ((k & 3) == 0) atomicMax(&sc[k], ~(unsigned long long)v);          // keys: 32-bit, stored as ~(u64)key
-		else if (v != 0xffffffffu) atomicMax(&sc[k], ~(unsigned long long)v);
+		part[k] = v;
 	}
-	bounds_tail(p, b, seg, gridDim.x);
+	if (!bounds_is_last(b, seg, gridDim.x)) return;
+	{
+		constexpr uint32_t W = 4 * NC, GROUPS = 256 / W;
+		__shared__ uint32_t s_f[GROUPS][W];
+		__shared__ unsigned long long s_fin[W];
+		const uint32_t k = threadIdx.x % W, g = threadIdx.x / W;
+		if (g < GROUPS) {
+			uint32_t v = (k & 3) == 1 ? 0u : 0xffffffffu;
+			const uint32_t *all = b.partial + (size_t)seg * gridDim.x * W;
+#pragma unroll 4
+			for (uint32_t blk = g; blk < gridDim.x; blk += GROUPS) {
+				const uint32_t x = __ldcg(all + (size_t)blk * W + k); // written by other SMs: L2
+				v = (k & 3) == 1 ? max(v, x) : min(v, x);
+			}
+			s_f[g][k] = v;
+		}
+		__syncthreads();
+		if (threadIdx.x < W) {
+			uint32_t v = s_f[0][k];
+			for (uint32_t gg = 1; gg < GROUPS; ++gg) v = (k & 3) == 1 ? max(v, s_f[gg][k]) : min(v, s_f[gg][k]);
+			// the finish reads u64 words combined with max: [0] ~min key, [1] max key, [2] / [3] ~first row of -0.0 / +0.0 (0 = none)
+			s_fin[k] = (k & 3) == 1 ? (unsigned long long)v : ((k & 3) == 0 || v != 0xffffffffu ? ~(unsigned long long)v : 0ull);
+		}
+		__syncthreads();
+		bounds_finish(p, b, seg, s_fin);
+	}
 }
 
 struct FlatRequant {
@@ -484,13 +525,21 @@ static uint32_t max_seg_rows(const DevList &dl)
 
 // blocks per segment of a flat kernel: the whole grid (blocks * nseg) should be ~8 blocks of 256 per SM, a
 // multiple of ncomp per segment, not more than the work of the largest segment
-static uint32_t flat_blocks(hb_ctx *ctx, uint32_t nvec, uint32_t ncomp, uint32_t nseg)
+template <typename K>
+static uint32_t flat_blocks(hb_ctx *ctx, K kernel, uint32_t nvec, uint32_t ncomp, uint32_t nseg)
 {
-	uint32_t blocks = hb_div_up((uint64_t)ctx->sm_count * 8, nseg);
+	// exactly one wave: as many blocks as are resident at once (a second, partly filled wave costs as much as a full one
+	// in a kernel that lasts a few tens of microseconds)
+	static const char *env = getenv("HARRY_B200_FLAT_BLOCKS_PER_SM"); // tuning knob
+	int resident = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 256, 0) != cudaSuccess || resident < 1) resident = 4;
+	const uint32_t per_sm = env && atoi(env) > 0 ? (uint32_t)atoi(env) : (uint32_t)resident;
+	uint32_t blocks = (uint32_t)((uint64_t)ctx->sm_count * per_sm / nseg);
 	const uint32_t need = hb_div_up(nvec ? nvec : 1, 256 * FLAT_UNROLL);
 	if (blocks > need) blocks = need;
 	if (blocks == 0) blocks = 1;
-	blocks = (blocks + ncomp - 1) / ncomp * ncomp;
+	blocks = blocks / ncomp * ncomp; // a multiple of ncomp (rounded down: never more than one wave)
+	if (blocks == 0) blocks = ncomp;
 	return blocks;
 }
 
@@ -527,8 +576,13 @@ int hb_list_bounds(hb_dmesh *m, uint32_t l, const uint8_t *groups)
 	if (groups) memcpy(b.groups, groups, p.ncomp);
 	b.err = ctx->d_err;
 	const uint32_t mxrows = max_seg_rows(dl);
+	uint32_t *partial = nullptr;
 	if (flat_f32(p) && (uint64_t)mxrows * p.ncomp < 0xffffffffull) {
-		const dim3 grid(flat_blocks(ctx, (mxrows * (uint32_t)p.ncomp) >> 2, (uint32_t)p.ncomp, nseg), nseg);
+		const uint32_t nvec = (mxrows * (uint32_t)p.ncomp) >> 2, nc = (uint32_t)p.ncomp;
+		const dim3 grid(p.ncomp == 1 ? flat_blocks(ctx, k_bounds_reduce_f32<1>, nvec, nc, nseg) : p.ncomp == 2 ? flat_blocks(ctx, k_bounds_reduce_f32<2>, nvec, nc, nseg)
+		                : p.ncomp == 3 ? flat_blocks(ctx, k_bounds_reduce_f32<3>, nvec, nc, nseg) : flat_blocks(ctx, k_bounds_reduce_f32<4>, nvec, nc, nseg), nseg);
+		HB_CUDA(ctx, cudaMallocAsync((void **)&partial, sizeof(uint32_t) * 4 * p.ncomp * (size_t)grid.x * nseg, ctx->stream));
+		b.partial = partial;
 		switch (p.ncomp) {
 		case 1: HB_LAUNCH(ctx, k_bounds_reduce_f32<1>, grid, 256, 0, p, b); break;
 		case 2: HB_LAUNCH(ctx, k_bounds_reduce_f32<2>, grid, 256, 0, p, b); break;
@@ -541,6 +595,7 @@ int hb_list_bounds(hb_dmesh *m, uint32_t l, const uint8_t *groups)
 		HB_LAUNCH(ctx, k_bounds_reduce, grid, 256, 0, p, b, rps);
 	}
 	HB_CUDA(ctx, cudaFreeAsync(scratch, ctx->stream));
+	if (partial) HB_CUDA(ctx, cudaFreeAsync(partial, ctx->stream));
 	return 0;
 }
 
@@ -602,10 +657,10 @@ int hb_list_requant(hb_dmesh *m, uint32_t l, const uint8_t *new_quant)
 			uni_q = uni_q && sq == 0 && dq != 0 && dq == new_quant[0];
 			uni_d = uni_d && dq == 0 && sq != 0 && sq == p.quant[0];
 		}
-		const dim3 grid(flat_blocks(ctx, (mxrows * (uint32_t)p.ncomp) >> 2, (uint32_t)p.ncomp, nseg), nseg);
-		if (uni_q) HB_LAUNCH(ctx, k_requant_f32<1>, grid, 256, 0, p, fr, sg);
-		else if (uni_d) HB_LAUNCH(ctx, k_requant_f32<2>, grid, 256, 0, p, fr, sg);
-		else HB_LAUNCH(ctx, k_requant_f32<0>, grid, 256, 0, p, fr, sg);
+		const uint32_t nvec = (mxrows * (uint32_t)p.ncomp) >> 2, nc = (uint32_t)p.ncomp;
+		if (uni_q) { const dim3 grid(flat_blocks(ctx, k_requant_f32<1>, nvec, nc, nseg), nseg); HB_LAUNCH(ctx, k_requant_f32<1>, grid, 256, 0, p, fr, sg); }
+		else if (uni_d) { const dim3 grid(flat_blocks(ctx, k_requant_f32<2>, nvec, nc, nseg), nseg); HB_LAUNCH(ctx, k_requant_f32<2>, grid, 256, 0, p, fr, sg); }
+		else { const dim3 grid(flat_blocks(ctx, k_requant_f32<0>, nvec, nc, nseg), nseg); HB_LAUNCH(ctx, k_requant_f32<0>, grid, 256, 0, p, fr, sg); }
 	} else if (any && mxrows) {
 		const uint32_t rps = pick_rows_per_step(ctx, p, mxrows, nseg);
 		const dim3 grid(hb_div_up((uint64_t)rps * p.ncomp, 256), nseg);
