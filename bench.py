@@ -271,11 +271,11 @@ def algorithmic_bytes(w: Workload) -> dict:
 
 def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` per launch, from the committed summary of the
-    last `ncu --set full` capture of this workload (profiles/r01b_*_ncu_full.txt); None if not captured."""
+    last `ncu --set full` capture of this workload (profiles/r02_kernels_10m_ncu_full.txt); None if not captured."""
     import glob
     import re
     units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01b_*_ncu_full.txt"))):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_kernels_10m_ncu_full.txt"))):
         cur, rd, wr = None, None, None
         for line in open(path):
             if line.startswith("## "):

@@ -218,21 +218,30 @@ __device__ __forceinline__ uint32_t nocomp_row(const NoCompArgs &a, uint32_t i, 
 	if (row >= a.rs.rownum[s]) { atomicExch(err, 7); return HB_NONE; }
 	return row + a.rs.rowbase[s];
 }
+// pass 1: first reference of every row; *dup is raised when some row is referenced twice (never for identity bindings)
 template <int CLS>
-__global__ void __launch_bounds__(256) k_nocomp_first(NoCompArgs a, int *err)
+__global__ void __launch_bounds__(256) k_nocomp_first(NoCompArgs a, uint32_t *dup, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= a.n) return;
 	const uint32_t row = nocomp_row<CLS>(a, i, err);
-	a.erow[i] = row;
-	if (row != HB_NONE) atomicMin(&a.first[row], i);
+	if (row != HB_NONE && atomicMin(&a.first[row], i) != HB_NONE) *dup = 1u;
 }
-__global__ void __launch_bounds__(256) k_nocomp_types(NoCompArgs a)
+// pass 2.  No row is shared (the usual case): every emission is a DATA row, the type stream stays the zeros it was
+// cleared to and only the per-segment counts are written -- nothing is gathered.  Otherwise: type symbols per element.
+template <int CLS>
+__global__ void __launch_bounds__(256) k_nocomp_types(NoCompArgs a, const uint32_t *dup, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (*dup == 0u) {
+		for (uint32_t sg = i; sg < a.rs.nseg; sg += gridDim.x * blockDim.x)
+			a.type_hist[(size_t)sg * a.hist_pitch + HB_DATA] = a.elem_base[sg + 1] - a.elem_base[sg]; // bound in every region
+		return;
+	}
 	int t = -1;
 	if (i < a.n) {
-		const uint32_t row = a.erow[i];
+		const uint32_t row = nocomp_row<CLS>(a, i, err);
+		a.erow[i] = row;
 		if (row != HB_NONE) {
 			t = a.first[row] == i ? HB_DATA : HB_HIST;
 			a.type[i] = (uint8_t)t;
@@ -497,7 +506,7 @@ __global__ void __launch_bounds__(256) k_gather_packed(ListParams p, const uint3
 }
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p, EncodeArgs a, const SpecRec<T, NC> *__restrict__ rec)
+__global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p, EncodeArgs a, const SpecRec<T, NC> *__restrict__ rec, uint32_t chunks_per_cta)
 {
 	typedef SpecRec<T, NC> Rec;
 	typedef typename std::conditional<(sizeof(T) <= 2), uint32_t, unsigned long long>::type Acc;
@@ -506,61 +515,81 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p,
 	for (int k = threadIdx.x; k < NCTX * 256 + 4; k += ENC_THREADS) s_hist[k] = 0;
 	__syncthreads();
 	uint32_t *s_type = s_hist + NCTX * 256;
-
-	const uint32_t i = blockIdx.x * ENC_THREADS + threadIdx.x;
-	uint32_t myseg;
-	const uint32_t bseg = block_segment(a, blockIdx.x * ENC_THREADS, myseg, i);
-	const bool agg = bseg != HB_NONE; // one segment in this block: shared-memory histograms
-	const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
-	int t = -1;
-	T res[NC];
+	int bits[NC];
 #pragma unroll
-	for (int j = 0; j < NC; ++j) res[j] = 0;
-	if (row != HB_NONE) {
-		const uint32_t k = a.ek ? a.ek[i] : i;
-		const uint32_t fi = a.first[row];
-		t = HB_DATA;
-		uint32_t aux = 0;
-		if (fi != i) {
-			t = HB_HIST;
-			aux = a.dord[i] - 1u - a.dord[fi]; // tidx - 1 - g, attrcode.h:43-52
+	for (int j = 0; j < NC; ++j) bits[j] = hb_stype_bits(p.stype[j], p.quant[j]);
+	// A CTA codes a contiguous run of chunks of ENC_THREADS elements and keeps ONE set of shared-memory histograms for
+	// the segment it is in: they are cleared and flushed when the segment changes and at the end, not once per chunk
+	// (zeroing + flushing 1536 bins cost a sixth of the instructions of the one-chunk-per-CTA version).
+	uint32_t cur_seg = HB_NONE;
+	auto flush = [&]() {
+		if (cur_seg == HB_NONE) return;
+		__syncthreads();
+		unsigned long long *bh = a.hist + (size_t)cur_seg * a.hist_pitch, *bt = a.type_hist + (size_t)cur_seg * a.hist_pitch;
+		for (int k = threadIdx.x; k < NCTX * 256; k += ENC_THREADS) {
+			const uint32_t v = s_hist[k];
+			if (v) { atomicAdd(&bh[k], (unsigned long long)v); s_hist[k] = 0; }
 		}
-		a.type[k] = (uint8_t)t;
-		a.aux[k] = aux;
-		const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
-		if (t == HB_DATA && a.wide && K > ENC_WIDE_K) {
-			const uint32_t slot = atomicAdd(&a.wide[0], 1u);
-			if (slot < a.wide_cap) { a.wide[1 + slot] = i; t = -2; } // residual + histogram by k_encode_wide_packed
-		}
-		if (t == HB_DATA) {
-			const Rec raw = rec[i];
-			Acc sum[NC];
+		if (threadIdx.x < 3 && s_type[threadIdx.x]) { atomicAdd(&bt[threadIdx.x], (unsigned long long)s_type[threadIdx.x]); s_type[threadIdx.x] = 0; }
+		__syncthreads();
+	};
+	const uint32_t nchunks = (a.n + ENC_THREADS - 1) / ENC_THREADS;
+	const uint32_t c_begin = blockIdx.x * chunks_per_cta, c_end = min(nchunks, c_begin + chunks_per_cta);
+	for (uint32_t chunk = c_begin; chunk < c_end; ++chunk) {
+		const uint32_t i = chunk * ENC_THREADS + threadIdx.x;
+		uint32_t myseg;
+		const uint32_t bseg = block_segment(a, chunk * ENC_THREADS, myseg, i);
+		const bool agg = bseg != HB_NONE; // one segment in this chunk: shared-memory histograms
+		if (agg && bseg != cur_seg) { flush(); cur_seg = bseg; }
+		const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
+		int t = -1;
+		T res[NC];
 #pragma unroll
-			for (int j = 0; j < NC; ++j) sum[j] = 0;
-			for (uint32_t kk = 0; kk < K; ++kk) {
-				const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
-				const Rec v0 = rec[tr[0]], v1 = rec[tr[1]], v2 = rec[tr[2]];
-#pragma unroll
-				for (int j = 0; j < NC; ++j) sum[j] += (Acc)IntOps<T>::predict(v0.c[j], v1.c[j], v2.c[j], hb_stype_bits(p.stype[j], p.quant[j]));
+		for (int j = 0; j < NC; ++j) res[j] = 0;
+		if (row != HB_NONE) {
+			const uint32_t k = a.ek ? a.ek[i] : i;
+			const uint32_t fi = a.first[row];
+			t = HB_DATA;
+			uint32_t aux = 0;
+			if (fi != i) {
+				t = HB_HIST;
+				aux = a.dord[i] - 1u - a.dord[fi]; // tidx - 1 - g, attrcode.h:43-52
 			}
-			uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+			a.type[k] = (uint8_t)t;
+			a.aux[k] = aux;
+			const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
+			if (t == HB_DATA && a.wide && K > ENC_WIDE_K) {
+				const uint32_t slot = atomicAdd(&a.wide[0], 1u);
+				if (slot < a.wide_cap) { a.wide[1 + slot] = i; t = -2; } // residual + histogram by k_encode_wide_packed
+			}
+			if (t == HB_DATA) {
+				const Rec raw = rec[i];
+				Acc sum[NC];
 #pragma unroll
-			for (int j = 0; j < NC; ++j) {
-				const T pred = K == 0 ? (T)0 : (K == 1 ? (T)sum[j] : (K == 2 ? (T)((sum[j] + 1) >> 1) : (T)hb_divround_i64((long long)sum[j], (int)K)));
-				res[j] = IntOps<T>::enc(raw.c[j], pred, hb_stype_bits(p.stype[j], p.quant[j]));
-				hb_st_bits(out + p.sym_off[j], (int)sizeof(T), res[j]);
+				for (int j = 0; j < NC; ++j) sum[j] = 0;
+				for (uint32_t kk = 0; kk < K; ++kk) {
+					const uint32_t *tr = a.cand + 3 * (size_t)(c0 + kk);
+					const Rec v0 = rec[tr[0]], v1 = rec[tr[1]], v2 = rec[tr[2]];
+#pragma unroll
+					for (int j = 0; j < NC; ++j) sum[j] += (Acc)IntOps<T>::predict(v0.c[j], v1.c[j], v2.c[j], bits[j]);
+				}
+				uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+#pragma unroll
+				for (int j = 0; j < NC; ++j) {
+					const T pred = K == 0 ? (T)0 : (K == 1 ? (T)sum[j] : (K == 2 ? (T)((sum[j] + 1) >> 1) : (T)hb_divround_i64((long long)sum[j], (int)K)));
+					res[j] = IntOps<T>::enc(raw.c[j], pred, bits[j]);
+					hb_st_bits(out + p.sym_off[j], (int)sizeof(T), res[j]);
+				}
 			}
 		}
-	}
-	// warp-aggregated histogram update (see k_encode_main)
-	{
+		// warp-aggregated histogram update (see k_encode_main)
 		const bool is_data = t == HB_DATA;
 #pragma unroll
 		for (int j = 0; j < NC; ++j) {
 #pragma unroll
 			for (int b = 0; b < (int)sizeof(T); ++b) {
 				const uint32_t ctx = p.sym_off[j] + b;
-				if (!agg) { // block across a segment boundary (rare): plain global atomics on the thread's own segment
+				if (!agg) { // chunk across a segment boundary (rare): plain global atomics on the thread's own segment
 					if (is_data) atomicAdd(&a.hist[(size_t)myseg * a.hist_pitch + (size_t)ctx * 256 + (((uint32_t)res[j] >> (8 * b)) & 0xffu)], 1ull);
 					continue;
 				}
@@ -578,13 +607,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p,
 			atomicAdd(&a.type_hist[(size_t)myseg * a.hist_pitch + (t == -2 ? HB_DATA : t)], 1ull);
 		}
 	}
-	__syncthreads();
-	if (agg) {
-		unsigned long long *bh = a.hist + (size_t)bseg * a.hist_pitch, *bt = a.type_hist + (size_t)bseg * a.hist_pitch;
-		for (int k = threadIdx.x; k < NCTX * 256; k += ENC_THREADS)
-			if (s_hist[k]) atomicAdd(&bh[k], (unsigned long long)s_hist[k]);
-		if (threadIdx.x < 3 && s_type[threadIdx.x]) atomicAdd(&bt[threadIdx.x], (unsigned long long)s_type[threadIdx.x]);
-	}
+	flush();
 }
 
 // one CTA per wide vertex (integer sums are order independent)
@@ -642,7 +665,10 @@ static int encode_vtx_packed_nc(hb_dmesh *m, DevList &dl, const EncodeArgs &a)
 	SpecRec<T, NC> *rec = (SpecRec<T, NC> *)dl.d_cx;
 	HB_LAUNCH(ctx, (k_gather_packed<T, NC>), hb_div_up(n, 256), 256, 0, dl.p, dl.d_erow, n, rec);
 	const size_t smem = sizeof(uint32_t) * ((size_t)NC * sizeof(T) * 256 + 4);
-	HB_LAUNCH(ctx, (k_encode_vtx_packed<T, NC>), hb_div_up(n, ENC_THREADS), ENC_THREADS, smem, dl.p, a, rec);
+	// contiguous runs of chunks per CTA, about 16 CTAs per SM in all (8 resident at 32 registers: two waves)
+	const uint32_t nchunks = hb_div_up(n, ENC_THREADS);
+	const uint32_t per = hb_div_up(nchunks, (uint32_t)ctx->sm_count * 16u);
+	HB_LAUNCH(ctx, (k_encode_vtx_packed<T, NC>), hb_div_up(nchunks, per ? per : 1u), ENC_THREADS, smem, dl.p, a, rec, per ? per : 1u);
 	if (a.wide) HB_LAUNCH(ctx, (k_encode_wide_packed<T, NC>), 2 * ctx->sm_count, ENC_WIDE_T, 0, dl.p, a, rec);
 	return 0;
 }
@@ -777,8 +803,11 @@ static int encode_nocomp(hb_dmesh *m, int l)
 	HB_TRY(hb_dalloc_t(m, &dl.d_type, (size_t)n + 1));
 	HB_TRY(hb_dalloc_t(m, &dl.d_hist, hist_pitch * m->nseg));
 	dl.d_type_hist = dl.d_hist;
+	HB_TRY(hb_dalloc_t(m, &dl.d_dup, 1));
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_first, 0xff, sizeof(uint32_t) * ((size_t)dl.p.nrows + 1), ctx->stream));
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_hist, 0, sizeof(unsigned long long) * hist_pitch * m->nseg, ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(dl.d_type, 0, (size_t)n + 1, ctx->stream));
+	HB_CUDA(ctx, cudaMemsetAsync(dl.d_dup, 0, sizeof(uint32_t), ctx->stream));
 	if (!n) return 0;
 	NoCompArgs a;
 	a.order_f = m->has_order_f ? (const uint32_t *)m->d_order_f : nullptr;
@@ -794,9 +823,13 @@ static int encode_nocomp(hb_dmesh *m, int l)
 	a.elem_base = cls == CLS_VTX ? m->d_obase : m->d_ofbase;
 	a.erow = dl.d_erow; a.first = dl.d_first; a.type = dl.d_type; a.type_hist = dl.d_type_hist; a.hist_pitch = hist_pitch;
 	const uint32_t g = hb_div_up(n, 256);
-	if (cls == CLS_VTX) HB_LAUNCH(ctx, k_nocomp_first<CLS_VTX>, g, 256, 0, a, ctx->d_err);
-	else HB_LAUNCH(ctx, k_nocomp_first<CLS_FACE>, g, 256, 0, a, ctx->d_err);
-	HB_LAUNCH(ctx, k_nocomp_types, g, 256, 0, a);
+	if (cls == CLS_VTX) {
+		HB_LAUNCH(ctx, k_nocomp_first<CLS_VTX>, g, 256, 0, a, dl.d_dup, ctx->d_err);
+		HB_LAUNCH(ctx, k_nocomp_types<CLS_VTX>, g, 256, 0, a, dl.d_dup, ctx->d_err);
+	} else {
+		HB_LAUNCH(ctx, k_nocomp_first<CLS_FACE>, g, 256, 0, a, dl.d_dup, ctx->d_err);
+		HB_LAUNCH(ctx, k_nocomp_types<CLS_FACE>, g, 256, 0, a, dl.d_dup, ctx->d_err);
+	}
 	return 0;
 }
 

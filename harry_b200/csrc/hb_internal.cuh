@@ -112,6 +112,7 @@ struct DevList {
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
 	bool rows_from_cache = false;       // the rows were already on the device (row cache): nothing was uploaded
+	uint32_t *d_dup = nullptr;          // zero-component list: some row is referenced twice
 	bool nocomp_fast = false;           // encode: zero-component list coded by the two-pass path (hb_encode.cu)
 	uint8_t *d_done = nullptr;          // decode: corner wavefront flags
 	uint32_t *d_remaining = nullptr;
