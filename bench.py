@@ -359,48 +359,83 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     w = Workload(nr, ns, workdir, keep_ref=want_cpu)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # two contexts (= two streams) on the GPU: the encode of the mesh and the decode of the decoder-side mesh are
+    # independent jobs, and the chain-bound vertex decode of ONE mesh occupies 48 of the 148 SMs -- the encode fits beside it
     ctx = capi.Context(local_rank)
+    ctx_d = ctx if args.one_stream else capi.Context(local_rank)
     vl = 1
     groups = w.raw.lists[vl].groups
     E = capi.DeviceMesh(ctx, w.raw)
     E.snapshot()
-    D = capi.DeviceMesh(ctx, w.dec)
+    D = capi.DeviceMesh(ctx_d, w.dec)
     for l, (mn, mx, sc) in enumerate(w.dec_bounds):
         if w.dec.lists[l].ncomp:
             D.set_bounds(l, mn, mx, sc)
     D.snapshot()
     ctx.sync()
+    ctx_d.sync()
 
     def step():
         E.restore()
         D.restore()
+        if ctx_d is not ctx:            # both streams start the step together, behind both restores
+            ctx.wait(ctx_d)
+            ctx_d.wait(ctx)
         ctx.mark(2)
+        ctx_d.mark(0)
         E.quantize(vl, w.new_quant[vl], groups)
         E.encode()
         ctx.mark(3)
         D.decode()
         D.dequantize(vl)
-        ctx.mark(4)
+        ctx_d.mark(1)
+        if ctx_d is not ctx:
+            ctx.wait(ctx_d)
+        ctx.mark(4)                     # both jobs done
 
     for _ in range(args.warmup):
         step()
     ctx.sync()
+    ctx_d.sync()
     if dist is not None:
         dist.barrier()
     sampler.begin_region()
-    launches0 = ctx.launches()
-    ctx.profile(True)
-    enc_ms = dec_ms = 0.0
+    launches0 = ctx.launches() + (ctx_d.launches() if ctx_d is not ctx else 0)
+    enc_ms = dec_ms = total_ms = 0.0
     for _ in range(args.steps):
         step()
         enc_ms += ctx.elapsed(2, 3)
-        dec_ms += ctx.elapsed(3, 4)
+        dec_ms += ctx_d.elapsed(0, 1)
+        total_ms += ctx.elapsed(2, 4)
     ctx.sync()
-    prof = ctx.profile_report()
-    ctx.profile(False)
+    ctx_d.sync()
     clocks = sampler.stop()
-    launches = ctx.launches() - launches0
-    total_ms, enc_ms, dec_ms = allreduce_max(dist, local_rank, [enc_ms + dec_ms, enc_ms, dec_ms])
+    launches = ctx.launches() + (ctx_d.launches() if ctx_d is not ctx else 0) - launches0
+    # per-kernel durations (roofline of the dominant kernel): CUDA events around every launch, in extra steps that run
+    # the two jobs one after the other -- a kernel timed while the other stream runs beside it measures the neighbour too
+    ctx.profile(True)
+    ctx_d.profile(True)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        E.restore()
+        D.restore()
+        E.quantize(vl, w.new_quant[vl], groups)
+        E.encode()
+        ctx_d.wait(ctx)
+        D.decode()
+        D.dequantize(vl)
+        ctx.wait(ctx_d)
+    ctx.sync()
+    ctx_d.sync()
+    prof = ctx.profile_report()
+    if ctx_d is not ctx:
+        for k, (n, ms) in ctx_d.profile_report().items():
+            n0, ms0 = prof.get(k, (0, 0.0))
+            prof[k] = (n0 + n, ms0 + ms)
+    ctx.profile(False)
+    ctx_d.profile(False)
+    serial_ms = sum(ms for _, ms in prof.values()) / prof_steps
+    total_ms, enc_ms, dec_ms = allreduce_max(dist, local_rank, [total_ms, enc_ms, dec_ms])
     if dist is not None:
         dist.barrier()
     ms_per_step = total_ms / args.steps
@@ -413,9 +448,9 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     tname, (tn, tms) = top
     per_launch_ms = tms / tn
     bytes_launch = alg.get(tname)
-    roof = {"bound": "hbm", "kernel": tname, "launches_per_step": tn / args.steps, "ms_per_launch": per_launch_ms,
-            "share_of_step": tms / total_ms if total_ms else None, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-            "traffic": ncu_traffic(tname)}
+    roof = {"bound": "hbm", "kernel": tname, "launches_per_step": tn / prof_steps, "ms_per_launch": per_launch_ms,
+            "share_of_step": (tms / prof_steps) / serial_ms if serial_ms else None, "share_of": "sum of the kernel times of a step",
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": ncu_traffic(tname)}
     if bytes_launch:
         roof["achieved"] = bytes_launch / (per_launch_ms * 1e-3) / 1e9
         roof["frac"] = roof["achieved"] / peak
@@ -426,7 +461,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     if tname == "k_decode_vertex_scan":
         roof["note"] = ("latency-bound dependency chain of ONE mesh (SURVEY 8d: reported as such, not hidden); the same kernel over a batch of "
                         "meshes is in batch.kernels")
-    kernels = kernel_table(prof, alg, peak, args.steps, total_ms)
+    kernels = kernel_table(prof, alg, peak, prof_steps, serial_ms * prof_steps)
 
     # ---- end to end through the host-buffer C ABI (rank-local, pinned host memory) ----------
     e2e = None
@@ -451,7 +486,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     batch = None
     if args.batch_meshes > 0 and ol.have_ref():
         try:
-            batch = run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak)
+            batch = run_batch(args, ctx, ctx_d, rank, world, local_rank, dist, workdir, peak)
         except Exception as e:  # the headline line must survive a failure of the extra measurement
             import traceback
             log(traceback.format_exc())
@@ -463,6 +498,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             configs = run_other_configs(ctx, workdir, peak)
         except Exception as e:
             configs = {"error": repr(e)}
+    if ctx_d is not ctx:
+        ctx_d.close()
     ctx.close()
     cli = None
     if rank == 0 and world == 1 and not args.no_cli:
@@ -485,6 +522,9 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
                        "inputs_prepared_by": Workload.source,
                        "vertex_attributes_per_gpu": n_attrs, "meshes": world, "parallelism": f"mesh-sharded x{world}, no collective",
                        "l2": "inputs (>= 1.3 GB of connectivity + rows per mesh) exceed the 126 MB L2; no explicit flush",
+                       "streams": ("one stream" if args.one_stream else "two streams of the same GPU: quantize + encode of the mesh on one, decode + dequantize of the decoder-side mesh "
+                                   "on the other (independent inputs; the chain-bound vertex decode of one mesh occupies 48 of 148 SMs); ms_per_step = both done; "
+                                   "encode_ms / decode_ms = each job on its own stream while the other runs"),
                        "batch_config": "configs[4] (the mesh batch north_star scales on) is measured in the same run at every N: see `batch`"},
             "encode_ms_per_step": enc_ms / args.steps, "decode_ms_per_step": dec_ms / args.steps,
             "encode_M_attrs_per_s": world * n_attrs / (enc_ms / args.steps * 1e-3) / 1e6 if enc_ms else None,
@@ -685,7 +725,7 @@ def batch_cpu_baseline(workdir):
                       f"AttrCoder<NullWriter>::encode + AttrDecoder<Replay>::decode + requant(clear); mean {1e3 * float(np.mean([t for _, t in res])):.0f} ms per mesh and core"}
 
 
-def run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak):
+def run_batch(args, ctx, ctx_d, rank, world, local_rank, dist, workdir, peak):
     """configs[4] on this rank: `--batch-meshes` independent meshes (cycled from `--batch-distinct` prepared ones).
     value: device resident -- `--batch-resident` meshes live in HBM as device meshes of one group each (one launch per
     stage over the group); a step runs quantize + encode + decode + dequantize over every group, `passes` times.
@@ -708,15 +748,20 @@ def run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak):
         idx = [(g * group + k) % distinct for k in range(group)]
         E = capi.DeviceMesh(ctx, [loads[i].raw for i in idx])
         E.snapshot()
-        D = capi.DeviceMesh(ctx, [loads[i].dec for i in idx])
+        D = capi.DeviceMesh(ctx_d, [loads[i].dec for i in idx])
         D.set_bounds(1, *(np.stack([loads[i].dec_bounds[wh] for i in idx]) for wh in (0, 1, 2)))
         D.snapshot()
         Es.append(E)
         Ds.append(D)
     ctx.sync()
+    ctx_d.sync()
     bm0 = loads[0]
 
     def step():
+        # encode groups on one stream, decode groups on the other (independent meshes)
+        if ctx_d is not ctx:
+            ctx.wait(ctx_d)
+            ctx_d.wait(ctx)
         ctx.mark(2)
         for _ in range(passes):
             for E, D in zip(Es, Ds):
@@ -726,11 +771,14 @@ def run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak):
                 E.encode()
                 D.decode()
                 D.dequantize(1)
+        if ctx_d is not ctx:
+            ctx.wait(ctx_d)
         ctx.mark(3)
 
     for _ in range(args.warmup):
         step()
     ctx.sync()
+    ctx_d.sync()
     # parity spot check inside the bench: first and last mesh of the last group against the reference's decode
     idx_last = [((n_groups - 1) * group + k) % distinct for k in range(group)]
     for seg in (0, group - 1):
@@ -738,16 +786,37 @@ def run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak):
             raise RuntimeError("batch decode differs from the reference")
     if dist is not None:
         dist.barrier()
-    launches0 = ctx.launches()
-    ctx.profile(True)
+    launches0 = ctx.launches() + (ctx_d.launches() if ctx_d is not ctx else 0)
     ms = 0.0
     for _ in range(args.steps):
         step()
         ms += ctx.elapsed(2, 3)
     ctx.sync()
+    ctx_d.sync()
+    launches = ctx.launches() + (ctx_d.launches() if ctx_d is not ctx else 0) - launches0
+    # per-kernel durations: one extra step with the two jobs one after the other (see run_ours)
+    ctx.profile(True)
+    ctx_d.profile(True)
+    for _ in range(passes):
+        for E, D in zip(Es, Ds):
+            E.restore()
+            E.quantize(1, bm0.new_quant, bm0.groups)
+            E.encode()
+            ctx_d.wait(ctx)
+            D.restore()
+            D.decode()
+            D.dequantize(1)
+            ctx.wait(ctx_d)
+    ctx.sync()
+    ctx_d.sync()
     prof = ctx.profile_report()
+    if ctx_d is not ctx:
+        for k, (n, kms) in ctx_d.profile_report().items():
+            n0, ms0 = prof.get(k, (0, 0.0))
+            prof[k] = (n0 + n, ms0 + kms)
     ctx.profile(False)
-    launches = ctx.launches() - launches0
+    ctx_d.profile(False)
+    serial_ms = sum(kms for _, kms in prof.values())
     ms = allreduce_max(dist, local_rank, [ms])[0]
     if dist is not None:
         dist.barrier()
@@ -761,9 +830,9 @@ def run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak):
     # per-launch figures: a kernel is launched passes * n_groups (* 2 for stages shared by encode and decode) times per step
     kernels = {}
     for name, (n, kms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-        k = {"launches_per_step": n / args.steps, "ms_per_step": kms / args.steps, "share_of_step": kms / ms if ms else None}
+        k = {"launches_per_step": n, "ms_per_step": kms, "share_of_kernel_time": kms / serial_ms if serial_ms else None}
         if alg.get(name):
-            k["GBps"] = alg[name] / (kms / args.steps * 1e-3) / 1e9
+            k["GBps"] = alg[name] / (kms * 1e-3) / 1e9
             k["frac_of_peak"] = k["GBps"] / peak
         kernels[name] = k
     for E, D in zip(Es, Ds):
@@ -773,7 +842,9 @@ def run_batch(args, ctx, rank, world, local_rank, dist, workdir, peak):
     out = {"value": value, "unit": UNIT, "ms_per_step": ms_step, "meshes_per_gpu_per_step": n_value, "vertices_per_mesh": bm0.nv, "attrs_per_mesh": attrs_per_mesh,
            "meshes_per_launch": group, "resident_meshes": resident, "passes_per_step": passes, "distinct_meshes": distinct, "n_gpus": world,
            "gpu_launches_per_step": launches / args.steps, "launches_per_mesh": launches / args.steps / n_value,
-           "ms_per_mesh_amortized": ms_step / n_value, "kernels": kernels,
+           "ms_per_mesh_amortized": ms_step / n_value, "kernels": kernels, "kernel_ms_serial_step": serial_ms,
+           "streams": "encode groups on one stream, decode groups on a second stream of the same GPU (independent meshes); kernels{} from one extra step "
+                      "that runs them one after the other",
            "workload": f"configs[4]: UV spheres {BATCH_SHAPE[0]}x{BATCH_SHAPE[1]} (100 130 vertices) with per-mesh seeded radial noise, -l1 -q{QBITS}, encode+decode; "
                        f"{n_value} meshes per GPU and step, sharded by mesh over {world} GPU(s), no collective",
            "timer": "CUDA events on the library stream around each step, max over ranks"}
@@ -1088,6 +1159,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the extra measurement of hb_twin_match (SURVEY 8f row f2)")
+    ap.add_argument("--one-stream", action="store_true", help="encode and decode one after the other on one stream (default: two streams, independent meshes)")
     ap.add_argument("--no-cli", action="store_true", help="skip the side-by-side run of the two CLIs on configs[1]")
     ap.add_argument("--no-configs", action="store_true", help="skip the lines for configs[0], [2], [3]")
     ap.add_argument("--batch-meshes", type=int, default=1250, help="configs[4]: independent 100K-vertex meshes per GPU and step (0 = skip)")

@@ -562,6 +562,8 @@ def load_library():
     lib.hb_dmesh_decode_stats.restype = C.c_int
     lib.hb_dmesh_fetch_bounds.argtypes = [vp, u32, vp, vp, vp]
     lib.hb_dmesh_fetch_bounds.restype = C.c_int
+    lib.hb_ctx_wait.argtypes = [vp, vp]
+    lib.hb_ctx_wait.restype = C.c_int
     lib.hb_ctx_sync.argtypes = [vp]
     lib.hb_ctx_sync.restype = C.c_int
     _lib = lib
@@ -576,7 +578,7 @@ EXPORTED_SYMBOLS = [
     "hb_dmesh_fetch_streams", "hb_dmesh_set_bounds", "hb_dmesh_snapshot", "hb_dmesh_restore", "hb_dmesh_decode", "hb_dmesh_fetch_rows",
     "hb_dmesh_fetch_bounds", "hb_dmesh_decode_stats", "hb_ctx_sync",
     "hb_dmesh_upload_batch", "hb_dmesh_segments", "hb_dmesh_fetch_streams_batch", "hb_dmesh_fetch_rows_seg",
-    "hb_encode_batch", "hb_decode_batch", "hb_batch_streams_free", "hb_ctx_set_row_cache",
+    "hb_encode_batch", "hb_decode_batch", "hb_batch_streams_free", "hb_ctx_set_row_cache", "hb_ctx_wait",
 ]
 
 
@@ -627,6 +629,10 @@ class Context:
 
     def sync(self):
         self._check(self.lib.hb_ctx_sync(self.h), "hb_ctx_sync")
+
+    def wait(self, other: "Context"):
+        """what is queued on `other` so far happens before what is queued on this context from now on"""
+        self._check(self.lib.hb_ctx_wait(self.h, other.h), "hb_ctx_wait")
 
     def profile(self, enable: bool):
         self._check(self.lib.hb_ctx_profile(self.h, 1 if enable else 0), "hb_ctx_profile")

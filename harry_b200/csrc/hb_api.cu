@@ -180,6 +180,20 @@ extern "C" int hb_ctx_elapsed(hb_ctx *ctx, int a, int b, float *ms)
 	return 0;
 }
 
+// everything queued on `other` so far happens before whatever is queued on `ctx` from now on (two contexts of one
+// device working on independent meshes: e.g. the encode of one mesh next to the decode of another)
+extern "C" int hb_ctx_wait(hb_ctx *ctx, hb_ctx *other)
+{
+	if (ctx->device != other->device) return hb_fail(ctx, HB_ERR_INVALID, "hb_ctx_wait: contexts of different devices");
+	HB_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaEvent_t e;
+	HB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	HB_CUDA(ctx, cudaEventRecord(e, other->stream));
+	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
+	HB_CUDA(ctx, cudaEventDestroy(e)); // released once it has completed
+	return 0;
+}
+
 extern "C" int hb_ctx_sync(hb_ctx *ctx)
 {
 	HB_CUDA(ctx, cudaSetDevice(ctx->device));

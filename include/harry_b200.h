@@ -287,6 +287,10 @@ int hb_dmesh_decode_stats(hb_dmesh *m, uint32_t l, uint64_t *out8);
 int hb_dmesh_snapshot(hb_dmesh *m);
 int hb_dmesh_restore(hb_dmesh *m);
 int hb_ctx_sync(hb_ctx *ctx);
+/* Orders the streams of two contexts of one device: what is queued on `other` so far happens before what is queued on
+ * `ctx` from now on.  Two contexts work concurrently on independent meshes (the chain-bound vertex decode of one mesh
+ * leaves most SMs idle: the encode of the next mesh fits beside it). */
+int hb_ctx_wait(hb_ctx *ctx, hb_ctx *other);
 
 #ifdef __cplusplus
 }
