@@ -293,3 +293,67 @@ def test_row_cache_pipeline(workdir, name):
                     assert np.array_equal(m.lists[l].rows, case.deq.lists[l].rows), f"rep {rep}: dequantized rows, list {l}"
     c.set_row_cache(False)
     c.close()
+
+
+# ---- malformed input: an error code, never an out-of-bounds access; the context stays usable ----------------------------
+def _corruptions():
+    def bad_org(m):
+        m.edges[5, 0] = m.nv + 7
+
+    def bad_twin_face(m):
+        m.edges[9, 1] = m.nf + 3
+
+    def bad_twin_edge(m):
+        m.edges[11, 2] = 200
+
+    def bad_order(m):
+        m.order[4, 0] = m.nf + 1
+
+    def bad_order_edge(m):
+        m.order[7, 1] = 9
+
+    def vertex_twice(m):
+        m.order[10] = m.order[3]        # a vertex listed twice in the traversal order (candidate bound 2 ne still holds or is flagged)
+
+    def bad_binding(m):
+        m.bind_vtx[2] = m.lists[1].nrows + 5
+
+    def bad_face_offsets(m):
+        m.face_off[3] = m.face_off[5] + 2   # not monotone: faces 2 / 3 have an impossible extent
+
+    return [bad_org, bad_twin_face, bad_twin_edge, bad_order, bad_order_edge, vertex_twice, bad_binding, bad_face_offsets]
+
+
+@pytest.mark.parametrize("corrupt", _corruptions(), ids=lambda f: f.__name__)
+def test_invalid_input_is_reported(corrupt):
+    from harry_b200 import flatten, meshgen
+    c = capi.Context(0)
+    good = flatten.mesh_arrays(meshgen.uv_sphere(14, 19, noise_seed=2))
+    want = c.attr_encode(good)
+    for batch in (False, True):
+        bad = good.copy()
+        for name in ("edges", "order", "bind_vtx", "face_off"):
+            setattr(bad, name, getattr(bad, name).copy())
+        corrupt(bad)
+        try:
+            if batch:
+                c.encode_batch([good, bad, good])
+            else:
+                c.attr_encode(bad)
+            ok = corrupt.__name__ == "vertex_twice"      # legal for the coder as long as the candidate bound holds
+            assert ok, "malformed mesh was accepted"
+        except capi.HarryError as e:
+            assert "(-2)" in str(e) or "(-3)" in str(e), str(e)
+        # the same context still produces the right streams afterwards
+        ok, why = c.attr_encode(good).equal(want)
+        assert ok, f"context unusable after {corrupt.__name__}: {why}"
+        bad2 = good.copy()
+        bad2.lists = capi.residual_rows_encoder_side(good, want)
+        for name in ("edges", "order", "bind_vtx", "face_off"):
+            setattr(bad2, name, getattr(bad2, name).copy())
+        corrupt(bad2)
+        try:
+            c.attr_decode(bad2)
+        except capi.HarryError:
+            pass
+    c.close()
