@@ -926,6 +926,9 @@ def run_other_configs(ctx, workdir, peak, reps=5):
         ("configs[0]: UV sphere 133x264 (34 850 vertices), lossless float32", (lambda d: cases._ply(d, "cfg1.ply", meshgen.uv_sphere(133, 264))), []),
         ("configs[2]: OBJ lat-long sphere 401x600 (240 600 vertices, 480 000 triangles) with vt + vn corner lists, -l0 -q14 -l2 -q10", obj, [(0, -1, 14), (2, -1, 10)]),
         ("configs[3]: polygon grid n=600 (tri / quad / 5- / 6-gons + non-manifold fin), per-vertex and per-face floats, lossless", (lambda d: cases._ply(d, "cfg4.ply", meshgen.poly_grid(600))), []),
+        ("mixed source types (SURVEY App. C.13): UV sphere 400x800 (319 202 vertices), float xyz at -a0..2 -q14 next to lossless uchar red / green / blue in ONE list",
+         (lambda d: cases._ply(d, "cfg_rgb.ply", meshgen.with_typed_props(meshgen.uv_sphere(400, 800, noise_seed=8), seed=3, vtx=(("red", np.uint8), ("green", np.uint8), ("blue", np.uint8))))),
+         [(1, 0, 14), (1, 1, 14), (1, 2, 14)]),
     ]
     out = []
     for title, gen, loq in todo:

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(32) k_decode_vertex_walkf(const SpecArgs *__re
 	// then per candidate four words: the shared-memory ADDRESSES of its three operand records (a value parked in the item
 	// itself, or the ring slot a rank of the last two batches will have filled by then), then the parked operand records.
 	// EXECUTE reads every operand with the same two loads, no selects.
-	constexpr int OFF_ADDR = 4 + RS, OFF_VAL = OFF_ADDR + 16, ITEM = OFF_VAL + 12 * RS;
+	constexpr int OFF_ADDR = (4 + RS + 3) & ~3, OFF_VAL = OFF_ADDR + 16, ITEM = (OFF_VAL + 12 * RS + 3) & ~3; // 16-byte aligned vector loads
 	if (!chain_like(chain, blockIdx.x)) return;
 	const SpecArgs a = args[blockIdx.x];
 	const uint32_t lane = threadIdx.x;
@@ -392,8 +392,15 @@ __global__ void __launch_bounds__(256) k_spec_prep(const uint32_t *__restrict__ 
 	src[i] = s;
 }
 
+// A vertex list is reconstructed in GROUPS of up to four components that share one storage type (u8 / u16 / u32 / float):
+// every group gets compact rank-space records of its own and runs through the scan decoder (integers) or the float
+// kernels; components of other storage types (signed, 64-bit) are left to the generic walker.
+struct CompMap {
+	int n;          // components of the group
+	int8_t comp[4]; // their indices in the list
+};
 // AoS rows -> compact rank-space records (ncp elements of esize bytes per element)
-__global__ void __launch_bounds__(256) k_gather_compact(ListParams p, const uint32_t *__restrict__ erow, uint32_t n, uint8_t *__restrict__ out, int esize, int ncp)
+__global__ void __launch_bounds__(256) k_gather_compact(ListParams p, CompMap cm, const uint32_t *__restrict__ erow, uint32_t n, uint8_t *__restrict__ out, int esize, int ncp)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -404,16 +411,16 @@ __global__ void __launch_bounds__(256) k_gather_compact(ListParams p, const uint
 		return;
 	}
 	const uint8_t *srcp = p.rows + (size_t)row * p.stride;
-	for (int j = 0; j < ncp; ++j) hb_st_bits(dst + j * esize, esize, j < p.ncomp ? hb_ld_bits(srcp + p.offset[j], esize) : 0);
+	for (int j = 0; j < ncp; ++j) hb_st_bits(dst + j * esize, esize, j < cm.n ? hb_ld_bits(srcp + p.offset[cm.comp[j]], esize) : 0);
 }
 
-__global__ void __launch_bounds__(256) k_scatter_compact(ListParams p, const uint32_t *__restrict__ erow, const uint8_t *__restrict__ kind, uint32_t n, const uint8_t *__restrict__ x, int esize, int ncp)
+__global__ void __launch_bounds__(256) k_scatter_compact(ListParams p, CompMap cm, const uint32_t *__restrict__ erow, const uint8_t *__restrict__ kind, uint32_t n, const uint8_t *__restrict__ x, int esize, int ncp)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n || kind[i] != 1) return;
 	uint8_t *dst = p.rows + (size_t)erow[i] * p.stride;
 	const uint8_t *srcp = x + (size_t)i * ncp * esize;
-	for (int j = 0; j < p.ncomp; ++j) hb_st_bits(dst + p.offset[j], esize, hb_ld_bits(srcp + j * esize, esize));
+	for (int j = 0; j < cm.n; ++j) hb_st_bits(dst + p.offset[cm.comp[j]], esize, hb_ld_bits(srcp + j * esize, esize));
 }
 
 template <typename T, int NC, bool FP>
@@ -491,88 +498,116 @@ static int scan_cluster_size(uint32_t n, uint32_t nseg, int ntb)
 	return c;
 }
 
-static bool spec_eligible(const ListParams &p)
+// components the compact kernels take: unsigned integer storage types up to 32 bits, and float
+static bool group_type(int st) { return st == HB_UCHAR || st == HB_USHORT || st == HB_UINT || st == HB_FLOAT; }
+// groups of up to four components of one storage type, in list order; `rest` = the components left to the generic walker
+static void plan_groups(const ListParams &p, std::vector<SpecGroup> &out, std::vector<int> &rest)
 {
-	if (p.ncomp < 1 || p.ncomp > 4) return false;
-	const int st = p.uniform_stype;
-	return st == HB_UCHAR || st == HB_USHORT || st == HB_UINT || st == HB_FLOAT;
+	std::vector<SpecGroup> groups;
+	rest.clear();
+	for (int j = 0; j < p.ncomp; ++j) {
+		const int st = p.stype[j];
+		if (!group_type(st)) { rest.push_back(j); continue; }
+		SpecGroup *g = nullptr;
+		for (SpecGroup &c : groups)
+			if (c.st == st && c.ncomp < 4) g = &c;
+		if (!g) { groups.push_back(SpecGroup()); g = &groups.back(); g->st = st; g->ncomp = 0; }
+		g->comp[g->ncomp++] = j;
+	}
+	// the same plan as in the last decode of this mesh: keep it, its buffers are reused
+	bool same = groups.size() == out.size();
+	for (size_t k = 0; same && k < groups.size(); ++k) {
+		same = groups[k].st == out[k].st && groups[k].ncomp == out[k].ncomp;
+		for (int j = 0; same && j < groups[k].ncomp; ++j) same = groups[k].comp[j] == out[k].comp[j];
+	}
+	if (!same) out = groups;
 }
 
-// reconstruct one vertex list with the speculative chunk-parallel kernel
-static int decode_vertex_spec(hb_dmesh *m, int l)
+// reconstruct the component groups of one vertex list (compact records per group; connectivity records shared)
+static int decode_vertex_groups(hb_dmesh *m, int l)
 {
 	hb_ctx *ctx = m->ctx;
 	DevList &dl = m->lists[l];
 	const ListParams &p = dl.p;
 	const uint32_t n = dl.n_elems;
-	const int st = p.uniform_stype;
-	const int esize = hb_type_size(st);
-	const int ncp = p.ncomp == 3 ? 4 : p.ncomp;
+	const uint32_t nseg = m->nseg;
+	const uint32_t g = hb_div_up(n, 256);
 	HB_TRY(hb_dalloc_t(m, &dl.d_kind, (size_t)n + 1));
 	HB_TRY(hb_dalloc_t(m, &dl.d_src, (size_t)n + 1));
-	HB_TRY(hb_dalloc_t(m, &dl.d_cres, (size_t)(n + 1) * ncp * esize));
-	HB_TRY(hb_dalloc_t(m, &dl.d_cx, (size_t)(n + 1) * ncp * esize));
 	HB_TRY(hb_dalloc_t(m, &dl.d_spec_stats, 8));
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_spec_stats, 0, 64, ctx->stream));
-	const uint32_t g = hb_div_up(n, 256);
 	HB_LAUNCH(ctx, k_spec_prep, g, 256, 0, dl.d_erow, dl.d_first, n, dl.d_kind, dl.d_src);
-	HB_LAUNCH(ctx, k_gather_compact, g, 256, 0, p, dl.d_erow, n, dl.d_cres, esize, ncp);
-	HB_CUDA(ctx, cudaMemsetAsync(dl.d_cx, 0, (size_t)(n + 1) * ncp * esize, ctx->stream));
+	bool any_int = false, any_float = false;
+	for (const SpecGroup &sg : dl.groups) { any_int = any_int || sg.st != HB_FLOAT; any_float = any_float || sg.st == HB_FLOAT; }
 	ScanRec *srec = nullptr;
-	if (st != HB_FLOAT) {
+	if (any_int) {
 		HB_TRY(hb_dalloc(m, &dl.d_srec, sizeof(ScanRec) * ((size_t)n + 1)));
 		srec = (ScanRec *)dl.d_srec;
 		HB_LAUNCH(ctx, k_scan_prep, g, 256, 0, dl.d_kind, dl.d_src, m->d_vc_off, m->d_vc_tri, n, srec);
 	}
-	// one argument block per segment (mesh of a batch): the kernels run one CTA / cluster set per block
-	const uint32_t nseg = m->nseg;
-	uint32_t max_n = 0;
-	m->h_spec_args.resize(nseg);
-	for (uint32_t sg = 0; sg < nseg; ++sg) {
-		SpecArgs &a = m->h_spec_args[sg];
-		a.srec = srec;
-		a.kind = dl.d_kind; a.src = dl.d_src; a.cand_off = m->d_vc_off; a.cand = m->d_vc_tri;
-		a.resid = dl.d_cres; a.x = dl.d_cx;
-		a.base = m->h_obase[sg]; a.n = m->h_obase[sg + 1];
-		a.stats = sg == 0 ? dl.d_spec_stats : nullptr;
-		for (int j = 0; j < 4; ++j) a.bits[j] = j < p.ncomp ? (p.quant[j] ? p.quant[j] : 8 * esize) : 8 * esize;
-		if (a.n - a.base > max_n) max_n = a.n - a.base;
-	}
-	HB_TRY(hb_dalloc_t(m, &dl.d_spec_args, nseg));
-	// pageable source: the runtime stages it before cudaMemcpyAsync returns, no synchronisation needed
-	HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_args, m->h_spec_args.data(), sizeof(SpecArgs) * nseg, cudaMemcpyHostToDevice, ctx->stream));
-	static const bool single_cta = getenv("HARRY_B200_SPEC1") != nullptr; // A/B switch: single-CTA kernel
-	if (st != HB_FLOAT && !single_cta) {
-		const int ntb = scan_ntb(nseg * (uint32_t)p.ncomp, ctx->sm_count);
-		const int cl = scan_cluster_size(max_n, nseg, ntb);
-		if (st == HB_UCHAR) HB_TRY(launch_scan<uint8_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg, ntb));
-		else if (st == HB_USHORT) HB_TRY(launch_scan<uint16_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg, ntb));
-		else HB_TRY(launch_scan<uint32_t>(ctx, p.ncomp, dl.d_spec_args, cl, nseg, ntb));
-	} else if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
-	else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
-	else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, p.ncomp, dl.d_spec_args, nseg)));
-	else {
-		// lossless float list: sequential walk for chain-like segments, Jacobi sweeps for shallow ones (decided on the device)
+	if (any_float) {
+		// lossless float components: sequential walk for chain-like segments, Jacobi sweeps for shallow ones (decided on the device)
 		HB_TRY(hb_dalloc_t(m, &dl.d_chain, 2 * (size_t)nseg));
 		HB_CUDA(ctx, cudaMemsetAsync(dl.d_chain, 0, sizeof(uint32_t) * 2 * nseg, ctx->stream));
 		HB_LAUNCH(ctx, k_chain_stat, g, 256, 0, dl.d_kind, m->d_vc_off, m->d_vc_tri, n, m->d_obase, nseg, dl.d_chain);
 		HB_CUDA(ctx, cudaMemcpyAsync(dl.d_spec_stats + 7, dl.d_chain, 8, cudaMemcpyDeviceToDevice, ctx->stream)); // diagnostics: segment 0
-		HB_TRY(launch_walkf(ctx, p.ncomp, dl.d_spec_args, nseg, dl.d_chain));
-		HB_TRY((launch_spec<uint32_t, true>(ctx, p.ncomp, dl.d_spec_args, nseg, dl.d_chain)));
 	}
-	HB_LAUNCH(ctx, k_scatter_compact, g, 256, 0, p, dl.d_erow, dl.d_kind, n, dl.d_cx, esize, ncp);
+	uint32_t max_n = 0;
+	for (uint32_t sg = 0; sg < nseg; ++sg) max_n = std::max(max_n, m->h_obase[sg + 1] - m->h_obase[sg]);
+	for (size_t gi = 0; gi < dl.groups.size(); ++gi) {
+		SpecGroup &sgp = dl.groups[gi];
+		const int st = sgp.st, esize = hb_type_size(st), nc = sgp.ncomp, ncp = nc == 3 ? 4 : nc;
+		CompMap cm;
+		cm.n = nc;
+		for (int j = 0; j < 4; ++j) cm.comp[j] = (int8_t)(j < nc ? sgp.comp[j] : 0);
+		HB_TRY(hb_dalloc_t(m, &sgp.d_cres, (size_t)(n + 1) * ncp * esize));
+		HB_TRY(hb_dalloc_t(m, &sgp.d_cx, (size_t)(n + 1) * ncp * esize));
+		HB_LAUNCH(ctx, k_gather_compact, g, 256, 0, p, cm, dl.d_erow, n, sgp.d_cres, esize, ncp);
+		HB_CUDA(ctx, cudaMemsetAsync(sgp.d_cx, 0, (size_t)(n + 1) * ncp * esize, ctx->stream));
+		// one argument block per segment (mesh of a batch): the kernels run one CTA / cluster set per block
+		m->h_spec_args.resize(nseg);
+		for (uint32_t sg = 0; sg < nseg; ++sg) {
+			SpecArgs &a = m->h_spec_args[sg];
+			a.srec = srec;
+			a.kind = dl.d_kind; a.src = dl.d_src; a.cand_off = m->d_vc_off; a.cand = m->d_vc_tri;
+			a.resid = sgp.d_cres; a.x = sgp.d_cx;
+			a.base = m->h_obase[sg]; a.n = m->h_obase[sg + 1];
+			a.stats = sg == 0 && gi == 0 ? dl.d_spec_stats : nullptr;
+			for (int j = 0; j < 4; ++j) a.bits[j] = j < nc ? (p.quant[sgp.comp[j]] ? p.quant[sgp.comp[j]] : 8 * esize) : 8 * esize;
+		}
+		HB_TRY(hb_dalloc_t(m, &sgp.d_args, nseg));
+		// pageable source: the runtime stages it before cudaMemcpyAsync returns, no synchronisation needed
+		HB_CUDA(ctx, cudaMemcpyAsync(sgp.d_args, m->h_spec_args.data(), sizeof(SpecArgs) * nseg, cudaMemcpyHostToDevice, ctx->stream));
+		static const bool single_cta = getenv("HARRY_B200_SPEC1") != nullptr; // A/B switch: single-CTA kernel
+		if (st != HB_FLOAT && !single_cta) {
+			const int ntb = scan_ntb(nseg * (uint32_t)nc, ctx->sm_count);
+			const int cl = scan_cluster_size(max_n, nseg, ntb);
+			if (st == HB_UCHAR) HB_TRY(launch_scan<uint8_t>(ctx, nc, sgp.d_args, cl, nseg, ntb));
+			else if (st == HB_USHORT) HB_TRY(launch_scan<uint16_t>(ctx, nc, sgp.d_args, cl, nseg, ntb));
+			else HB_TRY(launch_scan<uint32_t>(ctx, nc, sgp.d_args, cl, nseg, ntb));
+		} else if (st == HB_UCHAR) HB_TRY((launch_spec<uint8_t, false>(ctx, nc, sgp.d_args, nseg)));
+		else if (st == HB_USHORT) HB_TRY((launch_spec<uint16_t, false>(ctx, nc, sgp.d_args, nseg)));
+		else if (st == HB_UINT) HB_TRY((launch_spec<uint32_t, false>(ctx, nc, sgp.d_args, nseg)));
+		else {
+			HB_TRY(launch_walkf(ctx, nc, sgp.d_args, nseg, dl.d_chain));
+			HB_TRY((launch_spec<uint32_t, true>(ctx, nc, sgp.d_args, nseg, dl.d_chain)));
+		}
+		HB_LAUNCH(ctx, k_scatter_compact, g, 256, 0, p, cm, dl.d_erow, dl.d_kind, n, sgp.d_cx, esize, ncp);
+	}
 	return 0;
 }
 
 // rank-space records -> AoS rows (DATA elements own their row)
-__global__ void __launch_bounds__(256) k_scatter_rp(ListParams p, const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, const unsigned long long *__restrict__ rp)
+__global__ void __launch_bounds__(256) k_scatter_rp(ListParams p, const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, const unsigned long long *__restrict__ rp,
+                                                     uint32_t comp_mask /* components reconstructed in rp (the others went through compact records) */)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint32_t row = erow[i];
 	if (row == HB_NONE || first[row] != i) return;
 	uint8_t *dst = p.rows + (size_t)row * p.stride;
-	for (int j = 0; j < p.ncomp; ++j) hb_st_bits(dst + p.offset[j], p.size[j], rp[(size_t)i * p.ncomp + j]);
+	for (int j = 0; j < p.ncomp; ++j)
+		if ((comp_mask >> j) & 1u) hb_st_bits(dst + p.offset[j], p.size[j], rp[(size_t)i * p.ncomp + j]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -644,18 +679,21 @@ int hb_decode_lists(hb_dmesh *m)
 
 	std::vector<WalkArgs> walks;
 	std::vector<int> walk_lists;
+	std::vector<uint32_t> walk_masks;
 	for (int l = 0; l < m->nlists; ++l) {
 		DevList &dl = m->lists[l];
 		const ListParams &p = dl.p;
 		const int cls = p.target;
 		if (p.ncomp == 0 || (cls != CLS_VTX && cls != CLS_FACE && cls != CLS_CORNER)) continue;
 		if (cls == CLS_CORNER && !m->any_corner) continue;
-		const bool spec = cls == CLS_VTX && spec_eligible(p);
-		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE && !spec, true));
+		std::vector<int> rest;
+		if (cls == CLS_VTX) plan_groups(p, dl.groups, rest);
+		const bool all_grouped = cls == CLS_VTX && rest.empty();
+		HB_TRY(hb_prepare_list_elems(m, l, cls != CLS_FACE && !all_grouped, true));
 		const uint32_t n = dl.n_elems;
 		if (!n) continue;
-		if (spec) {
-			HB_TRY(decode_vertex_spec(m, l));
+		if (cls == CLS_VTX && !dl.groups.empty()) HB_TRY(decode_vertex_groups(m, l));
+		if (all_grouped) {
 		} else if (cls == CLS_FACE) {
 			HB_LAUNCH(ctx, k_decode_face, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, n);
 		} else if (cls == CLS_VTX) {
@@ -664,12 +702,15 @@ int hb_decode_lists(hb_dmesh *m)
 			w.erow = dl.d_erow; w.first = dl.d_first; w.cand_off = m->d_vc_off; w.cand = m->d_vc_tri; w.rp = dl.d_rp;
 			for (uint32_t sg = 0; sg < m->nseg; ++sg) { // one chain per segment (mesh of a batch) and component
 				w.base = m->h_obase[sg]; w.n = m->h_obase[sg + 1];
-				for (int j = 0; j < p.ncomp; ++j) {
+				for (int j : rest) { // the components no compact group takes (signed and 64-bit storage types)
 					w.comp = j; w.stype = p.stype[j]; w.quant = p.quant[j];
 					walks.push_back(w);
 				}
 			}
+			uint32_t mask = 0;
+			for (int j : rest) mask |= 1u << j;
 			walk_lists.push_back(l);
+			walk_masks.push_back(mask);
 		} else {
 			HB_TRY(hb_dalloc_t(m, &dl.d_done, (size_t)n + 1));   // kept with the list: reused by the next decode of this mesh
 			HB_TRY(hb_dalloc_t(m, &dl.d_remaining, 1));
@@ -687,7 +728,7 @@ int hb_decode_lists(hb_dmesh *m)
 				if (rem >= prev && sweep > 0) return hb_fail(ctx, HB_ERR_INVALID, "corner decode: dependency cycle (%u elements stuck)", rem);
 				prev = rem;
 			}
-			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, n, dl.d_rp);
+			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, n, dl.d_rp, 0xffffffffu);
 		}
 	}
 	if (!walks.empty()) {
@@ -697,7 +738,7 @@ int hb_decode_lists(hb_dmesh *m)
 		HB_LAUNCH(ctx, k_decode_vertex_walk, (uint32_t)walks.size(), 32, 0, d_walks); // (the pageable source was staged by the copy call)
 		for (size_t k = 0; k < walk_lists.size(); ++k) {
 			DevList &dl = m->lists[walk_lists[k]];
-			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(dl.n_elems, 256), 256, 0, dl.p, dl.d_erow, dl.d_first, dl.n_elems, dl.d_rp);
+			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(dl.n_elems, 256), 256, 0, dl.p, dl.d_erow, dl.d_first, dl.n_elems, dl.d_rp, walk_masks[k]);
 		}
 	}
 	return 0;

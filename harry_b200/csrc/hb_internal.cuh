@@ -75,6 +75,14 @@ struct ListParams {
 	uint16_t offset[HB_MAX_COMP], sym_off[HB_MAX_COMP];
 };
 
+// decode: up to four components of one storage type, reconstructed together on compact rank-space records
+struct SpecGroup {
+	int st = 0, ncomp = 0;
+	int comp[4] = { 0, 0, 0, 0 };
+	uint8_t *d_cres = nullptr, *d_cx = nullptr; // residual / value records
+	SpecArgs *d_args = nullptr;                 // one argument block per segment
+};
+
 struct DevList {
 	ListParams p;
 	// bounds rows (dequantized layout, `stride` bytes each): min, max, scale -- one triple per segment (mesh of a
@@ -103,8 +111,8 @@ struct DevList {
 	// speculative vertex decode (hb_decode_spec.cuh)
 	uint8_t *d_kind = nullptr;
 	uint32_t *d_src = nullptr;
-	uint8_t *d_cres = nullptr, *d_cx = nullptr; // compact residual / value records
-	SpecArgs *d_spec_args = nullptr;
+	uint8_t *d_cx = nullptr;            // encode: packed rank-space value records
+	std::vector<SpecGroup> groups;      // decode: component groups (hb_decode.cu)
 	unsigned long long *d_spec_stats = nullptr;
 	uint32_t *d_chain = nullptr;        // float lists: per segment {ranks reading their predecessor, DATA ranks}
 	void *d_srec = nullptr;             // hb_decode_scan.cuh records
