@@ -474,7 +474,7 @@ static int scan_ntb(uint32_t chains, int sm_count)
 	// the fixed cost of a sweep (two dependent memory round trips, four barriers, ~1000 dependent instructions) barely
 	// depends on the window length: the more chains an SM holds, the better it hides it (measured, 197 spheres of 100K
 	// vertices: 512 threads 8.3 ms per 196 meshes, 256: 6.3 ms, 128: 5.1 ms)
-	if (chains >= 4u * (uint32_t)sm_count - 4u) return 128;
+	if (2u * chains >= 7u * (uint32_t)sm_count) return 128;
 	return chains >= 2u * (uint32_t)sm_count - 2u ? 256 : 512;
 }
 template <typename T>
