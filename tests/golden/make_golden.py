@@ -26,7 +26,17 @@ GOLDEN = {
     "poly_q10": (lambda d: cases._ply(d, "g_p.ply", meshgen.poly_grid(7)), [(1, -1, 10)]),
     "poly_lossless": (lambda d: cases._ply(d, "g_p.ply", meshgen.poly_grid(7)), []),
     "obj_multi": (lambda d: _obj(d), [(0, -1, 12), (1, -1, 9), (2, -1, 10), (3, -1, 11)]),
+    # integer / mixed source types (round 2): uchar colours requantized next to quantized coordinates; int / short / uchar
+    # properties at misaligned offsets on an irregular triangulation, quantized from their integer types, and lossless
+    "rgb_q5_xyz_q14": (lambda d: cases._ply(d, "g_rgb.ply", meshgen.with_typed_props(meshgen.uv_sphere(11, 17, noise_seed=8), seed=3,
+                       vtx=(("red", "uint8"), ("green", "uint8"), ("blue", "uint8")))), [(1, 0, 14), (1, 1, 14), (1, 2, 14), (1, 3, 5), (1, 4, 5), (1, 5, 5)]),
+    "ints_irr_q": (lambda d: cases._ply(d, "g_int.ply", _ints(d)), [(1, 0, 10), (1, 1, 10), (1, 2, 10), (1, 3, 5), (1, 4, 13), (1, 5, 7), (0, 0, 9)]),
+    "ints_irr_lossless": (lambda d: cases._ply(d, "g_int.ply", _ints(d)), []),
 }
+
+
+def _ints(d):
+    return meshgen.with_typed_props(meshgen.tri_irregular(14, 9), seed=6, vtx=(("material", "int32"), ("temp", "int16"), ("red", "uint8")), face=(("group", "int16"),))
 
 
 def _obj(d):

@@ -32,11 +32,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_c(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "harry_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(hb_list_desc), sizeof(hb_mesh_desc), sizeof(hb_list_streams), sizeof(hb_streams));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "harry_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hb_list_desc), sizeof(hb_mesh_desc), sizeof(hb_list_streams), sizeof(hb_streams), sizeof(hb_batch_streams), sizeof(hb_quant_req), sizeof(hb_dequant_req));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [C.sizeof(capi.ListDesc), C.sizeof(capi.MeshDesc), C.sizeof(capi.ListStreams), C.sizeof(capi.Streams)]
+    assert sizes == [C.sizeof(capi.ListDesc), C.sizeof(capi.MeshDesc), C.sizeof(capi.ListStreams), C.sizeof(capi.Streams),
+                     C.sizeof(capi.BatchStreams), C.sizeof(capi.QuantReq), C.sizeof(capi.DequantReq)]
 
 
 @pytest.mark.skipif(not os.path.exists(capi.LIB_PATH), reason="libharry_b200.so not built")
