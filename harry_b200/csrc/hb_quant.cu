@@ -320,21 +320,22 @@ __global__ void __launch_bounds__(256) k_bounds_reduce_f32(ListParams p, BoundsS
 	const uint32_t G = gridDim.x * blockDim.x; // a multiple of ncomp
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t nvec = nscal >> 2;
-	uint32_t kmin[4], kmax[4], zneg[4], zpos[4];
+	// Running bounds as floats: fminf / fmaxf return the other operand when one is a NaN (a NaN never replaces a bound,
+	// quant.h:34-35) and cost one instruction each.  They order -0 below +0 where the reference's `<` sees a tie, so a
+	// ZERO minimum gets its sign from the first zero in row order (zneg / zpos; a zero maximum cannot occur: the seed
+	// numeric_limits<float>::min() is positive and only a larger value replaces it).
+	float fmin_[4], fmax_[4];
+	uint32_t zneg[4], zpos[4];
 #pragma unroll
 	for (int m = 0; m < 4; ++m) {
-		kmin[m] = 0x7f7fffffu ^ 0x80000000u;   // key of numeric_limits<float>::max()
-		kmax[m] = 0x00800000u ^ 0x80000000u;   // key of numeric_limits<float>::min() (quant.h:33)
+		fmin_[m] = FLT_MAX;   // numeric_limits<float>::max()
+		fmax_[m] = FLT_MIN;   // numeric_limits<float>::min() (quant.h:33)
 		zneg[m] = zpos[m] = 0xffffffffu;
 	}
-	// Branch-free per scalar: the order-preserving key of a NaN lies outside [key(-inf), key(+inf)], so one unsigned
-	// range test keeps NaNs from replacing a bound.  Zeros (their first row decides the sign of a zero minimum) are
-	// rare: one test per vector, details on the slow path.
 	auto take = [&](int m, uint32_t bits) {
-		const uint32_t k = bits ^ ((uint32_t)((int32_t)bits >> 31) | 0x80000000u);
-		const bool valid = k - 0x007fffffu <= 0xff800000u - 0x007fffffu;
-		kmin[m] = min(kmin[m], valid ? k : 0xffffffffu);
-		kmax[m] = max(kmax[m], valid ? k : 0u);
+		const float x = __uint_as_float(bits);
+		fmin_[m] = fminf(fmin_[m], x);
+		fmax_[m] = fmaxf(fmax_[m], x);
 	};
 	auto zeros = [&](const uint4 &q, uint32_t e) {
 		const uint32_t w[4] = { q.x, q.y, q.z, q.w };
@@ -358,6 +359,15 @@ __global__ void __launch_bounds__(256) k_bounds_reduce_f32(ListParams p, BoundsS
 			take(0, q[u].x); take(1, q[u].y); take(2, q[u].z); take(3, q[u].w);
 			if (min(min(q[u].x << 1, q[u].y << 1), min(q[u].z << 1, q[u].w << 1)) == 0u) zeros(q[u], 4u * (v + (uint32_t)u * G));
 		}
+	}
+	// order-preserving integer keys from here on (the reductions below compare unsigned)
+	uint32_t kmin[4], kmax[4];
+#pragma unroll
+	for (int m = 0; m < 4; ++m) {
+		const uint32_t bn = __float_as_uint(fmin_[m]) & (fmin_[m] == 0.f ? 0x7fffffffu : 0xffffffffu); // a zero minimum as +0: its sign is decided by zneg / zpos
+		const uint32_t bx = __float_as_uint(fmax_[m]);
+		kmin[m] = bn ^ ((uint32_t)((int32_t)bn >> 31) | 0x80000000u);
+		kmax[m] = bx ^ ((uint32_t)((int32_t)bx >> 31) | 0x80000000u);
 	}
 	// per-component accumulators of this thread, then a shuffle reduction over the warp, one shared-memory
 	// slot per warp, and one set of global atomics per block
