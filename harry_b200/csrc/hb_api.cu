@@ -817,13 +817,14 @@ __global__ void k_region_stream(const uint32_t *__restrict__ ent, const uint4 *_
 }
 
 // per segment: emission and DATA-row offsets of its first element (entries nseg: the totals)
-__global__ void k_segment_offsets(const uint32_t *__restrict__ elem_base, uint32_t nseg, const uint32_t *__restrict__ ek, const uint32_t *__restrict__ dord, uint32_t *__restrict__ out)
+__global__ void k_segment_offsets(const uint32_t *__restrict__ elem_base, uint32_t nseg, const uint32_t *__restrict__ ek, const uint32_t *__restrict__ dord, const uint32_t *__restrict__ dup,
+                                  uint32_t *__restrict__ out)
 {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s > nseg) return;
 	const uint32_t e = elem_base[s];
 	out[s] = ek ? ek[e] : e;
-	out[nseg + 1 + s] = dord[e];
+	out[nseg + 1 + s] = dup && *dup == 0u ? out[s] : dord[e]; // no row is shared: every emission is a DATA row
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -917,7 +918,7 @@ static int fetch_begin(hb_dmesh *m, cudaStream_t st, hb_batch_streams_priv *pv, 
 		}
 		FETCH_CUDA(cudaMallocAsync((void **)&d_offs[l], sizeof(uint32_t) * 2 * ((size_t)nseg + 1), st));
 		if (dl.n_elems) {
-			k_segment_offsets<<<hb_div_up(nseg + 1, 128), 128, 0, st>>>(elem_base, nseg, dl.d_ek, dl.d_dord, d_offs[l]);
+			k_segment_offsets<<<hb_div_up(nseg + 1, 128), 128, 0, st>>>(elem_base, nseg, dl.d_ek, dl.d_dord, dl.d_dup_active ? dl.d_dup : nullptr, d_offs[l]);
 			ctx->launches++;
 		} else {
 			FETCH_CUDA(cudaMemsetAsync(d_offs[l], 0, sizeof(uint32_t) * 2 * ((size_t)nseg + 1), st));

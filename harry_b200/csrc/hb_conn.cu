@@ -49,9 +49,11 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
 // bits 62..63 = 0 empty / 1 aggregate / 2 inclusive prefix, low 32 bits = value.
 #define SCAN_VEC (SCAN_ITEMS / 4)
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, unsigned long long *__restrict__ status,
-                                                               uint32_t *__restrict__ ticket, uint32_t n, uint32_t ntiles, uint32_t *__restrict__ out_total2)
+                                                               uint32_t *__restrict__ ticket, uint32_t n, uint32_t ntiles, uint32_t *__restrict__ out_total2,
+                                                               const uint32_t *__restrict__ skip_if_zero)
 {
 	__shared__ uint32_t s_tile, s_prefix;
+	if (skip_if_zero && *skip_if_zero == 0u) return; // the caller's consumers do not need the result (decided on the device)
 	if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
 	__syncthreads();
 	const uint32_t tile = s_tile;
@@ -136,7 +138,7 @@ __global__ void k_scan_empty(uint32_t *out, uint32_t *out_total2)
 }
 
 // d_out must hold n + 1 entries; d_out[n] = total.  in == out is allowed.
-int hb_scan_exclusive_u32(hb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint32_t n, uint32_t *d_total)
+int hb_scan_exclusive_u32(hb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint32_t n, uint32_t *d_total, const uint32_t *d_skip_if_zero)
 {
 	const uint32_t ntiles = n ? hb_div_up(n, SCAN_TILE) : 0;
 	if (!ntiles) {
@@ -146,7 +148,7 @@ int hb_scan_exclusive_u32(hb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, ui
 	unsigned long long *d_status = nullptr;
 	HB_CUDA(ctx, cudaMallocAsync((void **)&d_status, sizeof(unsigned long long) * ((size_t)ntiles + 1), ctx->stream));
 	HB_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(unsigned long long) * ((size_t)ntiles + 1), ctx->stream));
-	HB_LAUNCH(ctx, k_scan_lookback, ntiles, SCAN_THREADS, 0, d_in, d_out, d_status, (uint32_t *)(d_status + ntiles), n, ntiles, d_total);
+	HB_LAUNCH(ctx, k_scan_lookback, ntiles, SCAN_THREADS, 0, d_in, d_out, d_status, (uint32_t *)(d_status + ntiles), n, ntiles, d_total, d_skip_if_zero);
 	HB_CUDA(ctx, cudaFreeAsync(d_status, ctx->stream));
 	return 0;
 }
@@ -424,7 +426,7 @@ struct WideCtl {
 __global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__restrict__ he, const uint32_t *__restrict__ ord_h, const uint32_t *__restrict__ ord_v,
                                                                   const uint32_t *__restrict__ vrank, const uint16_t *__restrict__ vtx_regs, uint32_t n, uint32_t ne,
                                                                   uint32_t *__restrict__ cnt, uint32_t *__restrict__ stage, WideCtl *__restrict__ wide, uint32_t *__restrict__ vslot,
-                                                                  uint32_t walk_cap, int *err)
+                                                                  uint32_t *__restrict__ wbits, uint32_t walk_cap, int *err)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -446,6 +448,7 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__
 			wide->vtx[slot] = ord_v[i];
 			wide->rank[slot] = i;
 			vslot[ord_v[i]] = slot;
+			atomicOr(&wbits[ord_v[i] >> 5], 1u << (ord_v[i] & 31u));
 			cnt[i] = 0; // set by k_wide_rank
 			stage[(size_t)i * 3 * VC_STAGE] = VC_WIDE_MARK;
 			return;
@@ -496,13 +499,17 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_compact(const uint4 *
 // contiguous node lists and note every node's index (SCATTER = true)
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_wide_collect(const uint32_t *__restrict__ org_h, uint32_t ne, WideCtl *__restrict__ wide, const uint32_t *__restrict__ vslot,
-                                                      uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos)
+                                                      const uint32_t *__restrict__ wbits, uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos)
 {
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
 	if (nw == 0) return; // the usual mesh: no wide fan, nothing to stream
 	const uint32_t cap_per_slot = wide->per;
 	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
-		const uint32_t w = vslot[org_h[e]];
+		// one bit per vertex in front of the slot table: the bitmap of a 10M-vertex mesh is 1.2 MB and stays in cache, the
+		// slot table (4 bytes per vertex) would be gathered from L2 for every half-edge
+		const uint32_t v = org_h[e];
+		if (!((__ldg(wbits + (v >> 5)) >> (v & 31u)) & 1u)) continue;
+		const uint32_t w = vslot[v];
 		if (w == HB_NONE) continue;
 		if (!SCATTER) atomicAdd(&wide->deg[w], 1u);
 		else {
@@ -771,9 +778,11 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 		WideCtl *wide = (WideCtl *)m->d_vc_wide;
 		HB_CUDA(ctx, cudaMemsetAsync(wide, 0, sizeof(WideCtl), ctx->stream));
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_wslot, (size_t)m->nv + 1));
+		HB_TRY(hb_dalloc_t(m, &m->d_vc_wbits, ((size_t)m->nv >> 5) + 2));
 		HB_CUDA(ctx, cudaMemsetAsync(m->d_vc_wslot, 0xff, sizeof(uint32_t) * ((size_t)m->nv + 1), ctx->stream));
+		HB_CUDA(ctx, cudaMemsetAsync(m->d_vc_wbits, 0, sizeof(uint32_t) * (((size_t)m->nv >> 5) + 2), ctx->stream));
 		HB_LAUNCH(ctx, k_vertex_candidates_stage, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, wide,
-		          m->d_vc_wslot, (uint32_t)VC_WALK_CAP, ctx->d_err);
+		          m->d_vc_wslot, m->d_vc_wbits, (uint32_t)VC_WALK_CAP, ctx->d_err);
 		const size_t cap = VC_WIDE_ARENA;
 		m->vc_wide_cap = (uint32_t)cap;
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_wpos, (size_t)m->ne + 1));
@@ -783,7 +792,7 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_warena, 6 * cap + 6));
 		uint32_t *nodes = m->d_vc_wnodes, *pos = m->d_vc_wpos, *work = m->d_vc_wwork, *order = m->d_vc_worder, *arena = m->d_vc_warena;
 		HB_LAUNCH(ctx, k_wide_even_bases, 1, 256, 0, wide);
-		HB_LAUNCH(ctx, k_wide_collect<true>, (uint32_t)ctx->sm_count * 8, 256, 0, m->d_org_h, m->ne, wide, m->d_vc_wslot, nodes, pos);
+		HB_LAUNCH(ctx, k_wide_collect<true>, (uint32_t)ctx->sm_count * 8, 256, 0, m->d_org_h, m->ne, wide, m->d_vc_wslot, m->d_vc_wbits, nodes, pos);
 		HB_LAUNCH(ctx, k_wide_fill_to_deg, 1, 256, 0, wide);
 		HB_LAUNCH(ctx, k_wide_rank, VC_MAXWIDE, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + cap, work + 2 * cap, work + 3 * cap,
 		          work + 4 * cap, work + 5 * cap, order, arena, m->d_vc_off, stage, m->ne, ctx->d_err);

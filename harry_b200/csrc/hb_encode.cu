@@ -36,12 +36,16 @@ __global__ void __launch_bounds__(256) k_elem_rows(ElemCtx c, int l, RowSeg rs, 
 	if (bound_flag) bound_flag[i] = ok ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) k_first_ref(const uint32_t *__restrict__ erow, uint32_t n, uint32_t *__restrict__ first)
+// *dup (optional) is raised when some row is referenced twice: without shared rows every emission is a DATA row, its
+// ordinal is its emission index, and the consumers skip the first-reference gather and the ordinal scan
+__global__ void __launch_bounds__(256) k_first_ref(const uint32_t *__restrict__ erow, uint32_t n, uint32_t *__restrict__ first, uint32_t *dup)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint32_t row = erow[i];
-	if (row != HB_NONE) atomicMin(&first[row], i);
+	if (row == HB_NONE) return;
+	const uint32_t old = atomicMin(&first[row], i);
+	if (dup && old != HB_NONE) *dup = 1u;
 }
 
 // corner lists: an element answered by the local history never reaches the global history
@@ -72,10 +76,12 @@ __global__ void __launch_bounds__(256) k_owner_from_types(const uint32_t *__rest
 	if (types[k] == HB_DATA) first[row] = i;
 }
 
-__global__ void __launch_bounds__(256) k_data_flags(const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, uint32_t *__restrict__ dflag)
+__global__ void __launch_bounds__(256) k_data_flags(const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first, uint32_t n, uint32_t *__restrict__ dflag,
+                                                    const uint32_t *__restrict__ skip_if_zero)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
+	if (skip_if_zero && *skip_if_zero == 0u) return;
 	const uint32_t row = erow[i];
 	dflag[i] = (row != HB_NONE && first[row] == i) ? 1u : 0u;
 }
@@ -297,6 +303,7 @@ struct EncodeArgs {
 	int l;
 	uint32_t *wide;       // [0] = count, [1..] = element indices whose candidate count exceeds ENC_WIDE_K
 	uint32_t wide_cap;
+	const uint32_t *dup;       // device flag or nullptr: 0 = no row is shared (every emission a DATA row, ordinal = emission index)
 	// histograms are kept per segment (mesh of a batch): hist + s * hist_pitch, type counters behind the contexts
 	uint32_t nseg;
 	const uint32_t *elem_base; // first element of every segment (nseg + 1)
@@ -329,12 +336,13 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 	const uint32_t bseg = block_segment(a, blockIdx.x * ENC_THREADS, myseg, i);
 	const bool agg = bseg != HB_NONE; // one segment in this block: shared-memory histograms
 	unsigned long long *ghist = a.hist + (size_t)myseg * a.hist_pitch, *gtype = a.type_hist + (size_t)myseg * a.hist_pitch;
+	const bool fast = a.dup && *a.dup == 0u; // no row is shared: every emission is a DATA row, its ordinal the emission index
 	const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
 	int t = -1;                 // emission type of this element, -1 = no emission
 	unsigned long long res[HB_MAX_COMP > 8 ? 8 : HB_MAX_COMP]; // residuals of the first 8 components (register resident)
 	if (row != HB_NONE) {
 		const uint32_t k = a.ek ? a.ek[i] : i;
-		const uint32_t fi = a.first[row];
+		const uint32_t fi = fast ? i : a.first[row];
 		t = HB_DATA;
 		uint32_t aux = 0;
 		bool lhit = false;
@@ -350,14 +358,16 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_main(ListParams p, Encod
 			t = HB_HIST;
 			aux = a.dord[i] - 1u - a.dord[fi]; // tidx - 1 - g, attrcode.h:43-52
 		}
-		a.type[k] = (uint8_t)t;
-		a.aux[k] = aux;
+		if (!fast) { // (the streams were cleared: all DATA, no offsets)
+			a.type[k] = (uint8_t)t;
+			a.aux[k] = aux;
+		}
 		if (t == HB_DATA && CLS == CLS_VTX && a.wide && a.cand_off[i + 1] - a.cand_off[i] > ENC_WIDE_K) {
 			const uint32_t slot = atomicAdd(&a.wide[0], 1u);
 			if (slot < a.wide_cap) { a.wide[1 + slot] = i; t = -2; } // residual + histogram by k_encode_wide
 		}
 		if (t == HB_DATA) {
-			const uint32_t d = a.dord[i];
+			const uint32_t d = fast ? k : a.dord[i];
 			uint8_t *out = a.sym + (size_t)d * p.sym_stride;
 			uint32_t c0 = 0, K = 0;
 			if (CLS != CLS_FACE) { c0 = a.cand_off[i]; K = a.cand_off[i + 1] - c0; }
@@ -443,7 +453,8 @@ __global__ void __launch_bounds__(128) k_encode_wide(ListParams p, EncodeArgs a)
 	if (w >= nw) return;
 	const uint32_t i = a.wide[1 + w];
 	const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
-	uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+	const bool fast = a.dup && *a.dup == 0u;
+	uint8_t *out = a.sym + (size_t)(fast ? (a.ek ? a.ek[i] : i) : a.dord[i]) * p.sym_stride;
 	unsigned long long *ghist = a.hist + (size_t)hb_seg_find(a.elem_base, a.nseg, i) * a.hist_pitch;
 	for (int j = 0; j < p.ncomp; ++j) {
 		const int st = p.stype[j], q = p.quant[j];
@@ -521,6 +532,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p,
 	// A CTA codes a contiguous run of chunks of ENC_THREADS elements and keeps ONE set of shared-memory histograms for
 	// the segment it is in: they are cleared and flushed when the segment changes and at the end, not once per chunk
 	// (zeroing + flushing 1536 bins cost a sixth of the instructions of the one-chunk-per-CTA version).
+	const bool fast = a.dup && *a.dup == 0u; // no row is shared: no element-row / first-reference / ordinal loads, no type / offset stores
 	uint32_t cur_seg = HB_NONE;
 	auto flush = [&]() {
 		if (cur_seg == HB_NONE) return;
@@ -541,22 +553,24 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p,
 		const uint32_t bseg = block_segment(a, chunk * ENC_THREADS, myseg, i);
 		const bool agg = bseg != HB_NONE; // one segment in this chunk: shared-memory histograms
 		if (agg && bseg != cur_seg) { flush(); cur_seg = bseg; }
-		const uint32_t row = i < a.n ? a.erow[i] : HB_NONE;
+		const uint32_t row = i < a.n ? (fast ? 0u : a.erow[i]) : HB_NONE; // (the shortcut is only taken by lists every region binds)
 		int t = -1;
 		T res[NC];
 #pragma unroll
 		for (int j = 0; j < NC; ++j) res[j] = 0;
 		if (row != HB_NONE) {
 			const uint32_t k = a.ek ? a.ek[i] : i;
-			const uint32_t fi = a.first[row];
 			t = HB_DATA;
-			uint32_t aux = 0;
-			if (fi != i) {
-				t = HB_HIST;
-				aux = a.dord[i] - 1u - a.dord[fi]; // tidx - 1 - g, attrcode.h:43-52
+			if (!fast) {
+				const uint32_t fi = a.first[row];
+				uint32_t aux = 0;
+				if (fi != i) {
+					t = HB_HIST;
+					aux = a.dord[i] - 1u - a.dord[fi]; // tidx - 1 - g, attrcode.h:43-52
+				}
+				a.type[k] = (uint8_t)t;
+				a.aux[k] = aux;
 			}
-			a.type[k] = (uint8_t)t;
-			a.aux[k] = aux;
 			const uint32_t c0 = a.cand_off[i], K = a.cand_off[i + 1] - c0;
 			if (t == HB_DATA && a.wide && K > ENC_WIDE_K) {
 				const uint32_t slot = atomicAdd(&a.wide[0], 1u);
@@ -573,7 +587,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_vtx_packed(ListParams p,
 #pragma unroll
 					for (int j = 0; j < NC; ++j) sum[j] += (Acc)IntOps<T>::predict(v0.c[j], v1.c[j], v2.c[j], bits[j]);
 				}
-				uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+				uint8_t *out = a.sym + (size_t)(fast ? k : a.dord[i]) * p.sym_stride;
 #pragma unroll
 				for (int j = 0; j < NC; ++j) {
 					const T pred = K == 0 ? (T)0 : (K == 1 ? (T)sum[j] : (K == 2 ? (T)((sum[j] + 1) >> 1) : (T)hb_divround_i64((long long)sum[j], (int)K)));
@@ -641,7 +655,8 @@ __global__ void __launch_bounds__(ENC_WIDE_T) k_encode_wide_packed(ListParams p,
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			const Rec raw = rec[i];
-			uint8_t *out = a.sym + (size_t)a.dord[i] * p.sym_stride;
+			const bool fast = a.dup && *a.dup == 0u;
+			uint8_t *out = a.sym + (size_t)(fast ? (a.ek ? a.ek[i] : i) : a.dord[i]) * p.sym_stride;
 			unsigned long long *ghist = a.hist + (size_t)hb_seg_find(a.elem_base, a.nseg, i) * a.hist_pitch;
 #pragma unroll
 			for (int j = 0; j < NC; ++j) {
@@ -737,6 +752,15 @@ int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp, bool decode)
 	if (!everywhere) HB_TRY(hb_dalloc_t(m, &dl.d_ek, (size_t)n + 2));
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_first, 0xff, sizeof(uint32_t) * ((size_t)dl.p.nrows + 1), ctx->stream));
 	HB_CUDA(ctx, cudaMemsetAsync(dl.d_dord, 0, sizeof(uint32_t) * ((size_t)n + 2), ctx->stream));
+	// "no row is shared" shortcut (decided on the device): vertex / face lists that every region binds, first-reference
+	// ownership (no drained type symbols), encode side
+	dl.d_dup_active = false;
+	if (!decode && everywhere && cls != CLS_CORNER && n) {
+		HB_TRY(hb_dalloc_t(m, &dl.d_dup, 1));
+		HB_CUDA(ctx, cudaMemsetAsync(dl.d_dup, 0, sizeof(uint32_t), ctx->stream));
+		dl.d_dup_active = true;
+	}
+	uint32_t *const dup_arg = dl.d_dup_active ? dl.d_dup : nullptr;
 	if (n) {
 		const uint32_t g = hb_div_up(n, 256);
 		RowSeg rs;
@@ -752,9 +776,11 @@ int hb_prepare_list_elems(hb_dmesh *m, int l, bool need_rp, bool decode)
 		else if (!decode && cls == CLS_CORNER && m->d_lh)
 			HB_LAUNCH(ctx, k_first_ref_corner, g, 256, 0, dl.d_erow, n, m->d_he, m->d_celem_h, m->d_face_regs, m->d_slot_corner, (uint32_t)m->nlists, l, m->d_lh, m->n_corner_elems, dl.d_first);
 		else
-			HB_LAUNCH(ctx, k_first_ref, g, 256, 0, dl.d_erow, n, dl.d_first);
-		HB_LAUNCH(ctx, k_data_flags, g, 256, 0, dl.d_erow, dl.d_first, n, dl.d_dord);
-		HB_TRY(hb_scan_exclusive_u32(ctx, dl.d_dord, dl.d_dord, n, nullptr));
+			HB_LAUNCH(ctx, k_first_ref, g, 256, 0, dl.d_erow, n, dl.d_first, dup_arg);
+		if (!decode) { // ordinal of every DATA emission: positions in the symbol stream and history offsets (encode only)
+			HB_LAUNCH(ctx, k_data_flags, g, 256, 0, dl.d_erow, dl.d_first, n, dl.d_dord, (const uint32_t *)dup_arg);
+			HB_TRY(hb_scan_exclusive_u32(ctx, dl.d_dord, dl.d_dord, n, nullptr, dup_arg));
+		}
 		if (need_rp && dl.p.ncomp) {
 			HB_TRY(hb_dalloc_t(m, &dl.d_rp, (size_t)n * dl.p.ncomp + 1));
 			HB_LAUNCH(ctx, k_gather_rp, g, 256, 0, dl.p, dl.d_erow, n, dl.d_rp);
@@ -846,7 +872,7 @@ int hb_nocomp_finish(hb_dmesh *m, int l, cudaStream_t st)
 	int rc = 0;
 	do {
 		const uint32_t g = hb_div_up(n, 256);
-		k_data_flags<<<g, 256, 0, st>>>(dl.d_erow, dl.d_first, n, dl.d_dord);
+		k_data_flags<<<g, 256, 0, st>>>(dl.d_erow, dl.d_first, n, dl.d_dord, (const uint32_t *)nullptr);
 		ctx->launches++;
 		if ((rc = hb_scan_exclusive_u32(ctx, dl.d_dord, dl.d_dord, n, nullptr)) != 0) break;
 		k_nocomp_aux<<<g, 256, 0, st>>>(dl.d_erow, dl.d_first, dl.d_dord, n, dl.d_aux);
@@ -903,6 +929,11 @@ int hb_encode_lists(hb_dmesh *m)
 		a.celem_h = m->d_celem_h; a.he = m->d_he;
 		a.type = dl.d_type; a.aux = dl.d_aux; a.sym = dl.d_sym; a.hist = dl.d_hist; a.type_hist = dl.d_type_hist;
 		a.n = n; a.l = l;
+		a.dup = dl.d_dup_active ? dl.d_dup : nullptr;
+		if (a.dup) { // the fast path leaves the all-zero type / offset streams alone
+			HB_CUDA(ctx, cudaMemsetAsync(dl.d_type, 0, (size_t)n + 1, ctx->stream));
+			HB_CUDA(ctx, cudaMemsetAsync(dl.d_aux, 0, sizeof(uint32_t) * ((size_t)n + 1), ctx->stream));
+		}
 		a.nseg = m->nseg;
 		a.elem_base = cls == CLS_VTX ? m->d_obase : cls == CLS_FACE ? m->d_ofbase : m->d_cebase;
 		a.hist_pitch = hist_pitch;

@@ -120,7 +120,8 @@ struct DevList {
 	uint8_t *d_emit_type = nullptr;     // decode: drained type symbols (optional)
 	uint32_t emit_count = 0;
 	bool rows_from_cache = false;       // the rows were already on the device (row cache): nothing was uploaded
-	uint32_t *d_dup = nullptr;          // zero-component list: some row is referenced twice
+	uint32_t *d_dup = nullptr;          // device flag: some row is referenced twice (else the "no shared row" shortcuts apply)
+	bool d_dup_active = false;          // the flag is maintained for this encode (hb_prepare_list_elems)
 	bool nocomp_fast = false;           // encode: zero-component list coded by the two-pass path (hb_encode.cu)
 	uint8_t *d_done = nullptr;          // decode: corner wavefront flags
 	uint32_t *d_remaining = nullptr;
@@ -174,6 +175,7 @@ struct hb_dmesh {
 	uint32_t *d_vc_off = nullptr, *d_vc_tri = nullptr, *d_vc_stage = nullptr; uint32_t vc_total = 0;
 	void *d_vc_wide = nullptr;          // wide-fan control block and scratch (hb_conn.cu)
 	uint32_t *d_vc_wslot = nullptr;     // vertex -> wide slot
+	uint32_t *d_vc_wbits = nullptr;     // one bit per vertex: registered as wide
 	uint32_t *d_vc_wnodes = nullptr, *d_vc_wpos = nullptr, *d_vc_wwork = nullptr, *d_vc_worder = nullptr, *d_vc_warena = nullptr;
 	uint32_t vc_wide_cap = 0;
 	uint32_t *d_cc_off = nullptr, *d_cc_idx = nullptr; uint32_t cc_total = 0;
@@ -237,7 +239,8 @@ template <typename T> static inline int hb_dalloc_t(hb_dmesh *m, T **p, size_t n
 int hb_check_device_error(hb_ctx *ctx, const char *what);
 
 // stages (implemented across the .cu files) ----------------------------------------------------
-int hb_scan_exclusive_u32(hb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint32_t n, uint32_t *d_total /* device, may be null */);
+int hb_scan_exclusive_u32(hb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint32_t n, uint32_t *d_total /* device, may be null */,
+                          const uint32_t *d_skip_if_zero = nullptr /* device flag: 0 = return at once */);
 int hb_build_conn(hb_dmesh *m);             // he[], ranks, orders
 int hb_build_vertex_candidates(hb_dmesh *m); // vc_off / vc_tri
 int hb_build_corner_candidates(hb_dmesh *m); // cc_off / cc_idx
