@@ -545,6 +545,8 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
     n_e2e = max(1, args.steps)
     h2d = d2h = 0
     t_e2e = 0.0
+    CALLS = ("hb_bounds", "hb_requant", "hb_attr_encode", "hb_attr_decode", "hb_requant(clear)")
+    per_call = {k: 0.0 for k in CALLS}
     ctx.set_row_cache(True)      # what the CLI adapter does (host/bridge.cc): rows stay on the device between the calls of a pipeline
     for it in range(n_e2e + 1):
         for la, src in zip(hraw.lists, pristine_raw):
@@ -556,18 +558,25 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
         t0 = time.perf_counter()
         la = hraw.lists[vl]
         mn, mx = ctx.bounds(la)
+        t1 = time.perf_counter()
         sc = float_scale_row(la, mn, mx)
         ctx.requant(la, w.new_quant[vl], mn, sc)
+        t2 = time.perf_counter()
         streams, release = ctx.attr_encode_view(hraw)   # the library's page-locked output buffers, as a C++ caller sees them
+        t3 = time.perf_counter()
         ctx.attr_decode(hdec)
+        t4 = time.perf_counter()
         ld = hdec.lists[vl]
         ctx.requant(ld, [0] * ld.ncomp, w.dec_bounds[vl][0], w.dec_bounds[vl][2])
-        dt = time.perf_counter() - t0
+        t5 = time.perf_counter()
+        dt = t5 - t0
         if it == 0:      # warm-up
             del streams
             release()
             continue
         t_e2e += dt
+        for k, d in zip(CALLS, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            per_call[k] += d * 1e3 / n_e2e
         if it == 1:
             rows_b = la.rows.nbytes
             conn_b = sum(getattr(hraw, n).nbytes for n in ("edges", "face_off", "order", "order_f", "vtx_regs", "face_regs", "bind_face", "bind_vtx"))
@@ -585,7 +594,8 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
     ctx.set_row_cache(False)
     t_step = allreduce_max(dist, local_rank, [t_e2e / n_e2e])[0]
     return {"value": world * w.n_attrs / t_step / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": t_step * 1e3, "steps": n_e2e, "timer": "host wall clock around the synchronous C-ABI calls",
+            "ms_per_step": t_step * 1e3, "ms_per_call": {k: round(v, 3) for k, v in per_call.items()},
+            "steps": n_e2e, "timer": "host wall clock around the synchronous C-ABI calls",
             "calls": "hb_bounds, hb_requant, hb_attr_encode, hb_attr_decode, hb_requant(clear) -- what the drop-in CLI adapter calls"}
 
 

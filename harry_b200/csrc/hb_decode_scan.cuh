@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) k_scan_prep(const uint8_t *__restrict__ k
 	for (int w = 0; w < 3 * SCAN_KIN; ++w) tri[w] = 0;
 	if (kd == 2) {
 		if (src[i] != pr) farp1 = src[i] + 1;
-	} else if (kd == 1) {
+	} else if (kd == 1 && K <= SCAN_WIDE) { // (a wider rank ends every window and is evaluated from the CSR by a whole CTA: its
+		                                     // record is the header alone -- scanning the 4472 candidates of a pole here cost 0.5 ms)
 		for (uint32_t j = 0; j < K; ++j) {
 			const uint32_t r0 = cand[3 * (size_t)(c0 + j)], r1 = cand[3 * (size_t)(c0 + j) + 1], r2 = cand[3 * (size_t)(c0 + j) + 2];
 			const uint32_t nv = (uint32_t)(r0 == pr) + (uint32_t)(r1 == pr) + (uint32_t)(r2 == pr);
