@@ -547,6 +547,7 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
     t_e2e = 0.0
     CALLS = ("hb_bounds", "hb_requant", "hb_attr_encode", "hb_attr_decode", "hb_requant(clear)")
     per_call = {k: 0.0 for k in CALLS}
+    per_step = []
     ctx.set_row_cache(True)      # what the CLI adapter does (host/bridge.cc): rows stay on the device between the calls of a pipeline
     for it in range(n_e2e + 1):
         for la, src in zip(hraw.lists, pristine_raw):
@@ -555,6 +556,7 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
         for la, src, ref in zip(hdec.lists, pristine_dec, w.dec.lists):
             la.rows[...] = src
             la.quants = list(ref.quants)
+        up0 = ctx.h2d_bytes()
         t0 = time.perf_counter()
         la = hraw.lists[vl]
         mn, mx = ctx.bounds(la)
@@ -570,31 +572,29 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
         ctx.requant(ld, [0] * ld.ncomp, w.dec_bounds[vl][0], w.dec_bounds[vl][2])
         t5 = time.perf_counter()
         dt = t5 - t0
+        up1 = ctx.h2d_bytes()
         if it == 0:      # warm-up
             del streams
             release()
             continue
         t_e2e += dt
+        per_step.append([round(x * 1e3, 2) for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)])
         for k, d in zip(CALLS, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
             per_call[k] += d * 1e3 / n_e2e
         if it == 1:
             rows_b = la.rows.nbytes
-            conn_b = sum(getattr(hraw, n).nbytes for n in ("edges", "face_off", "order", "order_f", "vtx_regs", "face_regs", "bind_face", "bind_vtx"))
-            # hb_attr_decode of a mesh whose face / corner lists carry no components uploads no face-side arrays (target 1 == HB_VTX)
-            vertex_only = all(l.ncomp == 0 or l.nrows == 0 or l.target == 1 for l in hdec.lists)
-            dnames = ("edges", "face_off", "order", "vtx_regs", "bind_vtx") if vertex_only else ("edges", "face_off", "order", "vtx_regs", "face_regs", "bind_face", "bind_vtx")
-            dconn_b = sum(getattr(hdec, n).nbytes for n in dnames) + \
-                (hdec.order_f.nbytes if hdec.order_f is not None and not vertex_only else 0)
-            # rows: once for set_bounds (requant and encode find them on the device), once for decode (requant(clear) finds them)
-            h2d = rows_b + conn_b + dconn_b + ld.rows.nbytes + sum(len(t) for t in w.dec.emit_types)
-            h2d -= hraw.vtx_regs.nbytes + hraw.face_regs.nbytes + hdec.vtx_regs.nbytes   # single region: cleared on the device, not uploaded
+            # counted by the library at its host -> device copies: rows once for set_bounds (requant and encode find them on the device),
+            # once for decode; the connectivity of the encoder and of the decoder mesh (12 bytes per half-edge each); single-region
+            # arrays are cleared on the device; the decoder mesh goes without face-side arrays, the encoder mesh without the face
+            # order when the device finds that no face row is bound twice
+            h2d = up1 - up0
             d2h = rows_b + ld.rows.nbytes * 2 + streams.nbytes_copied   # all-zero streams come back as NULL, not copied
         del streams
         release()
     ctx.set_row_cache(False)
     t_step = allreduce_max(dist, local_rank, [t_e2e / n_e2e])[0]
     return {"value": world * w.n_attrs / t_step / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": t_step * 1e3, "ms_per_call": {k: round(v, 3) for k, v in per_call.items()},
+            "ms_per_step": t_step * 1e3, "ms_per_call": {k: round(v, 3) for k, v in per_call.items()}, "ms_per_call_by_step": per_step,
             "steps": n_e2e, "timer": "host wall clock around the synchronous C-ABI calls",
             "calls": "hb_bounds, hb_requant, hb_attr_encode, hb_attr_decode, hb_requant(clear) -- what the drop-in CLI adapter calls"}
 
@@ -891,12 +891,14 @@ def run_batch(args, ctx, ctx_d, rank, world, local_rank, dist, workdir, peak):
         for it in range(n_steps + 1):
             for i, m in enumerate(dec_meshes):       # fresh residual rows (untimed)
                 m.lists[1].rows[...] = pristine[i % distinct]
+            up0 = ctx.h2d_bytes()
             t0 = time.perf_counter()
             bp = C.POINTER(capi.BatchStreams)()
             ctx._check(lib.hb_encode_batch(ctx.h, enc_descs, n_e2e, req, 1, bptr, C.byref(bp)), "hb_encode_batch")
             ctx._check(lib.hb_decode_batch(ctx.h, dec_descs, n_e2e, dreq, 1), "hb_decode_batch")
             dt = time.perf_counter() - t0
             if it == 1:
+                h2d_step = ctx.h2d_bytes() - up0 + n_e2e * 3 * stride   # + the bounds rows of the dequantization requests
                 st = capi.streams_struct_to_py(bp.contents.mesh[n_e2e - 1], copy=False)
                 d2h_streams = st.nbytes_copied
                 if not np.array_equal(dec_meshes[n_e2e - 1].lists[1].rows, loads[(n_e2e - 1) % distinct].deq_rows):
@@ -906,12 +908,9 @@ def run_batch(args, ctx, ctx_d, rank, world, local_rank, dist, workdir, peak):
             if it:
                 t_sum += dt
         t_step = allreduce_max(dist, local_rank, [t_sum / n_steps])[0]
-        m0 = hraw[0]
-        up_enc = sum(getattr(m0, n).nbytes for n in ("edges", "face_off", "order", "order_f", "vtx_regs", "face_regs", "bind_face", "bind_vtx")) + m0.lists[1].rows.nbytes
         d0 = hdec[0]
-        up_dec = sum(getattr(d0, n).nbytes for n in ("edges", "face_off", "order", "vtx_regs", "bind_vtx")) + d0.lists[1].rows.nbytes + sum(len(t) for t in loads[0].dec.emit_types) + 3 * stride
         out["e2e"] = {"value": world * n_e2e * attrs_per_mesh / t_step / 1e6, "unit": UNIT, "ms_per_step": t_step * 1e3, "meshes_per_gpu_per_step": n_e2e, "steps": n_steps,
-                      "h2d_bytes_per_step": int(n_e2e * (up_enc + up_dec)), "d2h_bytes_per_step": int(n_e2e * (d2h_streams + 3 * stride + d0.lists[1].rows.nbytes)),
+                      "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(n_e2e * (d2h_streams + 3 * stride + d0.lists[1].rows.nbytes)),
                       "calls": "hb_encode_batch (set_bounds + set_scale + requant + encode) + hb_decode_batch (decode + requant(clear)), page-locked host buffers, "
                                "groups of meshes pipelined over copy / compute / download streams",
                       "timer": "host wall clock around the two synchronous C-ABI calls, max over ranks"}

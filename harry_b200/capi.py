@@ -502,6 +502,8 @@ def load_library():
     lib.hb_ctx_set_row_cache.restype = C.c_int
     lib.hb_kernel_launches.argtypes = [vp]
     lib.hb_kernel_launches.restype = C.c_uint64
+    lib.hb_h2d_bytes.argtypes = [vp]
+    lib.hb_h2d_bytes.restype = C.c_uint64
     lib.hb_ctx_profile.argtypes = [vp, C.c_int]
     lib.hb_ctx_profile.restype = C.c_int
     lib.hb_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
@@ -571,7 +573,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "hb_ctx_create", "hb_ctx_destroy", "hb_last_error", "hb_last_timing", "hb_kernel_launches",
+    "hb_ctx_create", "hb_ctx_destroy", "hb_last_error", "hb_last_timing", "hb_kernel_launches", "hb_h2d_bytes",
     "hb_ctx_profile", "hb_ctx_profile_report", "hb_ctx_mark", "hb_ctx_elapsed",
     "hb_bounds", "hb_requant", "hb_attr_encode", "hb_streams_free", "hb_attr_decode", "hb_twin_match",
     "hb_dmesh_upload", "hb_dmesh_free", "hb_dmesh_quantize", "hb_dmesh_dequantize", "hb_dmesh_encode",
@@ -626,6 +628,10 @@ class Context:
 
     def launches(self) -> int:
         return int(self.lib.hb_kernel_launches(self.h))
+
+    def h2d_bytes(self) -> int:
+        """Bytes of mesh arrays and rows copied host -> device since the context was created."""
+        return int(self.lib.hb_h2d_bytes(self.h))
 
     def sync(self):
         self._check(self.lib.hb_ctx_sync(self.h), "hb_ctx_sync")

@@ -80,6 +80,8 @@ extern "C" int hb_ctx_create(int device, hb_ctx **out)
 	CREATE_TRY(cudaMemset(ctx->d_err, 0, sizeof(int)));
 	CREATE_TRY(cudaMallocHost((void **)&ctx->h_err, sizeof(int)));
 	*ctx->h_err = 0;
+	CREATE_TRY(cudaMallocHost((void **)&ctx->h_flag, sizeof(uint32_t)));
+	CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_flag, cudaEventDisableTiming));
 	cudaDeviceProp prop;
 	CREATE_TRY(cudaGetDeviceProperties(&prop, device));
 	ctx->sm_count = prop.multiProcessorCount;
@@ -108,6 +110,8 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx)
 	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
 	if (ctx->d_err) cudaFree(ctx->d_err);
 	if (ctx->h_err) cudaFreeHost(ctx->h_err);
+	if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+	if (ctx->ev_flag) cudaEventDestroy(ctx->ev_flag);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -121,6 +125,7 @@ extern "C" void hb_last_timing(hb_ctx *ctx, float *kernel_ms, float *copy_ms)
 }
 
 extern "C" uint64_t hb_kernel_launches(hb_ctx *ctx) { return ctx->launches; }
+extern "C" uint64_t hb_h2d_bytes(hb_ctx *ctx) { return ctx->h2d_bytes; }
 
 cudaEvent_t hb_prof_event(hb_ctx *ctx)
 {
@@ -276,6 +281,7 @@ static int copy_in(hb_dmesh *m, void *dst, const void *src, size_t bytes)
 	if (!(bytes && src)) return 0;
 	hb_ctx *ctx = m->ctx;
 	HB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m->async_copy ? ctx->copy_stream : ctx->stream));
+	ctx->h2d_bytes += bytes;
 	return 0;
 }
 static int upload(hb_dmesh *m, void **dst, const void *src, size_t bytes)
@@ -450,10 +456,47 @@ static bool same_region_table(const int32_t *off_a, const uint16_t *la, const in
 }
 
 // Upload of `nseg` meshes of one schema as one device mesh (hb_internal.cuh, "segments").
+// ---- encoder uploads: is the face order needed at all? ---------------------------------------------------------
+// The traversal order of the faces (order_f, 8 bytes per face: 160 MB on the 10M-vertex mesh) only decides WHICH
+// element of a FACE / CORNER list emits a row as DATA and which ones refer back to it (attrcode.h:296-319); the
+// residuals of such a list depend on it through the same first-reference rule.  When no FACE / CORNER list carries
+// components, the mesh has one face region (the region stream is constant) and no row of those lists is bound twice,
+// every element emits DATA with an empty row whatever the order: the streams are those of the index order.  The first
+// two conditions are properties of the schema; the third is checked on the device from the binding arrays, which are
+// then uploaded FIRST: the answer (4 bytes) is back while the rest of the upload is still on the link.
+static bool order_f_maybe_unneeded(const hb_mesh_desc *descs, uint32_t nseg)
+{
+	const hb_mesh_desc *d = &descs[0];
+	if (!d->order_f || d->nregs_face != 1 || !d->lists) return false;
+	const char *env = getenv("HARRY_B200_KEEP_ORDER_F"); // A/B runs and tests: always upload the face order
+	if (env && env[0] == '1') return false;
+	for (uint32_t s = 0; s < nseg; ++s) {
+		const hb_mesh_desc &ds = descs[s];
+		if (!ds.order_f || ds.norder_f != ds.nf || ds.nlists != d->nlists || !ds.lists) return false;
+		for (int l = 0; l < ds.nlists; ++l)
+			if (ds.lists[l].target != HB_VTX && ds.lists[l].ncomp) return false;
+	}
+	return true;
+}
+// element i of segment s binds row bind[i * nb + slot] of the segment's rows [0, nrows[s]): one bit per row
+__global__ void __launch_bounds__(256) k_bind_twice(const uint32_t *__restrict__ bind, const uint32_t *__restrict__ elem_base, uint32_t nseg, uint32_t nb, uint32_t slot,
+                                                    const uint32_t *__restrict__ bitbase, uint32_t *__restrict__ bits, uint32_t *__restrict__ twice)
+{
+	const uint32_t n = elem_base[nseg];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t s = hb_seg_find(elem_base, nseg, i);
+		const uint32_t row = bind[(size_t)i * nb + slot];
+		const uint32_t w0 = bitbase[s], nrow = (bitbase[s + 1] - w0) * 32u; // (rounded up: a row behind the end is caught by the encoder proper)
+		if (row >= nrow) { *twice = 1u; continue; } // unbound / out of range: not the plain case
+		const uint32_t bit = 1u << (row & 31u);
+		if (atomicOr(&bits[w0 + (row >> 5)], bit) & bit) *twice = 1u;
+	}
+}
+
 // vertex_only: the caller will only reconstruct vertex lists (hb_attr_decode of a mesh whose face and
 // corner lists carry no components): the face-side arrays (order_f, face regions, face / corner bindings --
 // 280 MB on the 10M-vertex mesh) are then neither uploaded nor ranked
-static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t nseg, hb_dmesh *m, bool vertex_only = false)
+static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t nseg, hb_dmesh *m, bool vertex_only = false, bool for_encoder = false)
 {
 	if (nseg == 0) return hb_fail(ctx, HB_ERR_INVALID, "batch: no mesh");
 	const hb_mesh_desc *d = &descs[0];
@@ -514,13 +557,52 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 			if (m->h_slot_corner[(size_t)r * d->nlists + l] >= 0 && cls != HB_CORNER) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "list %d bound to corners but declared with target %d", l, cls);
 		}
 	}
+	cudaStream_t up_stream = m->async_copy ? ctx->copy_stream : ctx->stream;
+	// ---- encoder upload whose face order may be unneeded: bindings first, the check right behind them -------------
+	bool late = false;
+	if (for_encoder && !vertex_only && m->async_copy && order_f_maybe_unneeded(descs, nseg)) {
+		late = true;
+		HB_TRY(hb_dalloc(m, (void **)&m->d_face_regs, sizeof(uint16_t) * (size_t)m->nf));
+		HB_TRY(hb_dalloc(m, (void **)&m->d_bind_face, sizeof(uint32_t) * (size_t)m->nf * d->nb_face));
+		HB_TRY(hb_dalloc(m, (void **)&m->d_bind_corner, sizeof(uint32_t) * (size_t)m->ne * d->nb_corner));
+		for (uint32_t s = 0; s < nseg; ++s) {
+			const hb_mesh_desc &ds = descs[s];
+			HB_TRY(copy_in(m, m->d_bind_face + (size_t)m->h_fbase[s] * d->nb_face, ds.bind_face_attr, sizeof(uint32_t) * (size_t)ds.nf * d->nb_face));
+			HB_TRY(copy_in(m, m->d_bind_corner + (size_t)m->h_ebase[s] * d->nb_corner, ds.bind_corner_attr, sizeof(uint32_t) * (size_t)ds.ne * d->nb_corner));
+		}
+		uint32_t *d_twice = nullptr;
+		HB_TRY(hb_dalloc(m, (void **)&d_twice, sizeof(uint32_t)));
+		HB_CUDA(ctx, cudaMemsetAsync(d_twice, 0, sizeof(uint32_t), up_stream));
+		for (int l = 0; l < d->nlists; ++l) {
+			const int cls = d->lists[l].target;
+			if (cls != HB_FACE && cls != HB_CORNER) continue;
+			const int slot = cls == HB_FACE ? m->h_slot_face[(size_t)l] : m->h_slot_corner[(size_t)l]; // region 0 is the only one
+			const uint32_t nelem = cls == HB_FACE ? m->nf : m->ne;
+			if (slot < 0 || nelem == 0) continue;
+			std::vector<uint32_t> bitbase((size_t)nseg + 1, 0);
+			for (uint32_t s = 0; s < nseg; ++s) bitbase[s + 1] = bitbase[s] + (descs[s].lists[l].nrows + 31u) / 32u;
+			uint32_t *d_bitbase = nullptr, *d_bits = nullptr;
+			HB_TRY(upload(m, (void **)&d_bitbase, bitbase.data(), sizeof(uint32_t) * bitbase.size()));
+			if (bitbase[nseg]) {
+				HB_TRY(hb_dalloc(m, (void **)&d_bits, sizeof(uint32_t) * (size_t)bitbase[nseg]));
+				HB_CUDA(ctx, cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * (size_t)bitbase[nseg], up_stream));
+			}
+			const uint32_t grid = std::min<uint32_t>(hb_div_up(nelem, 256), (uint32_t)ctx->sm_count * 8u);
+			k_bind_twice<<<grid, 256, 0, up_stream>>>(cls == HB_FACE ? m->d_bind_face : m->d_bind_corner, cls == HB_FACE ? m->d_fbase : m->d_ebase, nseg,
+			                                          cls == HB_FACE ? d->nb_face : d->nb_corner, (uint32_t)slot, d_bitbase, d_bits, d_twice);
+			ctx->launches++;
+			HB_CUDA(ctx, cudaGetLastError());
+		}
+		HB_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, d_twice, sizeof(uint32_t), cudaMemcpyDeviceToHost, up_stream));
+		HB_CUDA(ctx, cudaEventRecord(ctx->ev_flag, up_stream));
+	}
 	// ---- allocate, then copy segment by segment ----------------------------------------------------------
 	const bool up_faces = !vertex_only;
 	HB_TRY(hb_dalloc(m, (void **)&m->d_edges_raw, 12 * (size_t)m->ne));
 	if (nseg == 1) HB_TRY(hb_dalloc(m, (void **)&m->d_face_off, sizeof(uint32_t) * ((size_t)m->nf + 1)));
 	else HB_TRY(hb_dalloc(m, (void **)&m->d_face_off_raw, sizeof(uint32_t) * ((size_t)m->nf + nseg)));
 	HB_TRY(hb_dalloc(m, (void **)&m->d_order, 8 * (size_t)m->norder));
-	if (m->has_order_f) HB_TRY(hb_dalloc(m, (void **)&m->d_order_f, 8 * (size_t)m->norder_f));
+	if (m->has_order_f && !late) HB_TRY(hb_dalloc(m, (void **)&m->d_order_f, 8 * (size_t)m->norder_f));
 	HB_TRY(hb_dalloc(m, (void **)&m->d_vtx_regs, sizeof(uint16_t) * (size_t)m->nv));
 	uint32_t *face_off_dst = nseg == 1 ? m->d_face_off : m->d_face_off_raw;
 	for (uint32_t s = 0; s < nseg; ++s) {
@@ -528,11 +610,10 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 		HB_TRY(copy_in(m, m->d_edges_raw + 12 * (size_t)m->h_ebase[s], ds.edges, 12 * (size_t)ds.ne));
 		HB_TRY(copy_in(m, face_off_dst + m->h_fbase[s] + s, ds.face_off, sizeof(uint32_t) * ((size_t)ds.nf + 1)));
 		HB_TRY(copy_in(m, m->d_order + 8 * (size_t)m->h_obase[s], ds.order, 8 * (size_t)ds.norder));
-		if (m->has_order_f) HB_TRY(copy_in(m, m->d_order_f + 8 * (size_t)m->h_ofbase[s], ds.order_f, 8 * (size_t)ds.norder_f));
+		if (m->has_order_f && !late) HB_TRY(copy_in(m, m->d_order_f + 8 * (size_t)m->h_ofbase[s], ds.order_f, 8 * (size_t)ds.norder_f));
 		if (d->nregs_vtx > 1) HB_TRY(copy_in(m, m->d_vtx_regs + m->h_vbase[s], ds.vtx_regs, sizeof(uint16_t) * (size_t)ds.nv));
 	}
 	// a single region: every entry is 0 by definition -- cleared on the device instead of uploaded
-	cudaStream_t up_stream = m->async_copy ? ctx->copy_stream : ctx->stream;
 	if (d->nregs_vtx <= 1 && m->nv) HB_CUDA(ctx, cudaMemsetAsync(m->d_vtx_regs, 0, sizeof(uint16_t) * (size_t)m->nv, up_stream));
 	// everything K0 / K3 / K4 read is on its way: first milestone of the copy stream
 	if (m->async_copy) {
@@ -540,7 +621,7 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_up[1], cudaEventDisableTiming));
 		HB_CUDA(ctx, cudaEventRecord(m->ev_up[0], ctx->copy_stream));
 	}
-	if (up_faces) {
+	if (up_faces && !late) {
 		HB_TRY(hb_dalloc(m, (void **)&m->d_face_regs, sizeof(uint16_t) * (size_t)m->nf));
 		HB_TRY(hb_dalloc(m, (void **)&m->d_bind_face, sizeof(uint32_t) * (size_t)m->nf * d->nb_face));
 		HB_TRY(hb_dalloc(m, (void **)&m->d_bind_corner, sizeof(uint32_t) * (size_t)m->ne * d->nb_corner));
@@ -548,7 +629,7 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 	HB_TRY(hb_dalloc(m, (void **)&m->d_bind_vtx, sizeof(uint32_t) * (size_t)m->nv * d->nb_vtx));
 	for (uint32_t s = 0; s < nseg; ++s) {
 		const hb_mesh_desc &ds = descs[s];
-		if (up_faces) {
+		if (up_faces && !late) {
 			if (d->nregs_face > 1) HB_TRY(copy_in(m, m->d_face_regs + m->h_fbase[s], ds.face_regs, sizeof(uint16_t) * (size_t)ds.nf));
 			HB_TRY(copy_in(m, m->d_bind_face + (size_t)m->h_fbase[s] * d->nb_face, ds.bind_face_attr, sizeof(uint32_t) * (size_t)ds.nf * d->nb_face));
 			HB_TRY(copy_in(m, m->d_bind_corner + (size_t)m->h_ebase[s] * d->nb_corner, ds.bind_corner_attr, sizeof(uint32_t) * (size_t)ds.ne * d->nb_corner));
@@ -584,17 +665,28 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 			}
 		}
 	}
+	if (late) {
+		// the answer has been back for a while: the link is still busy with what was queued behind the check
+		HB_CUDA(ctx, cudaEventSynchronize(ctx->ev_flag));
+		if (*ctx->h_flag) {
+			HB_TRY(hb_dalloc(m, (void **)&m->d_order_f, 8 * (size_t)m->norder_f));
+			for (uint32_t s = 0; s < nseg; ++s) HB_TRY(copy_in(m, m->d_order_f + 8 * (size_t)m->h_ofbase[s], descs[s].order_f, 8 * (size_t)descs[s].norder_f));
+			m->order_f_late = true;
+		} else {
+			m->has_order_f = false; // index order, gate corner 0 (norder_f == nf was required: the segment tables are the same)
+		}
+	}
 	if (m->async_copy) HB_CUDA(ctx, cudaEventRecord(m->ev_up[1], ctx->copy_stream));
 	m->alloc_on_copy_stream = false;
 	return 0;
 }
 
 // host-buffer entry points: connectivity stages under the tail of the upload, everything else behind it
-static int upload_overlapped(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t nseg, hb_dmesh *m, bool vertex_only)
+static int upload_overlapped(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t nseg, hb_dmesh *m, bool vertex_only, bool for_encoder)
 {
 	m->async_copy = true;
-	HB_TRY(dmesh_upload_impl(ctx, meshes, nseg, m, vertex_only));
-	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_up[0], 0));
+	HB_TRY(dmesh_upload_impl(ctx, meshes, nseg, m, vertex_only, for_encoder));
+	HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_up[m->order_f_late ? 1 : 0], 0));
 	HB_TRY(hb_build_conn(m));
 	bool need_v = false;
 	for (int l = 0; l < m->nlists; ++l)
@@ -1169,7 +1261,7 @@ extern "C" int hb_attr_encode(hb_ctx *ctx, const hb_mesh_desc *mesh, hb_streams 
 	m->take_cached_rows = true;
 	PhaseTimer t(ctx);
 	t.mark(0);
-	int rc = upload_overlapped(ctx, mesh, 1, m, false);
+	int rc = upload_overlapped(ctx, mesh, 1, m, false, true);
 	t.mark(1);
 	if (rc == 0) rc = hb_encode_lists(m);
 	t.mark(2);
@@ -1193,7 +1285,7 @@ extern "C" int hb_attr_decode(hb_ctx *ctx, const hb_mesh_desc *mesh)
 	hb_dmesh *m = new hb_dmesh();
 	PhaseTimer t(ctx);
 	t.mark(0);
-	int rc = upload_overlapped(ctx, mesh, 1, m, decode_is_vertex_only(mesh));
+	int rc = upload_overlapped(ctx, mesh, 1, m, decode_is_vertex_only(mesh), false);
 	t.mark(1);
 	if (rc == 0) rc = hb_decode_lists(m);
 	t.mark(2);
@@ -1254,7 +1346,7 @@ extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 	auto upload_group = [&](size_t g) -> int {
 		dm[g] = new hb_dmesh();
 		dm[g]->async_copy = true;
-		return dmesh_upload_impl(ctx, meshes + starts[g], starts[g + 1] - starts[g], dm[g], false);
+		return dmesh_upload_impl(ctx, meshes + starts[g], starts[g + 1] - starts[g], dm[g], false, true);
 	};
 	auto run_group = [&](size_t g) -> int {
 		hb_dmesh *m = dm[g];

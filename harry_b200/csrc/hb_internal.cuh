@@ -31,9 +31,12 @@ struct hb_ctx {
 	cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	std::string err;
 	uint64_t launches = 0;
+	uint64_t h2d_bytes = 0; // mesh arrays and rows copied host -> device (copy_in)
 	float kernel_ms = 0.f, copy_ms = 0.f;
 	int *d_err = nullptr;   // device error flag (fan walk overflow, binding out of range)
 	int *h_err = nullptr;   // pinned mirror
+	uint32_t *h_flag = nullptr; // pinned: answer of the 'is any face / corner row bound twice' check of an encoder upload
+	cudaEvent_t ev_flag = nullptr;
 	int sm_count = 148;
 	// Optional row cache (hb_ctx_set_row_cache): the device copy of a list's rows survives from one host-buffer call to
 	// the next of the same pipeline (set_bounds -> requant -> encode; decode -> requant(clear)), keyed by the host
@@ -145,6 +148,7 @@ struct hb_dmesh {
 	uint32_t nv = 0, nf = 0, ne = 0, norder = 0, norder_f = 0;
 	uint16_t nb_face = 0, nb_vtx = 0, nb_corner = 0, nregs_face = 0, nregs_vtx = 0, nlists = 0;
 	bool has_order_f = false;
+	bool order_f_late = false; // order_f was uploaded behind everything else (the face stages wait for the whole upload)
 	bool async_copy = false;     // uploads go to ctx->copy_stream (hb_attr_encode / hb_attr_decode)
 	bool alloc_on_copy_stream = false; // while the upload buffers are being allocated
 	bool take_cached_rows = false;     // rows may come from the context's row cache (requant / encode continue a pipeline)

@@ -196,6 +196,9 @@ void hb_last_timing(hb_ctx *ctx, float *kernel_ms, float *copy_ms);
 int hb_ctx_set_row_cache(hb_ctx *ctx, int enable);
 /* Number of kernels this library launched on the context since creation. */
 uint64_t hb_kernel_launches(hb_ctx *ctx);
+/* Bytes of mesh arrays and attribute rows this library copied host -> device on the context since creation
+ * (what an end-to-end measurement counts as its upload). */
+uint64_t hb_h2d_bytes(hb_ctx *ctx);
 
 /* Per-kernel timing: while enabled every kernel launch is bracketed by CUDA events on the
  * context stream; the report synchronizes, writes "name launches total_ms\n" lines and resets. */

@@ -250,6 +250,40 @@ def test_zero_component_list_with_shared_rows(ctx):
         ok, why = got.equal(ol.o_attr_encode(mesh))
         assert ok, why
     dm.close()
+    # host-buffer batch: the encoder uploads the face order only after the device found a row that is bound twice
+    up0 = ctx.h2d_bytes()
+    got_b, _ = ctx.encode_batch(meshes)
+    assert ctx.h2d_bytes() - up0 >= sum(m.order_f.nbytes for m in meshes)
+    for mesh, got in zip(meshes, got_b):
+        ok, why = got.equal(ol.o_attr_encode(mesh))
+        assert ok, why
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["sphere_q14", "poly_q10", "obj_multi_all"])
+def test_face_order_not_uploaded_when_unneeded(workdir, name, monkeypatch):
+    """hb_attr_encode / hb_encode_batch leave the face order (8 bytes per face) on the host when no FACE / CORNER list
+    carries components, the mesh has one face region and the device finds no face row bound twice: same streams as with
+    the order (HARRY_B200_KEEP_ORDER_F=1), fewer bytes on the link.  Meshes with face attributes keep uploading it."""
+    case = get_case(workdir, name)
+    c = capi.Context(0)
+    mesh = case.enc
+    droppable = mesh.order_f is not None and len(mesh.off_reg_face) == 2 and mesh.order_f.shape[0] == mesh.nf and \
+        all(la.ncomp == 0 or la.target == capi.T_VTX for la in mesh.lists)
+    up = []
+    for keep in ("1", "0"):
+        monkeypatch.setenv("HARRY_B200_KEEP_ORDER_F", keep)
+        u0 = c.h2d_bytes()
+        got = c.attr_encode(mesh)
+        up.append(c.h2d_bytes() - u0)
+        ok, why = got.equal(case.enc_streams)
+        assert ok, f"keep={keep}: {why}"
+        got_b, _ = c.encode_batch([mesh, mesh])
+        for g in got_b:
+            ok, why = g.equal(case.enc_streams)
+            assert ok, f"batch, keep={keep}: {why}"
+    assert up[0] - up[1] == (3 * mesh.order_f.nbytes if droppable else 0)   # one mesh through hb_attr_encode, two through hb_encode_batch
+    c.close()
 
 
 @needs_ref
