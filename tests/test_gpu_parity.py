@@ -275,10 +275,10 @@ def test_face_order_not_uploaded_when_unneeded(workdir, name, monkeypatch):
         monkeypatch.setenv("HARRY_B200_KEEP_ORDER_F", keep)
         u0 = c.h2d_bytes()
         got = c.attr_encode(mesh)
-        up.append(c.h2d_bytes() - u0)
         ok, why = got.equal(case.enc_streams)
         assert ok, f"keep={keep}: {why}"
         got_b, _ = c.encode_batch([mesh, mesh])
+        up.append(c.h2d_bytes() - u0)
         for g in got_b:
             ok, why = g.equal(case.enc_streams)
             assert ok, f"batch, keep={keep}: {why}"
