@@ -1190,6 +1190,10 @@ def main():
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
+        # one rank per GPU: stay on the CPUs of the GPU's NUMA node, so that the page-locked buffers allocated from here on
+        # (first touch) sit behind the same PCIe root as the GPU (no-op on a flat topology)
+        from harry_b200 import shard
+        shard.bind_rank_to_gpu_node(local_rank)
         dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
         dist = dist_mod
     run_ours(args, rank, world, local_rank, dist)

@@ -30,3 +30,43 @@ def reduce_stats(dist, device, elapsed_ms: float, units: float):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), float(u.item())
+
+
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_local_cpus(pci_domain: int, pci_bus: int, pci_device: int, sysfs: str = "/sys/bus/pci/devices") -> set:
+    """CPUs on the NUMA node the GPU hangs off (sysfs local_cpulist); empty when the kernel does not say."""
+    path = f"{sysfs}/{pci_domain:04x}:{pci_bus:02x}:{pci_device:02x}.0/local_cpulist"
+    try:
+        with open(path) as f:
+            return _parse_cpulist(f.read())
+    except (OSError, ValueError):
+        return set()
+
+
+def bind_rank_to_gpu_node(device: int, sysfs: str = "/sys/bus/pci/devices"):
+    """One process per GPU: keep the rank on the CPUs next to its GPU, so that the host buffers it allocates afterwards
+    (first touch) and the staging copies stay on the socket whose PCIe root the GPU is attached to -- on a two-socket
+    box the ranks of the far GPUs otherwise push every upload through the inter-socket link.  Returns the CPU set the
+    process runs on afterwards (unchanged when the topology is flat, unknown, or outside the allowed set)."""
+    import os
+    allowed = os.sched_getaffinity(0)
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        local = gpu_local_cpus(int(p.pci_domain_id), int(p.pci_bus_id), int(p.pci_device_id), sysfs)
+    except Exception:
+        return allowed
+    want = allowed & local
+    if want and want != allowed:
+        os.sched_setaffinity(0, want)
+        return want
+    return allowed

@@ -43,3 +43,15 @@ def test_reduce_stats_world2():
         assert p.exitcode == 0
     assert t == 20.0
     assert u == float(sum(100 * (i + 1) for i in range(7)))
+
+
+def test_gpu_local_cpus(tmp_path):
+    """bind_rank_to_gpu_node reads the GPU's local_cpulist from sysfs: list syntax, missing entries"""
+    from harry_b200 import shard
+    assert shard._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert shard._parse_cpulist("\n") == set()
+    dev = tmp_path / "0000:e5:00.0"
+    dev.mkdir()
+    (dev / "local_cpulist").write_text("0-1,64-65\n")
+    assert shard.gpu_local_cpus(0, 0xE5, 0, str(tmp_path)) == {0, 1, 64, 65}
+    assert shard.gpu_local_cpus(0, 0xE6, 0, str(tmp_path)) == set()
