@@ -340,6 +340,52 @@ def allreduce_max(dist, local_rank, vals):
     return [float(x) for x in t.tolist()]
 
 
+def link_probe(dist, local_rank, world, nbytes=1 << 30, reps=3):
+    """Host -> device bandwidth of one GPU while the others idle, and of every GPU when all ranks copy at once: the
+    end-to-end lines are link-bound, so their scaling over N is the platform's (GPUs sharing a PCIe uplink), measured here
+    with plain torch copies of 1 GiB from page-locked memory (CUDA events)."""
+    import torch
+    dev = torch.device(f"cuda:{local_rank}")
+    host = dst = None
+    try:
+        host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    except Exception:
+        pass
+    ok = torch.tensor([1.0 if dst is not None else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # every rank or none: nobody waits at a barrier for a rank that gave up
+    if ok.item() < 1.0:
+        return {"error": "could not allocate the probe buffers on every rank"}
+
+    def timed():
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(host, non_blocking=True)   # warm-up
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            dst.copy_(host, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        return reps * nbytes / (a.elapsed_time(b) * 1e-3) / 1e9
+
+    alone = []
+    for r in range(world):               # one rank at a time
+        dist.barrier()
+        alone.append(timed() if r == dist.get_rank() else 0.0)
+    dist.barrier()
+    together = timed()
+    t = torch.tensor(alone + [together, -together], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    v = t.tolist()
+    alone_all, tmax, tmin = v[:world], v[world], -v[world + 1]
+    s = torch.tensor([together], dtype=torch.float64, device=dev)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    del host, dst
+    return {"h2d_GBps_alone_per_gpu": [round(x, 1) for x in alone_all], "h2d_GBps_concurrent_min": round(tmin, 1), "h2d_GBps_concurrent_max": round(tmax, 1),
+            "h2d_GBps_concurrent_sum": round(float(s.item()), 1),
+            "note": "plain 1 GiB page-locked copies, no library code: what the platform gives N ranks at once; the e2e lines cannot scale past it"}
+
+
 def kernel_table(prof, alg, peak, steps, total_ms):
     kernels = {}
     for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
@@ -501,6 +547,12 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     if ctx_d is not ctx:
         ctx_d.close()
     ctx.close()
+    link = None
+    if world > 1:
+        try:
+            link = link_probe(dist, local_rank, world)
+        except Exception as e:
+            link = {"error": repr(e)}
     cli = None
     if rank == 0 and world == 1 and not args.no_cli:
         try:
@@ -532,6 +584,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu, "batch": batch, "cli": cli, "configs": configs, "twin_match": twin,
         }
+        if link is not None:
+            out["link"] = link
         print(json.dumps(out), flush=True)
 
 
