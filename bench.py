@@ -408,7 +408,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     # two contexts (= two streams) on the GPU: the encode of the mesh and the decode of the decoder-side mesh are
     # independent jobs, and the chain-bound vertex decode of ONE mesh occupies 48 of the 148 SMs -- the encode fits beside it
     ctx = capi.Context(local_rank)
-    ctx_d = ctx if args.one_stream else capi.Context(local_rank)
+    ctx_d = ctx if args.one_stream else capi.Context(local_rank, high_priority=not args.flat_priority)   # the chain-bound job goes first
     vl = 1
     groups = w.raw.lists[vl].groups
     E = capi.DeviceMesh(ctx, w.raw)
@@ -530,6 +530,10 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
 
     # ---- BASELINE configs[4]: the mesh batch, on every rank at every N ------------------------------
     batch = None
+    if ctx_d is not ctx and not args.flat_priority:
+        # the batch keeps every SM busy from both streams: no job to favour there
+        ctx_d.close()
+        ctx_d = capi.Context(local_rank)
     if args.batch_meshes > 0 and ol.have_ref():
         try:
             batch = run_batch(args, ctx, ctx_d, rank, world, local_rank, dist, workdir, peak)
@@ -575,7 +579,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
                        "vertex_attributes_per_gpu": n_attrs, "meshes": world, "parallelism": f"mesh-sharded x{world}, no collective",
                        "l2": "inputs (>= 1.3 GB of connectivity + rows per mesh) exceed the 126 MB L2; no explicit flush",
                        "streams": ("one stream" if args.one_stream else "two streams of the same GPU: quantize + encode of the mesh on one, decode + dequantize of the decoder-side mesh "
-                                   "on the other (independent inputs; the chain-bound vertex decode of one mesh occupies 48 of 148 SMs); ms_per_step = both done; "
+                                   "on the other, which has the higher stream priority (independent inputs; the chain-bound vertex decode of one mesh occupies 48 of 148 SMs, "
+                                   "the encode job takes what it leaves); ms_per_step = both done; "
                                    "encode_ms / decode_ms = each job on its own stream while the other runs"),
                        "batch_config": "configs[4] (the mesh batch north_star scales on) is measured in the same run at every N: see `batch`"},
             "encode_ms_per_step": enc_ms / args.steps, "decode_ms_per_step": dec_ms / args.steps,
@@ -1226,6 +1231,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the extra measurement of hb_twin_match (SURVEY 8f row f2)")
     ap.add_argument("--one-stream", action="store_true", help="encode and decode one after the other on one stream (default: two streams, independent meshes)")
+    ap.add_argument("--flat-priority", action="store_true", help="A/B: the decode context at the same stream priority as the encode context")
     ap.add_argument("--no-cli", action="store_true", help="skip the side-by-side run of the two CLIs on configs[1]")
     ap.add_argument("--no-configs", action="store_true", help="skip the lines for configs[0], [2], [3]")
     ap.add_argument("--batch-meshes", type=int, default=1250, help="configs[4]: independent 100K-vertex meshes per GPU and step (0 = skip)")

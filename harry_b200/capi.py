@@ -492,6 +492,8 @@ def load_library():
     vp, u32 = C.c_void_p, C.c_uint32
     lib.hb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.hb_ctx_create.restype = C.c_int
+    lib.hb_ctx_create_prio.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    lib.hb_ctx_create_prio.restype = C.c_int
     lib.hb_ctx_destroy.argtypes = [vp]
     lib.hb_ctx_destroy.restype = None
     lib.hb_last_error.argtypes = [vp]
@@ -573,7 +575,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "hb_ctx_create", "hb_ctx_destroy", "hb_last_error", "hb_last_timing", "hb_kernel_launches", "hb_h2d_bytes",
+    "hb_ctx_create", "hb_ctx_create_prio", "hb_ctx_destroy", "hb_last_error", "hb_last_timing", "hb_kernel_launches", "hb_h2d_bytes",
     "hb_ctx_profile", "hb_ctx_profile_report", "hb_ctx_mark", "hb_ctx_elapsed",
     "hb_bounds", "hb_requant", "hb_attr_encode", "hb_streams_free", "hb_attr_decode", "hb_twin_match",
     "hb_dmesh_upload", "hb_dmesh_free", "hb_dmesh_quantize", "hb_dmesh_dequantize", "hb_dmesh_encode",
@@ -594,10 +596,10 @@ def _desc_array(meshes):
 class Context:
     """RAII wrapper of hb_ctx with numpy-level calls mirroring the reference operators."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, high_priority: bool = False):
         self.lib = load_library()
         h = C.c_void_p()
-        rc = self.lib.hb_ctx_create(device, C.byref(h))
+        rc = self.lib.hb_ctx_create_prio(device, 1 if high_priority else 0, C.byref(h))
         if rc != 0:
             raise HarryError(f"hb_ctx_create failed ({rc}): {self.lib.hb_last_error(None).decode()}")
         self.h = h

@@ -52,7 +52,9 @@ int hb_check_device_error(hb_ctx *ctx, const char *what)
 	return 0;
 }
 
-extern "C" int hb_ctx_create(int device, hb_ctx **out)
+extern "C" int hb_ctx_create(int device, hb_ctx **out) { return hb_ctx_create_prio(device, 0, out); }
+
+extern "C" int hb_ctx_create_prio(int device, int high_priority, hb_ctx **out)
 {
 	*out = nullptr;
 	int ndev = 0;
@@ -72,9 +74,14 @@ extern "C" int hb_ctx_create(int device, hb_ctx **out)
 		}                                                                                                     \
 	} while (0)
 	CREATE_TRY(cudaSetDevice(device));
-	CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-	CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-	CREATE_TRY(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+	// a high-priority context: the blocks of its kernels are placed before pending blocks of other contexts' kernels
+	// (the chain-bound decode of a single mesh next to an encode job that only needs the SMs the chain leaves idle)
+	int prio_lo = 0, prio_hi = 0;
+	CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	const int prio = high_priority ? prio_hi : prio_lo;
+	CREATE_TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio));
+	CREATE_TRY(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio));
+	CREATE_TRY(cudaStreamCreateWithPriority(&ctx->out_stream, cudaStreamNonBlocking, prio));
 	for (int i = 0; i < 6; ++i) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
 	CREATE_TRY(cudaMalloc((void **)&ctx->d_err, sizeof(int)));
 	CREATE_TRY(cudaMemset(ctx->d_err, 0, sizeof(int)));

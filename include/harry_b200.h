@@ -182,6 +182,9 @@ typedef struct hb_ctx hb_ctx;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int hb_ctx_create(int device, hb_ctx **out);
+/* Same, with the context's streams at the device's highest stream priority when high_priority != 0: for the job whose
+ * latency matters when two contexts share a GPU (hb_ctx_wait).  Results do not depend on it. */
+int hb_ctx_create_prio(int device, int high_priority, hb_ctx **out);
 void hb_ctx_destroy(hb_ctx *ctx);
 const char *hb_last_error(hb_ctx *ctx); /* ctx may be NULL: last error of hb_ctx_create */
 /* Times (ms, CUDA events on the context stream) of the last call: kernels only, and the
