@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) k_global_face_off(const uint32_t *__restr
 	face_off[f] = raw[f + s] + sv.ebase[s];
 }
 
-__global__ void __launch_bounds__(256) k_flatten_halfedges(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ face_off, uint4 *__restrict__ he, uint32_t *__restrict__ org_h,
+__global__ void __launch_bounds__(256) k_flatten_halfedges(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ face_off, uint4 *__restrict__ he,
                                                            uint32_t nf, uint32_t ne, SegView sv, int *err)
 {
 	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) k_flatten_halfedges(const uint32_t *__res
 	if (e < b || e > ne) { atomicExch(err, 1); return; }
 	if (deg > 0xffffu) {
 		atomicExch(err, 1);
-		for (uint32_t h = b; h < e; ++h) { he[h] = make_uint4(vb, h, 0u | (1u << 16), f); org_h[h] = vb; }
+		for (uint32_t h = b; h < e; ++h) he[h] = make_uint4(vb, h, 0u | (1u << 16), f);
 		return;
 	}
 	for (uint32_t h = b; h < e; ++h) {
@@ -205,7 +205,6 @@ __global__ void __launch_bounds__(256) k_flatten_halfedges(const uint32_t *__res
 			else tw = tb + te;
 		}
 		he[h] = make_uint4(org + vb, tw, (h - b) | (deg << 16), f);
-		org_h[h] = org + vb; // the origins alone: the wide-fan collector streams 4 bytes per half-edge instead of 16
 	}
 }
 
@@ -498,7 +497,7 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_compact(const uint4 *
 // half-edges whose origin is a wide vertex: count per vertex (SCATTER = false), then scatter into
 // contiguous node lists and note every node's index (SCATTER = true)
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_wide_collect(const uint32_t *__restrict__ org_h, uint32_t ne, WideCtl *__restrict__ wide, const uint32_t *__restrict__ vslot,
+__global__ void __launch_bounds__(256) k_wide_collect(const uint4 *__restrict__ he, uint32_t ne, WideCtl *__restrict__ wide, const uint32_t *__restrict__ vslot,
                                                       const uint32_t *__restrict__ wbits, uint32_t *__restrict__ nodes, uint32_t *__restrict__ pos)
 {
 	const uint32_t nw = min(wide->n, (uint32_t)VC_MAXWIDE);
@@ -507,7 +506,8 @@ __global__ void __launch_bounds__(256) k_wide_collect(const uint32_t *__restrict
 	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
 		// one bit per vertex in front of the slot table: the bitmap of a 10M-vertex mesh is 1.2 MB and stays in cache, the
 		// slot table (4 bytes per vertex) would be gathered from L2 for every half-edge
-		const uint32_t v = org_h[e];
+		// (a packed copy of the origins, written by K0 for this pass, cost K0 four times what it saved here)
+		const uint32_t v = __ldg((const uint32_t *)(he + e));
 		if (!((__ldg(wbits + (v >> 5)) >> (v & 31u)) & 1u)) continue;
 		const uint32_t w = vslot[v];
 		if (w == HB_NONE) continue;
@@ -713,7 +713,6 @@ int hb_build_conn(hb_dmesh *m)
 	if (m->conn_ready) return 0;
 	const SegView sv = seg_view(m);
 	HB_TRY(hb_dalloc_t(m, &m->d_he, (size_t)m->ne + 1));
-	HB_TRY(hb_dalloc_t(m, &m->d_org_h, (size_t)m->ne + 1));
 	HB_TRY(hb_dalloc_t(m, &m->d_vrank, (size_t)m->nv + 1));
 	HB_TRY(hb_dalloc_t(m, &m->d_ord_h, (size_t)m->norder + 1));
 	HB_TRY(hb_dalloc_t(m, &m->d_ord_v, (size_t)m->norder + 1));
@@ -726,7 +725,7 @@ int hb_build_conn(hb_dmesh *m)
 		HB_TRY(hb_dalloc_t(m, &m->d_face_off, (size_t)m->nf + 1));
 		HB_LAUNCH(ctx, k_global_face_off, hb_div_up((uint64_t)m->nf + 1, 256), 256, 0, m->d_face_off_raw, sv, m->nf, m->d_face_off);
 	}
-	if (m->nf) HB_LAUNCH(ctx, k_flatten_halfedges, hb_div_up(m->nf, 256), 256, 0, (const uint32_t *)m->d_edges_raw, m->d_face_off, m->d_he, m->d_org_h, m->nf, m->ne, sv, ctx->d_err);
+	if (m->nf) HB_LAUNCH(ctx, k_flatten_halfedges, hb_div_up(m->nf, 256), 256, 0, (const uint32_t *)m->d_edges_raw, m->d_face_off, m->d_he, m->nf, m->ne, sv, ctx->d_err);
 	if (m->norder)
 		HB_LAUNCH(ctx, k_vertex_order, hb_div_up(m->norder, 256), 256, 0, (const uint32_t *)m->d_order, m->d_face_off, m->d_he, m->norder, sv, m->d_ord_h, m->d_ord_v, m->d_vrank, ctx->d_err);
 	// face ranks and gate half-edges are only needed by face lists with components (or partly bound ones), corner lists
@@ -792,7 +791,7 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_warena, 6 * cap + 6));
 		uint32_t *nodes = m->d_vc_wnodes, *pos = m->d_vc_wpos, *work = m->d_vc_wwork, *order = m->d_vc_worder, *arena = m->d_vc_warena;
 		HB_LAUNCH(ctx, k_wide_even_bases, 1, 256, 0, wide);
-		HB_LAUNCH(ctx, k_wide_collect<true>, (uint32_t)ctx->sm_count * 8, 256, 0, m->d_org_h, m->ne, wide, m->d_vc_wslot, m->d_vc_wbits, nodes, pos);
+		HB_LAUNCH(ctx, k_wide_collect<true>, (uint32_t)ctx->sm_count * 8, 256, 0, m->d_he, m->ne, wide, m->d_vc_wslot, m->d_vc_wbits, nodes, pos);
 		HB_LAUNCH(ctx, k_wide_fill_to_deg, 1, 256, 0, wide);
 		HB_LAUNCH(ctx, k_wide_rank, VC_MAXWIDE, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + cap, work + 2 * cap, work + 3 * cap,
 		          work + 4 * cap, work + 5 * cap, order, arena, m->d_vc_off, stage, m->ne, ctx->d_err);

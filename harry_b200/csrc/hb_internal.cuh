@@ -168,7 +168,6 @@ struct hb_dmesh {
 	bool any_corner = false;
 	// derived connectivity
 	uint4 *d_he = nullptr;
-	uint32_t *d_org_h = nullptr;        // origin vertex of every half-edge (the x of d_he, packed)
 	uint32_t *d_vrank = nullptr, *d_ord_h = nullptr, *d_ord_v = nullptr;
 	uint32_t *d_frank = nullptr, *d_ford_h = nullptr; // face rank by face, gate half-edge by face rank
 	uint32_t *d_he_celem = nullptr;   // half-edge -> corner element

@@ -282,7 +282,9 @@ def test_face_order_not_uploaded_when_unneeded(workdir, name, monkeypatch):
         for g in got_b:
             ok, why = g.equal(case.enc_streams)
             assert ok, f"batch, keep={keep}: {why}"
-    assert up[0] - up[1] == (3 * mesh.order_f.nbytes if droppable else 0)   # one mesh through hb_attr_encode, two through hb_encode_batch
+    # one mesh through hb_attr_encode, two through hb_encode_batch; the check itself uploads a few words (row-bitmap bases)
+    saved, want = up[0] - up[1], (3 * mesh.order_f.nbytes if droppable else 0)
+    assert want - 64 <= saved <= want, (saved, want)
     c.close()
 
 
