@@ -169,10 +169,15 @@ struct SegView {
 // starting at 0, stored at fbase[s] + s)
 __global__ void __launch_bounds__(256) k_global_face_off(const uint32_t *__restrict__ raw, SegView sv, uint32_t nf, uint32_t *__restrict__ face_off)
 {
-	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+	// one binary search per CTA, then a step or two forward: a segment is thousands of faces long
+	__shared__ uint32_t s_seg;
+	const uint32_t f0 = blockIdx.x * blockDim.x, f = f0 + threadIdx.x;
+	if (threadIdx.x == 0) s_seg = hb_seg_find(sv.fbase, sv.nseg, min(f0, nf ? nf - 1 : 0u));
+	__syncthreads();
 	if (f > nf) return;
 	if (f == nf) { face_off[f] = sv.ebase[sv.nseg]; return; }
-	const uint32_t s = hb_seg_find(sv.fbase, sv.nseg, f);
+	uint32_t s = s_seg;
+	while (s + 1 < sv.nseg && f >= sv.fbase[s + 1]) ++s;
 	face_off[f] = raw[f + s] + sv.ebase[s];
 }
 
@@ -313,19 +318,20 @@ __device__ __forceinline__ bool fan_walk(const uint4 *__restrict__ he, uint32_t 
 	return true;
 }
 
+// A candidate is kept when its three vertices were coded earlier and lie in the vertex's region (attrcode.h:117-121).
+// The ranks are tested one by one AS SOON AS a vertex is known: most fan faces of a vertex fail on the first or second
+// rank (their other corners come later in the traversal), and the kernel is bound by the number of scattered loads --
+// a face that fails early never loads the rest of the neighbouring face's records nor the remaining ranks.
 struct ParalSink {
 	const uint32_t *vrank;
-	const uint16_t *vtx_regs;
+	const uint16_t *vtx_regs; // nullptr: one vertex region
 	uint32_t self;   // traversal position of the vertex being coded
 	uint16_t reg;
 	uint32_t count;
 	uint32_t *out;   // nullptr in the counting pass
-	// attrcode.h:117-121: all three vertices coded earlier and in the same region
-	__device__ __forceinline__ void offer(uint32_t v0, uint32_t v1, uint32_t vo)
+	__device__ __forceinline__ void accept(uint32_t v0, uint32_t v1, uint32_t vo, uint32_t r0, uint32_t r1, uint32_t ro)
 	{
-		const uint32_t r0 = vrank[v0], r1 = vrank[v1], ro = vrank[vo];
-		if (r0 >= self || r1 >= self || ro >= self) return;
-		if (vtx_regs[v0] != reg || vtx_regs[v1] != reg || vtx_regs[vo] != reg) return;
+		if (vtx_regs && (vtx_regs[v0] != reg || vtx_regs[v1] != reg || vtx_regs[vo] != reg)) return;
 		if (out) {
 			out[3 * (size_t)count] = r0;
 			out[3 * (size_t)count + 1] = r1;
@@ -334,28 +340,6 @@ struct ParalSink {
 		++count;
 	}
 };
-
-// attrcode.h:155-171 (paral) applied to fan half-edge e
-__device__ __forceinline__ void paral_visit(const uint4 *__restrict__ he, uint32_t e, const uint4 &rec, ParalSink &sink)
-{
-	const uint32_t deg = rec.z >> 16;
-	if (deg == 3) {
-		const uint32_t e1 = he_next(e, rec.z);
-		const uint32_t t = he[e1].y;
-		if (t == e1) return;
-		const uint4 rt = he[t];
-		const uint32_t tn = he_next(t, rt.z);
-		const uint4 rtn = he[tn];
-		const uint32_t tnn = he_next(tn, rtn.z);
-		sink.offer(rt.x, rtn.x, he[tnn].x);
-		return;
-	}
-	const uint32_t e0 = he_next(e, rec.z), e1 = he_prev(e, rec.z);
-	const uint4 r0 = he[e0];
-	const uint32_t v0 = r0.x, v1 = he[e1].x;
-	sink.offer(v0, v1, he[he_next(e0, r0.z)].x);
-	if (deg > 4) sink.offer(v0, v1, v1); // second "parallelogram" of an n-gon degenerates (Appendix C.3)
-}
 
 // Pass 1 (MODE_STAGE): one fan walk per traversed vertex; the first VC_STAGE accepted
 // parallelograms are parked in a fixed-size staging slot, the count goes to cnt[].  After the scan
@@ -370,11 +354,9 @@ struct ParalStageSink {
 	uint16_t reg;
 	uint32_t count;
 	uint32_t *stage; // VC_STAGE triples
-	__device__ __forceinline__ void offer(uint32_t v0, uint32_t v1, uint32_t vo)
+	__device__ __forceinline__ void accept(uint32_t v0, uint32_t v1, uint32_t vo, uint32_t r0, uint32_t r1, uint32_t ro)
 	{
-		const uint32_t r0 = vrank[v0], r1 = vrank[v1], ro = vrank[vo];
-		if (r0 >= self || r1 >= self || ro >= self) return;
-		if (vtx_regs[v0] != reg || vtx_regs[v1] != reg || vtx_regs[vo] != reg) return;
+		if (vtx_regs && (vtx_regs[v0] != reg || vtx_regs[v1] != reg || vtx_regs[vo] != reg)) return;
 		if (count < VC_STAGE) {
 			stage[3 * count] = r0;
 			stage[3 * count + 1] = r1;
@@ -383,26 +365,49 @@ struct ParalStageSink {
 		++count;
 	}
 };
+// attrcode.h:155-171 (paral) applied to fan half-edge e
 template <typename Sink>
 __device__ __forceinline__ void paral_visit_t(const uint4 *__restrict__ he, uint32_t e, const uint4 &rec, Sink &sink)
 {
 	const uint32_t deg = rec.z >> 16;
 	if (deg == 3) {
+		// the face across the edge opposite to the vertex: (org(t), org(next t), org(next next t))
 		const uint32_t e1 = he_next(e, rec.z);
 		const uint32_t t = he[e1].y;
 		if (t == e1) return;
 		const uint4 rt = he[t];
+		const uint32_t r0 = sink.vrank[rt.x];
+		if (r0 >= sink.self) return;
 		const uint32_t tn = he_next(t, rt.z);
 		const uint4 rtn = he[tn];
-		const uint32_t tnn = he_next(tn, rtn.z);
-		sink.offer(rt.x, rtn.x, he[tnn].x);
+		const uint32_t r1 = sink.vrank[rtn.x];
+		if (r1 >= sink.self) return;
+		const uint32_t vo = he[he_next(tn, rtn.z)].x;
+		const uint32_t ro = sink.vrank[vo];
+		if (ro >= sink.self) return;
+		sink.accept(rt.x, rtn.x, vo, r0, r1, ro);
 		return;
 	}
 	const uint32_t e0 = he_next(e, rec.z), e1 = he_prev(e, rec.z);
-	const uint4 r0 = he[e0];
-	const uint32_t v0 = r0.x, v1 = he[e1].x;
-	sink.offer(v0, v1, he[he_next(e0, r0.z)].x);
-	if (deg > 4) sink.offer(v0, v1, v1); // second "parallelogram" of an n-gon degenerates (Appendix C.3)
+	const uint4 q0 = he[e0];
+	const uint32_t v0 = q0.x;
+	const uint32_t r0 = sink.vrank[v0];
+	if (r0 >= sink.self) return;
+	const uint32_t v1 = he[e1].x;
+	const uint32_t r1 = sink.vrank[v1];
+	if (r1 >= sink.self) return;
+	if (deg > 4) {
+		// the second "parallelogram" of an n-gon degenerates to (v0, v1, v1) (Appendix C.3); it follows the regular one
+		const uint32_t vo = he[he_next(e0, q0.z)].x;
+		const uint32_t ro = sink.vrank[vo];
+		if (ro < sink.self) sink.accept(v0, v1, vo, r0, r1, ro);
+		sink.accept(v0, v1, v1, r0, r1, r1);
+		return;
+	}
+	const uint32_t vo = he[he_next(e0, q0.z)].x;
+	const uint32_t ro = sink.vrank[vo];
+	if (ro >= sink.self) return;
+	sink.accept(v0, v1, vo, r0, r1, ro);
 }
 
 // Wide fans.  A fan is a linked list (e -> next(twin(e))): a thread that has not closed it after
@@ -436,7 +441,7 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_stage(const uint4 *__
 	sink.vrank = vrank;
 	sink.vtx_regs = vtx_regs;
 	sink.self = i;
-	sink.reg = vtx_regs[ord_v[i]];
+	sink.reg = vtx_regs ? vtx_regs[ord_v[i]] : (uint16_t)0;
 	sink.count = 0;
 	uint32_t st[3 * VC_STAGE];
 	sink.stage = st;
@@ -486,10 +491,10 @@ __global__ void __launch_bounds__(256) k_vertex_candidates_compact(const uint4 *
 	sink.vrank = vrank;
 	sink.vtx_regs = vtx_regs;
 	sink.self = i;
-	sink.reg = vtx_regs[ord_v[i]];
+	sink.reg = vtx_regs ? vtx_regs[ord_v[i]] : (uint16_t)0;
 	sink.count = 0;
 	sink.out = tri + 3 * (size_t)o0;
-	const bool ok = fan_walk(he, ord_h[i], ne + 2, [&](uint32_t e, const uint4 &rec) { paral_visit(he, e, rec, sink); });
+	const bool ok = fan_walk(he, ord_h[i], ne + 2, [&](uint32_t e, const uint4 &rec) { paral_visit_t(he, e, rec, sink); });
 	if (!ok) atomicExch(err, 5);
 }
 
@@ -552,7 +557,7 @@ __global__ void __launch_bounds__(WIDE_T) k_wide_rank(const uint4 *__restrict__ 
 	if (slot >= min(wide->n, (uint32_t)VC_MAXWIDE)) return;
 	const uint32_t b = wide->base[slot], d = wide->deg[slot], self = wide->rank[slot];
 	const uint32_t ein = ord_h[self];
-	const uint16_t reg = vtx_regs[wide->vtx[slot]];
+	const uint16_t reg = vtx_regs ? vtx_regs[wide->vtx[slot]] : (uint16_t)0;
 	__shared__ uint32_t s_warp[32], s_carry, s_total;
 	if (d > wide->per) {
 		// the fan does not fit its share of the arena (more than VC_WIDE_ARENA / #wide vertices half-edges around one
@@ -778,9 +783,10 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 		HB_CUDA(ctx, cudaMemsetAsync(wide, 0, sizeof(WideCtl), ctx->stream));
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_wslot, (size_t)m->nv + 1));
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_wbits, ((size_t)m->nv >> 5) + 2));
-		HB_CUDA(ctx, cudaMemsetAsync(m->d_vc_wslot, 0xff, sizeof(uint32_t) * ((size_t)m->nv + 1), ctx->stream));
+		// (the slot table is only read where the bitmap says a slot was written: no need to clear its 4 bytes per vertex)
 		HB_CUDA(ctx, cudaMemsetAsync(m->d_vc_wbits, 0, sizeof(uint32_t) * (((size_t)m->nv >> 5) + 2), ctx->stream));
-		HB_LAUNCH(ctx, k_vertex_candidates_stage, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, wide,
+		const uint16_t *vregs = m->nregs_vtx > 1 ? m->d_vtx_regs : nullptr; // one vertex region: no region test, no region gathers
+		HB_LAUNCH(ctx, k_vertex_candidates_stage, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, vregs, n, m->ne, m->d_vc_off, stage, wide,
 		          m->d_vc_wslot, m->d_vc_wbits, (uint32_t)VC_WALK_CAP, ctx->d_err);
 		const size_t cap = VC_WIDE_ARENA;
 		m->vc_wide_cap = (uint32_t)cap;
@@ -793,14 +799,14 @@ int hb_build_vertex_candidates(hb_dmesh *m)
 		HB_LAUNCH(ctx, k_wide_even_bases, 1, 256, 0, wide);
 		HB_LAUNCH(ctx, k_wide_collect<true>, (uint32_t)ctx->sm_count * 8, 256, 0, m->d_he, m->ne, wide, m->d_vc_wslot, m->d_vc_wbits, nodes, pos);
 		HB_LAUNCH(ctx, k_wide_fill_to_deg, 1, 256, 0, wide);
-		HB_LAUNCH(ctx, k_wide_rank, VC_MAXWIDE, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, m->d_vtx_regs, wide, nodes, pos, work, work + cap, work + 2 * cap, work + 3 * cap,
+		HB_LAUNCH(ctx, k_wide_rank, VC_MAXWIDE, WIDE_T, 0, m->d_he, m->d_ord_h, m->d_vrank, vregs, wide, nodes, pos, work, work + cap, work + 2 * cap, work + 3 * cap,
 		          work + 4 * cap, work + 5 * cap, order, arena, m->d_vc_off, stage, m->ne, ctx->d_err);
 		HB_TRY(hb_scan_exclusive_u32(ctx, m->d_vc_off, m->d_vc_off, n, nullptr));
 		const uint64_t tri_cap = 2 * (uint64_t)m->ne + 8;
 		if (tri_cap > 0xffffffffull) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "mesh (or batch) with more than 2^31 half-edges");
 		m->vc_total = (uint32_t)tri_cap;
 		HB_TRY(hb_dalloc_t(m, &m->d_vc_tri, 3 * (size_t)tri_cap + 3));
-		HB_LAUNCH(ctx, k_vertex_candidates_compact, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, m->d_vtx_regs, n, m->ne, m->d_vc_off, stage, m->d_vc_tri, (uint32_t)tri_cap, ctx->d_err);
+		HB_LAUNCH(ctx, k_vertex_candidates_compact, hb_div_up(n, 256), 256, 0, m->d_he, m->d_ord_h, m->d_ord_v, m->d_vrank, vregs, n, m->ne, m->d_vc_off, stage, m->d_vc_tri, (uint32_t)tri_cap, ctx->d_err);
 		HB_LAUNCH(ctx, k_wide_copy, VC_MAXWIDE, 256, 0, wide, m->d_vc_off, arena, m->d_vc_tri, (uint32_t)tri_cap);
 	} else {
 		HB_CUDA(ctx, cudaMemsetAsync(m->d_vc_off, 0, sizeof(uint32_t) * 2, ctx->stream));
