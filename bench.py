@@ -1236,8 +1236,10 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the lines for configs[0], [2], [3]")
     ap.add_argument("--batch-meshes", type=int, default=1250, help="configs[4]: independent 100K-vertex meshes per GPU and step (0 = skip)")
     ap.add_argument("--batch-distinct", type=int, default=16, help="distinct prepared meshes the batch cycles through")
-    ap.add_argument("--batch-resident", type=int, default=420, help="meshes kept resident in HBM for the device-resident batch value")
-    ap.add_argument("--batch-group-half-edges", type=int, default=112 << 20, help="half-edges per device mesh (group of meshes run by one launch per stage)")
+    ap.add_argument("--batch-resident", type=int, default=800, help="meshes kept resident in HBM for the device-resident batch value")
+    ap.add_argument("--batch-group-half-edges", type=int, default=224 << 20,
+                    help="half-edges per device mesh of the device-resident batch value (group of meshes run by one launch per stage; 391 spheres of 100K vertices = "
+                         "1173 chains = eight per SM in the scan decoder).  The host-buffer calls cut their own groups (112M half-edges: shorter pipeline fill and drain)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

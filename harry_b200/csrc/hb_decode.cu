@@ -444,7 +444,7 @@ static int launch_spec(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, uint32_t 
 }
 
 // cluster launch of the verified-scan kernel (integer lists): one cluster per component
-template <typename T, int NTB>
+template <typename T, int NTB, int MINB>
 static int launch_scan_ntb(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster, uint32_t nseg)
 {
 	cudaLaunchConfig_t cfg = {};
@@ -459,17 +459,17 @@ static int launch_scan_ntb(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int c
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	if (cluster > 8) HB_CUDA(ctx, cudaFuncSetAttribute((k_decode_vertex_scan<T, NTB>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	if (cluster > 8) HB_CUDA(ctx, cudaFuncSetAttribute((k_decode_vertex_scan<T, NTB, MINB>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 	cudaEvent_t pa = nullptr, pb = nullptr;
 	if (ctx->profiling) { pa = hb_prof_event(ctx); pb = hb_prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
-	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, (k_decode_vertex_scan<T, NTB>), d_args, (uint32_t)ncomp));
+	HB_CUDA(ctx, cudaLaunchKernelEx(&cfg, (k_decode_vertex_scan<T, NTB, MINB>), d_args, (uint32_t)ncomp));
 	ctx->launches++;
 	if (pa) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back(hb_ctx::ProfRec{ "k_decode_vertex_scan", pa, pb }); }
 	return 0;
 }
 static int scan_ntb(uint32_t chains, int sm_count)
 {
-	static const char *env = getenv("HARRY_B200_SCAN_NTB");
+	const char *env = getenv("HARRY_B200_SCAN_NTB"); // (read per call: tests switch it)
 	if (env && (atoi(env) == 128 || atoi(env) == 256 || atoi(env) == 512)) return atoi(env);
 	// the fixed cost of a sweep (two dependent memory round trips, four barriers, ~1000 dependent instructions) barely
 	// depends on the window length: the more chains an SM holds, the better it hides it (measured, 197 spheres of 100K
@@ -480,9 +480,15 @@ static int scan_ntb(uint32_t chains, int sm_count)
 template <typename T>
 static int launch_scan(hb_ctx *ctx, int ncomp, const SpecArgs *d_args, int cluster, uint32_t nseg, int ntb)
 {
-	if (ntb == 128) return launch_scan_ntb<T, 128>(ctx, ncomp, d_args, cluster, nseg);
-	if (ntb == 256) return launch_scan_ntb<T, 256>(ctx, ncomp, d_args, cluster, nseg);
-	return launch_scan_ntb<T, 512>(ctx, ncomp, d_args, cluster, nseg);
+	if (ntb == 128) {
+		// more chains than four per SM: the 64-register build keeps eight of them resident per SM
+		const char *env = getenv("HARRY_B200_SCAN_DENSE"); // A/B runs and tests (read per call): 0 = never, 1 = always
+		const bool dense = env ? atoi(env) != 0 : (uint64_t)nseg * (uint32_t)ncomp > 4ull * (uint32_t)ctx->sm_count;
+		if (dense && cluster == 1) return launch_scan_ntb<T, 128, 8>(ctx, ncomp, d_args, cluster, nseg);
+		return launch_scan_ntb<T, 128, 4>(ctx, ncomp, d_args, cluster, nseg);
+	}
+	if (ntb == 256) return launch_scan_ntb<T, 256, 2>(ctx, ncomp, d_args, cluster, nseg);
+	return launch_scan_ntb<T, 512, 1>(ctx, ncomp, d_args, cluster, nseg);
 }
 // CTAs per cluster: the window is about one cut-border length (~ sqrt(2 n) on a regular mesh);
 // two ranks per thread

@@ -442,8 +442,11 @@ __device__ __noinline__ uint32_t scan_generic_step(const uint32_t *__restrict__ 
 
 // NTB threads per CTA: 512 (one CTA per SM; a single mesh wants the widest window), or 256 / 128 with two / four CTAs
 // per SM -- a batch has more chains than SMs, and resident chains hide each other's latencies and barriers
-template <typename T, int NTB>
-__global__ void __launch_bounds__(NTB, 512 / NTB) k_decode_vertex_scan(const SpecArgs *__restrict__ args, uint32_t ncomp)
+// MINB = CTAs per SM the register allocation is sized for: 512 / NTB, or 8 with 128 threads (64 registers, ~250 bytes of
+// spills) when there are more than four chains per SM to keep resident -- measured on spheres of 100K vertices: 195 meshes
+// (585 chains) 5.1 ms with 4 CTAs per SM, 390 meshes (1170 chains) 8.2 ms with 8 per SM = 20.9 instead of 26.2 us per mesh
+template <typename T, int NTB, int MINB>
+__global__ void __launch_bounds__(NTB, MINB) k_decode_vertex_scan(const SpecArgs *__restrict__ args, uint32_t ncomp)
 {
 	constexpr uint32_t NWARP = NTB / 32;
 	typedef FMap<T> Map;

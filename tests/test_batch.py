@@ -147,6 +147,16 @@ def test_batch_device_resident_decode(ctx, workdir, name):
     dm.close()
 
 
+@pytest.mark.parametrize("ntb,dense", [("128", "1"), ("128", "0"), ("256", "0")])
+@pytest.mark.parametrize("name", ["spheres64_q14", "obj_multi_all"])
+def test_batch_decode_scan_variants(ctx, workdir, name, ntb, dense, monkeypatch):
+    """The scan decoder picks its CTA size and register budget from the number of chains (128 threads with 8 CTAs per SM
+    from four chains per SM on): every variant reconstructs the same rows, whatever the batch size that selects it"""
+    monkeypatch.setenv("HARRY_B200_SCAN_NTB", ntb)
+    monkeypatch.setenv("HARRY_B200_SCAN_DENSE", dense)
+    test_batch_device_resident_decode(ctx, workdir, name)
+
+
 def host_roundtrip(ctx, cases):
     reqs = quant_requests(cases[0])
     streams, bounds = ctx.encode_batch(encoder_inputs(cases), reqs)
