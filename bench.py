@@ -608,7 +608,8 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
     per_call = {k: 0.0 for k in CALLS}
     per_step = []
     ctx.set_row_cache(True)      # what the CLI adapter does (host/bridge.cc): rows stay on the device between the calls of a pipeline
-    for it in range(n_e2e + 1):
+    n_warm = max(1, args.warmup)   # untimed steps first: the second or third call can still grow the stream-ordered pool
+    for it in range(n_e2e + n_warm):
         for la, src in zip(hraw.lists, pristine_raw):
             la.rows[...] = src
             la.quants = [0] * la.ncomp
@@ -632,7 +633,7 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
         t5 = time.perf_counter()
         dt = t5 - t0
         up1 = ctx.h2d_bytes()
-        if it == 0:      # warm-up
+        if it < n_warm:      # warm-up
             del streams
             release()
             continue
@@ -640,7 +641,7 @@ def run_e2e(args, ctx, w, vl, dist, local_rank, world):
         per_step.append([round(x * 1e3, 2) for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)])
         for k, d in zip(CALLS, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
             per_call[k] += d * 1e3 / n_e2e
-        if it == 1:
+        if it == n_warm:
             rows_b = la.rows.nbytes
             # counted by the library at its host -> device copies: rows once for set_bounds (requant and encode find them on the device),
             # once for decode; the connectivity of the encoder and of the decoder mesh (12 bytes per half-edge each); single-region
@@ -947,7 +948,8 @@ def run_batch(args, ctx, ctx_d, rank, world, local_rank, dist, workdir, peak):
         dreq[0].bounds = dq_bounds.ctypes.data
         t_sum, d2h_streams = 0.0, 0
         n_steps = max(1, min(args.steps, 5))
-        for it in range(n_steps + 1):
+        n_warm = max(1, min(args.warmup, 3))
+        for it in range(n_steps + n_warm):
             for i, m in enumerate(dec_meshes):       # fresh residual rows (untimed)
                 m.lists[1].rows[...] = pristine[i % distinct]
             up0 = ctx.h2d_bytes()
@@ -956,7 +958,7 @@ def run_batch(args, ctx, ctx_d, rank, world, local_rank, dist, workdir, peak):
             ctx._check(lib.hb_encode_batch(ctx.h, enc_descs, n_e2e, req, 1, bptr, C.byref(bp)), "hb_encode_batch")
             ctx._check(lib.hb_decode_batch(ctx.h, dec_descs, n_e2e, dreq, 1), "hb_decode_batch")
             dt = time.perf_counter() - t0
-            if it == 1:
+            if it == n_warm:
                 h2d_step = ctx.h2d_bytes() - up0 + n_e2e * 3 * stride   # + the bounds rows of the dequantization requests
                 st = capi.streams_struct_to_py(bp.contents.mesh[n_e2e - 1], copy=False)
                 d2h_streams = st.nbytes_copied
@@ -964,7 +966,7 @@ def run_batch(args, ctx, ctx_d, rank, world, local_rank, dist, workdir, peak):
                     raise RuntimeError("hb_decode_batch differs from the reference")
                 del st
             lib.hb_batch_streams_free(bp)
-            if it:
+            if it >= n_warm:
                 t_sum += dt
         t_step = allreduce_max(dist, local_rank, [t_sum / n_steps])[0]
         d0 = hdec[0]
