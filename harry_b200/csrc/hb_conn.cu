@@ -167,18 +167,23 @@ struct SegView {
 
 // global CSR offsets of the concatenated faces from the per-segment ones (segment s uploaded nf_s + 1 offsets
 // starting at 0, stored at fbase[s] + s)
+#define FOFF_PER_THREAD 8 // (one face per thread made this copy-sized kernel wait for CTA slots: 1.6 TB/s)
 __global__ void __launch_bounds__(256) k_global_face_off(const uint32_t *__restrict__ raw, SegView sv, uint32_t nf, uint32_t *__restrict__ face_off)
 {
 	// one binary search per CTA, then a step or two forward: a segment is thousands of faces long
 	__shared__ uint32_t s_seg;
-	const uint32_t f0 = blockIdx.x * blockDim.x, f = f0 + threadIdx.x;
+	const uint32_t f0 = blockIdx.x * (blockDim.x * FOFF_PER_THREAD);
 	if (threadIdx.x == 0) s_seg = hb_seg_find(sv.fbase, sv.nseg, min(f0, nf ? nf - 1 : 0u));
 	__syncthreads();
-	if (f > nf) return;
-	if (f == nf) { face_off[f] = sv.ebase[sv.nseg]; return; }
 	uint32_t s = s_seg;
-	while (s + 1 < sv.nseg && f >= sv.fbase[s + 1]) ++s;
-	face_off[f] = raw[f + s] + sv.ebase[s];
+#pragma unroll
+	for (int k = 0; k < FOFF_PER_THREAD; ++k) {
+		const uint32_t f = f0 + k * blockDim.x + threadIdx.x;
+		if (f > nf) return;
+		if (f == nf) { face_off[f] = sv.ebase[sv.nseg]; return; }
+		while (s + 1 < sv.nseg && f >= sv.fbase[s + 1]) ++s;
+		face_off[f] = raw[f + s] + sv.ebase[s];
+	}
 }
 
 __global__ void __launch_bounds__(256) k_flatten_halfedges(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ face_off, uint4 *__restrict__ he,
@@ -728,7 +733,7 @@ int hb_build_conn(hb_dmesh *m)
 	HB_CUDA(ctx, cudaMemsetAsync(m->d_frank, 0xff, sizeof(uint32_t) * ((size_t)m->nf + 1), ctx->stream));
 	if (m->nseg > 1) {
 		HB_TRY(hb_dalloc_t(m, &m->d_face_off, (size_t)m->nf + 1));
-		HB_LAUNCH(ctx, k_global_face_off, hb_div_up((uint64_t)m->nf + 1, 256), 256, 0, m->d_face_off_raw, sv, m->nf, m->d_face_off);
+		HB_LAUNCH(ctx, k_global_face_off, hb_div_up((uint64_t)m->nf + 1, 256 * FOFF_PER_THREAD), 256, 0, m->d_face_off_raw, sv, m->nf, m->d_face_off);
 	}
 	if (m->nf) HB_LAUNCH(ctx, k_flatten_halfedges, hb_div_up(m->nf, 256), 256, 0, (const uint32_t *)m->d_edges_raw, m->d_face_off, m->d_he, m->nf, m->ne, sv, ctx->d_err);
 	if (m->norder)
