@@ -643,10 +643,13 @@ __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long
 // zero, exactly like the reference's zero-initialised rows (see harry_b200.h, emit_type).
 __global__ void __launch_bounds__(256) k_decode_corner_sweep(ListParams p, const uint32_t *__restrict__ erow, const uint32_t *__restrict__ first,
                                                               const uint32_t *__restrict__ cand_off, const uint32_t *__restrict__ cand, uint32_t n,
-                                                              unsigned long long *rp, volatile uint8_t *done, uint32_t *__restrict__ remaining)
+                                                              unsigned long long *rp, volatile uint8_t *done, uint32_t *__restrict__ remaining,
+                                                              const uint32_t *__restrict__ remaining_before /* nullptr: first sweep */)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
+	// sweeps are launched several at a time without asking the host in between: once nothing is left they return at once
+	if (remaining_before && *remaining_before == 0u) return;
 	const uint32_t row = erow[i];
 	if (row == HB_NONE || first[row] != i || done[i]) return;
 	const uint32_t c0 = cand_off[i], K = cand_off[i + 1] - c0;
@@ -719,19 +722,24 @@ int hb_decode_lists(hb_dmesh *m)
 			walk_masks.push_back(mask);
 		} else {
 			HB_TRY(hb_dalloc_t(m, &dl.d_done, (size_t)n + 1));   // kept with the list: reused by the next decode of this mesh
-			HB_TRY(hb_dalloc_t(m, &dl.d_remaining, 1));
+			// the DAG is shallow (a handful of levels): CORNER_SWEEPS sweeps go out back to back, each with its own counter
+			// of the elements it had to leave; the host looks at the last counter of the round only
+			constexpr uint32_t CORNER_SWEEPS = 4;
+			HB_TRY(hb_dalloc_t(m, &dl.d_remaining, CORNER_SWEEPS));
 			uint8_t *done = dl.d_done;
 			uint32_t *remaining = dl.d_remaining;
 			HB_CUDA(ctx, cudaMemsetAsync(done, 0, (size_t)n + 1, ctx->stream));
 			uint32_t prev = 0xffffffffu;
-			for (uint32_t sweep = 0;; ++sweep) {
-				HB_CUDA(ctx, cudaMemsetAsync(remaining, 0, sizeof(uint32_t), ctx->stream));
-				HB_LAUNCH(ctx, k_decode_corner_sweep, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, m->d_cc_off, m->d_cc_idx, n, dl.d_rp, done, remaining);
+			for (uint32_t round = 0;; ++round) {
+				HB_CUDA(ctx, cudaMemsetAsync(remaining, 0, sizeof(uint32_t) * CORNER_SWEEPS, ctx->stream));
+				for (uint32_t k = 0; k < CORNER_SWEEPS; ++k)
+					HB_LAUNCH(ctx, k_decode_corner_sweep, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, m->d_cc_off, m->d_cc_idx, n, dl.d_rp, done, remaining + k,
+					          k ? remaining + k - 1 : (const uint32_t *)nullptr);
 				uint32_t rem = 0;
-				HB_CUDA(ctx, cudaMemcpyAsync(&rem, remaining, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+				HB_CUDA(ctx, cudaMemcpyAsync(&rem, remaining + CORNER_SWEEPS - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 				HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-				if (rem == 0) break;
-				if (rem >= prev && sweep > 0) return hb_fail(ctx, HB_ERR_INVALID, "corner decode: dependency cycle (%u elements stuck)", rem);
+				if (rem == 0) break; // (a sweep that found nothing left wrote nothing: the counters behind it stay 0)
+				if (rem >= prev) return hb_fail(ctx, HB_ERR_INVALID, "corner decode: dependency cycle (%u elements stuck)", rem);
 				prev = rem;
 			}
 			HB_LAUNCH(ctx, k_scatter_rp, hb_div_up(n, 256), 256, 0, p, dl.d_erow, dl.d_first, n, dl.d_rp, 0xffffffffu);
