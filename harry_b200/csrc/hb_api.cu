@@ -282,11 +282,114 @@ static int validate_list(hb_ctx *ctx, const hb_list_desc &L, bool for_coder)
 	return 0;
 }
 
+// ---- gathered uploads (hb_internal.cuh, hb_dmesh::up_pending) -------------------------------------------------------
+#define UP_CHUNK (64u << 10)   // bytes one CTA moves per turn
+#define UP_CTAS 48             // 48 x 256 threads x 4 x 16 bytes in flight: far more than link rate x link latency
+// every CTA takes chunks of the concatenated descriptor list in turn; the HOST side is always read with aligned 16-byte
+// loads (a misaligned head / tail goes byte by byte), the device side is written as its alignment allows
+__global__ void __launch_bounds__(256) k_upload_gather(const hb_dmesh::UpDesc *__restrict__ descs, const uint32_t *__restrict__ first_chunk, uint32_t n, uint32_t total)
+{
+	for (uint32_t c = blockIdx.x; c < total; c += gridDim.x) {
+		uint32_t lo = 0, hi = n;
+		while (hi - lo > 1) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (first_chunk[mid] <= c) lo = mid;
+			else hi = mid;
+		}
+		const hb_dmesh::UpDesc d = descs[lo];
+		const unsigned long long off = (unsigned long long)(c - first_chunk[lo]) * UP_CHUNK;
+		const uint32_t len = (uint32_t)(d.bytes - off < UP_CHUNK ? d.bytes - off : UP_CHUNK);
+		const uint8_t *s = (const uint8_t *)d.src + off;
+		uint8_t *t = (uint8_t *)d.dst + off;
+		const uint32_t head = min(len, (uint32_t)((16u - (uint32_t)((uintptr_t)s & 15u)) & 15u));
+		if (threadIdx.x < head) t[threadIdx.x] = s[threadIdx.x];
+		const uint32_t nvec = (len - head) >> 4;
+		const uint4 *sv = (const uint4 *)(s + head);
+		uint8_t *tv = t + head;
+		const uint32_t dal = (uint32_t)((uintptr_t)tv & 15u);
+		if (dal == 0) {
+#pragma unroll 4
+			for (uint32_t v = threadIdx.x; v < nvec; v += 256) ((uint4 *)tv)[v] = sv[v];
+		} else if ((dal & 3u) == 0) {
+#pragma unroll 4
+			for (uint32_t v = threadIdx.x; v < nvec; v += 256) {
+				const uint4 q = sv[v];
+				uint32_t *w = (uint32_t *)(tv + 16 * (size_t)v);
+				w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+			}
+		} else {
+			for (uint32_t v = threadIdx.x; v < nvec; v += 256) {
+				const uint4 q = sv[v];
+				const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+				for (int k = 0; k < 16; ++k) tv[16 * (size_t)v + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+			}
+		}
+		for (uint32_t k = head + 16 * nvec + threadIdx.x; k < len; k += 256) t[k] = s[k];
+	}
+}
+// hands the queued descriptors to one kernel on the upload stream; called in front of everything that orders itself
+// behind the uploads (events, the face-order check)
+static int flush_uploads(hb_dmesh *m)
+{
+	if (m->up_pending.empty()) return 0;
+	hb_ctx *ctx = m->ctx;
+	cudaStream_t st = m->async_copy ? ctx->copy_stream : ctx->stream;
+	const size_t n = m->up_pending.size();
+	if (m->upload_mode == 2) {
+		// one call for all copies of the stage: the copy engines run them back to back
+		std::vector<void *> dsts(n), srcs(n);
+		std::vector<size_t> sizes(n);
+		for (size_t k = 0; k < n; ++k) { dsts[k] = m->up_pending[k].dst; srcs[k] = const_cast<void *>(m->up_pending[k].src); sizes[k] = (size_t)m->up_pending[k].bytes; }
+		cudaMemcpyAttributes at;
+		memset(&at, 0, sizeof(at));
+		at.srcAccessOrder = cudaMemcpySrcAccessOrderStream; // the caller's buffers stay valid until the call returns, which is behind the copies
+		size_t idx0 = 0, fail = 0;
+		if (cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), n, &at, &idx0, 1, &fail, st) == cudaSuccess) {
+			m->up_pending.clear();
+			return 0;
+		}
+		cudaGetLastError(); // a driver without batched copies: the kernel below
+	}
+	std::vector<uint32_t> first((size_t)n + 1, 0);
+	for (size_t k = 0; k < n; ++k) {
+		const unsigned long long nc = (m->up_pending[k].bytes + UP_CHUNK - 1) / UP_CHUNK;
+		if (first[k] + nc > 0xffffffffull) return hb_fail(ctx, HB_ERR_UNSUPPORTED, "batch: upload stage larger than 2^48 bytes");
+		first[k + 1] = first[k] + (uint32_t)nc;
+	}
+	hb_dmesh::UpDesc *d_desc = nullptr;
+	uint32_t *d_first = nullptr;
+	const bool keep = m->alloc_on_copy_stream;
+	m->alloc_on_copy_stream = m->async_copy;
+	int rc = hb_dalloc(m, (void **)&d_desc, sizeof(hb_dmesh::UpDesc) * n);
+	if (rc == 0) rc = hb_dalloc(m, (void **)&d_first, sizeof(uint32_t) * (n + 1));
+	m->alloc_on_copy_stream = keep;
+	if (rc) return rc;
+	// (pageable sources: staged by the runtime before the calls return)
+	HB_CUDA(ctx, cudaMemcpyAsync(d_desc, m->up_pending.data(), sizeof(hb_dmesh::UpDesc) * n, cudaMemcpyHostToDevice, st));
+	HB_CUDA(ctx, cudaMemcpyAsync(d_first, first.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+	const uint32_t total = first[n];
+	k_upload_gather<<<std::min<uint32_t>(total, UP_CTAS), 256, 0, st>>>(d_desc, d_first, (uint32_t)n, total);
+	ctx->launches++;
+	HB_CUDA(ctx, cudaGetLastError());
+	m->up_pending.clear();
+	return 0;
+}
+
 // host -> device copy of one uploaded array (on the copy stream for the host-buffer entry points)
 static int copy_in(hb_dmesh *m, void *dst, const void *src, size_t bytes)
 {
 	if (!(bytes && src)) return 0;
 	hb_ctx *ctx = m->ctx;
+	if (m->gather_uploads) {
+		// page-locked (allocated or registered) host memory is visible to the device: queue it for the gather kernel
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+			m->up_pending.push_back(hb_dmesh::UpDesc{ at.devicePointer, dst, (unsigned long long)bytes });
+			ctx->h2d_bytes += bytes;
+			return 0;
+		}
+		cudaGetLastError(); // (older runtimes report unregistered memory as an error)
+	}
 	HB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m->async_copy ? ctx->copy_stream : ctx->stream));
 	ctx->h2d_bytes += bytes;
 	return 0;
@@ -510,6 +613,12 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 	m->ctx = ctx;
 	m->nseg = nseg;
 	m->alloc_on_copy_stream = m->async_copy;
+	m->gather_uploads = m->async_copy && nseg > 1; // (a single mesh is a dozen large copies: nothing to gain)
+	m->upload_mode = 2;
+	if (const char *env = getenv("HARRY_B200_GATHER_UPLOADS")) { // A/B runs and tests: 0 = one copy per array, 1 = gather kernel, 2 = batched copies
+		m->upload_mode = atoi(env);
+		m->gather_uploads = m->async_copy && m->upload_mode != 0;
+	}
 	m->has_order_f = d->order_f != nullptr && !vertex_only;
 	m->nb_face = d->nb_face; m->nb_vtx = d->nb_vtx; m->nb_corner = d->nb_corner;
 	m->nregs_face = d->nregs_face; m->nregs_vtx = d->nregs_vtx; m->nlists = d->nlists;
@@ -577,6 +686,7 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 			HB_TRY(copy_in(m, m->d_bind_face + (size_t)m->h_fbase[s] * d->nb_face, ds.bind_face_attr, sizeof(uint32_t) * (size_t)ds.nf * d->nb_face));
 			HB_TRY(copy_in(m, m->d_bind_corner + (size_t)m->h_ebase[s] * d->nb_corner, ds.bind_corner_attr, sizeof(uint32_t) * (size_t)ds.ne * d->nb_corner));
 		}
+		HB_TRY(flush_uploads(m));
 		uint32_t *d_twice = nullptr;
 		HB_TRY(hb_dalloc(m, (void **)&d_twice, sizeof(uint32_t)));
 		HB_CUDA(ctx, cudaMemsetAsync(d_twice, 0, sizeof(uint32_t), up_stream));
@@ -623,6 +733,7 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 	// a single region: every entry is 0 by definition -- cleared on the device instead of uploaded
 	if (d->nregs_vtx <= 1 && m->nv) HB_CUDA(ctx, cudaMemsetAsync(m->d_vtx_regs, 0, sizeof(uint16_t) * (size_t)m->nv, up_stream));
 	// everything K0 / K3 / K4 read is on its way: first milestone of the copy stream
+	HB_TRY(flush_uploads(m));
 	if (m->async_copy) {
 		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_up[0], cudaEventDisableTiming));
 		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_up[1], cudaEventDisableTiming));
@@ -672,6 +783,7 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 			}
 		}
 	}
+	HB_TRY(flush_uploads(m));
 	if (late) {
 		// the answer has been back for a while: the link is still busy with what was queued behind the check
 		HB_CUDA(ctx, cudaEventSynchronize(ctx->ev_flag));
@@ -683,6 +795,8 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 			m->has_order_f = false; // index order, gate corner 0 (norder_f == nf was required: the segment tables are the same)
 		}
 	}
+	HB_TRY(flush_uploads(m));
+	m->gather_uploads = false;
 	if (m->async_copy) HB_CUDA(ctx, cudaEventRecord(m->ev_up[1], ctx->copy_stream));
 	m->alloc_on_copy_stream = false;
 	return 0;
@@ -1333,6 +1447,43 @@ static void make_groups(const hb_mesh_desc *meshes, uint32_t n, std::vector<uint
 	starts.push_back(n);
 }
 
+// HARRY_B200_TRACE_BATCH=1: per group, when its upload / kernels / download began and ended (ms from the start of the
+// call, CUDA events on the three streams), printed to stderr at the end of hb_encode_batch / hb_decode_batch
+struct BatchTrace {
+	bool on = false;
+	cudaEvent_t base = nullptr;
+	struct Row { cudaEvent_t e[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; };
+	std::vector<Row> rows;
+	void begin(hb_ctx *ctx, size_t G)
+	{
+		const char *env = getenv("HARRY_B200_TRACE_BATCH");
+		on = env && env[0] == '1';
+		if (!on) return;
+		rows.resize(G);
+		cudaEventCreate(&base);
+		cudaEventRecord(base, ctx->copy_stream);
+	}
+	void mark(size_t g, int k, cudaStream_t st)
+	{
+		if (!on) return;
+		cudaEventCreate(&rows[g].e[k]);
+		cudaEventRecord(rows[g].e[k], st);
+	}
+	void report(const char *what)
+	{
+		if (!on) return;
+		cudaDeviceSynchronize();
+		fprintf(stderr, "[trace] %s: group: upload begin-end | kernels begin-end | download begin-end (ms)\n", what);
+		for (size_t g = 0; g < rows.size(); ++g) {
+			float t[6] = { -1, -1, -1, -1, -1, -1 };
+			for (int k = 0; k < 6; ++k)
+				if (rows[g].e[k]) { cudaEventElapsedTime(&t[k], base, rows[g].e[k]); cudaEventDestroy(rows[g].e[k]); }
+			fprintf(stderr, "[trace]   %2zu: %8.2f - %8.2f | %8.2f - %8.2f | %8.2f - %8.2f\n", g, t[0], t[1], t[2], t[3], t[4], t[5]);
+		}
+		cudaEventDestroy(base);
+	}
+};
+
 extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t n, const hb_quant_req *q, uint32_t nq, void *const *bounds_out, hb_batch_streams **out)
 {
 	*out = nullptr;
@@ -1350,14 +1501,20 @@ extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 	std::vector<hb_dmesh *> dm(G, nullptr);
 	std::vector<FetchState> fs(G);
 	int rc = b->mesh ? 0 : hb_fail(ctx, HB_ERR_NOMEM, "out of host memory");
+	BatchTrace tr;
+	tr.begin(ctx, G);
 	auto upload_group = [&](size_t g) -> int {
 		dm[g] = new hb_dmesh();
 		dm[g]->async_copy = true;
-		return dmesh_upload_impl(ctx, meshes + starts[g], starts[g + 1] - starts[g], dm[g], false, true);
+		tr.mark(g, 0, ctx->copy_stream);
+		const int r = dmesh_upload_impl(ctx, meshes + starts[g], starts[g + 1] - starts[g], dm[g], false, true);
+		tr.mark(g, 1, ctx->copy_stream);
+		return r;
 	};
 	auto run_group = [&](size_t g) -> int {
 		hb_dmesh *m = dm[g];
 		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_up[1], 0));
+		tr.mark(g, 2, ctx->stream);
 		for (uint32_t k = 0; k < nq; ++k) {
 			if (q[k].list >= (uint32_t)m->nlists) return hb_fail(ctx, HB_ERR_INVALID, "batch: quantization request for list %u", q[k].list);
 			HB_TRY(hb_list_bounds(m, q[k].list, q[k].groups));
@@ -1366,11 +1523,13 @@ extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 		HB_TRY(hb_encode_lists(m));
 		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
 		HB_CUDA(ctx, cudaEventRecord(m->ev_done, ctx->stream));
+		tr.mark(g, 3, ctx->stream);
 		return 0;
 	};
 	auto download_group = [&](size_t g) -> int {
 		hb_dmesh *m = dm[g];
 		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, m->ev_done, 0));
+		tr.mark(g, 4, ctx->out_stream);
 		fs[g].seg0 = starts[g];
 		for (uint32_t k = 0; k < nq; ++k) { // bounds rows of the group's meshes: min, max, scale per mesh
 			if (!bounds_out || !bounds_out[k]) continue;
@@ -1379,6 +1538,7 @@ extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 			if (s3) HB_CUDA(ctx, cudaMemcpy2DAsync((uint8_t *)bounds_out[k] + s3 * starts[g], s3, dl.d_bounds, dl.bounds_pitch, s3, m->nseg, cudaMemcpyDeviceToHost, ctx->out_stream));
 		}
 		HB_TRY(fetch_begin(m, ctx->out_stream, pv, fs[g]));
+		tr.mark(g, 5, ctx->out_stream);
 		dmesh_release_device(m, ctx->out_stream);
 		return 0;
 	};
@@ -1395,6 +1555,7 @@ extern "C" int hb_encode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 		for (size_t g = 0; g < G; ++g)
 			for (uint32_t sg = 0; sg < dm[g]->nseg; ++sg) fetch_view(fs[g], pv, sg, &b->mesh[starts[g] + sg]);
 	cudaStreamSynchronize(ctx->out_stream);
+	tr.report("hb_encode_batch");
 	for (hb_dmesh *m : dm) hb_dmesh_free(m);
 	if (rc) { hb_batch_streams_free(b); return rc; }
 	*out = b;
@@ -1412,10 +1573,13 @@ extern "C" int hb_decode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 	bool vertex_only = true;
 	for (uint32_t i = 0; i < n; ++i) vertex_only = vertex_only && decode_is_vertex_only(&meshes[i]);
 	int rc = 0;
+	BatchTrace tr;
+	tr.begin(ctx, G);
 	auto upload_group = [&](size_t g) -> int {
 		dm[g] = new hb_dmesh();
 		dm[g]->async_copy = true;
 		hb_dmesh *m = dm[g];
+		tr.mark(g, 0, ctx->copy_stream);
 		HB_TRY(dmesh_upload_impl(ctx, meshes + starts[g], starts[g + 1] - starts[g], m, vertex_only));
 		for (uint32_t k = 0; k < nq; ++k) { // bounds rows of the lists to dequantize (min, max, scale per mesh)
 			if (q[k].list >= (uint32_t)m->nlists || !q[k].bounds) return hb_fail(ctx, HB_ERR_INVALID, "batch: dequantization request for list %u", q[k].list);
@@ -1424,18 +1588,22 @@ extern "C" int hb_decode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 			if (s3) HB_CUDA(ctx, cudaMemcpy2DAsync(dl.d_bounds, dl.bounds_pitch, (const uint8_t *)q[k].bounds + s3 * starts[g], s3, s3, m->nseg, cudaMemcpyHostToDevice, ctx->copy_stream));
 		}
 		HB_CUDA(ctx, cudaEventRecord(m->ev_up[1], ctx->copy_stream));
+		tr.mark(g, 1, ctx->copy_stream);
 		return 0;
 	};
 	auto run_group = [&](size_t g) -> int {
 		hb_dmesh *m = dm[g];
 		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_up[1], 0));
+		tr.mark(g, 2, ctx->stream);
 		HB_TRY(hb_decode_lists(m));
 		uint8_t zero[HB_MAX_COMP] = { 0 };
 		for (uint32_t k = 0; k < nq; ++k) HB_TRY(hb_list_requant(m, q[k].list, zero));
 		HB_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
 		HB_CUDA(ctx, cudaEventRecord(m->ev_done, ctx->stream));
+		tr.mark(g, 3, ctx->stream);
 		// rows back to the caller's lists
 		HB_CUDA(ctx, cudaStreamWaitEvent(ctx->out_stream, m->ev_done, 0));
+		tr.mark(g, 4, ctx->out_stream);
 		for (int l = 0; l < m->nlists; ++l) {
 			DevList &dl = m->lists[l];
 			if (!dl.p.ncomp) continue;
@@ -1445,6 +1613,7 @@ extern "C" int hb_decode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 				if (bytes) HB_CUDA(ctx, cudaMemcpyAsync(L.rows, dl.p.rows + (size_t)dl.h_rowbase[sg] * L.stride, bytes, cudaMemcpyDeviceToHost, ctx->out_stream));
 			}
 		}
+		tr.mark(g, 5, ctx->out_stream);
 		dmesh_release_device(m, ctx->out_stream);
 		return 0;
 	};
@@ -1457,6 +1626,7 @@ extern "C" int hb_decode_batch(hb_ctx *ctx, const hb_mesh_desc *meshes, uint32_t
 	}
 	if (cudaStreamSynchronize(ctx->out_stream) != cudaSuccess && rc == 0) rc = hb_fail(ctx, HB_ERR_CUDA, "batch download failed: %s", cudaGetErrorString(cudaGetLastError()));
 	if (rc == 0) rc = hb_check_device_error(ctx, "batch decode");
+	tr.report("hb_decode_batch");
 	for (hb_dmesh *m : dm) hb_dmesh_free(m);
 	return rc;
 }

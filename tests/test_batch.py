@@ -157,12 +157,47 @@ def test_batch_decode_scan_variants(ctx, workdir, name, ntb, dense, monkeypatch)
     test_batch_device_resident_decode(ctx, workdir, name)
 
 
-def host_roundtrip(ctx, cases):
+_pinned_keep = []
+
+
+def page_locked(mesh, salt):
+    """the mesh with every array in page-locked host memory (torch is only the allocator), at varying offsets from a
+    16-byte boundary: what the gathered upload of a batch reads directly from the device"""
+    import torch
+
+    def pin(a, k):
+        a = np.ascontiguousarray(a)
+        off = ((salt + k) % 4) * a.dtype.itemsize if a.dtype.itemsize < 16 else 0   # 0, 1, 2 or 3 elements off the boundary
+        buf = torch.empty(a.nbytes + 64, dtype=torch.uint8, pin_memory=True)
+        _pinned_keep.append(buf)
+        out = buf.numpy()[off: off + a.nbytes].view(a.dtype).reshape(a.shape)
+        out[...] = a
+        return out
+
+    m = mesh.copy()
+    for k, name in enumerate(("edges", "face_off", "order", "order_f", "vtx_regs", "face_regs", "bind_face", "bind_vtx", "bind_corner")):
+        a = getattr(m, name)
+        if a is not None and a.size:
+            setattr(m, name, pin(a, k))
+    for k, la in enumerate(m.lists):
+        if la.rows.size:
+            la.rows = pin(la.rows, 9 + k)
+    if m.emit_types is not None:
+        m.emit_types = [pin(t, 13 + k) if t is not None and t.size else t for k, t in enumerate(m.emit_types)]
+    return m
+
+
+def host_roundtrip(ctx, cases, pinned=False):
     reqs = quant_requests(cases[0])
-    streams, bounds = ctx.encode_batch(encoder_inputs(cases), reqs)
+    enc_in = encoder_inputs(cases)
+    if pinned:
+        enc_in = [page_locked(m, i) for i, m in enumerate(enc_in)]
+    streams, bounds = ctx.encode_batch(enc_in, reqs)
     check_streams(cases, streams)
     check_bounds(cases, reqs, bounds)
     ins = [c.decode_input() for c in cases]
+    if pinned:
+        ins = [page_locked(m, 3 + i) for i, m in enumerate(ins)]
     deq = []
     if cases[0].deq is not None:
         for l, la in enumerate(cases[0].dec.lists):
@@ -183,6 +218,22 @@ def test_batch_host_buffers(ctx, workdir, name, group, monkeypatch):
     if group:
         monkeypatch.setenv("HARRY_B200_GROUP_HALF_EDGES", str(group))
     host_roundtrip(ctx, family(workdir, name))
+
+
+@pytest.mark.parametrize("name", ["spheres64_q14", "poly_q10", "obj_multi_all", "spheres_lossless"])
+@pytest.mark.parametrize("group", [0, 20000])
+@pytest.mark.parametrize("mode", ["2", "1", "0"])
+def test_batch_host_buffers_page_locked(ctx, workdir, name, group, mode, monkeypatch):
+    """page-locked host arrays of a batch are not copied one by one: they are queued and issued per upload stage as ONE
+    batched copy (mode 2, cudaMemcpyBatchAsync) or fetched by one kernel that reads the host memory directly (mode 1: any
+    alignment of source and destination); mode 0 = one copy per array.  Same results every way."""
+    monkeypatch.setenv("HARRY_B200_GATHER_UPLOADS", mode)
+    if group:
+        monkeypatch.setenv("HARRY_B200_GROUP_HALF_EDGES", str(group))
+    launches0, up0 = ctx.launches(), ctx.h2d_bytes()
+    host_roundtrip(ctx, family(workdir, name), pinned=True)
+    assert ctx.h2d_bytes() > up0
+    _pinned_keep.clear()
 
 
 def test_batch_two_contexts_concurrently(workdir, monkeypatch):
