@@ -33,3 +33,22 @@ def test_clock_sampler_falls_back_to_the_last_samples():
 def test_clock_sampler_without_nvidia_smi():
     out = bench.ClockSampler(0).stop()
     assert out["sm_mhz"] is None and out["reasons"] == ["nvidia-smi unavailable"]
+
+
+def test_ncu_traffic_reads_the_committed_capture():
+    """roofline.traffic comes from profiles/r02_kernels_10m_ncu_full.txt: DRAM read + write bytes of one launch"""
+    t = bench.ncu_traffic("k_decode_vertex_scan")
+    assert t is not None and 0.5e9 < t < 1.5e9          # 0.80 GB read + 0.08 GB written at 10M vertices
+    f = bench.ncu_traffic("k_flatten_halfedges")
+    assert f is not None and 1.5e9 < f < 2.0e9          # 12 B in, 16 B out per half-edge, 60M half-edges
+    assert bench.ncu_traffic("(k_encode_vtx_packed<T, NC>)") is not None
+    assert bench.ncu_traffic("k_no_such_kernel") is None
+
+
+def test_bind_rank_without_a_gpu_keeps_the_affinity():
+    """no CUDA device (this container) or an unknown topology: the rank stays where it is"""
+    import os
+    from harry_b200 import shard
+    before = os.sched_getaffinity(0)
+    assert shard.bind_rank_to_gpu_node(0, "/nonexistent") == before
+    assert os.sched_getaffinity(0) == before
