@@ -340,6 +340,16 @@ def allreduce_max(dist, local_rank, vals):
     return [float(x) for x in t.tolist()]
 
 
+def arm_config(nr, ns, n_attrs, world):
+    """The `config` object of the bench line: the SAME dict in the GPU arm and in the `--impl reference` arm (both run this
+    workload: one configs[1] mesh per GPU / per reference process, prepared once, K timed steps)."""
+    nv, nf = (nr - 1) * ns + 2, 2 * ns * (nr - 1)
+    return {"workload": f"configs[1]: UV sphere {nr}x{ns}, {nv} vertices / {nf} triangles per mesh, float32 xyz, -l1 -q{QBITS}, encode+decode",
+            "vertex_attributes_per_gpu": int(n_attrs), "meshes": int(world),
+            "parallelism": f"{world} mesh(es), one per GPU (reference arm: one per host process), sharded by mesh, no collective",
+            "l2": "inputs (>= 1.3 GB of connectivity + rows per mesh) exceed the 126 MB L2; no explicit flush"}
+
+
 def link_probe(dist, local_rank, world, nbytes=1 << 30, reps=3):
     """Host -> device bandwidth of one GPU while the others idle, and of every GPU when all ranks copy at once: the
     end-to-end lines are link-bound, so their scaling over N is the platform's (GPUs sharing a PCIe uplink), measured here
@@ -574,15 +584,13 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16", "data": "synthetic",
-            "config": {"workload": f"configs[1]: UV sphere {nr}x{ns}, {nv} vertices / {nf} triangles per GPU, float32 xyz, -l1 -q{QBITS}, encode+decode",
-                       "inputs_prepared_by": Workload.source,
-                       "vertex_attributes_per_gpu": n_attrs, "meshes": world, "parallelism": f"mesh-sharded x{world}, no collective",
-                       "l2": "inputs (>= 1.3 GB of connectivity + rows per mesh) exceed the 126 MB L2; no explicit flush",
-                       "streams": ("one stream" if args.one_stream else "two streams of the same GPU: quantize + encode of the mesh on one, decode + dequantize of the decoder-side mesh "
-                                   "on the other, which has the higher stream priority (independent inputs; the chain-bound vertex decode of one mesh occupies 48 of 148 SMs, "
-                                   "the encode job takes what it leaves); ms_per_step = both done; "
-                                   "encode_ms / decode_ms = each job on its own stream while the other runs"),
-                       "batch_config": "configs[4] (the mesh batch north_star scales on) is measured in the same run at every N: see `batch`"},
+            "config": arm_config(nr, ns, n_attrs, world),
+            "notes": {"inputs_prepared_by": Workload.source,
+                      "streams": ("one stream" if args.one_stream else "two streams of the same GPU: quantize + encode of the mesh on one, decode + dequantize of the decoder-side mesh "
+                                  "on the other, which has the higher stream priority (independent inputs; the chain-bound vertex decode of one mesh occupies 48 of 148 SMs, "
+                                  "the encode job takes what it leaves); ms_per_step = both done; "
+                                  "encode_ms / decode_ms = each job on its own stream while the other runs"),
+                      "batch_config": "configs[4] (the mesh batch north_star scales on) is measured in the same run at every N: see `batch`"},
             "encode_ms_per_step": enc_ms / args.steps, "decode_ms_per_step": dec_ms / args.steps,
             "encode_M_attrs_per_s": world * n_attrs / (enc_ms / args.steps * 1e-3) / 1e6 if enc_ms else None,
             "decode_M_attrs_per_s": world * n_attrs / (dec_ms / args.steps * 1e-3) / 1e6 if dec_ms else None,
@@ -1211,9 +1219,8 @@ def run_reference(args, rank: int, world: int):
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": f"configs[1]: UV sphere {shape[0]}x{shape[1]}, float32 xyz, -l1 -q{QBITS}, encode+decode (same mesh as the GPU arm)",
-                   "vertex_attributes_per_gpu": n_attrs, "meshes": world,
-                   "parallelism": f"{nproc} host process(es), one mesh each (the reference is single-threaded per mesh)"},
+        "config": arm_config(shape[0], shape[1], n_attrs, world),
+        "notes": {"processes": f"{nproc} host process(es), one mesh each (the reference is single-threaded per mesh)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
