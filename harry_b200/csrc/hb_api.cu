@@ -577,11 +577,14 @@ static bool same_region_table(const int32_t *off_a, const uint16_t *la, const in
 static bool order_f_maybe_unneeded(const hb_mesh_desc *descs, uint32_t nseg)
 {
 	const hb_mesh_desc *d = &descs[0];
-	if (!d->order_f || d->nregs_face != 1 || !d->lists) return false;
+	bool any = false;
+	for (uint32_t s = 0; s < nseg; ++s) any = any || (descs[s].nf && descs[s].order_f);
+	if (!any || d->nregs_face != 1 || !d->lists) return false;
 	const char *env = getenv("HARRY_B200_KEEP_ORDER_F"); // A/B runs and tests: always upload the face order
 	if (env && env[0] == '1') return false;
 	for (uint32_t s = 0; s < nseg; ++s) {
 		const hb_mesh_desc &ds = descs[s];
+		if (ds.nf == 0 && ds.nlists == d->nlists && ds.lists) continue; // no faces: nothing to order
 		if (!ds.order_f || ds.norder_f != ds.nf || ds.nlists != d->nlists || !ds.lists) return false;
 		for (int l = 0; l < ds.nlists; ++l)
 			if (ds.lists[l].target != HB_VTX && ds.lists[l].ncomp) return false;
@@ -619,7 +622,10 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 		m->upload_mode = atoi(env);
 		m->gather_uploads = m->async_copy && m->upload_mode != 0;
 	}
-	m->has_order_f = d->order_f != nullptr && !vertex_only;
+	// (a mesh without faces says nothing about the face order: its pointer may be anything)
+	bool any_order_f = false;
+	for (uint32_t s = 0; s < nseg; ++s) any_order_f = any_order_f || (descs[s].nf && descs[s].order_f != nullptr);
+	m->has_order_f = any_order_f && !vertex_only;
 	m->nb_face = d->nb_face; m->nb_vtx = d->nb_vtx; m->nb_corner = d->nb_corner;
 	m->nregs_face = d->nregs_face; m->nregs_vtx = d->nregs_vtx; m->nlists = d->nlists;
 	if (d->nlists && !d->lists) return hb_fail(ctx, HB_ERR_INVALID, "mesh: lists == NULL");
@@ -634,9 +640,10 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 		if (ds.nf && ds.face_off[0] != 0) return hb_fail(ctx, HB_ERR_INVALID, "mesh: face_off[0] != 0");
 		if (ds.norder && !ds.order) return hb_fail(ctx, HB_ERR_INVALID, "mesh: order == NULL");
 		if ((ds.nv && !ds.vtx_regs) || (ds.nf && !ds.face_regs)) return hb_fail(ctx, HB_ERR_INVALID, "mesh: region arrays == NULL");
+		if (ds.nf && (ds.order_f != nullptr) != any_order_f) return hb_fail(ctx, HB_ERR_INVALID, "batch: a face order for some meshes only (mesh %u)", s);
 		if (s) {
 			if (ds.nlists != d->nlists || ds.nb_face != d->nb_face || ds.nb_vtx != d->nb_vtx || ds.nb_corner != d->nb_corner || ds.nregs_face != d->nregs_face ||
-			    ds.nregs_vtx != d->nregs_vtx || (ds.order_f != nullptr) != (d->order_f != nullptr) || (ds.emit_type != nullptr) != (d->emit_type != nullptr) ||
+			    ds.nregs_vtx != d->nregs_vtx || (ds.emit_type != nullptr) != (d->emit_type != nullptr) ||
 			    !same_region_table(d->off_reg_vtx, d->reg_vtxlist, ds.off_reg_vtx, ds.reg_vtxlist, d->nregs_vtx) ||
 			    !same_region_table(d->off_reg_face, d->reg_facelist, ds.off_reg_face, ds.reg_facelist, d->nregs_face) ||
 			    !same_region_table(d->off_reg_corner, d->reg_cornerlist, ds.off_reg_corner, ds.reg_cornerlist, d->nregs_face))
@@ -768,10 +775,11 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 			uint64_t total = 0;
 			dl.h_emitbase.assign((size_t)nseg + 1, 0);
 			for (uint32_t s = 0; s < nseg; ++s) {
+				dl.h_emitbase[s] = (uint32_t)total;
+				if (descs[s].nv == 0 && descs[s].nf == 0) continue; // an empty mesh emits nothing: neither given nor missing
 				const bool has = descs[s].emit_type && descs[s].emit_type[l];
 				any = any || has; all = all && has;
 				if (has && !descs[s].emit_count) return hb_fail(ctx, HB_ERR_INVALID, "mesh: emit_type without emit_count");
-				dl.h_emitbase[s] = (uint32_t)total;
 				if (has) total += descs[s].emit_count[l];
 			}
 			dl.h_emitbase[nseg] = (uint32_t)total;
@@ -779,7 +787,10 @@ static int dmesh_upload_impl(hb_ctx *ctx, const hb_mesh_desc *descs, uint32_t ns
 			if (all) {
 				dl.emit_count = (uint32_t)total;
 				HB_TRY(hb_dalloc(m, (void **)&dl.d_emit_type, total));
-				for (uint32_t s = 0; s < nseg; ++s) HB_TRY(copy_in(m, dl.d_emit_type + dl.h_emitbase[s], descs[s].emit_type[l], descs[s].emit_count[l]));
+				for (uint32_t s = 0; s < nseg; ++s) {
+					if (descs[s].nv == 0 && descs[s].nf == 0) continue;
+					HB_TRY(copy_in(m, dl.d_emit_type + dl.h_emitbase[s], descs[s].emit_type[l], descs[s].emit_count[l]));
+				}
 			}
 		}
 	}

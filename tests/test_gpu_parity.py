@@ -393,3 +393,54 @@ def test_invalid_input_is_reported(corrupt):
         except capi.HarryError:
             pass
     c.close()
+
+
+def _emptied(mesh):
+    """the same schema with no vertex, no face and no row"""
+    e = mesh.copy()
+    e.nv = e.nf = 0
+    e.edges = np.zeros((0, 3), np.uint32)
+    e.face_off = np.zeros(1, np.uint32)
+    e.order = np.zeros((0, 2), np.uint32)
+    e.order_f = np.zeros((0, 2), np.uint32) if mesh.order_f is not None else None
+    e.vtx_regs = np.zeros(0, np.uint16)
+    e.face_regs = np.zeros(0, np.uint16)
+    e.bind_face = np.zeros(0, np.uint32)
+    e.bind_vtx = np.zeros(0, np.uint32)
+    e.bind_corner = np.zeros(0, np.uint32)
+    for la in e.lists:
+        la.rows = np.zeros((0, la.rows.shape[1]), np.uint8)
+    return e
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["sphere_q14", "poly_q10"])
+def test_empty_mesh_alone_and_inside_a_batch(workdir, name):
+    """no vertex, no face, no row: empty streams (like the oracle's), and an empty mesh between two others leaves
+    their streams untouched (empty segments in every per-segment table)"""
+    case = get_case(workdir, name)
+    c = capi.Context(0)
+    full = case.enc
+    empty = _emptied(full)
+    want_empty = ol.o_attr_encode(empty)
+    ok, why = c.attr_encode(empty).equal(want_empty)
+    assert ok, why
+    got, _ = c.encode_batch([full, empty, full, empty])
+    for g, want in zip(got, (case.enc_streams, want_empty, case.enc_streams, want_empty)):
+        ok, why = g.equal(want)
+        assert ok, why
+    dm = capi.DeviceMesh(c, [empty, full, empty])
+    dm.encode()
+    for g, want in zip(dm.fetch_streams_batch(), (want_empty, case.enc_streams, want_empty)):
+        ok, why = g.equal(want)
+        assert ok, why
+    dm.close()
+    # decode side: the empty decoder mesh between two real ones
+    ins = [case.decode_input(), _emptied(case.decode_input()), case.decode_input()]
+    ins[1].emit_types = [np.zeros(0, np.uint8) for _ in ins[1].lists]
+    c.decode_batch(ins)
+    for m in (ins[0], ins[2]):
+        for l, la in enumerate(case.dec.lists):
+            if la.ncomp:
+                assert np.array_equal(m.lists[l].rows, la.rows)
+    c.close()
